@@ -1,0 +1,214 @@
+"""Generate tests/golden/ by executing the UNMODIFIED reference (build container only).
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz + tests/golden/msa/*.phy
+
+The reference (/root/reference, read-only, absent on the GPU box) is imported
+with the stub packages under oracle/ref_stubs/ standing in for its missing
+third-party imports (raxmlpy native binding, fvcore, ete3, dendropy, Bio).
+For every case it drives the reference's own `reinforce_rollout(eval=True,
+argmax=True, branch_optimize=False)` (finetune_rl_search.py:78-189) with
+`torch.manual_seed(0)` default-initialised weights (the shipped checkpoint is a
+missing blob) and records what the reference computed:
+the merge list, the logits of every step, selected_log_ps, the Newick string and
+a strided sample of the encoder output.  It then checks oracle/nnj_oracle.py
+against those records and prints the deviations.  Nothing from here is used at
+run time by the product.
+"""
+import hashlib
+import os
+import shutil
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = os.environ.get("NNJ_REFERENCE", "/root/reference")
+GOLD = os.path.join(REPO, "tests", "golden")
+
+sys.path.insert(0, os.path.join(HERE, "ref_stubs"))
+sys.path.insert(0, REF)
+sys.path.insert(0, HERE)
+
+import nnj_oracle as O  # noqa: E402
+
+CASES = [
+    # (case name, path relative to the reference)
+    ("ex50x1024_73", "examples/len1024taxa50/G_l_1024_n_50_0_0.03_73.phy"),
+    ("ex50x1024_71", "examples/len1024taxa50/G_l_1024_n_50_0_0.02_71.phy"),
+    ("t20x256_10", "data_gen/data/test/len256/taxa20/G_l_256_n_20_0_0.01_10.phy"),
+    ("t20x256_103", "data_gen/data/test/len256/taxa20/G_l_256_n_20_0_0.01_103.phy"),
+    ("t20x256_104", "data_gen/data/test/len256/taxa20/G_l_256_n_20_0_0.01_104.phy"),
+    ("t20x256_117", "data_gen/data/test/len256/taxa20/G_l_256_n_20_0_0.01_117.phy"),
+    ("t20x256_120", "data_gen/data/test/len256/taxa20/G_l_256_n_20_0_0.01_120.phy"),
+]
+
+
+def _pick(dirpath, k):
+    fs = sorted(f for f in os.listdir(os.path.join(REF, dirpath)) if f.endswith(".phy"))
+    return os.path.join(dirpath, fs[k])
+
+
+def main():
+    torch.set_num_threads(8)
+    import utils as ref_utils
+    import finetune_rl_search as ref_main
+    from environment import PhyInferEnv
+    from model import PhyloATTN
+    from phydata import load_pi_instance
+
+    torch.autograd.set_detect_anomaly(False)  # finetune_rl_search.py:33 turns it on globally; irrelevant under no_grad
+    cfgs = ref_utils.empty_config()
+    cfgs.merge_from_file(os.path.join(REF, "config/finetune_reinforce_search_example.yaml"))
+    ref_main.cfgs = cfgs
+    ref_main.device = torch.device("cpu")
+
+    cases = list(CASES)
+    cases.append(("t50x256_a", _pick("data_gen/data/test/len256/taxa50", 3)))
+    cases.append(("t100x256_a", _pick("data_gen/data/test/len256/taxa100", 5)))
+    cases.append(("t20x512_a", _pick("data_gen/data/test/len512/taxa20", 7)))
+    cases.append(("t50x512_a", _pick("data_gen/data/test/len512/taxa50", 11)))
+
+    os.makedirs(os.path.join(GOLD, "msa"), exist_ok=True)
+
+    torch.manual_seed(0)
+    model = PhyloATTN(cfgs).eval()
+    sd_ref = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    sd = O.init_state_dict(0)
+    assert list(sd.keys()) == list(sd_ref.keys()), "state_dict key order differs"
+    for k in sd:
+        assert torch.equal(sd[k], sd_ref[k]), f"seed-0 init differs at {k}"
+    h = hashlib.sha256()
+    for k in sd_ref:
+        h.update(sd_ref[k].numpy().tobytes())
+    with open(os.path.join(GOLD, "weights_seed0.sha256"), "w") as f:
+        f.write(h.hexdigest() + "\n")
+    np.savez_compressed(os.path.join(GOLD, "weights_seed0_sample.npz"),
+                        **{k.replace(".", "__"): v.numpy().ravel()[:8] for k, v in sd_ref.items()})
+    print("weights: oracle init == reference init, sha256", h.hexdigest()[:16])
+
+    def run_reference(batch):
+        """Drive the reference rollout, recording logits / actions through its own call sites."""
+        env = PhyInferEnv(cfgs, torch.device("cpu"))
+        rec = {"logits": [], "merges": [], "state0": None}
+        orig_dec, orig_enc, orig_step = model.decode_zxr, model.encode_zxr, env.step
+
+        def enc(*a, **k):
+            out = orig_enc(*a, **k)
+            rec["state0"] = out.detach().clone()
+            return out
+
+        def dec(*a, **k):
+            out = orig_dec(*a, **k)
+            rec["logits"].append(out["logits"].detach().clone())
+            return out
+
+        def step(actions, *a, **k):
+            n = env.states[0].num_trees
+            rec["merges"].append([list(map(int, env.tree_pairs_dict[n][int(x)])) for x in actions])
+            return orig_step(actions, *a, **k)
+
+        model.decode_zxr, model.encode_zxr, env.step = dec, enc, step
+        try:
+            t = time.time()
+            sel, log_ps, scores, best = ref_main.reinforce_rollout(
+                batch, model, env, cfgs, eval=True, argmax=True, branch_optimize=False)
+            dt = time.time() - t
+        finally:
+            del model.decode_zxr, model.encode_zxr
+        newicks = [s.subtrees[0].utree_op_str for s in env.states]
+        return rec, sel, newicks, dt
+
+    def save_case(name, batch, rec, sel, newicks, extra=None):
+        B = batch["data"].shape[0]
+        merges = np.array(rec["merges"], dtype=np.int32).transpose(1, 0, 2)  # [B,R-1,2]
+        logits = [l.numpy() for l in rec["logits"]]
+        offs = np.cumsum([0] + [l.shape[1] for l in logits]).astype(np.int64)
+        st = rec["state0"]
+        out = dict(
+            data=batch["data"].numpy().astype(np.int8),
+            seq_mask=(batch["seq_weights"] == 0).numpy(),
+            merges=merges,
+            logits=np.concatenate(logits, 1).astype(np.float32),
+            logit_offsets=offs,
+            selected_log_ps=sel.numpy().astype(np.float32),
+            state_sample=st[:, ::7, ::37, :].numpy().astype(np.float32),
+            state_abs_mean=np.array([float(st.abs().mean())], dtype=np.float64),
+            newick=np.array(newicks),
+            seq_keys=np.array(batch["seq_keys"]),
+        )
+        if extra:
+            out.update(extra)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+
+    def check_oracle(name, batch, rec, sel, newicks):
+        data = batch["data"]
+        mask = batch["seq_weights"] == 0
+        t = time.time()
+        r = O.rollout(sd, data, mask)
+        dt = time.time() - t
+        gm = torch.tensor(np.array(rec["merges"]).transpose(1, 0, 2))
+        same = bool(torch.equal(r["merges"], gm))
+        dl = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(r["logits"], rec["logits"]))
+        ds = float((r["state0"] - rec["state0"]).abs().max())
+        nw = [O.newick_from_merges([tuple(m) for m in r["merges"][b].tolist()], batch["seq_keys"][b])
+              for b in range(data.shape[0])]
+        print(f"  oracle vs reference [{name}]: merges identical={same} max rel dlogit={dl:.2e} "
+              f"max |dstate|={ds:.2e} newick identical={nw == list(newicks)} ({dt:.1f}s)")
+        assert same and nw == list(newicks) and dl < 1e-5
+
+    for name, rel in cases:
+        src = os.path.join(REF, rel)
+        dst = os.path.join(GOLD, "msa", name + ".phy")
+        shutil.copyfile(src, dst)
+        batch = load_pi_instance(src)
+        # the oracle's own PHYLIP reader must agree with the reference loader
+        d2, m2, keys2, _ = O.load_phy(dst)
+        assert torch.equal(d2, batch["data"]) and keys2 == batch["seq_keys"][0], name
+        rec, sel, newicks, dt = run_reference(batch)
+        print(f"[{name}] reference rollout {dt:.1f}s  data {tuple(batch['data'].shape)}")
+        save_case(name, batch, rec, sel, newicks)
+        check_oracle(name, batch, rec, sel, newicks)
+
+    # batch of two different MSAs of one shape (B>1 semantics), and a padded-column case
+    b1 = load_pi_instance(os.path.join(REF, CASES[2][1]))
+    b2 = load_pi_instance(os.path.join(REF, CASES[3][1]))
+    both = {"data": torch.cat([b1["data"], b2["data"]]), "seq_weights": torch.cat([b1["seq_weights"], b2["seq_weights"]]),
+            "seqs": b1["seqs"] + b2["seqs"], "seq_keys": b1["seq_keys"] + b2["seq_keys"]}
+    rec, sel, newicks, dt = run_reference(both)
+    print(f"[batch2_20x256] reference rollout {dt:.1f}s")
+    save_case("batch2_20x256", both, rec, sel, newicks)
+    check_oracle("batch2_20x256", both, rec, sel, newicks)
+
+    pad = {k: (v.clone() if torch.is_tensor(v) else list(v)) for k, v in b1.items() if k in ("data", "seq_weights", "seqs", "seq_keys")}
+    pad["data"][:, :, 200:, :] = 0          # '*' padding columns (phydata.py:45)
+    pad["seq_weights"][:, 200:] = 0
+    rec, sel, newicks, dt = run_reference(pad)
+    print(f"[padded_20x256] reference rollout {dt:.1f}s")
+    save_case("padded_20x256", pad, rec, sel, newicks)
+    check_oracle("padded_20x256", pad, rec, sel, newicks)
+
+    # tiny cases: 3, 4 and 5 taxa (R'>2 gate, last-step path), random tokens
+    for R, L, seed in ((3, 64, 11), (4, 96, 12), (5, 128, 13)):
+        data = O.evolved_msa(1, R, L, seed=seed)
+        keys = [[f"taxon{i + 1}" for i in range(R)]]
+        tiny = {"data": data, "seq_weights": torch.ones(1, L), "seqs": [["A" * L] * R], "seq_keys": keys}
+        rec, sel, newicks, dt = run_reference(tiny)
+        nm = f"tiny_{R}x{L}"
+        save_case(nm, tiny, rec, sel, newicks)
+        check_oracle(nm, tiny, rec, sel, newicks)
+
+    # closed-form cache index map against the reference's table-driven one (utils.py:213-251)
+    env = PhyInferEnv(cfgs, torch.device("cpu"))
+    env.init_states([["A"] * 12], [[f"t{i}" for i in range(12)]], None)
+    for n_new in range(2, 12):
+        for (a, b) in env.tree_pairs_dict[n_new + 1]:
+            ref_idx = ref_utils.get_score_indices_to_prev(torch.tensor([[a, b]]), env, n_new, 1)[0]
+            assert [int(x) for x in ref_idx] == O.score_indices_to_prev(int(a), int(b), n_new)
+    print("cache index map: closed form == reference for n<=12")
+
+
+if __name__ == "__main__":
+    main()
