@@ -1,0 +1,147 @@
+/* nnj.h — C ABI of libnnj: the B200-native NeuralNJ inference hot path.
+ *
+ * The reference (DingShizhe/NeuralNJ) has no FFI: its boundary for this path is
+ * a set of Python call signatures.  Each entry point
+ * below names the reference interface it replaces (file:line relative to the
+ * reference checkout).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative nnj_status otherwise, and
+ *     never aborts; nnj_last_error() returns a thread-local message.
+ *   - "dev" pointers are CUDA device pointers on the device the model was
+ *     created on; "host" pointers are ordinary (ideally pinned) host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream).  All device-pointer entry points are asynchronous on it.
+ *   - tensors are dense row-major; D = 64 embedding width, C = L / patch.
+ *   - the caller owns every buffer, including the workspace.
+ */
+#ifndef NNJ_H_
+#define NNJ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNJ_ABI_VERSION 1
+
+typedef enum nnj_status {
+    NNJ_OK = 0,
+    NNJ_ERR_INVALID = -1,     /* bad argument / unsupported shape or config        */
+    NNJ_ERR_CUDA = -2,        /* a CUDA runtime call failed (message has details)  */
+    NNJ_ERR_WORKSPACE = -3,   /* workspace too small                               */
+    NNJ_ERR_NOMEM = -4
+} nnj_status;
+
+/* Model hyper-parameters: cfgs.model.* of the reference (utils.py:44-51, YAML :24-30). */
+typedef struct nnj_config {
+    int32_t embed_dim;    /* must be 64                                   */
+    int32_t num_heads;    /* must be 8                                    */
+    int32_t num_layers;   /* >= 1 (6 in the shipped configs)              */
+    int32_t vocab_size;   /* must be 4                                    */
+    int32_t patch_size;   /* must be 1                                    */
+    int32_t precision;    /* nnj_precision                                */
+} nnj_config;
+
+typedef enum nnj_precision {
+    NNJ_PREC_FP32 = 0,        /* fp32 CUDA-core arithmetic everywhere                       */
+    NNJ_PREC_BF16X3 = 1       /* dense contractions on tcgen05: split-bf16 (hi*hi+hi*lo+lo*hi), fp32 accumulate */
+} nnj_precision;
+
+typedef enum nnj_select_mode {
+    NNJ_SELECT_ARGMAX = 0,    /* torch.argmax(logits)            finetune_rl_search.py:145 */
+    NNJ_SELECT_GUMBEL = 1     /* argmax(logits + gumbel noise) == Categorical(logits).sample()  :147 */
+} nnj_select_mode;
+
+typedef struct nnj_model nnj_model;   /* opaque: device copy of the state_dict tensors */
+
+const char* nnj_last_error(void);
+int nnj_abi_version(void);
+
+/* Replaces PhyloATTN.__init__ + load_state_dict + .to(device) (model.py:12-60,
+ * finetune_rl_search.py:482-484).  `tensors` are n_tensors host pointers to
+ * fp32 arrays in the reference's state_dict order (172 for 6 layers: 26 per layer + 16):
+ * per layer row{k,v,q,out}.{weight,bias}, row LN, col{k,v,q,out}, col LN,
+ * fc1, fc2, ffn LN; then embed.0, embed.2, h_linear_last, g_linear_last,
+ * g_attn_q, g_attn_k, s_out.0, s_out.2.  `numels` gives each array's length
+ * and is checked against the config. */
+int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const* tensors,
+                     const int64_t* numels, int n_tensors, int device);
+void nnj_model_destroy(nnj_model* m);
+
+/* Bytes of device workspace needed by the entry points below for a batch of
+ * B alignments of R taxa x L sites (what: 0 = encode, 1 = pair scoring /
+ * aggregate, 2 = fused rollout). */
+int64_t nnj_workspace_bytes(const nnj_model* m, int what, int B, int R, int L);
+
+/* PhyloATTN.encode_zxr(batch_input, batch_seq_mask) (model.py:67-88).
+ * data int8 [B,R,L,4]; seq_mask uint8 [B,L] (1 = padded column); out fp32 [B,R,C,64]. */
+int nnj_encode(nnj_model* m, const int8_t* data_dev, const uint8_t* seq_mask_dev, int B, int R, int L,
+               float* out_dev, void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* decode_zxr step 0 + decode_gg (model.py:168-181, :90-99): scores of all
+ * P = R'(R'-1)/2 pairs in itertools.combinations order.  state fp32 [B,R',C,64];
+ * logits fp32 [B,P]. */
+int nnj_pair_scores_full(nnj_model* m, const float* state_dev, const uint8_t* seq_mask_dev, int B, int Rp, int C,
+                         float* logits_dev, void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* decode_gg on an explicit pair list (model.py:184-197): scores of N pairs
+ * (pair_i[b,n], pair_j[b,n]) per tree against the node set `state`.
+ * pair_i/pair_j int32 [B,N]; scores fp32 [B,N]. */
+int nnj_pair_scores_list(nnj_model* m, const float* state_dev, const uint8_t* seq_mask_dev, int B, int Rp, int C,
+                         const int32_t* pair_i_dev, const int32_t* pair_j_dev, int N,
+                         float* scores_dev, void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* decode_zxr step t>=1 (model.py:184-201) with the cache index map of
+ * utils.get_score_indices_to_prev (utils.py:213-251) evaluated in closed form
+ * on the device.  prev_ij int32 [B,2] = pair merged to obtain `state` (R' nodes);
+ * logits_prev fp32 [B, (R'+1)R'/2]; logits_out fp32 [B, R'(R'-1)/2]. */
+int nnj_pair_scores_incr(nnj_model* m, const float* state_dev, const uint8_t* seq_mask_dev, int B, int Rp, int C,
+                         const int32_t* prev_ij_dev, const float* logits_prev_dev, float* logits_out_dev,
+                         void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* PhyloATTN.aggregate(x_i, x_j, (ii, jj), batchwise_ij_indices=True)
+ * (model.py:102-155, called from environment.py:829): merged-node embedding of
+ * pair ij[b] computed against the pre-merge node set.  ij int32 [B,2];
+ * out fp32 [B,C,64]. */
+int nnj_aggregate(nnj_model* m, const float* state_dev, int B, int Rp, int C, const int32_t* ij_dev,
+                  float* out_dev, void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* PhyInferEnv.step tensor half (environment.py:760-835): slot i <- aggregate(i,j),
+ * slot j removed, order kept.  state_in [B,R',C,64] -> state_out [B,R'-1,C,64]. */
+int nnj_merge(nnj_model* m, const float* state_in_dev, int B, int Rp, int C, const int32_t* ij_dev,
+              float* state_out_dev, void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* Fused reinforce_rollout(eval=True) device loop (finetune_rl_search.py:107-175):
+ * encode, then R-1 x (score -> select -> merge) without leaving the device.
+ * gumbel fp32 [B,R-1,P0] (P0 = R(R-1)/2) or NULL for argmax.
+ * merges int32 [B,R-1,2]; optional traces: logits_trace fp32 [B, sum_t P_t]
+ * (steps concatenated, P_t = (R-t)(R-t-1)/2), selected_logp fp32 [B,R-1]
+ * (log_softmax(logits)[action], the last entry belongs to the final 2-node step). */
+int nnj_rollout(nnj_model* m, const int8_t* data_dev, const uint8_t* seq_mask_dev, int B, int R, int L,
+                int select_mode, const float* gumbel_dev, int32_t* merges_dev,
+                float* logits_trace_dev, float* selected_logp_dev,
+                void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* Same, but starting from a supplied encoder output (state fp32 [B,R,C,64]) —
+ * used by Search mode to share one encoder pass across sampled rollouts. */
+int nnj_rollout_from_state(nnj_model* m, const float* state_dev, const uint8_t* seq_mask_dev, int B, int R, int C,
+                           int select_mode, const float* gumbel_dev, int32_t* merges_dev,
+                           float* logits_trace_dev, float* selected_logp_dev,
+                           void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* End-to-end convenience with HOST buffers: copies data/mask to the device,
+ * runs nnj_rollout in chunks sized to the free device memory, copies the merge
+ * lists back and synchronises.  data_host int8 [B,R,L,4]; merges_host int32 [B,R-1,2]. */
+int nnj_rollout_host(nnj_model* m, const int8_t* data_host, const uint8_t* seq_mask_host, int B, int R, int L,
+                     int select_mode, const float* gumbel_host, int32_t* merges_host, float* selected_logp_host);
+
+/* Number of kernel launches issued by this library on the calling thread since the last reset. */
+int64_t nnj_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNJ_H_ */

@@ -1,0 +1,97 @@
+"""ctypes binding of libnnj (include/nnj.h).  PyTorch is plumbing only: device memory,
+streams and pointers.  There is no CPU or eager fallback — if the CUDA library is missing
+or fails, the call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnnj.so")
+SOURCES = ["nnj_api.cu", "nnj_encoder.cu", "nnj_njloop.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+
+EXPORTS = ["nnj_last_error", "nnj_abi_version", "nnj_model_create", "nnj_model_destroy", "nnj_workspace_bytes",
+           "nnj_encode", "nnj_pair_scores_full", "nnj_pair_scores_list", "nnj_pair_scores_incr", "nnj_aggregate",
+           "nnj_merge", "nnj_rollout", "nnj_rollout_from_state", "nnj_rollout_host", "nnj_launch_count"]
+
+
+class NnjError(RuntimeError):
+    pass
+
+
+class nnj_config(C.Structure):
+    _fields_ = [("embed_dim", C.c_int32), ("num_heads", C.c_int32), ("num_layers", C.c_int32),
+                ("vocab_size", C.c_int32), ("patch_size", C.c_int32), ("precision", C.c_int32)]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    src_dir = os.path.join(_HERE, "csrc")
+    deps = [os.path.join(src_dir, f) for f in os.listdir(src_dir)] + [os.path.join(_HERE, "..", "include", "nnj.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into neuralnj_b200/libnnj.so (in-tree, travels with the repo)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
+          [os.path.join(_HERE, "csrc", s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise NnjError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libnnj.so and declare the prototypes of include/nnj.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NnjError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback for the NeuralNJ hot path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.nnj_last_error.restype = C.c_char_p
+    L.nnj_abi_version.restype = i32
+    L.nnj_model_create.argtypes = [C.POINTER(vp), C.POINTER(nnj_config), C.POINTER(vp), C.POINTER(i64), i32, i32]
+    L.nnj_model_destroy.argtypes = [vp]
+    L.nnj_model_destroy.restype = None
+    L.nnj_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
+    L.nnj_workspace_bytes.restype = i64
+    L.nnj_encode.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i64, vp]
+    L.nnj_pair_scores_full.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i64, vp]
+    L.nnj_pair_scores_list.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, vp, vp, i64, vp]
+    L.nnj_pair_scores_incr.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i64, vp]
+    L.nnj_aggregate.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp]
+    L.nnj_merge.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i64, vp]
+    L.nnj_rollout.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]
+    L.nnj_rollout_from_state.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]
+    L.nnj_rollout_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    L.nnj_launch_count.argtypes = [i32]
+    L.nnj_launch_count.restype = i64
+    for name in ("nnj_model_create", "nnj_encode", "nnj_pair_scores_full", "nnj_pair_scores_list", "nnj_pair_scores_incr",
+                 "nnj_aggregate", "nnj_merge", "nnj_rollout", "nnj_rollout_from_state", "nnj_rollout_host"):
+        getattr(L, name).restype = i32
+    if L.nnj_abi_version() != 1:
+        raise NnjError("libnnj ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "libnnj") -> None:
+    if rc != 0:
+        raise NnjError(f"{what} failed ({rc}): {lib().nnj_last_error().decode()}")

@@ -1,0 +1,268 @@
+// nnj_api.cu — the C ABI declared in include/nnj.h.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "nnj_internal.h"
+
+namespace nnj {
+
+thread_local long long g_launches = 0;
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+
+int set_cuda_error(cudaError_t e, const char* file, int line) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
+    return NNJ_ERR_CUDA;
+}
+
+#define CUDA_TRY(x)                                                        \
+    do {                                                                   \
+        cudaError_t e_ = (x);                                              \
+        if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__); \
+    } while (0)
+
+// host-side packing helpers -------------------------------------------------
+struct Packer {
+    std::vector<float> host;
+    size_t add(const float* p, size_t n) {          // plain copy, 16-byte aligned start
+        size_t off = (host.size() + 3) / 4 * 4;
+        host.resize(off + n);
+        memcpy(host.data() + off, p, n * sizeof(float));
+        return off;
+    }
+    size_t add_t(const float* w, int out, int in) { // W [out][in] -> Wt [in][out]
+        size_t off = (host.size() + 3) / 4 * 4;
+        host.resize(off + (size_t)out * in);
+        for (int o = 0; o < out; ++o)
+            for (int i = 0; i < in; ++i) host[off + (size_t)i * out + o] = w[(size_t)o * in + i];
+        return off;
+    }
+};
+
+}  // namespace nnj
+
+using namespace nnj;
+
+struct nnj_model : public nnj::Model {};
+
+extern "C" {
+
+const char* nnj_last_error(void) { return g_err; }
+int nnj_abi_version(void) { return NNJ_ABI_VERSION; }
+
+int64_t nnj_launch_count(int reset) {
+    long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const* tensors, const int64_t* numels, int n_tensors,
+                     int device) {
+    if (!out || !cfg || !tensors || !numels) return set_error(NNJ_ERR_INVALID, "model_create: null argument");
+    if (cfg->embed_dim != 64 || cfg->num_heads != 8 || cfg->vocab_size != 4 || cfg->patch_size != 1 || cfg->num_layers < 1)
+        return set_error(NNJ_ERR_INVALID,
+                         "model_create: unsupported config (need embed_dim 64, num_heads 8, vocab_size 4, patch_size 1, num_layers >= 1)");
+    if (cfg->precision != NNJ_PREC_FP32 && cfg->precision != NNJ_PREC_BF16X3)
+        return set_error(NNJ_ERR_INVALID, "model_create: unknown precision mode");
+    const int Lyr = cfg->num_layers;
+    if (n_tensors != Lyr * 26 + 16) return set_error(NNJ_ERR_INVALID, "model_create: expected 26 tensors per layer + 16");
+    // expected element counts in state_dict order
+    std::vector<int64_t> expect;
+    for (int l = 0; l < Lyr; ++l) {
+        for (int blk = 0; blk < 2; ++blk) {
+            for (int p = 0; p < 4; ++p) { expect.push_back(64 * 64); expect.push_back(64); }
+            expect.push_back(64); expect.push_back(64);
+        }
+        expect.push_back(256 * 64); expect.push_back(256); expect.push_back(64 * 256); expect.push_back(64);
+        expect.push_back(64); expect.push_back(64);
+    }
+    const int64_t tail[16] = {64 * 4, 64, 64 * 64, 64, 64 * 64, 64, 64 * 64, 64, 64 * 64, 64, 64 * 64, 64, 64 * 64, 64, 64, 1};
+    for (int i = 0; i < 16; ++i) expect.push_back(tail[i]);
+    for (int i = 0; i < n_tensors; ++i)
+        if (numels[i] != expect[i]) {
+            char msg[128];
+            snprintf(msg, sizeof(msg), "model_create: tensor %d has %lld elements, expected %lld", i, (long long)numels[i], (long long)expect[i]);
+            return set_error(NNJ_ERR_INVALID, msg);
+        }
+    CUDA_TRY(cudaSetDevice(device));
+    nnj_model* m = new (std::nothrow) nnj_model();
+    if (!m) return set_error(NNJ_ERR_NOMEM, "model_create: out of host memory");
+    m->cfg = *cfg; m->device = device; m->num_layers = Lyr; m->blob = nullptr;
+
+    Packer pk;
+    struct AttnOff { size_t ln_g, ln_b, qt, kt, vt, ot, qb, kb, vb, ob; };
+    struct LayerOff { AttnOff a[2]; size_t fln_g, fln_b, w1t, b1, w2t, b2; };
+    std::vector<LayerOff> lo(Lyr);
+    int ti = 0;
+    for (int l = 0; l < Lyr; ++l) {
+        for (int blk = 0; blk < 2; ++blk) {
+            AttnOff& a = lo[l].a[blk];
+            // state_dict order: k_proj, v_proj, q_proj, out_proj (axial_attention.py:24-28), then the block's LayerNorm
+            a.kt = pk.add_t(tensors[ti], 64, 64); a.kb = pk.add(tensors[ti + 1], 64);
+            a.vt = pk.add_t(tensors[ti + 2], 64, 64); a.vb = pk.add(tensors[ti + 3], 64);
+            a.qt = pk.add_t(tensors[ti + 4], 64, 64); a.qb = pk.add(tensors[ti + 5], 64);
+            a.ot = pk.add_t(tensors[ti + 6], 64, 64); a.ob = pk.add(tensors[ti + 7], 64);
+            a.ln_g = pk.add(tensors[ti + 8], 64); a.ln_b = pk.add(tensors[ti + 9], 64);
+            ti += 10;
+        }
+        // fc1 [256][64] -> 4 chunks of [64 k][64 col]; fc2 [64][256] -> 4 chunks of [64 hidden][64 out]
+        {
+            const float* w1 = tensors[ti];
+            std::vector<float> t1(4 * 4096), t2(4 * 4096);
+            for (int ch = 0; ch < 4; ++ch)
+                for (int k = 0; k < 64; ++k)
+                    for (int c = 0; c < 64; ++c) t1[ch * 4096 + k * 64 + c] = w1[(size_t)(ch * 64 + c) * 64 + k];
+            const float* w2 = tensors[ti + 2];
+            for (int ch = 0; ch < 4; ++ch)
+                for (int k = 0; k < 64; ++k)
+                    for (int o = 0; o < 64; ++o) t2[ch * 4096 + k * 64 + o] = w2[(size_t)o * 256 + ch * 64 + k];
+            lo[l].w1t = pk.add(t1.data(), t1.size()); lo[l].b1 = pk.add(tensors[ti + 1], 256);
+            lo[l].w2t = pk.add(t2.data(), t2.size()); lo[l].b2 = pk.add(tensors[ti + 3], 64);
+            lo[l].fln_g = pk.add(tensors[ti + 4], 64); lo[l].fln_b = pk.add(tensors[ti + 5], 64);
+            ti += 6;
+        }
+    }
+    size_t e_w1 = pk.add(tensors[ti], 256), e_b1 = pk.add(tensors[ti + 1], 64);
+    size_t e_w2t = pk.add_t(tensors[ti + 2], 64, 64), e_b2 = pk.add(tensors[ti + 3], 64);
+    size_t h_t = pk.add_t(tensors[ti + 4], 64, 64), h_b = pk.add(tensors[ti + 5], 64);
+    size_t g_t = pk.add_t(tensors[ti + 6], 64, 64), g_b = pk.add(tensors[ti + 7], 64);
+    size_t q_w = pk.add(tensors[ti + 8], 4096), q_b = pk.add(tensors[ti + 9], 64);
+    size_t k_t = pk.add_t(tensors[ti + 10], 64, 64), k_b = pk.add(tensors[ti + 11], 64);
+    size_t s_t = pk.add_t(tensors[ti + 12], 64, 64), s_b = pk.add(tensors[ti + 13], 64);
+    size_t s2_w = pk.add(tensors[ti + 14], 64);
+    const float s2_b = tensors[ti + 15][0];
+
+    cudaError_t e = cudaMalloc(&m->blob, pk.host.size() * sizeof(float));
+    if (e != cudaSuccess) { delete m; return set_cuda_error(e, __FILE__, __LINE__); }
+    e = cudaMemcpy(m->blob, pk.host.data(), pk.host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(m->blob); delete m; return set_cuda_error(e, __FILE__, __LINE__); }
+    const float* B0 = m->blob;
+    m->layers.resize(Lyr);
+    for (int l = 0; l < Lyr; ++l) {
+        AttnW* aw[2] = {&m->layers[l].row, &m->layers[l].col};
+        for (int blk = 0; blk < 2; ++blk) {
+            const AttnOff& a = lo[l].a[blk];
+            *aw[blk] = AttnW{B0 + a.ln_g, B0 + a.ln_b, B0 + a.qt, B0 + a.kt, B0 + a.vt, B0 + a.ot, B0 + a.qb, B0 + a.kb, B0 + a.vb, B0 + a.ob};
+        }
+        m->layers[l].ffn = FfnW{B0 + lo[l].fln_g, B0 + lo[l].fln_b, B0 + lo[l].w1t, B0 + lo[l].b1, B0 + lo[l].w2t, B0 + lo[l].b2};
+    }
+    m->embed = EmbedW{B0 + e_w1, B0 + e_b1, B0 + e_w2t, B0 + e_b2};
+    m->nj = NjW{B0 + h_t, B0 + h_b, B0 + g_t, B0 + g_b, B0 + q_w, B0 + q_b, B0 + k_t, B0 + k_b, B0 + s_t, B0 + s_b, B0 + s2_w, s2_b};
+    *out = m;
+    return NNJ_OK;
+}
+
+void nnj_model_destroy(nnj_model* m) {
+    if (!m) return;
+    if (m->blob) cudaFree(m->blob);
+    delete m;
+}
+
+int64_t nnj_workspace_bytes(const nnj_model* m, int what, int B, int R, int L) {
+    if (!m || B < 1 || R < 2 || L < 1) return set_error(NNJ_ERR_INVALID, "workspace_bytes: bad arguments");
+    switch (what) {
+        case 0: return (int64_t)encoder_ws_bytes(m, B, R, L);
+        case 1: return (int64_t)nj_scores_ws_bytes(m, B, R, L, 0);
+        case 2: return (int64_t)nj_rollout_ws_bytes(m, B, R, L);
+        default: return set_error(NNJ_ERR_INVALID, "workspace_bytes: unknown selector");
+    }
+}
+
+#define CHECK_ARGS(cond, msg) \
+    do { if (!(cond)) return set_error(NNJ_ERR_INVALID, msg); } while (0)
+
+int nnj_encode(nnj_model* m, const int8_t* data, const uint8_t* mask, int B, int R, int L, float* out, void* ws, int64_t ws_bytes,
+               void* stream) {
+    CHECK_ARGS(m && data && out && ws && B >= 1 && R >= 2 && L >= 1, "encode: bad arguments");
+    return run_encoder(m, data, mask, B, R, L, out, (size_t)R * L * D, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
+int nnj_pair_scores_full(nnj_model* m, const float* state, const uint8_t* mask, int B, int Rp, int C, float* logits, void* ws,
+                         int64_t ws_bytes, void* stream) {
+    CHECK_ARGS(m && state && logits && ws && B >= 1, "pair_scores_full: bad arguments");
+    return run_pair_scores(m, state, mask, B, Rp, C, nullptr, nullptr, 0, true, logits, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
+int nnj_pair_scores_list(nnj_model* m, const float* state, const uint8_t* mask, int B, int Rp, int C, const int32_t* pi,
+                         const int32_t* pj, int N, float* scores, void* ws, int64_t ws_bytes, void* stream) {
+    CHECK_ARGS(m && state && scores && ws && pi && pj && B >= 1 && N >= 1, "pair_scores_list: bad arguments");
+    return run_pair_scores(m, state, mask, B, Rp, C, pi, pj, N, false, scores, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
+int nnj_pair_scores_incr(nnj_model* m, const float* state, const uint8_t* mask, int B, int Rp, int C, const int32_t* prev_ij,
+                         const float* logits_prev, float* logits_out, void* ws, int64_t ws_bytes, void* stream) {
+    CHECK_ARGS(m && state && prev_ij && logits_prev && logits_out && ws && B >= 1, "pair_scores_incr: bad arguments");
+    return run_pair_scores_incr(m, state, mask, B, Rp, C, prev_ij, logits_prev, logits_out, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
+int nnj_aggregate(nnj_model* m, const float* state, int B, int Rp, int C, const int32_t* ij, float* out, void* ws, int64_t ws_bytes,
+                  void* stream) {
+    CHECK_ARGS(m && state && ij && out && ws && B >= 1, "aggregate: bad arguments");
+    return run_aggregate(m, state, B, Rp, C, ij, out, (size_t)C * D, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
+int nnj_merge(nnj_model* m, const float* state_in, int B, int Rp, int C, const int32_t* ij, float* state_out, void* ws,
+              int64_t ws_bytes, void* stream) {
+    CHECK_ARGS(m && state_in && ij && state_out && ws && B >= 1 && Rp >= 3, "merge: bad arguments (need R' >= 3)");
+    return run_merge(m, state_in, B, Rp, C, ij, state_out, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
+int nnj_rollout(nnj_model* m, const int8_t* data, const uint8_t* mask, int B, int R, int L, int select_mode, const float* gumbel,
+                int32_t* merges, float* logits_trace, float* selected_logp, void* ws, int64_t ws_bytes, void* stream) {
+    CHECK_ARGS(m && data && merges && ws && B >= 1 && R >= 2 && L >= 1, "rollout: bad arguments");
+    return run_rollout(m, data, nullptr, mask, B, R, L, select_mode, gumbel, merges, logits_trace, selected_logp, ws, (size_t)ws_bytes,
+                       (cudaStream_t)stream);
+}
+
+int nnj_rollout_from_state(nnj_model* m, const float* state, const uint8_t* mask, int B, int R, int C, int select_mode,
+                           const float* gumbel, int32_t* merges, float* logits_trace, float* selected_logp, void* ws,
+                           int64_t ws_bytes, void* stream) {
+    CHECK_ARGS(m && state && merges && ws && B >= 1 && R >= 2 && C >= 1, "rollout_from_state: bad arguments");
+    return run_rollout(m, nullptr, state, mask, B, R, C, select_mode, gumbel, merges, logits_trace, selected_logp, ws, (size_t)ws_bytes,
+                       (cudaStream_t)stream);
+}
+
+int nnj_rollout_host(nnj_model* m, const int8_t* data_h, const uint8_t* mask_h, int B, int R, int L, int select_mode,
+                     const float* gumbel_h, int32_t* merges_h, float* selected_logp_h) {
+    CHECK_ARGS(m && data_h && merges_h && B >= 1 && R >= 2 && L >= 1, "rollout_host: bad arguments");
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t ws_bytes = nj_rollout_ws_bytes(m, B, R, L);
+    const size_t n_data = (size_t)B * R * L * 4, n_mask = (size_t)B * L, n_mg = (size_t)B * (R - 1) * 2;
+    const size_t n_gum = gumbel_h ? (size_t)B * (R - 1) * (R * (R - 1) / 2) : 0;
+    char *ws = nullptr, *io = nullptr;
+    const size_t io_bytes = ((n_data + 255) & ~(size_t)255) + ((n_mask + 255) & ~(size_t)255) + ((n_mg * 4 + 255) & ~(size_t)255) +
+                            ((n_mg * 2 + 255) & ~(size_t)255) + n_gum * 4 + 256;
+    CUDA_TRY(cudaMalloc(&ws, ws_bytes));
+    cudaError_t e = cudaMalloc(&io, io_bytes);
+    if (e != cudaSuccess) { cudaFree(ws); return set_cuda_error(e, __FILE__, __LINE__); }
+    int8_t* d_data = (int8_t*)io;
+    uint8_t* d_mask = (uint8_t*)(io + ((n_data + 255) & ~(size_t)255));
+    int32_t* d_mg = (int32_t*)((char*)d_mask + ((n_mask + 255) & ~(size_t)255));
+    float* d_slp = (float*)((char*)d_mg + ((n_mg * 4 + 255) & ~(size_t)255));
+    float* d_gum = gumbel_h ? (float*)((char*)d_slp + ((n_mg * 2 + 255) & ~(size_t)255)) : nullptr;
+    cudaStream_t st = 0;
+    int rc = NNJ_OK;
+    do {
+        if ((e = cudaMemcpyAsync(d_data, data_h, n_data, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+        if (mask_h) { if ((e = cudaMemcpyAsync(d_mask, mask_h, n_mask, cudaMemcpyHostToDevice, st)) != cudaSuccess) break; }
+        if (gumbel_h) { if ((e = cudaMemcpyAsync(d_gum, gumbel_h, n_gum * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) break; }
+        rc = run_rollout(m, d_data, nullptr, mask_h ? d_mask : nullptr, B, R, L, select_mode, d_gum, d_mg, nullptr,
+                         selected_logp_h ? d_slp : nullptr, ws, ws_bytes, st);
+        if (rc != NNJ_OK) break;
+        if ((e = cudaMemcpyAsync(merges_h, d_mg, n_mg * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+        if (selected_logp_h) { if ((e = cudaMemcpyAsync(selected_logp_h, d_slp, n_mg * 2, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break; }
+        e = cudaStreamSynchronize(st);
+    } while (0);
+    cudaFree(io);
+    cudaFree(ws);
+    if (rc != NNJ_OK) return rc;
+    if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    return NNJ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// nnj_internal.h — host-side structures shared by the libnnj translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nnj.h"
+#include "nnj_common.cuh"
+
+namespace nnj {
+
+// "t" suffix: transposed to [in k][out col] so a CTA can copy it straight into shared memory.
+struct EmbedW { const float *w1, *b1, *w2t, *b2; };                 // model.py:39-43
+struct AttnW { const float *ln_g, *ln_b, *qt, *kt, *vt, *ot, *qb, *kb, *vb, *ob; };
+struct FfnW { const float *ln_g, *ln_b, *w1t, *b1, *w2t, *b2; };   // w1t/w2t: 4 chunks of [64][64]
+struct LayerW { AttnW row, col; FfnW ffn; };
+struct NjW {                                                        // model.py:46-59
+    const float *wht, *bh;      // h_linear_last
+    const float *wgt, *bg;      // g_linear_last
+    const float *wq, *bq;       // g_attn_q, NOT transposed: K' = K * Wq folds the query projection into the keys
+    const float *wkt, *bk;      // g_attn_k
+    const float *wst, *bs;      // s_out.0
+    const float *w2;            // s_out.2 weight [64]
+    float b2;                   // s_out.2 bias
+};
+
+struct Model {
+    nnj_config cfg;
+    int device;
+    int num_layers;
+    float* blob;                 // one device allocation holding every tensor
+    EmbedW embed;
+    std::vector<LayerW> layers;
+    NjW nj;
+};
+
+int set_error(int code, const char* msg);
+int set_cuda_error(cudaError_t e, const char* file, int line);
+
+// encoder (nnj_encoder.cu)
+size_t encoder_ws_bytes(const Model* m, int B, int R, int C);
+int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R, int L, float* x, size_t x_tree_stride,
+                void* ws, size_t ws_bytes, cudaStream_t st);
+
+// learned neighbour-joining loop (nnj_njloop.cu)
+struct NjBuffers;
+size_t nj_scores_ws_bytes(const Model* m, int B, int Rp, int C, int N);
+size_t nj_rollout_ws_bytes(const Model* m, int B, int R, int C);
+int nj_rollout_chunk(const Model* m, int B, int R, int C);
+int run_pair_scores(Model* m, const float* state, const uint8_t* mask, int B, int Rp, int C, const int32_t* pi,
+                    const int32_t* pj, int N, bool full, float* scores, void* ws, size_t ws_bytes, cudaStream_t st);
+int run_pair_scores_incr(Model* m, const float* state, const uint8_t* mask, int B, int Rp, int C, const int32_t* prev_ij,
+                         const float* logits_prev, float* logits_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int run_aggregate(Model* m, const float* state, int B, int Rp, int C, const int32_t* ij, float* out, size_t out_tree_stride,
+                  void* ws, size_t ws_bytes, cudaStream_t st);
+int run_merge(Model* m, const float* state_in, int B, int Rp, int C, const int32_t* ij, float* state_out, void* ws,
+              size_t ws_bytes, cudaStream_t st);
+int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t* mask, int B, int R, int L, int select_mode,
+                const float* gumbel, int32_t* merges, float* logits_trace, float* selected_logp, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+
+}  // namespace nnj

@@ -1,0 +1,977 @@
+// nnj_njloop.cu — learned neighbour-joining loop (fp32 CUDA-core path).
+//
+// Restates PhyloATTN.decode_zxr / decode_gg / aggregate (model.py:90-209), the select step
+// (finetune_rl_search.py:140-160), the stale-score cache map (utils.py:213-251) and the
+// tensor half of PhyInferEnv.step (environment.py:760-835) as device kernels over a node
+// pool.  Exact algebraic restructuring (rounding-level differences only):
+//   h = W_h(x_i - x_j) + b_h            = Y_i - Y_j + b_h,       Y  = W_h X        per node
+//   alpha = sum_{c,d} (W_q x + b_q).K   = sum x.K' + kappa,      K' = W_q^T K, kappa = sum_c b_q.K,  K = W_k X + b_k
+// so the per-pair work is: gate/blend (elementwise), alpha (pairs x nodes contraction over all
+// sites), x_glob = alpha.V, the W_g gate and the s_out MLP.  Node tensors live in pools
+// [B][S][C][64] addressed through a per-tree logical->physical slot table; a merge writes the
+// new node into a free slot ("slot i <- new, slot j removed" becomes a table update).
+// All cross-CTA reductions go through partial buffers summed in a fixed order: results are
+// run-to-run deterministic.
+#include "nnj_internal.h"
+
+namespace nnj {
+
+constexpr int SB_SITES = 32;   // sites per alpha partial / score partial
+constexpr int PAIR_CHUNK = 2048;
+
+struct Pool {
+    const float* X; const float* Y; const float* K;  // [B][S][C][64]
+    const float* kap;                                 // [B][S][nCT] partial sums of b_q . K
+    size_t tree_stride;                               // S*C*64
+    int S, nCT;
+};
+
+// ------------------------------------------------------------------ per-node derived tensors
+// xs: [128][LDA] tile of node rows (x).  Produces Y, K' (global) and the kappa partial of the tile.
+__device__ __forceinline__ void derive_tile(float* xs, float* tmp, float* Ws, const NjW& w, float* __restrict__ Yout,
+                                            float* __restrict__ Kout, float* __restrict__ kap_out, int row0, int C,
+                                            float* red) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[8][4];
+    // Y = x W_h^T   (bias b_h is added when the pair gate is formed)
+    load_w64(Ws, w.wht);
+    __syncthreads();
+    acc_set_bias(acc, nullptr, tx);
+    tile_mma64(acc, xs, Ws, ty, tx);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int c = row0 + ty * 8 + i;
+        if (c < C) st4(Yout + (size_t)c * D + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    }
+    __syncthreads();
+    // K = x W_k^T + b_k
+    load_w64(Ws, w.wkt);
+    __syncthreads();
+    acc_set_bias(acc, w.bk, tx);
+    tile_mma64(acc, xs, Ws, ty, tx);
+    acc_store_smem(acc, tmp, ty, tx);
+    {
+        float4 bq = __ldg(reinterpret_cast<const float4*>(w.bq) + tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float p = acc[i][0] * bq.x;
+            p = fmaf(acc[i][1], bq.y, p); p = fmaf(acc[i][2], bq.z, p); p = fmaf(acc[i][3], bq.w, p);
+            p = reduce16(p);
+            int c = row0 + ty * 8 + i;
+            if (tx == 0) red[ty * 8 + i] = (c < C) ? p : 0.f;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float s = (red[threadIdx.x] + red[threadIdx.x + 32]) + (red[threadIdx.x + 64] + red[threadIdx.x + 96]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) *kap_out = s;
+    }
+    // K' = K W_q   (Ws[k=d][col=e] = Wq[d][e], i.e. the untransposed torch weight)
+    load_w64(Ws, w.wq);
+    __syncthreads();
+    acc_set_bias(acc, nullptr, tx);
+    tile_mma64(acc, tmp, Ws, ty, tx);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int c = row0 + ty * 8 + i;
+        if (c < C) st4(Kout + (size_t)c * D + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    }
+}
+
+// grid (nCT, n_nodes, B): derive Y/K'/kappa for physical slots node_list[b][k] (or slot k when null)
+__global__ void __launch_bounds__(NTHREADS) k_node_derive(const float* __restrict__ X, float* __restrict__ Y, float* __restrict__ K,
+                                                          float* __restrict__ kap, size_t tree_stride, int S, int C, int nCT,
+                                                          const int32_t* __restrict__ node_list, int list_stride, NjW w) {
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;
+    float* tmp = xs + TILE_ROWS * LDA;
+    float* Ws = tmp + TILE_ROWS * LDA;
+    float* red = Ws + 4096;
+    const int b = blockIdx.z, ct = blockIdx.x;
+    const int slot = node_list ? node_list[(size_t)b * list_stride + blockIdx.y] : (int)blockIdx.y;
+    const size_t base = (size_t)b * tree_stride + (size_t)slot * C * D;
+    const int row0 = ct * TILE_ROWS;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        int idx = it * NTHREADS + threadIdx.x;
+        int row = idx >> 4, c4 = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + row < C) v = ld4(X + base + (size_t)(row0 + row) * D + c4 * 4);
+        st4(xs + row * LDA + c4 * 4, v);
+    }
+    __syncthreads();
+    derive_tile(xs, tmp, Ws, w, Y + base, K + base, kap + ((size_t)b * S + slot) * nCT + ct, row0, C, red);
+}
+
+// ------------------------------------------------------------------ pair blend helper
+// x = z*x_i + (1-z)*x_j,  z = sigmoid(Y_i - Y_j + b_h)     (model.py:105-108)
+__device__ __forceinline__ float4 blend4(float4 xi, float4 xj, float4 yi, float4 yj, float4 bh) {
+    float4 o;
+    float z;
+    z = sigmoidf_(yi.x - yj.x + bh.x); o.x = fmaf(z, xi.x, (1.0f - z) * xj.x);
+    z = sigmoidf_(yi.y - yj.y + bh.y); o.y = fmaf(z, xi.y, (1.0f - z) * xj.y);
+    z = sigmoidf_(yi.z - yj.z + bh.z); o.z = fmaf(z, xi.z, (1.0f - z) * xj.z);
+    z = sigmoidf_(yi.w - yj.w + bh.w); o.w = fmaf(z, xi.w, (1.0f - z) * xj.w);
+    return o;
+}
+
+// ------------------------------------------------------------------ alpha partials: pairs x nodes over a block of sites
+// grid (nSB, pair_tiles * node_tiles, B).  alpha_part[b][n][sb][r] = sum_{c in block, d} x[n,c,d] K'[r,c,d]
+__global__ void __launch_bounds__(NTHREADS) k_alpha(Pool pool, const int32_t* __restrict__ slot_of, int slot_stride, int Rp, int C,
+                                                    const int32_t* __restrict__ pair_i, const int32_t* __restrict__ pair_j,
+                                                    int pair_stride, int n0, int nc, int node_tiles, const float* __restrict__ bh,
+                                                    float* __restrict__ alpha_part, int nSB, int RP) {
+    __shared__ __align__(16) float As[64][LDA];   // [d][pair]
+    __shared__ __align__(16) float Bs[64][LDA];   // [d][node]
+    __shared__ int s_pi[64], s_pj[64], s_nd[64];
+    const int b = blockIdx.z, sb = blockIdx.x;
+    const int pt = blockIdx.y / node_tiles, nt = blockIdx.y - pt * node_tiles;
+    const int tid = threadIdx.x;
+    const int32_t* so = slot_of + (size_t)b * slot_stride;
+    if (tid < 64) {
+        int n = pt * 64 + tid;
+        int pi = -1, pj = -1;
+        if (n < nc) {
+            int li = pair_i[(size_t)b * pair_stride + n0 + n], lj = pair_j[(size_t)b * pair_stride + n0 + n];
+            if (li >= 0) { pi = so[li]; pj = so[lj]; }
+        }
+        s_pi[tid] = pi; s_pj[tid] = pj;
+        int r = nt * 64 + tid;
+        s_nd[tid] = r < Rp ? so[r] : -1;
+    }
+    __syncthreads();
+    const int lp = tid & 63, dq = tid >> 6;      // loader: pair/node lp, d range dq*16..+15
+    const int tx = tid & 15, ty = tid >> 4;      // compute: pairs ty*4..+3, nodes tx*4..+3
+    const size_t tb = (size_t)b * pool.tree_stride;
+    const int pi = s_pi[lp], pj = s_pj[lp], nd = s_nd[lp];
+    float4 bh4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bh4[e] = __ldg(reinterpret_cast<const float4*>(bh) + dq * 4 + e);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int c_end = min(C, (sb + 1) * SB_SITES);
+    for (int c = sb * SB_SITES; c < c_end; ++c) {
+        float4 xa[4], kb[4];
+        if (pi >= 0) {
+            const size_t oi = tb + ((size_t)pi * C + c) * D + dq * 16, oj = tb + ((size_t)pj * C + c) * D + dq * 16;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                xa[e] = blend4(ld4(pool.X + oi + e * 4), ld4(pool.X + oj + e * 4), ld4(pool.Y + oi + e * 4), ld4(pool.Y + oj + e * 4), bh4[e]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xa[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (nd >= 0) {
+            const size_t on = tb + ((size_t)nd * C + c) * D + dq * 16;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) kb[e] = ld4(pool.K + on + e * 4);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) kb[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();   // previous site's tiles fully consumed
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int d = dq * 16 + e * 4;
+            As[d][lp] = xa[e].x; As[d + 1][lp] = xa[e].y; As[d + 2][lp] = xa[e].z; As[d + 3][lp] = xa[e].w;
+            Bs[d][lp] = kb[e].x; Bs[d + 1][lp] = kb[e].y; Bs[d + 2][lp] = kb[e].z; Bs[d + 3][lp] = kb[e].w;
+        }
+        __syncthreads();
+#pragma unroll 16
+        for (int d = 0; d < 64; ++d) {
+            float4 a = ld4(&As[d][ty * 4]), k4 = ld4(&Bs[d][tx * 4]);
+            acc[0][0] = fmaf(a.x, k4.x, acc[0][0]); acc[0][1] = fmaf(a.x, k4.y, acc[0][1]); acc[0][2] = fmaf(a.x, k4.z, acc[0][2]); acc[0][3] = fmaf(a.x, k4.w, acc[0][3]);
+            acc[1][0] = fmaf(a.y, k4.x, acc[1][0]); acc[1][1] = fmaf(a.y, k4.y, acc[1][1]); acc[1][2] = fmaf(a.y, k4.z, acc[1][2]); acc[1][3] = fmaf(a.y, k4.w, acc[1][3]);
+            acc[2][0] = fmaf(a.z, k4.x, acc[2][0]); acc[2][1] = fmaf(a.z, k4.y, acc[2][1]); acc[2][2] = fmaf(a.z, k4.z, acc[2][2]); acc[2][3] = fmaf(a.z, k4.w, acc[2][3]);
+            acc[3][0] = fmaf(a.w, k4.x, acc[3][0]); acc[3][1] = fmaf(a.w, k4.y, acc[3][1]); acc[3][2] = fmaf(a.w, k4.z, acc[3][2]); acc[3][3] = fmaf(a.w, k4.w, acc[3][3]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int n = pt * 64 + ty * 4 + i;
+        if (n >= nc) continue;
+        float* o = alpha_part + (((size_t)b * PAIR_CHUNK + n) * nSB + sb) * RP;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int r = nt * 64 + tx * 4 + j;
+            if (r < Rp) o[r] = acc[i][j];
+        }
+    }
+}
+
+// single pair per tree (the merge pair): grid (nSB, B).  Writes alpha_part[b][0][sb][r].
+__global__ void __launch_bounds__(NTHREADS) k_alpha1(Pool pool, const int32_t* __restrict__ slot_of, int slot_stride, int Rp, int C,
+                                                     const int32_t* __restrict__ merge_ij, int ij_stride, const float* __restrict__ bh,
+                                                     float* __restrict__ alpha_part, int nSB, int RP) {
+    __shared__ __align__(16) float xs[SB_SITES * D];
+    const int b = blockIdx.y, sb = blockIdx.x, tid = threadIdx.x;
+    const int32_t* so = slot_of + (size_t)b * slot_stride;
+    const int li = merge_ij[(size_t)b * ij_stride], lj = merge_ij[(size_t)b * ij_stride + 1];
+    const int pi = so[li], pj = so[lj];
+    const size_t tb = (size_t)b * pool.tree_stride;
+    const int c0 = sb * SB_SITES;
+    {
+        int s = tid >> 3, d8 = (tid & 7) * 8;
+        int c = c0 + s;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < C) {
+                size_t oi = tb + ((size_t)pi * C + c) * D + d8 + e * 4, oj = tb + ((size_t)pj * C + c) * D + d8 + e * 4;
+                o = blend4(ld4(pool.X + oi), ld4(pool.X + oj), ld4(pool.Y + oi), ld4(pool.Y + oj),
+                           __ldg(reinterpret_cast<const float4*>(bh + d8 + e * 4)));
+            }
+            st4(xs + s * D + d8 + e * 4, o);
+        }
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nsite = min(SB_SITES, C - c0);
+    for (int r = warp; r < Rp; r += 8) {
+        const float* kp = pool.K + tb + ((size_t)so[r] * C + c0) * D;
+        float s = 0.f;
+        for (int m = 0; m < 16; ++m) {
+            int f4 = lane + 32 * m;               // float4 index within the [32 sites][64] block
+            if ((f4 >> 4) < nsite) {
+                float4 kv = ld4(kp + f4 * 4), xv = ld4(xs + f4 * 4);
+                s = fmaf(kv.x, xv.x, s); s = fmaf(kv.y, xv.y, s); s = fmaf(kv.z, xv.z, s); s = fmaf(kv.w, xv.w, s);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) alpha_part[(((size_t)b * PAIR_CHUNK) * nSB + sb) * RP + r] = s;
+    }
+}
+
+// one warp per (tree, pair): reduce partials, add kappa, scale, mask i/j, softmax over nodes  (model.py:118-146)
+__global__ void __launch_bounds__(NTHREADS) k_alpha_softmax(const float* __restrict__ alpha_part, const float* __restrict__ kap,
+                                                            const int32_t* __restrict__ slot_of, int slot_stride, int S, int nCT,
+                                                            int Rp, const int32_t* __restrict__ pair_i, const int32_t* __restrict__ pair_j,
+                                                            int pair_stride, int n0, int nc, int nSB, int RP, float inv_scale,
+                                                            float* __restrict__ alpha) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + warp, b = blockIdx.y;
+    if (n >= nc) return;
+    const int li = pair_i[(size_t)b * pair_stride + n0 + n], lj = pair_j[(size_t)b * pair_stride + n0 + n];
+    float* out = alpha + ((size_t)b * PAIR_CHUNK + n) * RP;
+    if (li < 0) {
+        for (int r = lane; r < Rp; r += 32) out[r] = 0.f;
+        return;
+    }
+    const float* ap = alpha_part + ((size_t)b * PAIR_CHUNK + n) * nSB * RP;
+    const int32_t* so = slot_of + (size_t)b * slot_stride;
+    float m = -INFINITY;
+    for (int r = lane; r < Rp; r += 32) {
+        float s = 0.f;
+        for (int k = 0; k < nSB; ++k) s += ap[(size_t)k * RP + r];
+        const float* kp = kap + ((size_t)b * S + so[r]) * nCT;
+        float kk = 0.f;
+        for (int k = 0; k < nCT; ++k) kk += kp[k];
+        s = (s + kk) * inv_scale;
+        if (r == li || r == lj) s = -INFINITY;
+        out[r] = s;
+        m = fmaxf(m, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = 0.f;
+    for (int r = lane; r < Rp; r += 32) {
+        float e = expf(out[r] - m);
+        out[r] = e;
+        l += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float inv = 1.0f / l;
+    for (int r = lane; r < Rp; r += 32) out[r] *= inv;
+}
+
+// ------------------------------------------------------------------ pair scores
+// grid (nSG, ceil(nc/32), B).  CTA tile = 32 pairs x 4 sites per iteration, 8 iterations (32 sites).
+// rows of the [128][64] tile: row = site_local*32 + pair_local.
+template <bool GLOB>
+__global__ void __launch_bounds__(NTHREADS) k_score(Pool pool, const int32_t* __restrict__ slot_of, int slot_stride, int Rp, int C,
+                                                    const int32_t* __restrict__ pair_i, const int32_t* __restrict__ pair_j,
+                                                    int pair_stride, int n0, int nc, const float* __restrict__ alpha, int RP,
+                                                    NjW w, const uint8_t* __restrict__ mask, float* __restrict__ score_part, int nSG) {
+    extern __shared__ __align__(16) float smem[];
+    float* Wg = smem;                          // [64][64]
+    float* Wsd = Wg + 4096;                    // [64][64]
+    float* xs = Wsd + 4096;                    // [128][LDA]
+    float* xg = xs + TILE_ROWS * LDA;          // [128][LDA]; also the V chunk [32 nodes][4 sites][64]
+    float* tot = xg + TILE_ROWS * LDA;         // [16][8]
+    int* s_pi = reinterpret_cast<int*>(tot + 128);   // [32]
+    int* s_pj = s_pi + 32;                     // [32]
+    int* s_slot = s_pj + 32;                   // [Rp]
+    float* al = reinterpret_cast<float*>(s_slot + ((Rp + 3) & ~3));   // [Rp][32]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int b = blockIdx.z, ptile = blockIdx.y, sg = blockIdx.x;
+    const int32_t* so = slot_of + (size_t)b * slot_stride;
+    const size_t tb = (size_t)b * pool.tree_stride;
+    if (GLOB) load_w64(Wg, w.wgt);
+    load_w64(Wsd, w.wst);
+    if (tid < 32) {
+        int n = ptile * 32 + tid, pi = -1, pj = -1;
+        if (n < nc) {
+            int li = pair_i[(size_t)b * pair_stride + n0 + n], lj = pair_j[(size_t)b * pair_stride + n0 + n];
+            if (li >= 0) { pi = so[li]; pj = so[lj]; }
+        }
+        s_pi[tid] = pi; s_pj[tid] = pj;
+    }
+    if (GLOB) {
+        for (int r = tid; r < Rp; r += NTHREADS) s_slot[r] = so[r];
+        for (int idx = tid; idx < Rp * 32; idx += NTHREADS) {
+            int p = idx / Rp, r = idx - p * Rp;
+            int n = ptile * 32 + p;
+            al[r * 32 + p] = (n < nc) ? alpha[((size_t)b * PAIR_CHUNK + n) * RP + r] : 0.f;
+        }
+    }
+    __syncthreads();
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(w.w2) + tx);
+    float sc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc[i] = 0.f;
+    const int sl = ty >> 2, pg = (ty & 3) * 8;
+    for (int it = 0; it < SB_SITES / 4; ++it) {
+        const int s0 = sg * SB_SITES + it * 4;
+        if (s0 >= C) break;
+        // (a) blended pair rows
+        {
+            int row = tid >> 1, half = tid & 1;
+            int rs = row >> 5, rp = row & 31;
+            int c = s0 + rs;
+            int pi = s_pi[rp], pj = s_pj[rp];
+            float* dst = xs + row * LDA + half * 32;
+            if (pi >= 0 && c < C) {
+                size_t oi = tb + ((size_t)pi * C + c) * D + half * 32, oj = tb + ((size_t)pj * C + c) * D + half * 32;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    st4(dst + e * 4, blend4(ld4(pool.X + oi + e * 4), ld4(pool.X + oj + e * 4), ld4(pool.Y + oi + e * 4),
+                                            ld4(pool.Y + oj + e * 4), __ldg(reinterpret_cast<const float4*>(w.bh) + half * 8 + e)));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) st4(dst + e * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+        }
+        float acc[8][4];
+        if (GLOB) {
+            // (b) x_glob = sum_r alpha[pair][r] * V[r][site]     (model.py:148)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+            for (int r0 = 0; r0 < Rp; r0 += 32) {
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    int idx = k * NTHREADS + tid;
+                    int node = idx >> 6, rem = idx & 63, site = rem >> 4, c4 = rem & 15;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r0 + node < Rp && s0 + site < C)
+                        v = ld4(pool.X + tb + ((size_t)s_slot[r0 + node] * C + s0 + site) * D + c4 * 4);
+                    st4(xg + (node * 4 + site) * D + c4 * 4, v);
+                }
+                __syncthreads();
+                const int nn = min(32, Rp - r0);
+                for (int node = 0; node < nn; ++node) {
+                    float4 v = ld4(xg + (node * 4 + sl) * D + tx * 4);
+                    float4 a0 = ld4(al + (r0 + node) * 32 + pg), a1 = ld4(al + (r0 + node) * 32 + pg + 4);
+                    float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        acc[i][0] = fmaf(a[i], v.x, acc[i][0]); acc[i][1] = fmaf(a[i], v.y, acc[i][1]);
+                        acc[i][2] = fmaf(a[i], v.z, acc[i][2]); acc[i][3] = fmaf(a[i], v.w, acc[i][3]);
+                    }
+                }
+            }
+            __syncthreads();
+            // (c) x_glob tile -> smem
+            acc_store_smem(acc, xg, ty, tx);
+            __syncthreads();
+            // (d) w = sigmoid(W_g x_glob + b_g);  x' = (1-w) x + w x_glob    (model.py:150-153)
+            float g[8][4];
+            acc_set_bias(g, w.bg, tx);
+            tile_mma64(g, xg, Wg, ty, tx);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float* xp = xs + (ty * 8 + i) * LDA + tx * 4;
+                float4 xv = ld4(xp);
+                float wv;
+                wv = sigmoidf_(g[i][0]); xv.x = fmaf(wv, acc[i][0], (1.0f - wv) * xv.x);
+                wv = sigmoidf_(g[i][1]); xv.y = fmaf(wv, acc[i][1], (1.0f - wv) * xv.y);
+                wv = sigmoidf_(g[i][2]); xv.z = fmaf(wv, acc[i][2], (1.0f - wv) * xv.z);
+                wv = sigmoidf_(g[i][3]); xv.w = fmaf(wv, acc[i][3], (1.0f - wv) * xv.w);
+                st4(xp, xv);
+            }
+        }
+        __syncthreads();
+        // (e) score = w2 . GELU(W_s x' + b_s) + b2, masked site sum        (model.py:95-97)
+        acc_set_bias(acc, w.bs, tx);
+        tile_mma64(acc, xs, Wsd, ty, tx);
+        {
+            int c = s0 + sl;
+            float valid = (c < C && !(mask && mask[(size_t)b * C + c])) ? 1.0f : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float p = gelu_erf(acc[i][0]) * w2.x;
+                p = fmaf(gelu_erf(acc[i][1]), w2.y, p); p = fmaf(gelu_erf(acc[i][2]), w2.z, p); p = fmaf(gelu_erf(acc[i][3]), w2.w, p);
+                p = reduce16(p);
+                sc[i] += (p + w.b2) * valid;
+            }
+        }
+        __syncthreads();
+    }
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot[ty * 8 + i] = sc[i];
+    }
+    __syncthreads();
+    if (tid < 32) {
+        int n = ptile * 32 + tid;
+        if (n < nc) {
+            int g8 = tid >> 3, i = tid & 7;
+            float s = 0.f;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) s += tot[(s4 * 4 + g8) * 8 + i];
+            score_part[((size_t)b * PAIR_CHUNK + n) * nSG + sg] = (s_pi[tid] >= 0) ? s : 0.f;
+        }
+    }
+}
+
+__global__ void k_score_reduce(const float* __restrict__ score_part, int nSG, int nc, float* __restrict__ scores, int score_stride, int n0) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (n >= nc) return;
+    const float* p = score_part + ((size_t)b * PAIR_CHUNK + n) * nSG;
+    float s = 0.f;
+    for (int k = 0; k < nSG; ++k) s += p[k];
+    scores[(size_t)b * score_stride + n0 + n] = s;
+}
+
+// ------------------------------------------------------------------ merged-node embedding (+ derived tensors)
+// grid (nCT, B).  Rows = 128 sites of the merge pair.  out_x: where x' goes ([B] stride out_stride);
+// when `derive` the Y/K'/kappa of the new node are produced as well (physical slot new_slot[b]).
+template <bool GLOB>
+__global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict__ Xw, float* __restrict__ Yw, float* __restrict__ Kw,
+                                                    float* __restrict__ kapw, const int32_t* __restrict__ slot_of, int slot_stride,
+                                                    int Rp, int C, const int32_t* __restrict__ merge_ij, int ij_stride,
+                                                    const float* __restrict__ alpha, int RP, NjW w, float* __restrict__ out_x,
+                                                    size_t out_stride, const int32_t* __restrict__ new_slot, int derive) {
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;
+    float* xg = xs + TILE_ROWS * LDA;
+    float* Ws = xg + TILE_ROWS * LDA;
+    float* red = Ws + 4096;          // [128]
+    float* al = red + 128;           // [Rp]
+    int* s_slot = reinterpret_cast<int*>(al + ((Rp + 3) & ~3));
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int b = blockIdx.y, ct = blockIdx.x, row0 = ct * TILE_ROWS;
+    const int32_t* so = slot_of + (size_t)b * slot_stride;
+    const size_t tb = (size_t)b * pool.tree_stride;
+    const int li = merge_ij[(size_t)b * ij_stride], lj = merge_ij[(size_t)b * ij_stride + 1];
+    const int pi = so[li], pj = so[lj];
+    if (GLOB) {
+        load_w64(Ws, w.wgt);
+        for (int r = tid; r < Rp; r += NTHREADS) { s_slot[r] = so[r]; al[r] = alpha[(size_t)b * PAIR_CHUNK * RP + r]; }
+    }
+    {
+        int row = tid >> 1, half = tid & 1;
+        int c = row0 + row;
+        float* dst = xs + row * LDA + half * 32;
+        if (c < C) {
+            size_t oi = tb + ((size_t)pi * C + c) * D + half * 32, oj = tb + ((size_t)pj * C + c) * D + half * 32;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                st4(dst + e * 4, blend4(ld4(pool.X + oi + e * 4), ld4(pool.X + oj + e * 4), ld4(pool.Y + oi + e * 4),
+                                        ld4(pool.Y + oj + e * 4), __ldg(reinterpret_cast<const float4*>(w.bh) + half * 8 + e)));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) st4(dst + e * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+    }
+    __syncthreads();
+    float* xo = out_x + (size_t)b * out_stride;
+    if (GLOB) {
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+        for (int r = 0; r < Rp; ++r) {
+            if (r == li || r == lj) continue;   // alpha is exactly 0 there (softmax of -inf)
+            const float a = al[r];
+            const float* vp = pool.X + tb + ((size_t)s_slot[r] * C + row0 + ty * 8) * D + tx * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (row0 + ty * 8 + i < C) {
+                    float4 v = ld4(vp + (size_t)i * D);
+                    acc[i][0] = fmaf(a, v.x, acc[i][0]); acc[i][1] = fmaf(a, v.y, acc[i][1]);
+                    acc[i][2] = fmaf(a, v.z, acc[i][2]); acc[i][3] = fmaf(a, v.w, acc[i][3]);
+                }
+            }
+        }
+        acc_store_smem(acc, xg, ty, tx);
+        __syncthreads();
+        float g[8][4];
+        acc_set_bias(g, w.bg, tx);
+        tile_mma64(g, xg, Ws, ty, tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float* xp = xs + (ty * 8 + i) * LDA + tx * 4;
+            float4 xv = ld4(xp);
+            float wv;
+            wv = sigmoidf_(g[i][0]); xv.x = fmaf(wv, acc[i][0], (1.0f - wv) * xv.x);
+            wv = sigmoidf_(g[i][1]); xv.y = fmaf(wv, acc[i][1], (1.0f - wv) * xv.y);
+            wv = sigmoidf_(g[i][2]); xv.z = fmaf(wv, acc[i][2], (1.0f - wv) * xv.z);
+            wv = sigmoidf_(g[i][3]); xv.w = fmaf(wv, acc[i][3], (1.0f - wv) * xv.w);
+            st4(xp, xv);
+        }
+        __syncthreads();
+    }
+    if (derive) {
+        const int ns = new_slot[b];
+        const size_t nb = tb + (size_t)ns * C * D;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int c = row0 + ty * 8 + i;
+            if (c < C) st4(Xw + nb + (size_t)c * D + tx * 4, ld4(xs + (ty * 8 + i) * LDA + tx * 4));
+        }
+        derive_tile(xs, xg, Ws, w, Yw + nb, Kw + nb, kapw + ((size_t)b * pool.S + ns) * pool.nCT + ct, row0, C, red);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int c = row0 + ty * 8 + i;
+            if (c < C) st4(xo + (size_t)c * D + tx * 4, ld4(xs + (ty * 8 + i) * LDA + tx * 4));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ small index / select kernels
+__global__ void k_fill_pairs_full(int32_t* __restrict__ pair_i, int32_t* __restrict__ pair_j, int stride, int n, int B) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int P = n * (n - 1) / 2;
+    if (p >= P) return;
+    int i, j;
+    pair_from_index(p, n, i, j);
+    for (int b = blockIdx.y; b < B; b += gridDim.y) { pair_i[(size_t)b * stride + p] = i; pair_j[(size_t)b * stride + p] = j; }
+}
+
+__global__ void k_fill_slots(int32_t* __restrict__ slot_of, int stride, int n, int32_t* __restrict__ free_slot) {
+    int b = blockIdx.x;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) slot_of[(size_t)b * stride + r] = r;
+    if (free_slot && threadIdx.x == 0) free_slot[b] = n;
+}
+
+// pairs (a, r) for r = 0..n-1 of the current node list, a = prev_ij[b][0]; the self pair is flagged -1  (model.py:186-197)
+__global__ void k_fill_pairs_incr(int32_t* __restrict__ pair_i, int32_t* __restrict__ pair_j, int stride, int n,
+                                  const int32_t* __restrict__ prev_ij, int ij_stride) {
+    int b = blockIdx.x;
+    int a = prev_ij[(size_t)b * ij_stride];
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        int lo = min(a, r), hi = max(a, r);
+        pair_i[(size_t)b * stride + r] = (r == a) ? -1 : lo;
+        pair_j[(size_t)b * stride + r] = (r == a) ? -1 : hi;
+    }
+}
+
+// logits of the n-node list from [logits_prev | new_scores]  (utils.py:213-251 in closed form)
+__device__ __forceinline__ float cached_logit(int p, int n, int a, int bb, const float* __restrict__ prev, const float* __restrict__ nw) {
+    int ii, jj;
+    pair_from_index(p, n, ii, jj);
+    if (ii == a) return nw[jj];
+    if (jj == a) return nw[ii];
+    return prev[pair_index(ii + (ii >= bb ? 1 : 0), jj + (jj >= bb ? 1 : 0), n + 1)];
+}
+
+__global__ void k_assemble_logits(const float* __restrict__ logits_prev, int prev_stride, const float* __restrict__ new_scores,
+                                  int new_stride, const int32_t* __restrict__ prev_ij, int ij_stride, int n, float* __restrict__ out,
+                                  int out_stride) {
+    int b = blockIdx.y;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n * (n - 1) / 2) return;
+    int a = prev_ij[(size_t)b * ij_stride], bb = prev_ij[(size_t)b * ij_stride + 1];
+    out[(size_t)b * out_stride + p] = cached_logit(p, n, a, bb, logits_prev + (size_t)b * prev_stride, new_scores + (size_t)b * new_stride);
+}
+
+// One CTA per tree: assemble this step's logits, select (argmax / Gumbel-max, lowest index wins ties),
+// record the merge, the selected log-probability, the next slot table and the next step's pair list.
+__global__ void __launch_bounds__(NTHREADS) k_select(int t, int n, int R, const float* __restrict__ logits_prev, const float* __restrict__ new_scores,
+                                                     int new_stride, float* __restrict__ logits_cur, int logit_stride,
+                                                     const float* __restrict__ gumbel, int32_t* __restrict__ merges,
+                                                     float* __restrict__ selected_logp, float* __restrict__ logits_trace,
+                                                     size_t trace_stride, size_t trace_off, const int32_t* __restrict__ slot_cur,
+                                                     int32_t* __restrict__ slot_next, int slot_stride, int32_t* __restrict__ free_slot,
+                                                     int32_t* __restrict__ new_slot, int32_t* __restrict__ pair_i,
+                                                     int32_t* __restrict__ pair_j, int pair_stride) {
+    __shared__ float s_val[NTHREADS];
+    __shared__ int s_idx[NTHREADS];
+    __shared__ float s_red[NTHREADS];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int P = n * (n - 1) / 2, P0 = R * (R - 1) / 2;
+    float* cur = logits_cur + (size_t)b * logit_stride;
+    if (t > 0) {
+        const int32_t* pm = merges + ((size_t)b * (R - 1) + (t - 1)) * 2;
+        const int a = pm[0], bb = pm[1];
+        const float* prev = logits_prev + (size_t)b * logit_stride;
+        const float* nw = new_scores + (size_t)b * new_stride;
+        for (int p = tid; p < P; p += NTHREADS) cur[p] = cached_logit(p, n, a, bb, prev, nw);
+        __syncthreads();
+    }
+    const float* gb = gumbel ? gumbel + ((size_t)b * (R - 1) + t) * P0 : nullptr;
+    float best = -INFINITY, mx = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int p = tid; p < P; p += NTHREADS) {
+        float v = cur[p];
+        if (logits_trace) logits_trace[(size_t)b * trace_stride + trace_off + p] = v;
+        mx = fmaxf(mx, v);
+        float s = gb ? v + gb[p] : v;
+        if (s > best || (s == best && p < bi) || bi == 0x7fffffff) { best = s; bi = p; }
+    }
+    s_val[tid] = best; s_idx[tid] = bi; s_red[tid] = mx;
+    __syncthreads();
+    for (int o = NTHREADS / 2; o > 0; o >>= 1) {
+        if (tid < o) {
+            float v2 = s_val[tid + o]; int i2 = s_idx[tid + o];
+            if (i2 != 0x7fffffff && (s_idx[tid] == 0x7fffffff || v2 > s_val[tid] || (v2 == s_val[tid] && i2 < s_idx[tid]))) { s_val[tid] = v2; s_idx[tid] = i2; }
+            s_red[tid] = fmaxf(s_red[tid], s_red[tid + o]);
+        }
+        __syncthreads();
+    }
+    const int act = s_idx[0];
+    const float gmax = s_red[0];
+    __syncthreads();
+    float se = 0.f;
+    for (int p = tid; p < P; p += NTHREADS) se += expf(cur[p] - gmax);
+    s_red[tid] = se;
+    __syncthreads();
+    for (int o = NTHREADS / 2; o > 0; o >>= 1) {
+        if (tid < o) s_red[tid] += s_red[tid + o];
+        __syncthreads();
+    }
+    int i, j;
+    pair_from_index(act, n, i, j);
+    if (tid == 0) {
+        merges[((size_t)b * (R - 1) + t) * 2] = i;
+        merges[((size_t)b * (R - 1) + t) * 2 + 1] = j;
+        if (selected_logp) selected_logp[(size_t)b * (R - 1) + t] = (cur[act] - gmax) - logf(s_red[0]);
+    }
+    if (n > 2) {
+        const int32_t* sc = slot_cur + (size_t)b * slot_stride;
+        int32_t* sn = slot_next + (size_t)b * slot_stride;
+        const int ns = free_slot[b];
+        const int pj_phys = sc[j];
+        __syncthreads();
+        for (int r = tid; r < n - 1; r += NTHREADS) {
+            int src = r + (r >= j ? 1 : 0);
+            sn[r] = (r == i) ? ns : sc[src];
+            pair_i[(size_t)b * pair_stride + r] = (r == i) ? -1 : min(i, r);
+            pair_j[(size_t)b * pair_stride + r] = (r == i) ? -1 : max(i, r);
+        }
+        if (tid == 0) { new_slot[b] = ns; free_slot[b] = pj_phys; }
+    }
+}
+
+// state_out[b][r] = r == i ? new : state_in[b][r + (r >= j)]      (environment.py:764-768, 833-835)
+__global__ void k_reindex_copy(const float* __restrict__ in, const float* __restrict__ newx, float* __restrict__ out, int Rp, size_t CD,
+                               const int32_t* __restrict__ ij) {
+    const int b = blockIdx.z, r = blockIdx.y;
+    const int i = ij[b * 2], j = ij[b * 2 + 1];
+    const float* src = (r == i) ? newx + (size_t)b * CD : in + ((size_t)b * Rp + r + (r >= j ? 1 : 0)) * CD;
+    float* dst = out + ((size_t)b * (Rp - 1) + r) * CD;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < CD / 4; k += (size_t)gridDim.x * blockDim.x)
+        st4(dst + k * 4, ld4(src + k * 4));
+}
+
+// ------------------------------------------------------------------ host side
+#define LAUNCH_CHECK()                                                         \
+    do {                                                                       \
+        ++g_launches;                                                          \
+        cudaError_t e_ = cudaGetLastError();                                   \
+        if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__);  \
+    } while (0)
+
+static inline size_t aup(size_t v) { return (v + 255) / 256 * 256; }
+
+struct NjBuffers {
+    float *Y, *K, *kap, *alpha_part, *alpha, *score_part, *new_scores, *logits[2], *newx;
+    int32_t *slot[2], *free_slot, *new_slot, *pair_i, *pair_j;
+    float* X;         // pool X when owned by the workspace (rollout), else null
+    int S, nCT, nSB, RP, pair_stride, P0;
+    size_t total;
+};
+
+// carve the NJ workspace; X_in_ws: the node pool X lives in the workspace too (rollout)
+static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws, bool need_newx) {
+    NjBuffers nb{};
+    nb.S = S; nb.nCT = (C + TILE_ROWS - 1) / TILE_ROWS; nb.nSB = (C + SB_SITES - 1) / SB_SITES;
+    nb.RP = (R + 3) & ~3;
+    nb.P0 = R * (R - 1) / 2;
+    nb.pair_stride = nb.P0 > R ? nb.P0 : R;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += aup(bytes); return p; };
+    const size_t pool = (size_t)B * S * C * D * sizeof(float);
+    nb.X = X_in_ws ? (float*)take(pool) : nullptr;
+    nb.Y = (float*)take(pool);
+    nb.K = (float*)take(pool);
+    nb.kap = (float*)take((size_t)B * S * nb.nCT * sizeof(float));
+    nb.alpha_part = (float*)take((size_t)B * PAIR_CHUNK * nb.nSB * nb.RP * sizeof(float));
+    nb.alpha = (float*)take((size_t)B * PAIR_CHUNK * nb.RP * sizeof(float));
+    nb.score_part = (float*)take((size_t)B * PAIR_CHUNK * nb.nSB * sizeof(float));
+    nb.new_scores = (float*)take((size_t)B * nb.pair_stride * sizeof(float));
+    nb.logits[0] = (float*)take((size_t)B * nb.P0 * sizeof(float));
+    nb.logits[1] = (float*)take((size_t)B * nb.P0 * sizeof(float));
+    nb.newx = need_newx ? (float*)take((size_t)B * C * D * sizeof(float)) : nullptr;
+    nb.slot[0] = (int32_t*)take((size_t)B * S * sizeof(int32_t));
+    nb.slot[1] = (int32_t*)take((size_t)B * S * sizeof(int32_t));
+    nb.free_slot = (int32_t*)take((size_t)B * sizeof(int32_t));
+    nb.new_slot = (int32_t*)take((size_t)B * sizeof(int32_t));
+    nb.pair_i = (int32_t*)take((size_t)B * nb.pair_stride * sizeof(int32_t));
+    nb.pair_j = (int32_t*)take((size_t)B * nb.pair_stride * sizeof(int32_t));
+    nb.total = off + 256;
+    return nb;
+}
+
+static inline char* ws_align(void* ws) { return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256); }
+
+static size_t smem_score(int Rp) { return (2 * 4096 + 2 * TILE_ROWS * LDA + 128 + 64 + ((Rp + 3) & ~3) + (size_t)Rp * 32) * sizeof(float); }
+static size_t smem_merge(int Rp) { return (2 * TILE_ROWS * LDA + 4096 + 128 + 2 * ((Rp + 3) & ~3) + 8) * sizeof(float); }
+static const size_t smem_derive = (2 * TILE_ROWS * LDA + 4096 + 128) * sizeof(float);
+
+static int set_attrs() {
+    static bool done = false;
+    if (done) return 0;
+    const int big = 220 * 1024;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    if ((e = cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    if ((e = cudaFuncSetAttribute(k_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    if ((e = cudaFuncSetAttribute(k_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    if ((e = cudaFuncSetAttribute(k_node_derive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_derive)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    done = true;
+    return 0;
+}
+
+static int check_dims(int Rp, int C) {
+    if (Rp < 2) return set_error(NNJ_ERR_INVALID, "need at least 2 nodes");
+    if (C < 1) return set_error(NNJ_ERR_INVALID, "need at least 1 site");
+    if (smem_score(Rp) > 220 * 1024) return set_error(NNJ_ERR_INVALID, "too many nodes for the pair-score kernel (max ~1000)");
+    return 0;
+}
+
+// scores of N listed pairs per tree against Rp nodes; pool tensors must be derived already.
+static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, const int32_t* slot, int Rp, int C, int N,
+                       const uint8_t* mask, int B, float* scores, int score_stride, cudaStream_t st) {
+    const bool glob = Rp > 2;     // model.py:111
+    const float inv_scale = 1.0f / sqrtf((float)D * (float)C);   // model.py:118 (patch_num == C)
+    for (int n0 = 0; n0 < N; n0 += PAIR_CHUNK) {
+        const int nc = (N - n0 < PAIR_CHUNK) ? (N - n0) : PAIR_CHUNK;
+        if (glob) {
+            const int node_tiles = (Rp + 63) / 64, pair_tiles = (nc + 63) / 64;
+            k_alpha<<<dim3(nb.nSB, pair_tiles * node_tiles, B), NTHREADS, 0, st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j, nb.pair_stride,
+                                                                                   n0, nc, node_tiles, m->nj.bh, nb.alpha_part, nb.nSB, nb.RP);
+            LAUNCH_CHECK();
+            k_alpha_softmax<<<dim3((nc + 7) / 8, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
+                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha);
+            LAUNCH_CHECK();
+            k_score<true><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
+                                                                                            nb.pair_stride, n0, nc, nb.alpha, nb.RP, m->nj, mask,
+                                                                                            nb.score_part, nb.nSB);
+            LAUNCH_CHECK();
+        } else {
+            k_score<false><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
+                                                                                             nb.pair_stride, n0, nc, nb.alpha, nb.RP, m->nj, mask,
+                                                                                             nb.score_part, nb.nSB);
+            LAUNCH_CHECK();
+        }
+        k_score_reduce<<<dim3((nc + 127) / 128, B), 128, 0, st>>>(nb.score_part, nb.nSB, nc, scores, score_stride, n0);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// merged-node embedding for pair ij[b] against Rp nodes
+static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, float* Xw, const int32_t* slot, int Rp, int C,
+                      const int32_t* ij, int ij_stride, int B, float* out_x, size_t out_stride, bool derive, cudaStream_t st) {
+    const float inv_scale = 1.0f / sqrtf((float)D * (float)C);
+    if (Rp > 2) {
+        k_alpha1<<<dim3(nb.nSB, B), NTHREADS, 0, st>>>(pool, slot, nb.S, Rp, C, ij, ij_stride, m->nj.bh, nb.alpha_part, nb.nSB, nb.RP);
+        LAUNCH_CHECK();
+        // pair list for the softmax kernel: reuse it with one pair per tree = ij itself
+        k_alpha_softmax<<<dim3(1, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, ij, ij + 1, ij_stride, 0, 1,
+                                                         nb.nSB, nb.RP, inv_scale, nb.alpha);
+        LAUNCH_CHECK();
+        k_merge<true><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
+                                                                         nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0);
+        LAUNCH_CHECK();
+    } else {
+        k_merge<false><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
+                                                                          nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static int derive_all(const Model* m, const float* X, const NjBuffers& nb, int B, int S, int nodes, int C, cudaStream_t st) {
+    k_node_derive<<<dim3(nb.nCT, nodes, B), NTHREADS, smem_derive, st>>>(X, nb.Y, nb.K, nb.kap, (size_t)S * C * D, S, C, nb.nCT, nullptr, 0, m->nj);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+size_t nj_scores_ws_bytes(const Model* m, int B, int Rp, int C, int N) {
+    (void)m; (void)N;
+    return nj_layout(nullptr, B, Rp, Rp, C, false, true).total;
+}
+
+static Pool make_pool(const float* X, const NjBuffers& nb, int S, int C) {
+    Pool p;
+    p.X = X; p.Y = nb.Y; p.K = nb.K; p.kap = nb.kap;
+    p.tree_stride = (size_t)S * C * D; p.S = S; p.nCT = nb.nCT;
+    return p;
+}
+
+int run_pair_scores(Model* m, const float* state, const uint8_t* mask, int B, int Rp, int C, const int32_t* pi, const int32_t* pj, int N,
+                    bool full, float* scores, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (int e = check_dims(Rp, C)) return e;
+    if (int e = set_attrs()) return e;
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
+    if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "pair scores: workspace too small");
+    if (full) N = Rp * (Rp - 1) / 2;
+    if (N > nb.pair_stride) return set_error(NNJ_ERR_INVALID, "pair scores: more pairs than R(R-1)/2");
+    k_fill_slots<<<B, 128, 0, st>>>(nb.slot[0], nb.S, Rp, nullptr);
+    LAUNCH_CHECK();
+    if (full) {
+        k_fill_pairs_full<<<dim3((N + 127) / 128, B < 64 ? B : 64), 128, 0, st>>>(nb.pair_i, nb.pair_j, nb.pair_stride, Rp, B);
+        LAUNCH_CHECK();
+    } else {
+        cudaError_t e1 = cudaMemcpy2DAsync(nb.pair_i, nb.pair_stride * sizeof(int32_t), pi, N * sizeof(int32_t), N * sizeof(int32_t), B, cudaMemcpyDeviceToDevice, st);
+        cudaError_t e2 = cudaMemcpy2DAsync(nb.pair_j, nb.pair_stride * sizeof(int32_t), pj, N * sizeof(int32_t), N * sizeof(int32_t), B, cudaMemcpyDeviceToDevice, st);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return set_cuda_error(e1 != cudaSuccess ? e1 : e2, __FILE__, __LINE__);
+    }
+    if (int e = derive_all(m, state, nb, B, Rp, Rp, C, st)) return e;
+    Pool pool = make_pool(state, nb, Rp, C);
+    return score_pairs(m, pool, nb, nb.slot[0], Rp, C, N, mask, B, scores, N, st);
+}
+
+int run_pair_scores_incr(Model* m, const float* state, const uint8_t* mask, int B, int Rp, int C, const int32_t* prev_ij,
+                         const float* logits_prev, float* logits_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (int e = check_dims(Rp, C)) return e;
+    if (int e = set_attrs()) return e;
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
+    if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "pair scores: workspace too small");
+    k_fill_slots<<<B, 128, 0, st>>>(nb.slot[0], nb.S, Rp, nullptr);
+    LAUNCH_CHECK();
+    k_fill_pairs_incr<<<B, 128, 0, st>>>(nb.pair_i, nb.pair_j, nb.pair_stride, Rp, prev_ij, 2);
+    LAUNCH_CHECK();
+    if (int e = derive_all(m, state, nb, B, Rp, Rp, C, st)) return e;
+    Pool pool = make_pool(state, nb, Rp, C);
+    if (int e = score_pairs(m, pool, nb, nb.slot[0], Rp, C, Rp, mask, B, nb.new_scores, nb.pair_stride, st)) return e;
+    const int P = Rp * (Rp - 1) / 2;
+    k_assemble_logits<<<dim3((P + 127) / 128, B), 128, 0, st>>>(logits_prev, (Rp + 1) * Rp / 2, nb.new_scores, nb.pair_stride, prev_ij, 2, Rp,
+                                                                logits_out, P);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int run_aggregate(Model* m, const float* state, int B, int Rp, int C, const int32_t* ij, float* out, size_t out_tree_stride, void* ws,
+                  size_t ws_bytes, cudaStream_t st) {
+    if (int e = check_dims(Rp, C)) return e;
+    if (int e = set_attrs()) return e;
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
+    if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "aggregate: workspace too small");
+    k_fill_slots<<<B, 128, 0, st>>>(nb.slot[0], nb.S, Rp, nullptr);
+    LAUNCH_CHECK();
+    if (int e = derive_all(m, state, nb, B, Rp, Rp, C, st)) return e;
+    Pool pool = make_pool(state, nb, Rp, C);
+    return merge_pair(m, pool, nb, nullptr, nb.slot[0], Rp, C, ij, 2, B, out, out_tree_stride, false, st);
+}
+
+int run_merge(Model* m, const float* state_in, int B, int Rp, int C, const int32_t* ij, float* state_out, void* ws, size_t ws_bytes,
+              cudaStream_t st) {
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
+    if (int e = run_aggregate(m, state_in, B, Rp, C, ij, nb.newx, (size_t)C * D, ws, ws_bytes, st)) return e;
+    k_reindex_copy<<<dim3(8, Rp - 1, B), 256, 0, st>>>(state_in, nb.newx, state_out, Rp, (size_t)C * D, ij);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- fused rollout
+int nj_rollout_chunk(const Model* m, int B, int R, int C) {
+    size_t per = nj_layout(nullptr, 1, R + 1, R, C, true, false).total + encoder_ws_bytes(m, 1, R, C);
+    size_t budget = (size_t)16 << 30;
+    int ch = (int)(budget / per);
+    if (ch < 1) ch = 1;
+    if (ch > 128) ch = 128;
+    if (ch > B) ch = B;
+    return ch;
+}
+
+size_t nj_rollout_ws_bytes(const Model* m, int B, int R, int C) {
+    int ch = nj_rollout_chunk(m, B, R, C);
+    return nj_layout(nullptr, ch, R + 1, R, C, true, false).total + encoder_ws_bytes(m, ch, R, C) + 512;
+}
+
+int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t* mask, int B, int R, int L, int select_mode,
+                const float* gumbel, int32_t* merges, float* logits_trace, float* selected_logp, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
+    const int C = L;
+    if (R < 2) return set_error(NNJ_ERR_INVALID, "rollout: need at least 2 taxa");
+    if (int e = check_dims(R, C)) return e;
+    if (int e = set_attrs()) return e;
+    if (select_mode == NNJ_SELECT_GUMBEL && !gumbel) return set_error(NNJ_ERR_INVALID, "rollout: gumbel noise required for NNJ_SELECT_GUMBEL");
+    if (select_mode == NNJ_SELECT_ARGMAX) gumbel = nullptr;
+    if (ws_bytes < nj_rollout_ws_bytes(m, B, R, C)) return set_error(NNJ_ERR_WORKSPACE, "rollout: workspace too small");
+    const int chunk = nj_rollout_chunk(m, B, R, C);
+    const int S = R + 1;
+    char* base = ws_align(ws);
+    NjBuffers nb = nj_layout(base, chunk, S, R, C, true, false);
+    void* enc_ws = base + nb.total;
+    const size_t enc_bytes = encoder_ws_bytes(m, chunk, R, C);
+    const size_t tree_stride = (size_t)S * C * D;
+    const int P0 = nb.P0;
+    size_t trace_stride = 0;
+    for (int n = R; n >= 2; --n) trace_stride += (size_t)n * (n - 1) / 2;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nbt = (B - b0 < chunk) ? (B - b0) : chunk;
+        const uint8_t* mk = mask ? mask + (size_t)b0 * C : nullptr;
+        if (state0) {
+            cudaError_t e = cudaMemcpy2DAsync(nb.X, tree_stride * sizeof(float), state0 + (size_t)b0 * R * C * D, (size_t)R * C * D * sizeof(float),
+                                              (size_t)R * C * D * sizeof(float), nbt, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+        } else {
+            if (int e = run_encoder(m, data + (size_t)b0 * R * L * 4, mk, nbt, R, L, nb.X, tree_stride, enc_ws, enc_bytes, st)) return e;
+        }
+        k_fill_slots<<<nbt, 128, 0, st>>>(nb.slot[0], S, R, nb.free_slot);
+        LAUNCH_CHECK();
+        k_fill_pairs_full<<<dim3((P0 + 127) / 128, nbt < 64 ? nbt : 64), 128, 0, st>>>(nb.pair_i, nb.pair_j, nb.pair_stride, R, nbt);
+        LAUNCH_CHECK();
+        k_node_derive<<<dim3(nb.nCT, R, nbt), NTHREADS, smem_derive, st>>>(nb.X, nb.Y, nb.K, nb.kap, tree_stride, S, C, nb.nCT, nullptr, 0, m->nj);
+        LAUNCH_CHECK();
+        Pool pool = make_pool(nb.X, nb, S, C);
+        int32_t* mg = merges + (size_t)b0 * (R - 1) * 2;
+        float* slp = selected_logp ? selected_logp + (size_t)b0 * (R - 1) : nullptr;
+        float* ltr = logits_trace ? logits_trace + (size_t)b0 * trace_stride : nullptr;
+        const float* gmb = gumbel ? gumbel + (size_t)b0 * (R - 1) * P0 : nullptr;
+        size_t trace_off = 0;
+        int cur = 0;
+        for (int t = 0; t < R - 1; ++t) {
+            const int n = R - t;
+            const int32_t* slot = nb.slot[t & 1];
+            if (t == 0) {
+                if (int e = score_pairs(m, pool, nb, slot, n, C, P0, mk, nbt, nb.logits[0], P0, st)) return e;
+            } else {
+                if (int e = score_pairs(m, pool, nb, slot, n, C, n, mk, nbt, nb.new_scores, nb.pair_stride, st)) return e;
+                cur ^= 1;
+            }
+            k_select<<<nbt, NTHREADS, 0, st>>>(t, n, R, nb.logits[cur ^ 1], nb.new_scores, nb.pair_stride, nb.logits[cur], P0, gmb, mg, slp, ltr,
+                                               trace_stride, trace_off, slot, nb.slot[(t + 1) & 1], S, nb.free_slot, nb.new_slot, nb.pair_i,
+                                               nb.pair_j, nb.pair_stride);
+            LAUNCH_CHECK();
+            trace_off += (size_t)n * (n - 1) / 2;
+            if (n == 2) break;
+            if (int e = merge_pair(m, pool, nb, nb.X, slot, n, C, mg + (size_t)t * 2, (R - 1) * 2, nbt, nullptr, 0, true, st)) return e;
+        }
+    }
+    return 0;
+}
+
+}  // namespace nnj

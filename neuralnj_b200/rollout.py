@@ -1,0 +1,258 @@
+"""Rollout drivers and entry points with the reference's signatures (finetune_rl_search.py).
+
+    reinforce_rollout(batch, agent, env, cfgs, ..., eval=True, argmax=...)      :78-189
+    Agmax_one_instance(cfgs, MSA_file, policy_network, env, ...)                 :430-475
+    Argmax_inference(test_file_path, write_dir, write_file_name, ...)            :478-509
+    RL_Search(cfgs, MSA_file, policy_network, env, ...)                          :338-427
+    Search_inference(test_file_path, write_dir, write_file_name)                 :512-541
+
+Inference only (eval=True).  Two execution modes give the same results:
+  * fused   — one `nnj_rollout` call does encode + all NJ steps on the device, then the merge list is
+              replayed into `PhyInferEnv` so every host object ends up as in the reference;
+  * stepwise — the reference's own loop (decode_zxr -> select -> env.step) over the drop-in methods.
+Sampling (argmax=False) uses the Gumbel-max trick on the device; it draws from the same categorical
+distribution as `Categorical(logits=logits).sample()` but not from the same RNG stream.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .config import empty_config
+from .environment import PhyInferEnv
+from .model import PhyloATTN
+from .phydata import load_pi_instance
+from .treeutil import normalized_rf, rf_distance
+
+EXPLORE_TEMPERTURE = lambda step: 1.0   # finetune_rl_search.py:39
+STOP_STEP = 100                          # --stop_step default, finetune_rl_search.py:588
+cfgs = None                              # module-level config like the reference's __main__ (set by main())
+
+
+def _device_of(agent) -> torch.device:
+    return next(agent.parameters()).device
+
+
+def _step_slices(R: int):
+    off, out = 0, []
+    for n in range(R, 1, -1):
+        p = n * (n - 1) // 2
+        out.append((off, off + p))
+        off += p
+    return out
+
+
+def sample_gumbel(shape, device, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    u = torch.rand(shape, device=device, generator=generator).clamp_(1e-20, 1.0 - 1e-7)
+    return -torch.log(-torch.log(u))
+
+
+def reinforce_rollout(batch, agent, env, cfgs, replay_buffer=None, eval=False, argmax=False, get_all_tree=False,
+                      branch_optimize=False, fused=True, generator: Optional[torch.Generator] = None):
+    if not eval:
+        raise NotImplementedError("reinforce_rollout(eval=False) is REINFORCE training (finetune_rl_search.py:192-335): "
+                                  "outside the inference hot path")
+    device = _device_of(agent)
+    batch_seqs, batch_seq_keys, batch_array = batch["seqs"], batch["seq_keys"], batch["data"]
+    batch_array = batch_array.to(device)
+    batch_seq_mask = batch["seq_weights"].to(device) == 0
+    env.init_states(batch_seqs, batch_seq_keys, batch_array)
+    agent.eval()
+    B, R = batch_array.shape[:2]
+
+    if fused and hasattr(agent, "rollout_fused") and not branch_optimize:
+        with torch.no_grad():
+            gumbel = None if argmax else sample_gumbel((B, R - 1, R * (R - 1) // 2), device, generator)
+            merges, slp, trace = agent.rollout_fused(batch_array, batch_seq_mask, gumbel=gumbel, want_logits=True)
+            log_ps = [torch.log_softmax(trace[:, a:b] / EXPLORE_TEMPERTURE(t), dim=-1) for t, (a, b) in enumerate(_step_slices(R))][:-1]
+            selected_log_ps = slp[:, :R - 2]
+        env.replay_merges(merges)
+    else:
+        selected, log_ps = [], []
+        actions_ij_prev = logits_prev = None
+        step = 0
+        with torch.no_grad():
+            env.state_tensor = agent.encode_zxr(env.init_state_tensor, batch_seq_mask)
+            while True:
+                nb_seq = env.state_tensor.shape[1]
+                ret = agent.decode_zxr(env.state_tensor, batch_seq_mask, (actions_ij_prev, None, logits_prev))
+                logits = ret["logits"]
+                log_p = torch.log_softmax(logits / EXPLORE_TEMPERTURE(step), dim=-1)
+                if argmax:
+                    actions = torch.argmax(logits, dim=-1)
+                else:
+                    actions = torch.argmax(logits / EXPLORE_TEMPERTURE(step) + sample_gumbel(logits.shape, device, generator), dim=-1)
+                acts = actions.tolist()
+                actions_ij_prev = torch.tensor([env.tree_pairs_dict[nb_seq][a] for a in acts], dtype=torch.int32, device=device)
+                done = env.step(actions, [(None, None)] * B, branch_optimize=branch_optimize, agent=agent)
+                if done:
+                    break
+                step += 1
+                selected.append(torch.gather(log_p, 1, actions.unsqueeze(1)))
+                log_ps.append(log_p)
+                logits_prev = logits
+        selected_log_ps = torch.cat(selected, dim=1) if selected else torch.zeros(B, 0, device=device)
+
+    scores, best_rtree_tuple, best_tree_tuple, best_tree = env.evaluate_loglikelihood(get_all_tree=get_all_tree)
+    return selected_log_ps, log_ps, scores, best_tree
+
+
+def _expand(batch: dict, n: int) -> dict:
+    out = {}
+    for k, v in batch.items():
+        one = v[0:1]
+        out[k] = one * n if isinstance(one, list) else one.expand(n, *one.shape[1:])
+    return out
+
+
+def _tree_string(path: Optional[str]) -> Optional[str]:
+    if not path:
+        return None
+    with open(path) as f:
+        return f.readline().strip()
+
+
+def Agmax_one_instance(cfgs, MSA_file, policy_network, env, c_best_tree_file=None, raw_tree_file=None, branch_optimize=False):
+    batch = _expand(load_pi_instance(MSA_file), cfgs.env.batch_size)
+    raw_tree_str, c_best_tree_str = _tree_string(raw_tree_file), _tree_string(c_best_tree_file)
+    _, _, scores, best_tree = reinforce_rollout(batch, policy_network, env, cfgs, eval=True, argmax=True, branch_optimize=branch_optimize)
+    out = dict(best_tree_str=best_tree, score=float(scores[0]), raw_tree_score=None, c_best_tree_score=None,
+               rf_distance=None, rf_distance_raw=None, rf_distance_c_raw=None)
+    # the reference scores the comparison trees with RAxML-NG (not available); topological distances need no likelihood
+    if c_best_tree_str:
+        out["rf_distance"] = normalized_rf(c_best_tree_str, best_tree)
+    if raw_tree_str:
+        out["rf_distance_raw"] = normalized_rf(raw_tree_str, best_tree)
+    if raw_tree_str and c_best_tree_str:
+        out["rf_distance_c_raw"] = normalized_rf(raw_tree_str, c_best_tree_str)
+    return out
+
+
+def _load_policy(cfgs, device) -> PhyloATTN:
+    net = PhyloATTN(cfgs).to(device)
+    if cfgs.reload_checkpoint_path and os.path.exists(cfgs.reload_checkpoint_path):
+        ckpt = torch.load(cfgs.reload_checkpoint_path, map_location="cpu")
+        net.load_state_dict(ckpt["model_state_dict"])
+        print(f"Reloaded checkpoint at epoch {ckpt.get('epoch')}, accumulated_steps {ckpt.get('accumulated_steps')}")
+    elif cfgs.reload_checkpoint_path:
+        print(f"checkpoint {cfgs.reload_checkpoint_path} not found: using default-initialised weights")
+    return net.eval()
+
+
+def _cfg(c):
+    c = c if c is not None else cfgs
+    if c is None:
+        raise ValueError("no configuration: pass cfgs=... or set neuralnj_b200.rollout.cfgs")
+    return c
+
+
+def Argmax_inference(test_file_path, write_dir, write_file_name=None, branch_optimize=False, cfgs=None, device=None):
+    c = _cfg(cfgs)
+    device = device or torch.device("cuda")
+    env = PhyInferEnv(c, device)
+    policy = _load_policy(c, device)
+    os.makedirs(write_dir, exist_ok=True)
+    written = []
+    for file in sorted(f for f in os.listdir(test_file_path) if f.endswith(".phy")):
+        res = Agmax_one_instance(c, os.path.join(test_file_path, file), policy, env, branch_optimize=branch_optimize)
+        dst = os.path.join(write_dir, file[:-4] + ".tre")
+        with open(dst, "w") as f:
+            f.write(res["best_tree_str"])
+        written.append(dst)
+    return written
+
+
+def RL_Search(cfgs, MSA_file, policy_network, env, c_best_tree_file=None, raw_tree_file=None, scorer=None, stop_step=None,
+              generator: Optional[torch.Generator] = None):
+    """NeuralNJ-MC: sampled rollouts, keep the best-scoring tree (finetune_rl_search.py:338-427).
+
+    One encoder pass is shared by every sampled rollout (the reference re-encodes the same MSA each
+    time, :112).  `scorer(newick, seq_keys, seqs) -> float` stands in for the RAxML-NG likelihood
+    (`optimize_brlen`, environment.py:365-379), which is not part of this path; without a scorer the
+    policy's own trajectory log-probability ranks the candidates.
+    """
+    stop = STOP_STEP if stop_step is None else stop_step
+    device = _device_of(policy_network)
+    batch = _expand(load_pi_instance(MSA_file), cfgs.env.batch_size)
+    data = batch["data"].to(device)
+    mask = batch["seq_weights"].to(device) == 0
+    B, R = data.shape[:2]
+    raw_tree_str = _tree_string(raw_tree_file)
+    policy_network.eval()
+    start = time.time()
+    best_tree, best_score, t_best = None, -np.inf, None
+    seen = {}
+    with torch.no_grad():
+        state = policy_network.encode_zxr(data[:1], mask[:1]).expand(B, -1, -1, -1).contiguous()
+        step_cur = 0
+        for epoch in range(1, cfgs.num_epoch):
+            for episode in range(cfgs.num_episodes):
+                gumbel = sample_gumbel((B, R - 1, R * (R - 1) // 2), device, generator)
+                merges, slp, _ = policy_network.rollout_fused(batch_seq_mask=mask, gumbel=gumbel, state=state)
+                env.init_states(batch["seqs"], batch["seq_keys"], data)
+                env.replay_merges(merges)
+                traj_logp = slp[:, :R - 2].sum(1).tolist()
+                for b, st in enumerate(env.states):
+                    tree = st.subtrees[0]
+                    if tree.topo_repr in seen:
+                        score = seen[tree.topo_repr]
+                    else:
+                        score = scorer(tree.utree_op_str, batch["seq_keys"][b], batch["seqs"][b]) if scorer else traj_logp[b]
+                        seen[tree.topo_repr] = score
+                    if best_tree is None or score > best_score:
+                        best_tree, best_score, t_best = tree.utree_op_str, score, time.time() - start
+                step_cur = 1 + episode + (epoch - 1) * cfgs.num_episodes
+            if step_cur >= stop:
+                break
+    rel_rf = normalized_rf(raw_tree_str, best_tree) if raw_tree_str else None
+    return dict(the_best_tree=best_tree, the_best_score=best_score, raw_tree_score=None, c_best_tree_score=None,
+                time_when_best_score_max=t_best, relative_rf_distance=rel_rf, step_cur=step_cur, distinct_topologies=len(seen))
+
+
+def Search_inference(test_file_path, write_dir, write_file_name=None, cfgs=None, device=None, scorer=None, stop_step=None):
+    c = _cfg(cfgs)
+    device = device or torch.device("cuda")
+    env = PhyInferEnv(c, device)
+    policy = _load_policy(c, device)
+    os.makedirs(write_dir, exist_ok=True)
+    written = []
+    for file in sorted(f for f in os.listdir(test_file_path) if f.endswith(".phy")):
+        res = RL_Search(c, os.path.join(test_file_path, file), policy, env, scorer=scorer, stop_step=stop_step)
+        dst = os.path.join(write_dir, file[:-4] + ".tre")
+        with open(dst, "w") as f:
+            f.write(res["the_best_tree"])
+        written.append(dst)
+        print(f"finish NerualNJ-MC for {file}")
+    return written
+
+
+def main(argv=None):
+    """CLI with the reference's flags (finetune_rl_search.py:583-621)."""
+    import argparse
+    global cfgs, STOP_STEP
+    ap = argparse.ArgumentParser(description="NeuralNJ inference (B200 path)")
+    ap.add_argument("--config_path", type=str, default="")
+    ap.add_argument("--infer_opt", type=str, default="Argmax", help='"Argmax" (NeuralNJ) or "Search" (NeuralNJ-MC)')
+    ap.add_argument("--stop_step", type=int, default=100)
+    ap.add_argument("--evolution_model", type=str, default="GTR+I+G")
+    ap.add_argument("--branch_optimize", action="store_true")
+    args = ap.parse_args(argv)
+    cfgs = empty_config()
+    if args.config_path:
+        cfgs.merge_from_file(args.config_path)
+    STOP_STEP = args.stop_step
+    name = os.path.basename(os.path.normpath(cfgs.instance_path))
+    write_dir = f"output/{args.infer_opt}_dim{cfgs.model.embed_dim}_patch{cfgs.model.patch_size}/{name}"
+    if args.infer_opt == "Argmax":
+        return Argmax_inference(cfgs.instance_path, write_dir, None, branch_optimize=args.branch_optimize)
+    if args.infer_opt == "Search":
+        return Search_inference(cfgs.instance_path, write_dir, None)
+    raise SystemExit(f'--infer_opt {args.infer_opt}: "Finetune" (NeuralNJ-RL) trains the policy and is outside this path')
+
+
+if __name__ == "__main__":
+    main()

@@ -45,7 +45,7 @@ State = Dict[str, torch.Tensor]
 # weights
 # --------------------------------------------------------------------------
 def state_dict_keys(num_layers: int = 6) -> List[str]:
-    """The 78 reference state_dict keys in construction order (model.py:12-60)."""
+    """The reference state_dict keys (172 for 6 layers) in construction order (model.py:12-60)."""
     keys = []
     for l in range(num_layers):
         for blk in ("row_self_attention", "column_self_attention"):
