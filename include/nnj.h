@@ -138,6 +138,14 @@ int nnj_rollout_from_state(nnj_model* m, const float* state_dev, const uint8_t* 
 int nnj_rollout_host(nnj_model* m, const int8_t* data_host, const uint8_t* seq_mask_host, int B, int R, int L,
                      int select_mode, const float* gumbel_host, int32_t* merges_host, float* selected_logp_host);
 
+/* Optional per-kernel-class timing with CUDA events recorded on the launching stream (used by bench.py for the
+ * roofline numbers).  enable(1) clears and starts recording on the calling thread, enable(0) stops.
+ * read() synchronises the device and returns summed milliseconds / launch counts per class. */
+int nnj_profile_enable(int on);
+int nnj_profile_classes(void);
+const char* nnj_profile_name(int cls);
+int nnj_profile_read(int n, double* ms, int64_t* launches);
+
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 int64_t nnj_launch_count(int reset);
 

@@ -16,7 +16,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 EXPORTS = ["nnj_last_error", "nnj_abi_version", "nnj_model_create", "nnj_model_destroy", "nnj_workspace_bytes",
            "nnj_encode", "nnj_pair_scores_full", "nnj_pair_scores_list", "nnj_pair_scores_incr", "nnj_aggregate",
-           "nnj_merge", "nnj_rollout", "nnj_rollout_from_state", "nnj_rollout_host", "nnj_launch_count"]
+           "nnj_merge", "nnj_rollout", "nnj_rollout_from_state", "nnj_rollout_host", "nnj_launch_count",
+           "nnj_profile_enable", "nnj_profile_classes", "nnj_profile_name", "nnj_profile_read"]
 
 
 class NnjError(RuntimeError):
@@ -83,6 +84,10 @@ def lib() -> C.CDLL:
     L.nnj_rollout_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
     L.nnj_launch_count.argtypes = [i32]
     L.nnj_launch_count.restype = i64
+    L.nnj_profile_enable.argtypes = [i32]
+    L.nnj_profile_name.argtypes = [i32]
+    L.nnj_profile_name.restype = C.c_char_p
+    L.nnj_profile_read.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(i64)]
     for name in ("nnj_model_create", "nnj_encode", "nnj_pair_scores_full", "nnj_pair_scores_list", "nnj_pair_scores_incr",
                  "nnj_aggregate", "nnj_merge", "nnj_rollout", "nnj_rollout_from_state", "nnj_rollout_host"):
         getattr(L, name).restype = i32

@@ -20,6 +20,37 @@ int set_cuda_error(cudaError_t e, const char* file, int line) {
     return NNJ_ERR_CUDA;
 }
 
+// ---- optional per-kernel-class timing with CUDA events on the launching stream ----
+struct ProfRec { int cls; cudaEvent_t a, b; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_prof;
+static thread_local std::vector<cudaEvent_t> g_prof_pool;
+static thread_local int g_prof_open = -1;
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void prof_begin(int cls, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r{cls, prof_event(), prof_event()};
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+    g_prof_open = (int)g_prof.size() - 1;
+}
+
+void prof_end(cudaStream_t st) {
+    if (!g_prof_on || g_prof_open < 0) return;
+    cudaEventRecord(g_prof[g_prof_open].b, st);
+    g_prof_open = -1;
+}
+
+static const char* kclass_names[KC_COUNT] = {"embed", "ln_qkv", "row_qk_gemm", "row_softmax", "row_pv_gemm", "out_proj", "col_attn",
+                                             "ffn", "node_derive", "alpha", "alpha_softmax", "pair_score", "select", "merge", "misc"};
+
 #define CUDA_TRY(x)                                                        \
     do {                                                                   \
         cudaError_t e_ = (x);                                              \
@@ -54,6 +85,29 @@ extern "C" {
 
 const char* nnj_last_error(void) { return g_err; }
 int nnj_abi_version(void) { return NNJ_ABI_VERSION; }
+
+int nnj_profile_enable(int on) {
+    for (auto& r : g_prof) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    g_prof.clear();
+    g_prof_open = -1;
+    g_prof_on = on != 0;
+    return NNJ_OK;
+}
+
+int nnj_profile_classes(void) { return KC_COUNT; }
+
+const char* nnj_profile_name(int cls) { return (cls >= 0 && cls < KC_COUNT) ? kclass_names[cls] : ""; }
+
+int nnj_profile_read(int n, double* ms, int64_t* launches) {
+    if (n < KC_COUNT || !ms || !launches) return set_error(NNJ_ERR_INVALID, "profile_read: need room for nnj_profile_classes() entries");
+    for (int i = 0; i < n; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (auto& r : g_prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += t; launches[r.cls] += 1; }
+    }
+    return NNJ_OK;
+}
 
 int64_t nnj_launch_count(int reset) {
     long long v = g_launches;

@@ -423,6 +423,7 @@ size_t encoder_ws_bytes(const Model* m, int B, int R, int C) {
 #define LAUNCH_CHECK()                                                         \
     do {                                                                       \
         ++g_launches;                                                          \
+        prof_end(st);                                                          \
         cudaError_t e_ = cudaGetLastError();                                   \
         if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__);  \
     } while (0)
@@ -461,32 +462,42 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
         float* xb = x + (size_t)b0 * x_tree_stride;
         const int8_t* db = data + (size_t)b0 * R * L * 4;
         const uint8_t* mb = mask ? mask + (size_t)b0 * C : nullptr;
+        prof_begin(KC_EMBED, st);
         k_embed<<<dim3((T + 1023) / 1024, nb), NTHREADS, 0, st>>>(db, xb, x_tree_stride, R, L, m->embed);
         LAUNCH_CHECK();
         for (int l = 0; l < m->num_layers; ++l) {
             const LayerW& lw = m->layers[l];
             // --- tied row attention
+            prof_begin(KC_LN_QKV, st);
             k_ln_qkv<true><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, lw.row, row_scale, mb, q, k, v);
             LAUNCH_CHECK();
+            prof_begin(KC_ROW_QK, st);
             k_gemm<true><<<dim3((C + 127) / 128, (C + 127) / 128, nb * H), NTHREADS, 0, st>>>(
                 q, k, S, C, C, R * DH, (size_t)C * R * DH, (size_t)C * R * DH, (size_t)C * C, R * DH, R * DH, C);
             LAUNCH_CHECK();
+            prof_begin(KC_ROW_SOFTMAX, st);
             k_softmax_rows<<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, C, C, mb);
             LAUNCH_CHECK();
+            prof_begin(KC_ROW_PV, st);
             k_gemm<false><<<dim3((R * DH + 127) / 128, (C + 127) / 128, nb * H), NTHREADS, 0, st>>>(
                 S, v, q /*ctx*/, C, R * DH, C, (size_t)C * C, (size_t)C * R * DH, (size_t)C * R * DH, C, R * DH, R * DH);
             LAUNCH_CHECK();
+            prof_begin(KC_OUT_PROJ, st);
             k_out_proj<true><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, q, lw.row.ot, lw.row.ob);
             LAUNCH_CHECK();
             // --- column attention
             if (R == 1) return set_error(NNJ_ERR_INVALID, "encode: R == 1 is not supported");
+            prof_begin(KC_LN_QKV, st);
             k_ln_qkv<false><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, lw.col, col_scale, mb, q, k, v);
             LAUNCH_CHECK();
+            prof_begin(KC_COL_ATTN, st);
             k_col_attn<<<dim3(C, nb), NTHREADS, smem_col, st>>>(q, k, v, S /*ctx [B,R,C,64]*/, R, C, mb);
             LAUNCH_CHECK();
+            prof_begin(KC_OUT_PROJ, st);
             k_out_proj<false><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, S, lw.col.ot, lw.col.ob);
             LAUNCH_CHECK();
             // --- feed forward
+            prof_begin(KC_FFN, st);
             k_ffn<<<dim3(tiles, nb), NTHREADS, smem_ffn, st>>>(xb, x_tree_stride, R, C, lw.ffn);
             LAUNCH_CHECK();
         }

@@ -36,6 +36,12 @@ struct Model {
     NjW nj;
 };
 
+// kernel classes for the optional per-class CUDA-event profiler (nnj_profile_*)
+enum KClass { KC_EMBED = 0, KC_LN_QKV, KC_ROW_QK, KC_ROW_SOFTMAX, KC_ROW_PV, KC_OUT_PROJ, KC_COL_ATTN, KC_FFN, KC_DERIVE,
+              KC_ALPHA, KC_ALPHA_SOFTMAX, KC_SCORE, KC_SELECT, KC_MERGE, KC_MISC, KC_COUNT };
+void prof_begin(int cls, cudaStream_t st);   // no-op unless profiling is enabled
+void prof_end(cudaStream_t st);
+
 int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* file, int line);
 

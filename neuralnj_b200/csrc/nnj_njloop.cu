@@ -686,6 +686,7 @@ __global__ void k_reindex_copy(const float* __restrict__ in, const float* __rest
 #define LAUNCH_CHECK()                                                         \
     do {                                                                       \
         ++g_launches;                                                          \
+        prof_end(st);                                                          \
         cudaError_t e_ = cudaGetLastError();                                   \
         if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__);  \
     } while (0)
@@ -767,22 +768,27 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
         const int nc = (N - n0 < PAIR_CHUNK) ? (N - n0) : PAIR_CHUNK;
         if (glob) {
             const int node_tiles = (Rp + 63) / 64, pair_tiles = (nc + 63) / 64;
+            prof_begin(KC_ALPHA, st);
             k_alpha<<<dim3(nb.nSB, pair_tiles * node_tiles, B), NTHREADS, 0, st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j, nb.pair_stride,
                                                                                    n0, nc, node_tiles, m->nj.bh, nb.alpha_part, nb.nSB, nb.RP);
             LAUNCH_CHECK();
+            prof_begin(KC_ALPHA_SOFTMAX, st);
             k_alpha_softmax<<<dim3((nc + 7) / 8, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
                                                                         nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha);
             LAUNCH_CHECK();
+            prof_begin(KC_SCORE, st);
             k_score<true><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
                                                                                             nb.pair_stride, n0, nc, nb.alpha, nb.RP, m->nj, mask,
                                                                                             nb.score_part, nb.nSB);
             LAUNCH_CHECK();
         } else {
+            prof_begin(KC_SCORE, st);
             k_score<false><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
                                                                                              nb.pair_stride, n0, nc, nb.alpha, nb.RP, m->nj, mask,
                                                                                              nb.score_part, nb.nSB);
             LAUNCH_CHECK();
         }
+        prof_begin(KC_MISC, st);
         k_score_reduce<<<dim3((nc + 127) / 128, B), 128, 0, st>>>(nb.score_part, nb.nSB, nc, scores, score_stride, n0);
         LAUNCH_CHECK();
     }
@@ -794,16 +800,20 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
                       const int32_t* ij, int ij_stride, int B, float* out_x, size_t out_stride, bool derive, cudaStream_t st) {
     const float inv_scale = 1.0f / sqrtf((float)D * (float)C);
     if (Rp > 2) {
+        prof_begin(KC_ALPHA, st);
         k_alpha1<<<dim3(nb.nSB, B), NTHREADS, 0, st>>>(pool, slot, nb.S, Rp, C, ij, ij_stride, m->nj.bh, nb.alpha_part, nb.nSB, nb.RP);
         LAUNCH_CHECK();
         // pair list for the softmax kernel: reuse it with one pair per tree = ij itself
+        prof_begin(KC_ALPHA_SOFTMAX, st);
         k_alpha_softmax<<<dim3(1, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, ij, ij + 1, ij_stride, 0, 1,
                                                          nb.nSB, nb.RP, inv_scale, nb.alpha);
         LAUNCH_CHECK();
+        prof_begin(KC_MERGE, st);
         k_merge<true><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
                                                                          nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0);
         LAUNCH_CHECK();
     } else {
+        prof_begin(KC_MERGE, st);
         k_merge<false><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
                                                                           nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0);
         LAUNCH_CHECK();
@@ -812,6 +822,7 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
 }
 
 static int derive_all(const Model* m, const float* X, const NjBuffers& nb, int B, int S, int nodes, int C, cudaStream_t st) {
+    prof_begin(KC_DERIVE, st);
     k_node_derive<<<dim3(nb.nCT, nodes, B), NTHREADS, smem_derive, st>>>(X, nb.Y, nb.K, nb.kap, (size_t)S * C * D, S, C, nb.nCT, nullptr, 0, m->nj);
     LAUNCH_CHECK();
     return 0;
@@ -837,9 +848,11 @@ int run_pair_scores(Model* m, const float* state, const uint8_t* mask, int B, in
     if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "pair scores: workspace too small");
     if (full) N = Rp * (Rp - 1) / 2;
     if (N > nb.pair_stride) return set_error(NNJ_ERR_INVALID, "pair scores: more pairs than R(R-1)/2");
+    prof_begin(KC_MISC, st);
     k_fill_slots<<<B, 128, 0, st>>>(nb.slot[0], nb.S, Rp, nullptr);
     LAUNCH_CHECK();
     if (full) {
+        prof_begin(KC_MISC, st);
         k_fill_pairs_full<<<dim3((N + 127) / 128, B < 64 ? B : 64), 128, 0, st>>>(nb.pair_i, nb.pair_j, nb.pair_stride, Rp, B);
         LAUNCH_CHECK();
     } else {
@@ -858,14 +871,17 @@ int run_pair_scores_incr(Model* m, const float* state, const uint8_t* mask, int 
     if (int e = set_attrs()) return e;
     NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
     if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "pair scores: workspace too small");
+    prof_begin(KC_MISC, st);
     k_fill_slots<<<B, 128, 0, st>>>(nb.slot[0], nb.S, Rp, nullptr);
     LAUNCH_CHECK();
+    prof_begin(KC_MISC, st);
     k_fill_pairs_incr<<<B, 128, 0, st>>>(nb.pair_i, nb.pair_j, nb.pair_stride, Rp, prev_ij, 2);
     LAUNCH_CHECK();
     if (int e = derive_all(m, state, nb, B, Rp, Rp, C, st)) return e;
     Pool pool = make_pool(state, nb, Rp, C);
     if (int e = score_pairs(m, pool, nb, nb.slot[0], Rp, C, Rp, mask, B, nb.new_scores, nb.pair_stride, st)) return e;
     const int P = Rp * (Rp - 1) / 2;
+    prof_begin(KC_MISC, st);
     k_assemble_logits<<<dim3((P + 127) / 128, B), 128, 0, st>>>(logits_prev, (Rp + 1) * Rp / 2, nb.new_scores, nb.pair_stride, prev_ij, 2, Rp,
                                                                 logits_out, P);
     LAUNCH_CHECK();
@@ -878,6 +894,7 @@ int run_aggregate(Model* m, const float* state, int B, int Rp, int C, const int3
     if (int e = set_attrs()) return e;
     NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
     if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "aggregate: workspace too small");
+    prof_begin(KC_MISC, st);
     k_fill_slots<<<B, 128, 0, st>>>(nb.slot[0], nb.S, Rp, nullptr);
     LAUNCH_CHECK();
     if (int e = derive_all(m, state, nb, B, Rp, Rp, C, st)) return e;
@@ -889,6 +906,7 @@ int run_merge(Model* m, const float* state_in, int B, int Rp, int C, const int32
               cudaStream_t st) {
     NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
     if (int e = run_aggregate(m, state_in, B, Rp, C, ij, nb.newx, (size_t)C * D, ws, ws_bytes, st)) return e;
+    prof_begin(KC_MISC, st);
     k_reindex_copy<<<dim3(8, Rp - 1, B), 256, 0, st>>>(state_in, nb.newx, state_out, Rp, (size_t)C * D, ij);
     LAUNCH_CHECK();
     return 0;
@@ -940,10 +958,13 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
         } else {
             if (int e = run_encoder(m, data + (size_t)b0 * R * L * 4, mk, nbt, R, L, nb.X, tree_stride, enc_ws, enc_bytes, st)) return e;
         }
+        prof_begin(KC_MISC, st);
         k_fill_slots<<<nbt, 128, 0, st>>>(nb.slot[0], S, R, nb.free_slot);
         LAUNCH_CHECK();
+        prof_begin(KC_MISC, st);
         k_fill_pairs_full<<<dim3((P0 + 127) / 128, nbt < 64 ? nbt : 64), 128, 0, st>>>(nb.pair_i, nb.pair_j, nb.pair_stride, R, nbt);
         LAUNCH_CHECK();
+        prof_begin(KC_DERIVE, st);
         k_node_derive<<<dim3(nb.nCT, R, nbt), NTHREADS, smem_derive, st>>>(nb.X, nb.Y, nb.K, nb.kap, tree_stride, S, C, nb.nCT, nullptr, 0, m->nj);
         LAUNCH_CHECK();
         Pool pool = make_pool(nb.X, nb, S, C);
@@ -962,6 +983,7 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
                 if (int e = score_pairs(m, pool, nb, slot, n, C, n, mk, nbt, nb.new_scores, nb.pair_stride, st)) return e;
                 cur ^= 1;
             }
+            prof_begin(KC_SELECT, st);
             k_select<<<nbt, NTHREADS, 0, st>>>(t, n, R, nb.logits[cur ^ 1], nb.new_scores, nb.pair_stride, nb.logits[cur], P0, gmb, mg, slp, ltr,
                                                trace_stride, trace_off, slot, nb.slot[(t + 1) & 1], S, nb.free_slot, nb.new_slot, nb.pair_i,
                                                nb.pair_j, nb.pair_stride);
