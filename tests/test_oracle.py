@@ -1,0 +1,96 @@
+"""CPU: the oracle restatement against the records the executed reference produced (tests/golden, oracle/make_golden.py)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD, SMALL_CASES
+
+import nnj_oracle as O
+
+
+def test_seed0_weights_match_reference_hash(sd0):
+    h = hashlib.sha256()
+    for k in sd0:
+        h.update(sd0[k].numpy().tobytes())
+    with open(os.path.join(GOLD, "weights_seed0.sha256")) as f:
+        assert h.hexdigest() == f.read().strip()
+    z = np.load(os.path.join(GOLD, "weights_seed0_sample.npz"))
+    assert len(z.files) == len(sd0) == 172
+    for k in sd0:
+        assert np.array_equal(z[k.replace(".", "__")], sd0[k].numpy().ravel()[:8])
+
+
+@pytest.mark.parametrize("case", SMALL_CASES)
+def test_oracle_rollout_matches_reference(case, golden, sd0):
+    g = golden(case)
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    r = O.rollout(sd0, g.data, g.mask)
+    assert torch.equal(r["merges"], g.merges)
+    for t, (a, b) in enumerate(zip(r["logits"], g.logits)):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-5, t
+    if g.selected_log_ps.numel():
+        assert float((r["selected_log_ps"] - g.selected_log_ps).abs().max()) < 1e-4
+    assert float((r["state0"][:, ::7, ::37, :] - g.state_sample).abs().max()) < 2e-5
+    for b in range(g.data.shape[0]):
+        nw = O.newick_from_merges([tuple(m) for m in r["merges"][b].tolist()], g.seq_keys[b])
+        assert nw == g.newick[b]
+        assert O.rf_distance(nw, g.newick[b]) == 0
+
+
+def test_oracle_phylip_reader_matches_reference_arrays(golden):
+    for case in ("t20x256_10", "t50x256_a", "ex50x1024_73"):
+        g = golden(case)
+        data, mask, keys, _ = O.load_phy(os.path.join(GOLD, "msa", case + ".phy"))
+        assert torch.equal(data, g.data) and keys == g.seq_keys[0] and not bool(mask.any())
+
+
+def test_unchunked_and_pair_chunked_variants_agree(golden, sd0):
+    g = golden("t20x256_10")
+    a = O.encode(sd0, g.data, g.mask, chunked=True)
+    b = O.encode(sd0, g.data, g.mask, chunked=False)
+    assert float((a - b).abs().max()) < 1e-5
+    r1 = O.rollout(sd0, g.data, g.mask, state=a)
+    r2 = O.rollout(sd0, g.data, g.mask, state=a, pair_chunk=37)
+    assert torch.equal(r1["merges"], r2["merges"])
+    assert float((r1["logits"][0] - r2["logits"][0]).abs().max()) < 1e-4
+
+
+def test_cache_index_map_closed_form():
+    """Brute force: where does pair (ii,jj) of the new list live in [old logits | new scores]?"""
+    for n_new in range(2, 9):
+        n_old = n_new + 1
+        old_pairs = O.pair_list(n_old)
+        for (a, b) in old_pairs:
+            # node labels after merging (a,b): slot a <- 'new', slot b removed
+            labels = [("new" if r == a else r) for r in range(n_old) if r != b]
+            got = O.score_indices_to_prev(a, b, n_new)
+            for p, (ii, jj) in enumerate(O.pair_list(n_new)):
+                li, lj = labels[ii], labels[jj]
+                if li == "new":
+                    want = len(old_pairs) + jj
+                elif lj == "new":
+                    want = len(old_pairs) + ii
+                else:
+                    want = old_pairs.index((li, lj))
+                assert got[p] == want
+    assert [O.pair_index(i, j, 7) for i, j in O.pair_list(7)] == list(range(21))
+
+
+def test_forced_and_gumbel_rollouts(golden, sd0):
+    g = golden("tiny_5x128")
+    r = O.rollout(sd0, g.data, g.mask)
+    f = O.rollout(sd0, g.data, g.mask, forced_merges=r["merges"])
+    assert torch.equal(f["merges"], r["merges"]) and torch.equal(f["logits"][1], r["logits"][1])
+    z = torch.zeros(1, 4, 10)
+    assert torch.equal(O.rollout(sd0, g.data, g.mask, gumbel=z)["merges"], r["merges"])
+
+
+def test_rf_distance():
+    a = "((t1:1, t2:1):1, (t3:1, t4:1):1, t5:1);"
+    b = "((t1:1, t3:1):1, (t2:1, t4:1):1, t5:1);"
+    assert O.rf_distance(a, a) == 0 and O.rf_distance(a, b) == 4
+    assert O.rf_distance("(((t1:1, t2:1):1, (t3:1, t4:1):1):1, t5:1);", a) == 0   # rooted vs unrooted reading
+    assert O.rf_distance("(((t1:1, t2:1):1, t3:1):1, (t4:1, t5:1):1);", a) == 2
