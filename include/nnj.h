@@ -138,6 +138,13 @@ int nnj_rollout_from_state(nnj_model* m, const float* state_dev, const uint8_t* 
 int nnj_rollout_host(nnj_model* m, const int8_t* data_host, const uint8_t* seq_mask_host, int B, int R, int L,
                      int select_mode, const float* gumbel_host, int32_t* merges_host, float* selected_logp_host);
 
+/* Building block of the tensor-core path (precision NNJ_PREC_BF16X3), exposed for unit tests and reuse:
+ * C[z] = A[z] * B[z]^T with fp32 A [Z,M,K], B [Z,N,K], C [Z,M,N]; operands are split into bf16 hi/lo planes and
+ * multiplied on tcgen05 as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM.  K must be a multiple of 8;
+ * ws needs 4*(Z*M*K + Z*N*K) + 2048 bytes.  Replaces the einsum contractions of axial_attention.py:97,114. */
+int nnj_gemm_split_bf16(const float* A_dev, const float* B_dev, float* C_dev, int Z, int M, int N, int K,
+                        void* ws_dev, int64_t ws_bytes, void* stream);
+
 /* Optional per-kernel-class timing with CUDA events recorded on the launching stream (used by bench.py for the
  * roofline numbers).  enable(1) clears and starts recording on the calling thread, enable(0) stops.
  * read() synchronises the device and returns summed milliseconds / launch counts per class. */

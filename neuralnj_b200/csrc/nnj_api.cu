@@ -281,6 +281,11 @@ int nnj_rollout_from_state(nnj_model* m, const float* state, const uint8_t* mask
                        (cudaStream_t)stream);
 }
 
+int nnj_gemm_split_bf16(const float* A, const float* B, float* Cm, int Z, int M, int N, int K, void* ws, int64_t ws_bytes, void* stream) {
+    CHECK_ARGS(A && B && Cm && ws && Z >= 1 && M >= 1 && N >= 1 && K >= 8, "gemm_split_bf16: bad arguments");
+    return run_gemm_split_bf16(A, B, Cm, Z, M, N, K, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
 int nnj_rollout_host(nnj_model* m, const int8_t* data_h, const uint8_t* mask_h, int B, int R, int L, int select_mode,
                      const float* gumbel_h, int32_t* merges_h, float* selected_logp_h) {
     CHECK_ARGS(m && data_h && merges_h && B >= 1 && R >= 2 && L >= 1, "rollout_host: bad arguments");

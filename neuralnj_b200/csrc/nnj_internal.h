@@ -67,4 +67,9 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
                 const float* gumbel, int32_t* merges, float* logits_trace, float* selected_logp, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 
+// tcgen05 split-bf16 GEMM (nnj_tc.cu)
+int launch_tc_gemm(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
+                   size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st);
+int run_gemm_split_bf16(const float* A, const float* B, float* Cm, int Z, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace nnj
