@@ -11,6 +11,8 @@
 //   k_col_attn       per-site attention over taxa (:216-234)
 //   k_out_proj       out_proj + residual add (:116,236; msa_modules.py:120)
 //   k_ffn            LN + fc1 + GELU + fc2 + residual (msa_modules.py:144-151)
+#include <cuda_bf16.h>
+
 #include "nnj_internal.h"
 
 namespace nnj {
@@ -396,19 +398,145 @@ __global__ void __launch_bounds__(NTHREADS) k_softmax_rows(float* __restrict__ S
     for (int j = lane; j < C; j += 32) p[j] *= inv;
 }
 
+
+// ------------------------------------------------------------------ tensor-core row attention (precision bf16x3)
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// LN + q/k/v projections of the tied row attention, written as bf16 hi/lo planes for the tcgen05 GEMMs:
+//   Q, K : [B,H,C,R*8]   (K-major operands of S = Q K^T, contraction over (taxon, head-dim))
+//   V^T  : [B,H,R*8,C]   (K-major B operand of ctx = P V, contraction over key sites)
+// NATURAL token order (one taxon, 128 consecutive sites per tile) so V^T rows are written 8 sites (16 B) at a time.
+__global__ void __launch_bounds__(NTHREADS) k_ln_qkv_rowtc(const float* __restrict__ x, size_t x_tree_stride, int R, int C, AttnW w,
+                                                           float q_scale, const uint8_t* __restrict__ mask,
+                                                           __nv_bfloat16* __restrict__ qh, __nv_bfloat16* __restrict__ ql,
+                                                           __nv_bfloat16* __restrict__ kh, __nv_bfloat16* __restrict__ kl,
+                                                           __nv_bfloat16* __restrict__ vth, __nv_bfloat16* __restrict__ vtl) {
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;
+    float* Ws = smem + TILE_ROWS * LDA;
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int T = R * C, KD = R * DH;
+    load_x_tile<false>(xs, x + (size_t)b * x_tree_stride, tile, R, C);
+    __syncthreads();
+    tile_layernorm(xs, w.ln_g, w.ln_b);
+    __syncthreads();
+    const float* wt[3] = {w.qt, w.kt, w.vt};
+    const float* bs[3] = {w.qb, w.kb, w.vb};
+    const int h = tx >> 1, d0 = (tx & 1) * 4;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        load_w64(Ws, wt[p]);
+        __syncthreads();
+        float acc[8][4];
+        acc_set_bias(acc, bs[p], tx);
+        tile_mma64(acc, xs, Ws, ty, tx);
+        const int t0 = tile * TILE_ROWS + ty * 8;
+        if (p < 2) {
+            __nv_bfloat16* oh = p == 0 ? qh : kh;
+            __nv_bfloat16* ol = p == 0 ? ql : kl;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int t = t0 + i;
+                if (t >= T) continue;
+                int r = t / C, c = t - r * C;
+                float s = 1.0f;
+                if (p == 0) s = (mask && mask[(size_t)b * C + c]) ? 0.f : q_scale;   // axial_attention.py:81-82
+                __align__(8) __nv_bfloat16 hv[4], lv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split_bf16(acc[i][j] * s, hv[j], lv[j]);
+                size_t off = (((size_t)b * H + h) * C + c) * KD + r * DH + d0;
+                *reinterpret_cast<uint2*>(oh + off) = *reinterpret_cast<uint2*>(hv);
+                *reinterpret_cast<uint2*>(ol + off) = *reinterpret_cast<uint2*>(lv);
+            }
+        } else {
+            const int r0 = t0 / C, c0 = t0 - r0 * C;
+            const bool fast = (t0 + 7 < T) && (c0 + 7 < C) && ((c0 & 7) == 0) && ((C & 7) == 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (fast) {
+                    __align__(16) __nv_bfloat16 hv[8], lv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) split_bf16(acc[i][j], hv[i], lv[i]);
+                    size_t off = (((size_t)b * H + h) * KD + r0 * DH + d0 + j) * C + c0;
+                    *reinterpret_cast<uint4*>(vth + off) = *reinterpret_cast<uint4*>(hv);
+                    *reinterpret_cast<uint4*>(vtl + off) = *reinterpret_cast<uint4*>(lv);
+                } else {
+                    for (int i = 0; i < 8; ++i) {
+                        int t = t0 + i;
+                        if (t >= T) continue;
+                        int r = t / C, c = t - r * C;
+                        __nv_bfloat16 hv, lv;
+                        split_bf16(acc[i][j], hv, lv);
+                        size_t off = (((size_t)b * H + h) * KD + r * DH + d0 + j) * C + c;
+                        vth[off] = hv; vtl[off] = lv;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// softmax over key sites of S [Z, C, C] (fp32) -> probabilities as bf16 hi/lo planes; one warp per row; C even.
+__global__ void __launch_bounds__(NTHREADS) k_softmax_rows_split(const float* __restrict__ S, __nv_bfloat16* __restrict__ Ph,
+                                                                 __nv_bfloat16* __restrict__ Pl, int C, const uint8_t* __restrict__ mask) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= C) return;
+    const int z = blockIdx.y, b = z / H;
+    const size_t base = ((size_t)z * C + row) * C;
+    const float2* p = reinterpret_cast<const float2*>(S + base);
+    const uint8_t* mk = mask ? mask + (size_t)b * C : nullptr;
+    const int C2 = C >> 1;
+    float m = -INFINITY;
+    for (int j = lane; j < C2; j += 32) {
+        float2 v = p[j];
+        if (mk) { if (mk[2 * j]) v.x = -10000.0f; if (mk[2 * j + 1]) v.y = -10000.0f; }
+        m = fmaxf(m, fmaxf(v.x, v.y));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = 0.f;
+    for (int j = lane; j < C2; j += 32) {
+        float2 v = p[j];
+        if (mk) { if (mk[2 * j]) v.x = -10000.0f; if (mk[2 * j + 1]) v.y = -10000.0f; }
+        l += expf(v.x - m) + expf(v.y - m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float inv = 1.0f / l;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(Ph + base);
+    __nv_bfloat162* ol = reinterpret_cast<__nv_bfloat162*>(Pl + base);
+    for (int j = lane; j < C2; j += 32) {
+        float2 v = p[j];
+        if (mk) { if (mk[2 * j]) v.x = -10000.0f; if (mk[2 * j + 1]) v.y = -10000.0f; }
+        float e0 = expf(v.x - m) * inv, e1 = expf(v.y - m) * inv;
+        __nv_bfloat162 hh, ll;
+        split_bf16(e0, hh.x, ll.x);
+        split_bf16(e1, hh.y, ll.y);
+        oh[j] = hh; ol[j] = ll;
+    }
+}
+
 // ------------------------------------------------------------------ host-side driver
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // per-tree workspace floats for the encoder
-static size_t enc_tree_floats(int R, int C) {
+static bool use_tc(const Model* m, int C) { return m->cfg.precision == NNJ_PREC_BF16X3 && (C % 8) == 0; }
+
+static size_t enc_tree_floats(const Model* m, int R, int C) {
     size_t act = (size_t)R * C * D;
     size_t s = (size_t)H * C * C;         // row-attention logits; also holds the column-attention context
-    return 3 * act + (s > act ? s : act); // q (row ctx), k, v, S
+    size_t p = use_tc(m, C) ? s : 0;      // probabilities as bf16 hi/lo planes (tensor-core path)
+    return 3 * act + (s > act ? s : act) + p; // q (row ctx), k, v, S [, P]
 }
 
 int encoder_chunk(const Model* m, int B, int R, int C) {
-    (void)m;
-    size_t per = enc_tree_floats(R, C) * sizeof(float);
+    size_t per = enc_tree_floats(m, R, C) * sizeof(float);
     size_t budget = (size_t)6 << 30;
     int ch = (int)(budget / per);
     if (ch < 1) ch = 1;
@@ -417,7 +545,7 @@ int encoder_chunk(const Model* m, int B, int R, int C) {
 }
 
 size_t encoder_ws_bytes(const Model* m, int B, int R, int C) {
-    return align_up(enc_tree_floats(R, C) * sizeof(float) * encoder_chunk(m, B, R, C), 256) + 256;
+    return align_up(enc_tree_floats(m, R, C) * sizeof(float) * encoder_chunk(m, B, R, C), 256) + 256;
 }
 
 #define LAUNCH_CHECK()                                                         \
@@ -439,6 +567,9 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
     float* k = q + act * chunk;
     float* v = k + act * chunk;
     float* S = v + act * chunk;   // region of chunk * max(H*C*C, act) floats
+    const bool tc = use_tc(m, C);
+    const size_t s_floats = (size_t)H * C * C > act ? (size_t)H * C * C : act;
+    __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(S + s_floats * chunk);   // [2 planes][chunk*H][C][C] (tensor-core path only)
     const int T = R * C;
     const int tiles = (T + TILE_ROWS - 1) / TILE_ROWS;
     const size_t smem_qkv = (TILE_ROWS * LDA + 4096) * sizeof(float);
@@ -449,6 +580,7 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
         cudaFuncSetAttribute(k_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ffn);
         cudaFuncSetAttribute(k_ln_qkv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qkv);
         cudaFuncSetAttribute(k_ln_qkv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qkv);
+        cudaFuncSetAttribute(k_ln_qkv_rowtc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qkv);
         cudaFuncSetAttribute(k_out_proj<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qkv);
         cudaFuncSetAttribute(k_out_proj<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qkv);
         cudaFuncSetAttribute(k_col_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -468,20 +600,38 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
         for (int l = 0; l < m->num_layers; ++l) {
             const LayerW& lw = m->layers[l];
             // --- tied row attention
-            prof_begin(KC_LN_QKV, st);
-            k_ln_qkv<true><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, lw.row, row_scale, mb, q, k, v);
-            LAUNCH_CHECK();
-            prof_begin(KC_ROW_QK, st);
-            k_gemm<true><<<dim3((C + 127) / 128, (C + 127) / 128, nb * H), NTHREADS, 0, st>>>(
-                q, k, S, C, C, R * DH, (size_t)C * R * DH, (size_t)C * R * DH, (size_t)C * C, R * DH, R * DH, C);
-            LAUNCH_CHECK();
-            prof_begin(KC_ROW_SOFTMAX, st);
-            k_softmax_rows<<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, C, C, mb);
-            LAUNCH_CHECK();
-            prof_begin(KC_ROW_PV, st);
-            k_gemm<false><<<dim3((R * DH + 127) / 128, (C + 127) / 128, nb * H), NTHREADS, 0, st>>>(
-                S, v, q /*ctx*/, C, R * DH, C, (size_t)C * C, (size_t)C * R * DH, (size_t)C * R * DH, C, R * DH, R * DH);
-            LAUNCH_CHECK();
+            if (tc) {
+                const size_t pl = act * chunk;                 // elements per bf16 plane of q / k / v^T
+                __nv_bfloat16 *qh = reinterpret_cast<__nv_bfloat16*>(q), *ql = qh + pl;
+                __nv_bfloat16 *kh = reinterpret_cast<__nv_bfloat16*>(k), *kl = kh + pl;
+                __nv_bfloat16 *vh = reinterpret_cast<__nv_bfloat16*>(v), *vl = vh + pl;
+                const size_t pp = (size_t)chunk * H * C * C;   // elements per plane of P
+                const int KD = R * DH;
+                prof_begin(KC_LN_QKV, st);
+                k_ln_qkv_rowtc<<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, lw.row, row_scale, mb, qh, ql, kh, kl, vh, vl);
+                LAUNCH_CHECK();
+                if (int e = launch_tc_gemm(KC_ROW_QK, qh, ql, kh, kl, S, nb * H, C, C, KD, KD, (size_t)C * KD, KD, (size_t)C * KD, C, (size_t)C * C, st)) return e;
+                prof_begin(KC_ROW_SOFTMAX, st);
+                k_softmax_rows_split<<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, P + pp, C, mb);
+                LAUNCH_CHECK();
+                if (int e = launch_tc_gemm(KC_ROW_PV, P, P + pp, vh, vl, q /*ctx fp32 [B,H,C,R*8]*/, nb * H, C, KD, C, C, (size_t)C * C, C,
+                                           (size_t)KD * C, KD, (size_t)C * KD, st)) return e;
+            } else {
+                prof_begin(KC_LN_QKV, st);
+                k_ln_qkv<true><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, lw.row, row_scale, mb, q, k, v);
+                LAUNCH_CHECK();
+                prof_begin(KC_ROW_QK, st);
+                k_gemm<true><<<dim3((C + 127) / 128, (C + 127) / 128, nb * H), NTHREADS, 0, st>>>(
+                    q, k, S, C, C, R * DH, (size_t)C * R * DH, (size_t)C * R * DH, (size_t)C * C, R * DH, R * DH, C);
+                LAUNCH_CHECK();
+                prof_begin(KC_ROW_SOFTMAX, st);
+                k_softmax_rows<<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, C, C, mb);
+                LAUNCH_CHECK();
+                prof_begin(KC_ROW_PV, st);
+                k_gemm<false><<<dim3((R * DH + 127) / 128, (C + 127) / 128, nb * H), NTHREADS, 0, st>>>(
+                    S, v, q /*ctx*/, C, R * DH, C, (size_t)C * C, (size_t)C * R * DH, (size_t)C * R * DH, C, R * DH, R * DH);
+                LAUNCH_CHECK();
+            }
             prof_begin(KC_OUT_PROJ, st);
             k_out_proj<true><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, q, lw.row.ot, lw.row.ob);
             LAUNCH_CHECK();

@@ -67,9 +67,18 @@ def sd0():
 
 
 @pytest.fixture(scope="session")
-def gpu_model():
+def gpu_models():
+    """One model per precision mode, same seed-0 weights: fp32 CUDA-core path and tcgen05 split-bf16 path."""
     from neuralnj_b200 import PhyloATTN, inference_config
     import __graft_entry__ as g
     g.build()
-    torch.manual_seed(0)
-    return PhyloATTN(inference_config()).to("cuda:0").eval()
+    out = {}
+    for prec in ("fp32", "bf16x3"):
+        torch.manual_seed(0)
+        out[prec] = PhyloATTN(inference_config(), precision=prec).to("cuda:0").eval()
+    return out
+
+
+@pytest.fixture(scope="session")
+def gpu_model(gpu_models):
+    return gpu_models["fp32"]

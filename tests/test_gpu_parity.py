@@ -1,6 +1,7 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the reference's golden records.
 
-Tolerances (fp32 path): logits are compared as max|delta| / max|logit| of the step <= 2e-5 (the oracle
+Both precision modes are held to the same bar (fp32 CUDA-core path; bf16x3 = split-bf16 on tcgen05 for the dense
+contractions that have been moved to tensor cores).  Tolerances: logits are compared as max|delta| / max|logit| of the step <= 2e-5 (the oracle
 itself moves by ~4e-7 against the reference and ~1e-6 with thread count); encoder output
 <= 2e-4 absolute on values of order 1; merge lists and Newick strings must be identical.
 """
@@ -46,12 +47,13 @@ def _assert_equivalent_trajectory(sd, data, mask, merges, trace):
         off += p
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("case", ["t20x256_10", "padded_20x256", "tiny_5x128", "t50x256_a"])
-def test_encoder_matches_oracle(case, golden, sd0, gpu_model):
+def test_encoder_matches_oracle(case, prec, golden, sd0, gpu_models):
     import nnj_oracle as O
     g = golden(case)
     want = O.encode(sd0, g.data, g.mask)
-    got = gpu_model.encode_zxr(g.data.cuda(), g.mask.cuda()).cpu()
+    got = gpu_models[prec].encode_zxr(g.data.cuda(), g.mask.cuda()).cpu()
     assert got.shape == want.shape
     assert float((got - want).abs().max()) < STATE_TOL
     # and the strided sample the reference itself produced
@@ -124,14 +126,15 @@ def test_incremental_scores_and_merge_match_oracle(golden, sd0, gpu_model):
         logits_prev = out_closed
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("case", ALL_CASES)
-def test_rollout_matches_reference_golden(case, golden, sd0, gpu_model):
+def test_rollout_matches_reference_golden(case, prec, golden, sd0, gpu_models):
     """Fused device rollout vs the executed reference: identical merges / Newick (RF = 0), logits and log-probs close.
     Only a record whose own top-1/top-2 gap falls below TIE_TOL somewhere (t100x256_a: 9.9e-8 at step 67, under one
     fp32 ulp) is allowed the tie-aware comparison instead."""
     from neuralnj_b200 import PhyInferEnv, inference_config, rf_distance
     g = golden(case)
-    merges, slp, trace = gpu_model.rollout_fused(g.data.cuda(), g.mask.cuda(), want_logits=True)
+    merges, slp, trace = gpu_models[prec].rollout_fused(g.data.cuda(), g.mask.cuda(), want_logits=True)
     merges, slp, trace = merges.cpu().long(), slp.cpu(), trace.cpu()
     if not torch.equal(merges, g.merges) and _min_rel_gap(g.logits) < TIE_TOL:
         _assert_equivalent_trajectory(sd0, g.data, g.mask, merges, trace)
@@ -210,19 +213,20 @@ def test_full_size_properties(gpu_model):
     assert bool(torch.isfinite(s1).all()) and bool((s1 <= 1e-6).all())
 
 
-def test_oracle_parity_50x1024_synthetic(sd0, gpu_model):
-    """One config-2 sized alignment with phylogenetic signal against the oracle run on the box's CPU."""
+def test_oracle_parity_50x1024_synthetic(sd0, gpu_models):
+    """One config-2 sized alignment with phylogenetic signal against the oracle run on the box's CPU, both precisions."""
     import nnj_oracle as O
     data = O.evolved_msa(1, 50, 1024, seed=33)
     mask = torch.zeros(1, 1024, dtype=torch.bool)
     ref = O.rollout(sd0, data, mask)
-    merges, slp, trace = gpu_model.rollout_fused(data.cuda(), mask.cuda(), want_logits=True)
-    assert torch.equal(merges.cpu().long(), ref["merges"])
-    off = 0
-    for lg in ref["logits"]:
-        p = lg.shape[1]
-        assert _rel(trace[:, off:off + p].cpu(), lg) < LOGIT_TOL
-        off += p
+    for prec in ("fp32", "bf16x3"):
+        merges, slp, trace = gpu_models[prec].rollout_fused(data.cuda(), mask.cuda(), want_logits=True)
+        assert torch.equal(merges.cpu().long(), ref["merges"]), prec
+        off = 0
+        for lg in ref["logits"]:
+            p = lg.shape[1]
+            assert _rel(trace[:, off:off + p].cpu(), lg) < LOGIT_TOL, prec
+            off += p
 
 
 def test_error_paths(gpu_model):
