@@ -10,14 +10,14 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnnj.so")
-SOURCES = ["nnj_api.cu", "nnj_encoder.cu", "nnj_njloop.cu", "nnj_tc.cu"]
+SOURCES = ["nnj_api.cu", "nnj_encoder.cu", "nnj_njloop.cu", "nnj_tc.cu", "nnj_score_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
 EXPORTS = ["nnj_last_error", "nnj_abi_version", "nnj_model_create", "nnj_model_destroy", "nnj_workspace_bytes",
            "nnj_encode", "nnj_pair_scores_full", "nnj_pair_scores_list", "nnj_pair_scores_incr", "nnj_aggregate",
            "nnj_merge", "nnj_rollout", "nnj_rollout_from_state", "nnj_rollout_host", "nnj_launch_count",
-           "nnj_profile_enable", "nnj_profile_classes", "nnj_profile_name", "nnj_profile_read", "nnj_gemm_split_bf16"]
+           "nnj_profile_enable", "nnj_profile_classes", "nnj_profile_name", "nnj_profile_read", "nnj_gemm_split_bf16", "nnj_tc_selftest"]
 
 
 class NnjError(RuntimeError):
@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
     L.nnj_rollout_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
     L.nnj_gemm_split_bf16.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, i64, vp]
     L.nnj_gemm_split_bf16.restype = i32
+    L.nnj_tc_selftest.argtypes = [vp, vp, vp, vp]
+    L.nnj_tc_selftest.restype = i32
     L.nnj_launch_count.argtypes = [i32]
     L.nnj_launch_count.restype = i64
     L.nnj_profile_enable.argtypes = [i32]

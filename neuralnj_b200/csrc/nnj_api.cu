@@ -3,6 +3,8 @@
 #include <cstring>
 #include <new>
 
+#include <cuda_bf16.h>
+
 #include "nnj_internal.h"
 
 namespace nnj {
@@ -49,7 +51,7 @@ void prof_end(cudaStream_t st) {
 }
 
 static const char* kclass_names[KC_COUNT] = {"embed", "ln_qkv", "row_qk_gemm", "row_softmax", "row_pv_gemm", "out_proj", "col_attn",
-                                             "ffn", "node_derive", "alpha", "alpha_softmax", "pair_score", "select", "merge", "misc"};
+                                             "ffn", "node_derive", "alpha", "alpha_softmax", "pair_score", "select", "merge", "misc", "pair_blend"};
 
 #define CUDA_TRY(x)                                                        \
     do {                                                                   \
@@ -146,7 +148,7 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
     CUDA_TRY(cudaSetDevice(device));
     nnj_model* m = new (std::nothrow) nnj_model();
     if (!m) return set_error(NNJ_ERR_NOMEM, "model_create: out of host memory");
-    m->cfg = *cfg; m->device = device; m->num_layers = Lyr; m->blob = nullptr;
+    m->cfg = *cfg; m->device = device; m->num_layers = Lyr; m->blob = nullptr; m->blob_bf = nullptr;
 
     Packer pk;
     struct AttnOff { size_t ln_g, ln_b, qt, kt, vt, ot, qb, kb, vb, ob; };
@@ -207,6 +209,22 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
     }
     m->embed = EmbedW{B0 + e_w1, B0 + e_b1, B0 + e_w2t, B0 + e_b2};
     m->nj = NjW{B0 + h_t, B0 + h_b, B0 + g_t, B0 + g_b, B0 + q_w, B0 + q_b, B0 + k_t, B0 + k_b, B0 + s_t, B0 + s_b, B0 + s2_w, s2_b};
+    {   // bf16 hi/lo planes of the two [64][64] weights used as K-major B operands by the tensor-core pair-score kernel
+        std::vector<uint16_t> planes(4 * 4096);
+        const float* src[2] = {tensors[ti + 6] /*g_linear_last*/, tensors[ti + 12] /*s_out.0*/};
+        for (int w = 0; w < 2; ++w)
+            for (int i = 0; i < 4096; ++i) {
+                __nv_bfloat16 h = __float2bfloat16_rn(src[w][i]);
+                __nv_bfloat16 l = __float2bfloat16_rn(src[w][i] - __bfloat162float(h));
+                planes[(2 * w) * 4096 + i] = __bfloat16_as_ushort(h);
+                planes[(2 * w + 1) * 4096 + i] = __bfloat16_as_ushort(l);
+            }
+        e = cudaMalloc(&m->blob_bf, planes.size() * 2);
+        if (e == cudaSuccess) e = cudaMemcpy(m->blob_bf, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(m->blob); if (m->blob_bf) cudaFree(m->blob_bf); delete m; return set_cuda_error(e, __FILE__, __LINE__); }
+        const uint16_t* pb = reinterpret_cast<const uint16_t*>(m->blob_bf);
+        m->nj_bf = NjBf{pb, pb + 4096, pb + 8192, pb + 12288};
+    }
     *out = m;
     return NNJ_OK;
 }
@@ -214,6 +232,7 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
 void nnj_model_destroy(nnj_model* m) {
     if (!m) return;
     if (m->blob) cudaFree(m->blob);
+    if (m->blob_bf) cudaFree(m->blob_bf);
     delete m;
 }
 
@@ -284,6 +303,11 @@ int nnj_rollout_from_state(nnj_model* m, const float* state, const uint8_t* mask
 int nnj_gemm_split_bf16(const float* A, const float* B, float* Cm, int Z, int M, int N, int K, void* ws, int64_t ws_bytes, void* stream) {
     CHECK_ARGS(A && B && Cm && ws && Z >= 1 && M >= 1 && N >= 1 && K >= 8, "gemm_split_bf16: bad arguments");
     return run_gemm_split_bf16(A, B, Cm, Z, M, N, K, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
+int nnj_tc_selftest(const float* A, const float* B, float* Dm, void* stream) {
+    CHECK_ARGS(A && B && Dm, "tc_selftest: bad arguments");
+    return run_tc_unit(A, B, Dm, (cudaStream_t)stream);
 }
 
 int nnj_rollout_host(nnj_model* m, const int8_t* data_h, const uint8_t* mask_h, int B, int R, int L, int select_mode,

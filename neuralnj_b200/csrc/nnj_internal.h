@@ -26,6 +26,8 @@ struct NjW {                                                        // model.py:
     float b2;                   // s_out.2 bias
 };
 
+struct NjBf { const void *wgh, *wgl, *wsh, *wsl; };   // g_linear_last / s_out.0 weights [out][in] as bf16 hi/lo planes
+
 struct Model {
     nnj_config cfg;
     int device;
@@ -34,11 +36,13 @@ struct Model {
     EmbedW embed;
     std::vector<LayerW> layers;
     NjW nj;
+    NjBf nj_bf;
+    void* blob_bf;               // device allocation behind nj_bf
 };
 
 // kernel classes for the optional per-class CUDA-event profiler (nnj_profile_*)
 enum KClass { KC_EMBED = 0, KC_LN_QKV, KC_ROW_QK, KC_ROW_SOFTMAX, KC_ROW_PV, KC_OUT_PROJ, KC_COL_ATTN, KC_FFN, KC_DERIVE,
-              KC_ALPHA, KC_ALPHA_SOFTMAX, KC_SCORE, KC_SELECT, KC_MERGE, KC_MISC, KC_COUNT };
+              KC_ALPHA, KC_ALPHA_SOFTMAX, KC_SCORE, KC_SELECT, KC_MERGE, KC_MISC, KC_BLEND, KC_COUNT };
 void prof_begin(int cls, cudaStream_t st);   // no-op unless profiling is enabled
 void prof_end(cudaStream_t st);
 
@@ -70,6 +74,14 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
 // tcgen05 split-bf16 GEMM (nnj_tc.cu)
 int launch_tc_gemm(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                    size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st);
+int launch_blend_planes(const float* X, const float* Y, size_t tree_stride, const int32_t* slot_of, int slot_stride, int C, const int32_t* pair_i,
+                        const int32_t* pair_j, int pair_stride, int n0, int nc, int B, const float* bh, void* xh, void* xl, int pc,
+                        cudaStream_t st);
+int launch_pool_to_planes(const float* X, size_t tree_stride, int S, int C, int n_used, int B, void* ph, void* pl, cudaStream_t st);
+int launch_score_tc(const Model* m, const void* xh, const void* xl, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
+                    int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,
+                    int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, cudaStream_t st);
+int run_tc_unit(const float* A, const float* B, float* Dm, cudaStream_t st);
 int run_gemm_split_bf16(const float* A, const float* B, float* Cm, int Z, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace nnj

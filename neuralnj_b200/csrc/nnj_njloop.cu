@@ -13,6 +13,7 @@
 // All cross-CTA reductions go through partial buffers summed in a fixed order: results are
 // run-to-run deterministic.
 #include "nnj_internal.h"
+#include "nnj_tc.cuh"
 
 namespace nnj {
 
@@ -458,7 +459,8 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
                                                     float* __restrict__ kapw, const int32_t* __restrict__ slot_of, int slot_stride,
                                                     int Rp, int C, const int32_t* __restrict__ merge_ij, int ij_stride,
                                                     const float* __restrict__ alpha, int RP, NjW w, float* __restrict__ out_x,
-                                                    size_t out_stride, const int32_t* __restrict__ new_slot, int derive) {
+                                                    size_t out_stride, const int32_t* __restrict__ new_slot, int derive,
+                                                    uint2* __restrict__ nodes_h, uint2* __restrict__ nodes_l) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
     float* xg = xs + TILE_ROWS * LDA;
@@ -534,7 +536,18 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             int c = row0 + ty * 8 + i;
-            if (c < C) st4(Xw + nb + (size_t)c * D + tx * 4, ld4(xs + (ty * 8 + i) * LDA + tx * 4));
+            if (c < C) {
+                const float4 v = ld4(xs + (ty * 8 + i) * LDA + tx * 4);
+                st4(Xw + nb + (size_t)c * D + tx * 4, v);
+                if (nodes_h) {   // site-major bf16 hi/lo planes read by the tensor-core pair-score kernel
+                    uint2 oh, ol;
+                    split2(v.x, v.y, oh.x, ol.x);
+                    split2(v.z, v.w, oh.y, ol.y);
+                    const size_t o = (((size_t)b * C + c) * pool.S + ns) * 16 + tx;
+                    nodes_h[o] = oh;
+                    nodes_l[o] = ol;
+                }
+            }
         }
         derive_tile(xs, xg, Ws, w, Yw + nb, Kw + nb, kapw + ((size_t)b * pool.S + ns) * pool.nCT + ct, row0, C, red);
     } else {
@@ -697,12 +710,19 @@ struct NjBuffers {
     float *Y, *K, *kap, *alpha_part, *alpha, *score_part, *new_scores, *logits[2], *newx;
     int32_t *slot[2], *free_slot, *new_slot, *pair_i, *pair_j;
     float* X;         // pool X when owned by the workspace (rollout), else null
+    void *xh, *xl;            // tensor-core path: x planes of the current pair chunk [B][TC_PAIRS][C][64] bf16
+    void *nodes_h, *nodes_l;  // tensor-core path: site-major node planes [B][C][S][64] bf16
+    bool tc;
     int S, nCT, nSB, RP, pair_stride, P0;
     size_t total;
 };
 
 // carve the NJ workspace; X_in_ws: the node pool X lives in the workspace too (rollout)
-static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws, bool need_newx) {
+constexpr int TC_PAIRS = 256;   // pairs per launch on the tensor-core pair-score path
+
+static bool nj_use_tc(const Model* m, int S) { return m->cfg.precision == NNJ_PREC_BF16X3 && S <= 64; }
+
+static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws, bool need_newx, bool tc) {
     NjBuffers nb{};
     nb.S = S; nb.nCT = (C + TILE_ROWS - 1) / TILE_ROWS; nb.nSB = (C + SB_SITES - 1) / SB_SITES;
     nb.RP = (R + 3) & ~3;
@@ -728,6 +748,11 @@ static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws,
     nb.new_slot = (int32_t*)take((size_t)B * sizeof(int32_t));
     nb.pair_i = (int32_t*)take((size_t)B * nb.pair_stride * sizeof(int32_t));
     nb.pair_j = (int32_t*)take((size_t)B * nb.pair_stride * sizeof(int32_t));
+    nb.tc = tc;
+    if (tc) {
+        const size_t xp = (size_t)B * TC_PAIRS * C * D * 2, np = (size_t)B * C * S * D * 2;
+        nb.xh = take(xp); nb.xl = take(xp); nb.nodes_h = take(np); nb.nodes_l = take(np);
+    }
     nb.total = off + 256;
     return nb;
 }
@@ -763,9 +788,11 @@ static int check_dims(int Rp, int C) {
 static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, const int32_t* slot, int Rp, int C, int N,
                        const uint8_t* mask, int B, float* scores, int score_stride, cudaStream_t st) {
     const bool glob = Rp > 2;     // model.py:111
+    const bool tc = nb.tc && glob;
+    const int step = tc ? TC_PAIRS : PAIR_CHUNK;
     const float inv_scale = 1.0f / sqrtf((float)D * (float)C);   // model.py:118 (patch_num == C)
-    for (int n0 = 0; n0 < N; n0 += PAIR_CHUNK) {
-        const int nc = (N - n0 < PAIR_CHUNK) ? (N - n0) : PAIR_CHUNK;
+    for (int n0 = 0; n0 < N; n0 += step) {
+        const int nc = (N - n0 < step) ? (N - n0) : step;
         if (glob) {
             const int node_tiles = (Rp + 63) / 64, pair_tiles = (nc + 63) / 64;
             prof_begin(KC_ALPHA, st);
@@ -776,11 +803,18 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
             k_alpha_softmax<<<dim3((nc + 7) / 8, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
                                                                         nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha);
             LAUNCH_CHECK();
-            prof_begin(KC_SCORE, st);
-            k_score<true><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
-                                                                                            nb.pair_stride, n0, nc, nb.alpha, nb.RP, m->nj, mask,
-                                                                                            nb.score_part, nb.nSB);
-            LAUNCH_CHECK();
+            if (tc) {
+                if (int e = launch_blend_planes(pool.X, pool.Y, pool.tree_stride, slot, nb.S, C, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, B,
+                                                m->nj.bh, nb.xh, nb.xl, TC_PAIRS, st)) return e;
+                if (int e = launch_score_tc(m, nb.xh, nb.xl, TC_PAIRS, nb.nodes_h, nb.nodes_l, nb.alpha, nb.RP, PAIR_CHUNK, slot, nb.S, nb.pair_i,
+                                            nb.pair_stride, n0, nc, Rp, nb.S, C, B, mask, nb.score_part, nb.nSB, st)) return e;
+            } else {
+                prof_begin(KC_SCORE, st);
+                k_score<true><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
+                                                                                                nb.pair_stride, n0, nc, nb.alpha, nb.RP, m->nj, mask,
+                                                                                                nb.score_part, nb.nSB);
+                LAUNCH_CHECK();
+            }
         } else {
             prof_begin(KC_SCORE, st);
             k_score<false><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
@@ -810,12 +844,14 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
         LAUNCH_CHECK();
         prof_begin(KC_MERGE, st);
         k_merge<true><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
-                                                                         nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0);
+                                                                         nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0,
+                                                                         (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr, (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr);
         LAUNCH_CHECK();
     } else {
         prof_begin(KC_MERGE, st);
         k_merge<false><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
-                                                                          nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0);
+                                                                          nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0,
+                                                                         (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr, (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr);
         LAUNCH_CHECK();
     }
     return 0;
@@ -829,8 +865,8 @@ static int derive_all(const Model* m, const float* X, const NjBuffers& nb, int B
 }
 
 size_t nj_scores_ws_bytes(const Model* m, int B, int Rp, int C, int N) {
-    (void)m; (void)N;
-    return nj_layout(nullptr, B, Rp, Rp, C, false, true).total;
+    (void)N;
+    return nj_layout(nullptr, B, Rp, Rp, C, false, true, nj_use_tc(m, Rp)).total;
 }
 
 static Pool make_pool(const float* X, const NjBuffers& nb, int S, int C) {
@@ -844,7 +880,7 @@ int run_pair_scores(Model* m, const float* state, const uint8_t* mask, int B, in
                     bool full, float* scores, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (int e = check_dims(Rp, C)) return e;
     if (int e = set_attrs()) return e;
-    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp));
     if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "pair scores: workspace too small");
     if (full) N = Rp * (Rp - 1) / 2;
     if (N > nb.pair_stride) return set_error(NNJ_ERR_INVALID, "pair scores: more pairs than R(R-1)/2");
@@ -861,6 +897,7 @@ int run_pair_scores(Model* m, const float* state, const uint8_t* mask, int B, in
         if (e1 != cudaSuccess || e2 != cudaSuccess) return set_cuda_error(e1 != cudaSuccess ? e1 : e2, __FILE__, __LINE__);
     }
     if (int e = derive_all(m, state, nb, B, Rp, Rp, C, st)) return e;
+    if (nb.tc) { if (int e = launch_pool_to_planes(state, (size_t)Rp * C * D, Rp, C, Rp, B, nb.nodes_h, nb.nodes_l, st)) return e; }
     Pool pool = make_pool(state, nb, Rp, C);
     return score_pairs(m, pool, nb, nb.slot[0], Rp, C, N, mask, B, scores, N, st);
 }
@@ -869,7 +906,7 @@ int run_pair_scores_incr(Model* m, const float* state, const uint8_t* mask, int 
                          const float* logits_prev, float* logits_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (int e = check_dims(Rp, C)) return e;
     if (int e = set_attrs()) return e;
-    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp));
     if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "pair scores: workspace too small");
     prof_begin(KC_MISC, st);
     k_fill_slots<<<B, 128, 0, st>>>(nb.slot[0], nb.S, Rp, nullptr);
@@ -878,6 +915,7 @@ int run_pair_scores_incr(Model* m, const float* state, const uint8_t* mask, int 
     k_fill_pairs_incr<<<B, 128, 0, st>>>(nb.pair_i, nb.pair_j, nb.pair_stride, Rp, prev_ij, 2);
     LAUNCH_CHECK();
     if (int e = derive_all(m, state, nb, B, Rp, Rp, C, st)) return e;
+    if (nb.tc) { if (int e = launch_pool_to_planes(state, (size_t)Rp * C * D, Rp, C, Rp, B, nb.nodes_h, nb.nodes_l, st)) return e; }
     Pool pool = make_pool(state, nb, Rp, C);
     if (int e = score_pairs(m, pool, nb, nb.slot[0], Rp, C, Rp, mask, B, nb.new_scores, nb.pair_stride, st)) return e;
     const int P = Rp * (Rp - 1) / 2;
@@ -892,7 +930,7 @@ int run_aggregate(Model* m, const float* state, int B, int Rp, int C, const int3
                   size_t ws_bytes, cudaStream_t st) {
     if (int e = check_dims(Rp, C)) return e;
     if (int e = set_attrs()) return e;
-    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp));
     if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "aggregate: workspace too small");
     prof_begin(KC_MISC, st);
     k_fill_slots<<<B, 128, 0, st>>>(nb.slot[0], nb.S, Rp, nullptr);
@@ -904,7 +942,7 @@ int run_aggregate(Model* m, const float* state, int B, int Rp, int C, const int3
 
 int run_merge(Model* m, const float* state_in, int B, int Rp, int C, const int32_t* ij, float* state_out, void* ws, size_t ws_bytes,
               cudaStream_t st) {
-    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true);
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp));
     if (int e = run_aggregate(m, state_in, B, Rp, C, ij, nb.newx, (size_t)C * D, ws, ws_bytes, st)) return e;
     prof_begin(KC_MISC, st);
     k_reindex_copy<<<dim3(8, Rp - 1, B), 256, 0, st>>>(state_in, nb.newx, state_out, Rp, (size_t)C * D, ij);
@@ -914,7 +952,7 @@ int run_merge(Model* m, const float* state_in, int B, int Rp, int C, const int32
 
 // ---- fused rollout
 int nj_rollout_chunk(const Model* m, int B, int R, int C) {
-    size_t per = nj_layout(nullptr, 1, R + 1, R, C, true, false).total + encoder_ws_bytes(m, 1, R, C);
+    size_t per = nj_layout(nullptr, 1, R + 1, R, C, true, false, nj_use_tc(m, R + 1)).total + encoder_ws_bytes(m, 1, R, C);
     size_t budget = (size_t)16 << 30;
     int ch = (int)(budget / per);
     if (ch < 1) ch = 1;
@@ -925,7 +963,7 @@ int nj_rollout_chunk(const Model* m, int B, int R, int C) {
 
 size_t nj_rollout_ws_bytes(const Model* m, int B, int R, int C) {
     int ch = nj_rollout_chunk(m, B, R, C);
-    return nj_layout(nullptr, ch, R + 1, R, C, true, false).total + encoder_ws_bytes(m, ch, R, C) + 512;
+    return nj_layout(nullptr, ch, R + 1, R, C, true, false, nj_use_tc(m, R + 1)).total + encoder_ws_bytes(m, ch, R, C) + 512;
 }
 
 int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t* mask, int B, int R, int L, int select_mode,
@@ -941,7 +979,7 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
     const int chunk = nj_rollout_chunk(m, B, R, C);
     const int S = R + 1;
     char* base = ws_align(ws);
-    NjBuffers nb = nj_layout(base, chunk, S, R, C, true, false);
+    NjBuffers nb = nj_layout(base, chunk, S, R, C, true, false, nj_use_tc(m, S));
     void* enc_ws = base + nb.total;
     const size_t enc_bytes = encoder_ws_bytes(m, chunk, R, C);
     const size_t tree_stride = (size_t)S * C * D;
@@ -967,6 +1005,7 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
         prof_begin(KC_DERIVE, st);
         k_node_derive<<<dim3(nb.nCT, R, nbt), NTHREADS, smem_derive, st>>>(nb.X, nb.Y, nb.K, nb.kap, tree_stride, S, C, nb.nCT, nullptr, 0, m->nj);
         LAUNCH_CHECK();
+        if (nb.tc) { if (int e = launch_pool_to_planes(nb.X, tree_stride, S, C, R, nbt, nb.nodes_h, nb.nodes_l, st)) return e; }
         Pool pool = make_pool(nb.X, nb, S, C);
         int32_t* mg = merges + (size_t)b0 * (R - 1) * 2;
         float* slp = selected_logp ? selected_logp + (size_t)b0 * (R - 1) : nullptr;

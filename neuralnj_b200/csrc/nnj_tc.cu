@@ -11,10 +11,8 @@
 //   warp 1   : TMEM allocator + single-thread MMA issuer (12 x UMMA 128x128x16 per stage), tcgen05.commit
 //   warps 2-5: epilogue, one TMEM lane quarter each: tcgen05.ld -> registers -> global (fp32, or softmax-ready)
 // Every mbarrier wait is bounded (trap after ~2 s) so that a protocol bug surfaces as an error, not a hang.
-#include <cuda.h>
-#include <cuda_bf16.h>
-
 #include "nnj_internal.h"
+#include "nnj_tc.cuh"
 
 namespace nnj {
 
@@ -23,78 +21,6 @@ constexpr int TC_PLANE_BYTES = TC_BM * TC_BK * 2;          // 16 KB: 128 rows x 
 constexpr int TC_STAGE_BYTES = 4 * TC_PLANE_BYTES;         // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_THREADS = 192;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 1.9 GHz: protocol error, fail loudly instead of hanging
-    }
-}
-
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4 = 1024 B (8 rows x 128 B),
-// [46,48) version = 1 (sm_100), [61,64) layout = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, both K-major, M x N.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // grid (N tiles, M tiles, Z).  C row-major with leading dimension ldc, batch stride sC (elements).
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -205,6 +131,82 @@ __global__ void k_split_bf16(const float* __restrict__ x, __nv_bfloat16* __restr
         hi[i] = h;
         lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
+}
+
+
+// ------------------------------------------------------------------ operand staging helpers shared with nnj_score_tc.cu
+// Unit-test kernel for the two operand forms the fused pair-score kernel relies on:
+//   A [128 x 64] K-major, written into SWIZZLE_128B shared memory by threads (not TMA), and
+//   B [64 (K) x 64 (N)] MN-major (N contiguous, one 128-byte row per k), also thread-written.
+// D [128 x 64] = (A_hi + A_lo)(B_hi + B_lo) with the 3-product split.  One CTA, 128 threads.
+__global__ void __launch_bounds__(128, 1) k_tc_unit(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ Dm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *a_hi = base, *a_lo = base + 16384, *b_hi = base + 32768, *b_lo = base + 32768 + 8192;
+    uint64_t* done = reinterpret_cast<uint64_t*>(base + 49152);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {   // A row `tid`: 64 values -> 8 chunks of 8 bf16, chunk j stored at position j ^ (row & 7)
+        const float* ar = A + (size_t)tid * 64;
+        for (int j = 0; j < 8; ++j) {
+            __align__(16) __nv_bfloat16 h[8], l[8];
+            for (int e = 0; e < 8; ++e) { float v = ar[j * 8 + e]; h[e] = __float2bfloat16_rn(v); l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e])); }
+            const int off = tid * 128 + ((j ^ (tid & 7)) << 4);
+            *reinterpret_cast<uint4*>(a_hi + off) = *reinterpret_cast<uint4*>(h);
+            *reinterpret_cast<uint4*>(a_lo + off) = *reinterpret_cast<uint4*>(l);
+        }
+        if (tid < 64) {   // B row k = tid: 64 n-values
+            const float* br = Bm + (size_t)tid * 64;
+            for (int j = 0; j < 8; ++j) {
+                __align__(16) __nv_bfloat16 h[8], l[8];
+                for (int e = 0; e < 8; ++e) { float v = br[j * 8 + e]; h[e] = __float2bfloat16_rn(v); l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e])); }
+                const int off = tid * 128 + ((j ^ (tid & 7)) << 4);
+                *reinterpret_cast<uint4*>(b_hi + off) = *reinterpret_cast<uint4*>(h);
+                *reinterpret_cast<uint4*>(b_lo + off) = *reinterpret_cast<uint4*>(l);
+            }
+        }
+    }
+    fence_async_smem();   // generic-proxy smem writes -> visible to the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 16);   // B is MN-major
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t dah = umma_desc_k128(smem_u32(a_hi) + k * 32), dal = umma_desc_k128(smem_u32(a_lo) + k * 32);
+            const uint64_t dbh = umma_desc_k128(smem_u32(b_hi) + k * 2048), dbl = umma_desc_k128(smem_u32(b_lo) + k * 2048);
+            umma_bf16(tmem_base, dal, dbh, idesc, k ? 1u : 0u);
+            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit(done);
+    }
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int cb = 0; cb < 2; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+        for (int j = 0; j < 32; ++j) Dm[(size_t)tid * 64 + cb * 32 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64)); }
+}
+
+int run_tc_unit(const float* A, const float* B, float* Dm, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_unit, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024);
+    if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    k_tc_unit<<<1, 128, 52 * 1024, st>>>(A, B, Dm);
+    ++g_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    return 0;
 }
 
 // ------------------------------------------------------------------ host side
