@@ -31,7 +31,7 @@ struct Pool {
 // xs: [128][LDA] tile of node rows (x).  Produces Y, K' (global) and the kappa partial of the tile.
 __device__ __forceinline__ void derive_tile(float* xs, float* tmp, float* Ws, const NjW& w, float* __restrict__ Yout,
                                             float* __restrict__ Kout, float* __restrict__ kap_out, int row0, int C,
-                                            float* red) {
+                                            float* red, uint2* __restrict__ Kh = nullptr, uint2* __restrict__ Kl = nullptr) {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     float acc[8][4];
     // Y = x W_h^T   (bias b_h is added when the pair gate is formed)
@@ -77,14 +77,24 @@ __device__ __forceinline__ void derive_tile(float* xs, float* tmp, float* Ws, co
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         int c = row0 + ty * 8 + i;
-        if (c < C) st4(Kout + (size_t)c * D + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        if (c < C) {
+            st4(Kout + (size_t)c * D + tx * 4, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+            if (Kh) {   // bf16 hi/lo planes of K' (B operand of the tensor-core alpha GEMM)
+                uint2 oh, ol;
+                split2(acc[i][0], acc[i][1], oh.x, ol.x);
+                split2(acc[i][2], acc[i][3], oh.y, ol.y);
+                Kh[(size_t)c * 16 + tx] = oh;
+                Kl[(size_t)c * 16 + tx] = ol;
+            }
+        }
     }
 }
 
 // grid (nCT, n_nodes, B): derive Y/K'/kappa for physical slots node_list[b][k] (or slot k when null)
 __global__ void __launch_bounds__(NTHREADS) k_node_derive(const float* __restrict__ X, float* __restrict__ Y, float* __restrict__ K,
                                                           float* __restrict__ kap, size_t tree_stride, int S, int C, int nCT,
-                                                          const int32_t* __restrict__ node_list, int list_stride, NjW w) {
+                                                          const int32_t* __restrict__ node_list, int list_stride, NjW w,
+                                                          uint2* __restrict__ Kh, uint2* __restrict__ Kl) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
     float* tmp = xs + TILE_ROWS * LDA;
@@ -103,7 +113,8 @@ __global__ void __launch_bounds__(NTHREADS) k_node_derive(const float* __restric
         st4(xs + row * LDA + c4 * 4, v);
     }
     __syncthreads();
-    derive_tile(xs, tmp, Ws, w, Y + base, K + base, kap + ((size_t)b * S + slot) * nCT + ct, row0, C, red);
+    derive_tile(xs, tmp, Ws, w, Y + base, K + base, kap + ((size_t)b * S + slot) * nCT + ct, row0, C, red,
+                Kh ? Kh + base / 4 : nullptr, Kl ? Kl + base / 4 : nullptr);
 }
 
 // ------------------------------------------------------------------ pair blend helper
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS) k_alpha_softmax(const float* __restr
                                                             const int32_t* __restrict__ slot_of, int slot_stride, int S, int nCT,
                                                             int Rp, const int32_t* __restrict__ pair_i, const int32_t* __restrict__ pair_j,
                                                             int pair_stride, int n0, int nc, int nSB, int RP, float inv_scale,
-                                                            float* __restrict__ alpha) {
+                                                            float* __restrict__ alpha, int by_slot) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * 8 + warp, b = blockIdx.y;
     if (n >= nc) return;
@@ -269,7 +280,8 @@ __global__ void __launch_bounds__(NTHREADS) k_alpha_softmax(const float* __restr
     float m = -INFINITY;
     for (int r = lane; r < Rp; r += 32) {
         float s = 0.f;
-        for (int k = 0; k < nSB; ++k) s += ap[(size_t)k * RP + r];
+        const int col = by_slot ? so[r] : r;   // tensor-core alpha partials are indexed by physical slot
+        for (int k = 0; k < nSB; ++k) s += ap[(size_t)k * RP + col];
         const float* kp = kap + ((size_t)b * S + so[r]) * nCT;
         float kk = 0.f;
         for (int k = 0; k < nCT; ++k) kk += kp[k];
@@ -460,7 +472,8 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
                                                     int Rp, int C, const int32_t* __restrict__ merge_ij, int ij_stride,
                                                     const float* __restrict__ alpha, int RP, NjW w, float* __restrict__ out_x,
                                                     size_t out_stride, const int32_t* __restrict__ new_slot, int derive,
-                                                    uint2* __restrict__ nodes_h, uint2* __restrict__ nodes_l) {
+                                                    uint2* __restrict__ nodes_h, uint2* __restrict__ nodes_l, uint2* __restrict__ kp_h,
+                                                    uint2* __restrict__ kp_l) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
     float* xg = xs + TILE_ROWS * LDA;
@@ -549,7 +562,8 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
                 }
             }
         }
-        derive_tile(xs, xg, Ws, w, Yw + nb, Kw + nb, kapw + ((size_t)b * pool.S + ns) * pool.nCT + ct, row0, C, red);
+        derive_tile(xs, xg, Ws, w, Yw + nb, Kw + nb, kapw + ((size_t)b * pool.S + ns) * pool.nCT + ct, row0, C, red,
+                    kp_h ? kp_h + nb / 4 : nullptr, kp_l ? kp_l + nb / 4 : nullptr);
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -712,6 +726,7 @@ struct NjBuffers {
     float* X;         // pool X when owned by the workspace (rollout), else null
     void *xh, *xl;            // tensor-core path: x planes of the current pair chunk [B][TC_PAIRS][C][64] bf16
     void *nodes_h, *nodes_l;  // tensor-core path: site-major node planes [B][C][S][64] bf16
+    void *kp_h, *kp_l;        // tensor-core path: K' planes [B][S][C][64] bf16 (B operand of the alpha GEMM)
     bool tc;
     int S, nCT, nSB, RP, pair_stride, P0;
     size_t total;
@@ -725,7 +740,7 @@ static bool nj_use_tc(const Model* m, int S) { return m->cfg.precision == NNJ_PR
 static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws, bool need_newx, bool tc) {
     NjBuffers nb{};
     nb.S = S; nb.nCT = (C + TILE_ROWS - 1) / TILE_ROWS; nb.nSB = (C + SB_SITES - 1) / SB_SITES;
-    nb.RP = (R + 3) & ~3;
+    nb.RP = (S + 3) & ~3;     // >= S: tensor-core alpha partials are indexed by physical slot
     nb.P0 = R * (R - 1) / 2;
     nb.pair_stride = nb.P0 > R ? nb.P0 : R;
     size_t off = 0;
@@ -751,7 +766,7 @@ static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws,
     nb.tc = tc;
     if (tc) {
         const size_t xp = (size_t)B * TC_PAIRS * C * D * 2, np = (size_t)B * C * S * D * 2;
-        nb.xh = take(xp); nb.xl = take(xp); nb.nodes_h = take(np); nb.nodes_l = take(np);
+        nb.xh = take(xp); nb.xl = take(xp); nb.nodes_h = take(np); nb.nodes_l = take(np); nb.kp_h = take(np); nb.kp_l = take(np);
     }
     nb.total = off + 256;
     return nb;
@@ -793,7 +808,21 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
     const float inv_scale = 1.0f / sqrtf((float)D * (float)C);   // model.py:118 (patch_num == C)
     for (int n0 = 0; n0 < N; n0 += step) {
         const int nc = (N - n0 < step) ? (N - n0) : step;
-        if (glob) {
+        if (glob && tc) {
+            // x planes -> alpha partials on tcgen05 (split-K over site blocks, indexed by physical slot) -> softmax -> fused score kernel
+            if (int e = launch_blend_planes(pool.X, pool.Y, pool.tree_stride, slot, nb.S, C, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, B,
+                                            m->nj.bh, nb.xh, nb.xl, TC_PAIRS, st)) return e;
+            const size_t KK = (size_t)C * D;
+            if (int e = launch_tc_gemm_ex(KC_ALPHA, nb.xh, nb.xl, nb.kp_h, nb.kp_l, nb.alpha_part, B, nc, nb.S, (int)KK, KK, (size_t)TC_PAIRS * KK, KK,
+                                          (size_t)nb.S * KK, nb.nSB * nb.RP, (size_t)PAIR_CHUNK * nb.nSB * nb.RP, 64, nb.nSB, SB_SITES, nb.RP, st))
+                return e;
+            prof_begin(KC_ALPHA_SOFTMAX, st);
+            k_alpha_softmax<<<dim3((nc + 7) / 8, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
+                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha, 1);
+            LAUNCH_CHECK();
+            if (int e = launch_score_tc(m, nb.xh, nb.xl, TC_PAIRS, nb.nodes_h, nb.nodes_l, nb.alpha, nb.RP, PAIR_CHUNK, slot, nb.S, nb.pair_i,
+                                        nb.pair_stride, n0, nc, Rp, nb.S, C, B, mask, nb.score_part, nb.nSB, st)) return e;
+        } else if (glob) {
             const int node_tiles = (Rp + 63) / 64, pair_tiles = (nc + 63) / 64;
             prof_begin(KC_ALPHA, st);
             k_alpha<<<dim3(nb.nSB, pair_tiles * node_tiles, B), NTHREADS, 0, st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j, nb.pair_stride,
@@ -801,20 +830,13 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
             LAUNCH_CHECK();
             prof_begin(KC_ALPHA_SOFTMAX, st);
             k_alpha_softmax<<<dim3((nc + 7) / 8, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
-                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha);
+                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha, 0);
             LAUNCH_CHECK();
-            if (tc) {
-                if (int e = launch_blend_planes(pool.X, pool.Y, pool.tree_stride, slot, nb.S, C, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, B,
-                                                m->nj.bh, nb.xh, nb.xl, TC_PAIRS, st)) return e;
-                if (int e = launch_score_tc(m, nb.xh, nb.xl, TC_PAIRS, nb.nodes_h, nb.nodes_l, nb.alpha, nb.RP, PAIR_CHUNK, slot, nb.S, nb.pair_i,
-                                            nb.pair_stride, n0, nc, Rp, nb.S, C, B, mask, nb.score_part, nb.nSB, st)) return e;
-            } else {
-                prof_begin(KC_SCORE, st);
-                k_score<true><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
-                                                                                                nb.pair_stride, n0, nc, nb.alpha, nb.RP, m->nj, mask,
-                                                                                                nb.score_part, nb.nSB);
-                LAUNCH_CHECK();
-            }
+            prof_begin(KC_SCORE, st);
+            k_score<true><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
+                                                                                            nb.pair_stride, n0, nc, nb.alpha, nb.RP, m->nj, mask,
+                                                                                            nb.score_part, nb.nSB);
+            LAUNCH_CHECK();
         } else {
             prof_begin(KC_SCORE, st);
             k_score<false><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
@@ -840,18 +862,20 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
         // pair list for the softmax kernel: reuse it with one pair per tree = ij itself
         prof_begin(KC_ALPHA_SOFTMAX, st);
         k_alpha_softmax<<<dim3(1, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, ij, ij + 1, ij_stride, 0, 1,
-                                                         nb.nSB, nb.RP, inv_scale, nb.alpha);
+                                                         nb.nSB, nb.RP, inv_scale, nb.alpha, 0);
         LAUNCH_CHECK();
         prof_begin(KC_MERGE, st);
         k_merge<true><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
                                                                          nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0,
-                                                                         (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr, (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr);
+                                                                         (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr, (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr,
+                                                                         (derive && nb.tc) ? (uint2*)nb.kp_h : nullptr, (derive && nb.tc) ? (uint2*)nb.kp_l : nullptr);
         LAUNCH_CHECK();
     } else {
         prof_begin(KC_MERGE, st);
         k_merge<false><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
                                                                           nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0,
-                                                                         (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr, (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr);
+                                                                         (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr, (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr,
+                                                                         (derive && nb.tc) ? (uint2*)nb.kp_h : nullptr, (derive && nb.tc) ? (uint2*)nb.kp_l : nullptr);
         LAUNCH_CHECK();
     }
     return 0;
@@ -859,7 +883,8 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
 
 static int derive_all(const Model* m, const float* X, const NjBuffers& nb, int B, int S, int nodes, int C, cudaStream_t st) {
     prof_begin(KC_DERIVE, st);
-    k_node_derive<<<dim3(nb.nCT, nodes, B), NTHREADS, smem_derive, st>>>(X, nb.Y, nb.K, nb.kap, (size_t)S * C * D, S, C, nb.nCT, nullptr, 0, m->nj);
+    k_node_derive<<<dim3(nb.nCT, nodes, B), NTHREADS, smem_derive, st>>>(X, nb.Y, nb.K, nb.kap, (size_t)S * C * D, S, C, nb.nCT, nullptr, 0, m->nj,
+                                                                         nb.tc ? (uint2*)nb.kp_h : nullptr, nb.tc ? (uint2*)nb.kp_l : nullptr);
     LAUNCH_CHECK();
     return 0;
 }
@@ -1003,7 +1028,8 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
         k_fill_pairs_full<<<dim3((P0 + 127) / 128, nbt < 64 ? nbt : 64), 128, 0, st>>>(nb.pair_i, nb.pair_j, nb.pair_stride, R, nbt);
         LAUNCH_CHECK();
         prof_begin(KC_DERIVE, st);
-        k_node_derive<<<dim3(nb.nCT, R, nbt), NTHREADS, smem_derive, st>>>(nb.X, nb.Y, nb.K, nb.kap, tree_stride, S, C, nb.nCT, nullptr, 0, m->nj);
+        k_node_derive<<<dim3(nb.nCT, R, nbt), NTHREADS, smem_derive, st>>>(nb.X, nb.Y, nb.K, nb.kap, tree_stride, S, C, nb.nCT, nullptr, 0, m->nj,
+                                                                           nb.tc ? (uint2*)nb.kp_h : nullptr, nb.tc ? (uint2*)nb.kp_l : nullptr);
         LAUNCH_CHECK();
         if (nb.tc) { if (int e = launch_pool_to_planes(nb.X, tree_stride, S, C, R, nbt, nb.nodes_h, nb.nodes_l, st)) return e; }
         Pool pool = make_pool(nb.X, nb, S, C);

@@ -313,7 +313,6 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------ host side
-int make_tmap_k_major(CUtensorMap* map, const void* base, int K, int rows, int Z, size_t ld, size_t sz);   // nnj_tc.cu
 
 // box {64, 64, 1} over site-major node planes [B*C][S][64]
 static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC) {

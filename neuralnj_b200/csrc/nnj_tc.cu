@@ -20,31 +20,41 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3;
 constexpr int TC_PLANE_BYTES = TC_BM * TC_BK * 2;          // 16 KB: 128 rows x 128 B
 constexpr int TC_STAGE_BYTES = 4 * TC_PLANE_BYTES;         // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-// grid (N tiles, M tiles, Z).  C row-major with leading dimension ldc, batch stride sC (elements).
+// grid (N tiles * nsplit, M tiles, Z).  C row-major with leading dimension ldc, batch stride sC (elements).
+// Split-K: split s = blockIdx.x % nsplit handles K chunks [s*cps, (s+1)*cps) and writes to C + s*split_stride.
+struct TcGemmArgs {
+    float* C; int M, N, K, ldc; size_t sC;
+    int nsplit, chunks_per_split; size_t split_stride;
+};
+
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
-          const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, float* __restrict__ Cm, int M, int N,
-          int K, int ldc, size_t sC) {
+          const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcGemmArgs g) {
+    constexpr int B_PLANE = BN * TC_BK * 2;
+    constexpr int STAGE = 2 * TC_PLANE_BYTES + 2 * B_PLANE;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * STAGE);
     uint64_t* empty = full + TC_STAGES;
     uint64_t* accum_done = empty + TC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * TC_BN, m0 = blockIdx.y * TC_BM, z = blockIdx.z;
-    const int nchunks = (K + TC_BK - 1) / TC_BK;
+    const int split = blockIdx.x % g.nsplit, ntile = blockIdx.x / g.nsplit;
+    const int n0 = ntile * BN, m0 = blockIdx.y * TC_BM, z = blockIdx.z;
+    const int total_chunks = (g.K + TC_BK - 1) / TC_BK;
+    const int kc0 = split * g.chunks_per_split;
+    const int nchunks = max(0, min(total_chunks - kc0, g.chunks_per_split));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(accum_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM: 128 fp32 columns for the 128 x 128 accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    if (warp == 1) {   // TMEM: BN fp32 columns for the 128 x BN accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -54,33 +64,33 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kc = 0; kc < nchunks; ++kc) {
-                const int s = kc % TC_STAGES;
-                if (kc >= TC_STAGES) mbar_wait(&empty[s], ((kc / TC_STAGES) - 1) & 1);
-                uint8_t* st = tiles + s * TC_STAGE_BYTES;
-                mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+            for (int kk = 0; kk < nchunks; ++kk) {
+                const int s = kk % TC_STAGES, kc = kc0 + kk;
+                if (kk >= TC_STAGES) mbar_wait(&empty[s], ((kk / TC_STAGES) - 1) & 1);
+                uint8_t* st = tiles + s * STAGE;
+                mbar_expect_tx(&full[s], STAGE);
                 tma_load_3d(st, &mapAh, &full[s], kc * TC_BK, m0, z);
                 tma_load_3d(st + TC_PLANE_BYTES, &mapAl, &full[s], kc * TC_BK, m0, z);
                 tma_load_3d(st + 2 * TC_PLANE_BYTES, &mapBh, &full[s], kc * TC_BK, n0, z);
-                tma_load_3d(st + 3 * TC_PLANE_BYTES, &mapBl, &full[s], kc * TC_BK, n0, z);
+                tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE, &mapBl, &full[s], kc * TC_BK, n0, z);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
-            for (int kc = 0; kc < nchunks; ++kc) {
-                const int s = kc % TC_STAGES;
-                mbar_wait(&full[s], (kc / TC_STAGES) & 1);
+            const uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+            for (int kk = 0; kk < nchunks; ++kk) {
+                const int s = kk % TC_STAGES, kc = kc0 + kk;
+                mbar_wait(&full[s], (kk / TC_STAGES) & 1);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(tiles + s * TC_STAGE_BYTES), a_lo = a_hi + TC_PLANE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = a_hi + 3 * TC_PLANE_BYTES;
-                const int kvalid = min(TC_BK, K - kc * TC_BK);
+                const uint32_t a_hi = smem_u32(tiles + s * STAGE), a_lo = a_hi + TC_PLANE_BYTES;
+                const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = b_hi + B_PLANE;
+                const int kvalid = min(TC_BK, g.K - kc * TC_BK);
                 const int ksteps = (kvalid + 15) / 16;
                 for (int k = 0; k < ksteps; ++k) {
                     const uint32_t ko = k * 32;   // 16 bf16 = 32 B inside the 128 B swizzle row
                     const uint64_t dah = umma_desc_k128(a_hi + ko), dal = umma_desc_k128(a_lo + ko);
                     const uint64_t dbh = umma_desc_k128(b_hi + ko), dbl = umma_desc_k128(b_lo + ko);
-                    umma_bf16(tmem_base, dal, dbh, idesc, (kc | k) ? 1u : 0u);   // small terms first
+                    umma_bf16(tmem_base, dal, dbh, idesc, (kk | k) ? 1u : 0u);   // small terms first
                     umma_bf16(tmem_base, dah, dbl, idesc, 1u);
                     umma_bf16(tmem_base, dah, dbh, idesc, 1u);
                 }
@@ -93,14 +103,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
         mbar_wait(accum_done, 0);
         tc_fence_after();
         const int m = m0 + q * 32 + lane;
-        float* crow = Cm + (size_t)z * sC + (size_t)m * ldc;
+        float* crow = g.C + (size_t)z * g.sC + (size_t)m * g.ldc + (size_t)split * g.split_stride;
 #pragma unroll 1
-        for (int cb = 0; cb < TC_BN / 32; ++cb) {
+        for (int cb = 0; cb < BN / 32; ++cb) {
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+            if (nchunks > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
             const int n = n0 + cb * 32;
-            if (m < M) {
-                if (n + 31 < N && (ldc & 3) == 0) {
+            if (m < g.M) {
+                if (n + 31 < g.N && (g.ldc & 3) == 0 && (g.split_stride & 3) == 0) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         st4(crow + n + j * 4, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
@@ -108,7 +122,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (n + j < N) crow[n + j] = __uint_as_float(v[j]);
+                        if (n + j < g.N) crow[n + j] = __uint_as_float(v[j]);
                 }
             }
         }
@@ -117,7 +131,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
     }
 }
 
@@ -226,14 +240,14 @@ static PFN_tmapEncodeTiled tmap_encoder() {
 }
 
 // 3-D bf16 tensor [Z][rows][K] (K contiguous, row pitch ld elements, batch stride sz elements), box 64 x 128 x 1, SWIZZLE_128B.
-int make_tmap_k_major(CUtensorMap* map, const void* base, int K, int rows, int Z, size_t ld, size_t sz) {
+int make_tmap_k_major(CUtensorMap* map, const void* base, int K, int rows, int Z, size_t ld, size_t sz, int box_rows) {
     PFN_tmapEncodeTiled enc = tmap_encoder();
     if (!enc) return set_error(NNJ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     if ((ld * 2) % 16 != 0 || (sz * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15))
         return set_error(NNJ_ERR_INVALID, "tensor-core path: operand rows must be 16-byte aligned (K and site count multiples of 8)");
     cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)Z};
     cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)sz * 2};
-    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM, 1};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -246,26 +260,40 @@ int make_tmap_k_major(CUtensorMap* map, const void* base, int K, int rows, int Z
 }
 
 // C[z] = (Ah+Al)[z] * (Bh+Bl)[z]^T.  A planes [Z][M][K] (pitch lda, batch stride sA), B planes [Z][N][K].
-int launch_tc_gemm(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
-                   size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st) {
+// bn = 128 or 64 (N tile); nsplit > 1 splits K into nsplit ranges of chunks_per_split 64-element chunks, split s writing
+// its partial tile at C + s*split_stride.
+int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
+                      size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, int bn, int nsplit, int chunks_per_split, size_t split_stride,
+                      cudaStream_t st) {
     static bool attr = false;
+    constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256;
+    constexpr int SMEM64 = TC_STAGES * (3 * TC_PLANE_BYTES) + 1024 + 256;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
         attr = true;
     }
     CUtensorMap mAh, mAl, mBh, mBl;
-    if (int e = make_tmap_k_major(&mAh, Ah, K, M, Z, lda, sA)) return e;
-    if (int e = make_tmap_k_major(&mAl, Al, K, M, Z, lda, sA)) return e;
-    if (int e = make_tmap_k_major(&mBh, Bh, K, N, Z, ldb, sB)) return e;
-    if (int e = make_tmap_k_major(&mBl, Bl, K, N, Z, ldb, sB)) return e;
+    if (int e = make_tmap_k_major(&mAh, Ah, K, M, Z, lda, sA, TC_BM)) return e;
+    if (int e = make_tmap_k_major(&mAl, Al, K, M, Z, lda, sA, TC_BM)) return e;
+    if (int e = make_tmap_k_major(&mBh, Bh, K, N, Z, ldb, sB, bn)) return e;
+    if (int e = make_tmap_k_major(&mBl, Bl, K, N, Z, ldb, sB, bn)) return e;
+    TcGemmArgs g{Cm, M, N, K, ldc, sC, nsplit, chunks_per_split, split_stride};
+    const dim3 grid(((N + bn - 1) / bn) * nsplit, (M + TC_BM - 1) / TC_BM, Z);
     prof_begin(cls, st);
-    k_tc_gemm<<<dim3((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM, Z), TC_THREADS, TC_SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, Cm, M, N, K, ldc, sC);
+    if (bn == 128) k_tc_gemm<128><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g);
+    else k_tc_gemm<64><<<grid, TC_THREADS, SMEM64, st>>>(mAh, mAl, mBh, mBl, g);
     ++g_launches;
     prof_end(st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     return 0;
+}
+
+int launch_tc_gemm(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
+                   size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st) {
+    return launch_tc_gemm_ex(cls, Ah, Al, Bh, Bl, Cm, Z, M, N, K, lda, sA, ldb, sB, ldc, sC, 128, 1, (K + TC_BK - 1) / TC_BK, 0, st);
 }
 
 // Stand-alone building block (also the unit-test entry): fp32 A [Z][M][K], B [Z][N][K] -> C [Z][M][N].
