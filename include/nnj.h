@@ -145,9 +145,10 @@ int nnj_rollout_host(nnj_model* m, const int8_t* data_host, const uint8_t* seq_m
 int nnj_gemm_split_bf16(const float* A_dev, const float* B_dev, float* C_dev, int Z, int M, int N, int K,
                         void* ws_dev, int64_t ws_bytes, void* stream);
 
-/* Hardware self-test of the operand forms used inside the fused tensor-core kernels: D [128,64] = A [128,64] * B [64,64]
- * with A written K-major / B written MN-major into SWIZZLE_128B shared memory by threads (no TMA), split-bf16. */
-int nnj_tc_selftest(const float* A_dev, const float* B_dev, float* D_dev, void* stream);
+/* Hardware self-test of the operand forms used inside the fused tensor-core kernels: D [128,N] = A [128,64] * B [64,N]
+ * (N = 64 or 128) with A written K-major / B written MN-major into SWIZZLE_128B shared memory by threads (no TMA),
+ * split-bf16; N = 128 exercises the leading-byte-offset form of the MN-major descriptor. */
+int nnj_tc_selftest(const float* A_dev, const float* B_dev, float* D_dev, int N, void* stream);
 
 /* Optional per-kernel-class timing with CUDA events recorded on the launching stream (used by bench.py for the
  * roofline numbers).  enable(1) clears and starts recording on the calling thread, enable(0) stops.

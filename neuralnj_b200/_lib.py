@@ -84,7 +84,7 @@ def lib() -> C.CDLL:
     L.nnj_rollout_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
     L.nnj_gemm_split_bf16.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, i64, vp]
     L.nnj_gemm_split_bf16.restype = i32
-    L.nnj_tc_selftest.argtypes = [vp, vp, vp, vp]
+    L.nnj_tc_selftest.argtypes = [vp, vp, vp, i32, vp]
     L.nnj_tc_selftest.restype = i32
     L.nnj_launch_count.argtypes = [i32]
     L.nnj_launch_count.restype = i64

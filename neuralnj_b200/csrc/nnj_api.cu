@@ -305,9 +305,9 @@ int nnj_gemm_split_bf16(const float* A, const float* B, float* Cm, int Z, int M,
     return run_gemm_split_bf16(A, B, Cm, Z, M, N, K, ws, (size_t)ws_bytes, (cudaStream_t)stream);
 }
 
-int nnj_tc_selftest(const float* A, const float* B, float* Dm, void* stream) {
+int nnj_tc_selftest(const float* A, const float* B, float* Dm, int N, void* stream) {
     CHECK_ARGS(A && B && Dm, "tc_selftest: bad arguments");
-    return run_tc_unit(A, B, Dm, (cudaStream_t)stream);
+    return run_tc_unit(A, B, Dm, N, (cudaStream_t)stream);
 }
 
 int nnj_rollout_host(nnj_model* m, const int8_t* data_h, const uint8_t* mask_h, int B, int R, int L, int select_mode,

@@ -77,14 +77,13 @@ int launch_tc_gemm(int cls, const void* Ah, const void* Al, const void* Bh, cons
 int launch_blend_planes(const float* X, const float* Y, size_t tree_stride, const int32_t* slot_of, int slot_stride, int C, const int32_t* pair_i,
                         const int32_t* pair_j, int pair_stride, int n0, int nc, int B, const float* bh, void* xh, void* xl, int pc,
                         cudaStream_t st);
-int launch_pool_to_planes(const float* X, size_t tree_stride, int S, int C, int n_used, int B, void* ph, void* pl, cudaStream_t st);
 int launch_score_tc(const Model* m, const void* xh, const void* xl, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
                     int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,
                     int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, cudaStream_t st);
 int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, int bn, int nsplit, int chunks_per_split, size_t split_stride,
                       cudaStream_t st);
-int run_tc_unit(const float* A, const float* B, float* Dm, cudaStream_t st);
+int run_tc_unit(const float* A, const float* B, float* Dm, int bn, cudaStream_t st);
 int run_gemm_split_bf16(const float* A, const float* B, float* Cm, int Z, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace nnj

@@ -31,7 +31,8 @@ struct Pool {
 // xs: [128][LDA] tile of node rows (x).  Produces Y, K' (global) and the kappa partial of the tile.
 __device__ __forceinline__ void derive_tile(float* xs, float* tmp, float* Ws, const NjW& w, float* __restrict__ Yout,
                                             float* __restrict__ Kout, float* __restrict__ kap_out, int row0, int C,
-                                            float* red, uint2* __restrict__ Kh = nullptr, uint2* __restrict__ Kl = nullptr) {
+                                            float* red, uint2* __restrict__ Kh = nullptr, uint2* __restrict__ Kl = nullptr,
+                                            uint2* __restrict__ Nh = nullptr, uint2* __restrict__ Nl = nullptr, int S = 0, int slot = 0) {
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     float acc[8][4];
     // Y = x W_h^T   (bias b_h is added when the pair gate is formed)
@@ -88,13 +89,37 @@ __device__ __forceinline__ void derive_tile(float* xs, float* tmp, float* Ws, co
             }
         }
     }
+    if (Nh) {
+        // site-major node planes [C][S][128] = [X | G], G = x W_g^T (no bias): the B operand of the fused pair-score UMMA
+        __syncthreads();
+        load_w64(Ws, w.wgt);
+        __syncthreads();
+        acc_set_bias(acc, nullptr, tx);
+        tile_mma64(acc, xs, Ws, ty, tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int c = row0 + ty * 8 + i;
+            if (c < C) {
+                const float4 xv = ld4(xs + (ty * 8 + i) * LDA + tx * 4);
+                const size_t o = ((size_t)c * S + slot) * 32 + tx;
+                uint2 oh, ol;
+                split2(xv.x, xv.y, oh.x, ol.x);
+                split2(xv.z, xv.w, oh.y, ol.y);
+                Nh[o] = oh; Nl[o] = ol;
+                split2(acc[i][0], acc[i][1], oh.x, ol.x);
+                split2(acc[i][2], acc[i][3], oh.y, ol.y);
+                Nh[o + 16] = oh; Nl[o + 16] = ol;
+            }
+        }
+    }
 }
 
 // grid (nCT, n_nodes, B): derive Y/K'/kappa for physical slots node_list[b][k] (or slot k when null)
 __global__ void __launch_bounds__(NTHREADS) k_node_derive(const float* __restrict__ X, float* __restrict__ Y, float* __restrict__ K,
                                                           float* __restrict__ kap, size_t tree_stride, int S, int C, int nCT,
                                                           const int32_t* __restrict__ node_list, int list_stride, NjW w,
-                                                          uint2* __restrict__ Kh, uint2* __restrict__ Kl) {
+                                                          uint2* __restrict__ Kh, uint2* __restrict__ Kl, uint2* __restrict__ Nh,
+                                                          uint2* __restrict__ Nl) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
     float* tmp = xs + TILE_ROWS * LDA;
@@ -114,7 +139,8 @@ __global__ void __launch_bounds__(NTHREADS) k_node_derive(const float* __restric
     }
     __syncthreads();
     derive_tile(xs, tmp, Ws, w, Y + base, K + base, kap + ((size_t)b * S + slot) * nCT + ct, row0, C, red,
-                Kh ? Kh + base / 4 : nullptr, Kl ? Kl + base / 4 : nullptr);
+                Kh ? Kh + base / 4 : nullptr, Kl ? Kl + base / 4 : nullptr, Nh ? Nh + (size_t)b * C * S * 32 : nullptr,
+                Nl ? Nl + (size_t)b * C * S * 32 : nullptr, S, slot);
 }
 
 // ------------------------------------------------------------------ pair blend helper
@@ -454,12 +480,12 @@ __global__ void __launch_bounds__(NTHREADS) k_score(Pool pool, const int32_t* __
     }
 }
 
-__global__ void k_score_reduce(const float* __restrict__ score_part, int nSG, int nc, float* __restrict__ scores, int score_stride, int n0) {
+__global__ void k_score_reduce(const float* __restrict__ score_part, int nSG, int count, int nc, float* __restrict__ scores, int score_stride, int n0) {
     int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (n >= nc) return;
     const float* p = score_part + ((size_t)b * PAIR_CHUNK + n) * nSG;
     float s = 0.f;
-    for (int k = 0; k < nSG; ++k) s += p[k];
+    for (int k = 0; k < count; ++k) s += p[k];
     scores[(size_t)b * score_stride + n0 + n] = s;
 }
 
@@ -552,18 +578,11 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
             if (c < C) {
                 const float4 v = ld4(xs + (ty * 8 + i) * LDA + tx * 4);
                 st4(Xw + nb + (size_t)c * D + tx * 4, v);
-                if (nodes_h) {   // site-major bf16 hi/lo planes read by the tensor-core pair-score kernel
-                    uint2 oh, ol;
-                    split2(v.x, v.y, oh.x, ol.x);
-                    split2(v.z, v.w, oh.y, ol.y);
-                    const size_t o = (((size_t)b * C + c) * pool.S + ns) * 16 + tx;
-                    nodes_h[o] = oh;
-                    nodes_l[o] = ol;
-                }
             }
         }
         derive_tile(xs, xg, Ws, w, Yw + nb, Kw + nb, kapw + ((size_t)b * pool.S + ns) * pool.nCT + ct, row0, C, red,
-                    kp_h ? kp_h + nb / 4 : nullptr, kp_l ? kp_l + nb / 4 : nullptr);
+                    kp_h ? kp_h + nb / 4 : nullptr, kp_l ? kp_l + nb / 4 : nullptr, nodes_h ? nodes_h + (size_t)b * C * pool.S * 32 : nullptr,
+                    nodes_l ? nodes_l + (size_t)b * C * pool.S * 32 : nullptr, pool.S, ns);
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -725,7 +744,7 @@ struct NjBuffers {
     int32_t *slot[2], *free_slot, *new_slot, *pair_i, *pair_j;
     float* X;         // pool X when owned by the workspace (rollout), else null
     void *xh, *xl;            // tensor-core path: x planes of the current pair chunk [B][TC_PAIRS][C][64] bf16
-    void *nodes_h, *nodes_l;  // tensor-core path: site-major node planes [B][C][S][64] bf16
+    void *nodes_h, *nodes_l;  // tensor-core path: site-major node planes [B][C][S][128] bf16 = [X | W_g X]
     void *kp_h, *kp_l;        // tensor-core path: K' planes [B][S][C][64] bf16 (B operand of the alpha GEMM)
     bool tc;
     int S, nCT, nSB, RP, pair_stride, P0;
@@ -766,7 +785,7 @@ static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws,
     nb.tc = tc;
     if (tc) {
         const size_t xp = (size_t)B * TC_PAIRS * C * D * 2, np = (size_t)B * C * S * D * 2;
-        nb.xh = take(xp); nb.xl = take(xp); nb.nodes_h = take(np); nb.nodes_l = take(np); nb.kp_h = take(np); nb.kp_l = take(np);
+        nb.xh = take(xp); nb.xl = take(xp); nb.nodes_h = take(2 * np); nb.nodes_l = take(2 * np); nb.kp_h = take(np); nb.kp_l = take(np);
     }
     nb.total = off + 256;
     return nb;
@@ -845,7 +864,7 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
             LAUNCH_CHECK();
         }
         prof_begin(KC_MISC, st);
-        k_score_reduce<<<dim3((nc + 127) / 128, B), 128, 0, st>>>(nb.score_part, nb.nSB, nc, scores, score_stride, n0);
+        k_score_reduce<<<dim3((nc + 127) / 128, B), 128, 0, st>>>(nb.score_part, nb.nSB, (glob && tc) ? (C + 63) / 64 : nb.nSB, nc, scores, score_stride, n0);
         LAUNCH_CHECK();
     }
     return 0;
@@ -884,7 +903,8 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
 static int derive_all(const Model* m, const float* X, const NjBuffers& nb, int B, int S, int nodes, int C, cudaStream_t st) {
     prof_begin(KC_DERIVE, st);
     k_node_derive<<<dim3(nb.nCT, nodes, B), NTHREADS, smem_derive, st>>>(X, nb.Y, nb.K, nb.kap, (size_t)S * C * D, S, C, nb.nCT, nullptr, 0, m->nj,
-                                                                         nb.tc ? (uint2*)nb.kp_h : nullptr, nb.tc ? (uint2*)nb.kp_l : nullptr);
+                                                                         nb.tc ? (uint2*)nb.kp_h : nullptr, nb.tc ? (uint2*)nb.kp_l : nullptr,
+        nb.tc ? (uint2*)nb.nodes_h : nullptr, nb.tc ? (uint2*)nb.nodes_l : nullptr);
     LAUNCH_CHECK();
     return 0;
 }
@@ -922,7 +942,6 @@ int run_pair_scores(Model* m, const float* state, const uint8_t* mask, int B, in
         if (e1 != cudaSuccess || e2 != cudaSuccess) return set_cuda_error(e1 != cudaSuccess ? e1 : e2, __FILE__, __LINE__);
     }
     if (int e = derive_all(m, state, nb, B, Rp, Rp, C, st)) return e;
-    if (nb.tc) { if (int e = launch_pool_to_planes(state, (size_t)Rp * C * D, Rp, C, Rp, B, nb.nodes_h, nb.nodes_l, st)) return e; }
     Pool pool = make_pool(state, nb, Rp, C);
     return score_pairs(m, pool, nb, nb.slot[0], Rp, C, N, mask, B, scores, N, st);
 }
@@ -940,7 +959,6 @@ int run_pair_scores_incr(Model* m, const float* state, const uint8_t* mask, int 
     k_fill_pairs_incr<<<B, 128, 0, st>>>(nb.pair_i, nb.pair_j, nb.pair_stride, Rp, prev_ij, 2);
     LAUNCH_CHECK();
     if (int e = derive_all(m, state, nb, B, Rp, Rp, C, st)) return e;
-    if (nb.tc) { if (int e = launch_pool_to_planes(state, (size_t)Rp * C * D, Rp, C, Rp, B, nb.nodes_h, nb.nodes_l, st)) return e; }
     Pool pool = make_pool(state, nb, Rp, C);
     if (int e = score_pairs(m, pool, nb, nb.slot[0], Rp, C, Rp, mask, B, nb.new_scores, nb.pair_stride, st)) return e;
     const int P = Rp * (Rp - 1) / 2;
@@ -1028,10 +1046,15 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
         k_fill_pairs_full<<<dim3((P0 + 127) / 128, nbt < 64 ? nbt : 64), 128, 0, st>>>(nb.pair_i, nb.pair_j, nb.pair_stride, R, nbt);
         LAUNCH_CHECK();
         prof_begin(KC_DERIVE, st);
+        if (nb.tc) {   // the free slot's rows are read (with weight 0) by the pair-score UMMA: they must be finite
+            const size_t npb = (size_t)nbt * C * S * 2 * D * 2;
+            cudaError_t e1 = cudaMemsetAsync(nb.nodes_h, 0, npb, st), e2 = cudaMemsetAsync(nb.nodes_l, 0, npb, st);
+            if (e1 != cudaSuccess || e2 != cudaSuccess) return set_cuda_error(e1 != cudaSuccess ? e1 : e2, __FILE__, __LINE__);
+        }
         k_node_derive<<<dim3(nb.nCT, R, nbt), NTHREADS, smem_derive, st>>>(nb.X, nb.Y, nb.K, nb.kap, tree_stride, S, C, nb.nCT, nullptr, 0, m->nj,
-                                                                           nb.tc ? (uint2*)nb.kp_h : nullptr, nb.tc ? (uint2*)nb.kp_l : nullptr);
+                                                                           nb.tc ? (uint2*)nb.kp_h : nullptr, nb.tc ? (uint2*)nb.kp_l : nullptr,
+        nb.tc ? (uint2*)nb.nodes_h : nullptr, nb.tc ? (uint2*)nb.nodes_l : nullptr);
         LAUNCH_CHECK();
-        if (nb.tc) { if (int e = launch_pool_to_planes(nb.X, tree_stride, S, C, R, nbt, nb.nodes_h, nb.nodes_l, st)) return e; }
         Pool pool = make_pool(nb.X, nb, S, C);
         int32_t* mg = merges + (size_t)b0 * (R - 1) * 2;
         float* slp = selected_logp ? selected_logp + (size_t)b0 * (R - 1) : nullptr;

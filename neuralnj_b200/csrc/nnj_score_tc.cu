@@ -2,30 +2,33 @@
 //
 // For every (pair, site) row the reference computes (model.py:90-99, 102-155)
 //     x      = z*x_i + (1-z)*x_j                       (k_blend_planes, stored as bf16 hi/lo planes)
-//     x_glob = sum_r alpha[pair,r] * X[r,site,:]        -> UMMA 1: [128 pairs x slots] . [slots x 64]   (B MN-major, TMA)
-//     w      = sigmoid(W_g x_glob + b_g)                -> UMMA 2: [128 x 64] . W_g^T
-//     x'     = (1-w)*x + w*x_glob
-//     score += w2 . GELU(W_s x' + b_s) + b2             -> UMMA 3: [128 x 64] . W_s^T
-// One CTA = 128 pairs x 32 sites.  Sites alternate between two pipelines, each with its own TMEM accumulators
-// (x_glob, g, s: 3 x 64 columns), operand buffers and a group of 8 epilogue warps (4 TMEM lane quarters x 2 column
+//     x_glob = sum_r alpha[pair,r] * X[r,site,:]   \
+//     g      = W_g x_glob + b_g = sum_r alpha[pair,r] * (W_g X[r,site,:]) + b_g   (sum_r alpha = 1)
+//                                                       -> UMMA 1: [128 pairs x slots] . [slots x (64 | 64)]  (B MN-major, TMA)
+//     w      = sigmoid(g);  x' = (1-w)*x + w*x_glob
+//     score += w2 . GELU(W_s x' + b_s) + b2             -> UMMA 2: [128 x 64] . W_s^T
+// G = W_g X is kept per node next to X in the node planes, which removes one GEMM and one operand round trip per row.
+// One CTA = 128 pairs x 64 sites.  Sites alternate between two pipelines, each with its own TMEM accumulators
+// ([x_glob | g]: 128 columns, s: 64), operand buffers and a group of 8 epilogue warps (4 TMEM lane quarters x 2 column
 // halves); two control warps issue TMA + tcgen05.mma, so the tensor core works on one site while the CUDA cores run
-// the sigmoid / blend / GELU epilogue of the other.  Every product is split-bf16 (hi*hi + hi*lo + lo*hi, fp32
+// the sigmoid / blend / GELU epilogue of the other.  With <= 64 pairs (every step after the first) the pairs are
+// duplicated into rows 64..127 so that all four lane quarters - hence all 16 epilogue warps - have work.  Every product is split-bf16 (hi*hi + hi*lo + lo*hi, fp32
 // accumulate); operands produced on the fly are written by the epilogue threads straight into SWIZZLE_128B shared
-// memory (validated by nnj_tc_selftest).  Node state for UMMA 1 comes from site-major bf16 planes [B][C][S][64]
-// indexed by PHYSICAL slot, so alpha is scattered to slot order and dead / free slots simply get weight 0.
+// memory (validated by nnj_tc_selftest).  Node state for UMMA 1 comes from site-major bf16 planes [B][C][S][128]
+// [X | W_g X], indexed by PHYSICAL slot, so alpha is scattered to slot order and dead / free slots simply get weight 0.
 #include "nnj_internal.h"
 #include "nnj_tc.cuh"
 
 namespace nnj {
 
 constexpr int ST_THREADS = 576;            // 16 epilogue warps + 2 control warps
-constexpr int ST_SITES = 32;               // sites per CTA (= SB_SITES of the partial buffers)
+constexpr int ST_SITES = 64;               // sites per CTA
 constexpr int ST_A0 = 0;                   // alpha operand   hi 16 KB | lo 16 KB
-constexpr int ST_W = 32768;                // Wg_h, Wg_l, Ws_h, Ws_l: 4 x 8 KB
-constexpr int ST_PIPE = 65536;             // per pipeline: Bx_h 8K | Bx_l 8K | A1_h 16K | A1_l 16K = 48 KB
-constexpr int ST_PIPE_BYTES = 49152;
-constexpr int ST_MISC = ST_PIPE + 2 * ST_PIPE_BYTES;   // biases (768 B) | part (2 KB) | barriers | tmem slot
-constexpr int ST_SMEM = ST_MISC + 768 + 2048 + 256 + 1024;
+constexpr int ST_W = 32768;                // Ws_h, Ws_l: 2 x 8 KB
+constexpr int ST_PIPE = 49152;             // per pipeline: [X|G]_h 16K | [X|G]_l 16K | A1_h 16K | A1_l 16K = 64 KB
+constexpr int ST_PIPE_BYTES = 65536;
+constexpr int ST_MISC = ST_PIPE + 2 * ST_PIPE_BYTES;   // biases (768 B) | part (4 KB) | barriers | tmem slot
+constexpr int ST_SMEM = ST_MISC + 768 + 4096 + 256 + 1024;
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -67,24 +70,6 @@ __global__ void __launch_bounds__(256) k_blend_planes(const float* __restrict__ 
     xl[o] = ol;
 }
 
-// fp32 node pool [B][S][C][64] -> site-major bf16 hi/lo planes [B][C][S][64] for slots < n_used (others zeroed).  grid (C, B).
-__global__ void __launch_bounds__(256) k_pool_to_planes(const float* __restrict__ X, size_t tree_stride, int S, int C, int n_used,
-                                                        uint2* __restrict__ ph, uint2* __restrict__ pl) {
-    const int c = blockIdx.x, b = blockIdx.y;
-    for (int idx = threadIdx.x; idx < S * 16; idx += 256) {
-        const int slot = idx >> 4, q = idx & 15;
-        uint2 oh = make_uint2(0u, 0u), ol = make_uint2(0u, 0u);
-        if (slot < n_used) {
-            const float4 v = ld4(X + (size_t)b * tree_stride + ((size_t)slot * C + c) * D + q * 4);
-            split2(v.x, v.y, oh.x, ol.x);
-            split2(v.z, v.w, oh.y, ol.y);
-        }
-        const size_t o = (((size_t)b * C + c) * S + slot) * 16 + q;
-        ph[o] = oh;
-        pl[o] = ol;
-    }
-}
-
 struct ScoreTcArgs {
     const uint4* xh; const uint4* xl;      // x planes [B][pc][C][64] bf16
     int pc;                                 // pairs capacity of the x planes
@@ -93,34 +78,120 @@ struct ScoreTcArgs {
     const int32_t* slot_of; int slot_stride;
     const int32_t* pair_i; int pair_stride; int n0; int nc;
     int Rp, S, C;
-    const uint4* wgh; const uint4* wgl; const uint4* wsh; const uint4* wsl;   // [64][64] bf16 planes
+    const uint4* wsh; const uint4* wsl;     // s_out.0 weight [64][64] as bf16 planes
     const float* bg; const float* bs; const float* w2; float b2;
     const uint8_t* mask;
     float* score_part; int nSG;
 };
+
+struct EpiCtx {
+    uint64_t* pb; uint8_t* a1h; uint8_t* a1l; uint32_t t_d1; uint32_t t_s;
+    const float* s_bias; int my_sites; int c_base; int p; int b;
+};
+
+// Epilogue of one warp over its sites.  NSUB 16-column sub-chunks per thread (2: one of two 32-column halves of a
+// 128-pair tile; 1: one of four 16-column quarters when <= 64 pairs are duplicated into rows 64..127).
+template <int NSUB>
+__device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiCtx& e, int prow, int n, bool row_ok, int col0, bool dup) {
+    const float* bgv = e.s_bias + col0;
+    const float* bsv = e.s_bias + 64 + col0;
+    const float* w2v = e.s_bias + 128 + col0;
+    float score = 0.f;
+    for (int i = 0; i < e.my_sites; ++i) {
+        const uint32_t par = i & 1;
+        const int c = e.c_base + 2 * i + e.p;
+        uint4 xh4[2 * NSUB], xl4[2 * NSUB];
+        if (row_ok) {
+            const size_t o = ((((size_t)e.b * a.pc + n) * a.C + c) * 64 + col0) >> 3;
+#pragma unroll
+            for (int j = 0; j < 2 * NSUB; ++j) { xh4[j] = __ldg(a.xh + o + j); xl4[j] = __ldg(a.xl + o + j); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2 * NSUB; ++j) { xh4[j] = make_uint4(0u, 0u, 0u, 0u); xl4[j] = xh4[j]; }
+        }
+        const uint32_t* xhw = reinterpret_cast<const uint32_t*>(xh4);
+        const uint32_t* xlw = reinterpret_cast<const uint32_t*>(xl4);
+        // ---- gate: w = sigmoid(g + b_g), x' = (1-w) x + w x_glob  -> A1 operand of the s_out GEMM
+        mbar_wait(e.pb + 1, par);
+        tc_fence_after();
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+            uint32_t g[16], xg[16];
+            tmem_ld16(e.t_d1 + 64 + col0 + sub * 16, g);
+            tmem_ld16(e.t_d1 + col0 + sub * 16, xg);
+            float xp[16];
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+                const uint32_t wh = xhw[sub * 8 + (k >> 1)], wl = xlw[sub * 8 + (k >> 1)];
+                const float x0 = bf_lo(wh) + bf_lo(wl), x1 = bf_hi(wh) + bf_hi(wl);
+                const float w0 = fast_sigmoid(__uint_as_float(g[k]) + bgv[sub * 16 + k]);
+                const float w1 = fast_sigmoid(__uint_as_float(g[k + 1]) + bgv[sub * 16 + k + 1]);
+                xp[k] = fmaf(w0, __uint_as_float(xg[k]), (1.0f - w0) * x0);
+                xp[k + 1] = fmaf(w1, __uint_as_float(xg[k + 1]), (1.0f - w1) * x1);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint4 hh, ll;
+                split2(xp[8 * j + 0], xp[8 * j + 1], hh.x, ll.x);
+                split2(xp[8 * j + 2], xp[8 * j + 3], hh.y, ll.y);
+                split2(xp[8 * j + 4], xp[8 * j + 5], hh.z, ll.z);
+                split2(xp[8 * j + 6], xp[8 * j + 7], hh.w, ll.w);
+                const int off = prow * 128 + (((((col0 + sub * 16) >> 3) + j) ^ (prow & 7)) << 4);
+                *reinterpret_cast<uint4*>(e.a1h + off) = hh;
+                *reinterpret_cast<uint4*>(e.a1l + off) = ll;
+                if (dup) {
+                    *reinterpret_cast<uint4*>(e.a1h + off + 8192) = hh;
+                    *reinterpret_cast<uint4*>(e.a1l + off + 8192) = ll;
+                }
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(e.pb + 2);
+        // ---- score: w2 . GELU(s + b_s) (+ b2 once per row), masked site sum
+        mbar_wait(e.pb + 3, par);
+        tc_fence_after();
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+            uint32_t sv[16];
+            tmem_ld16(e.t_s + col0 + sub * 16, sv);
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+                acc0 = fmaf(gelu_erf(__uint_as_float(sv[k]) + bsv[sub * 16 + k]), w2v[sub * 16 + k], acc0);
+                acc1 = fmaf(gelu_erf(__uint_as_float(sv[k + 1]) + bsv[sub * 16 + k + 1]), w2v[sub * 16 + k + 1], acc1);
+            }
+        }
+        tc_fence_before();
+        const bool site_ok = !(a.mask && a.mask[(size_t)e.b * a.C + c]);
+        if (site_ok) score += (acc0 + acc1) + (col0 == 0 ? a.b2 : 0.f);
+    }
+    return row_ok ? score : 0.f;
+}
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
 k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl, const ScoreTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* s_bias = reinterpret_cast<float*>(sm + ST_MISC);            // bg[64] | bs[64] | w2[64]
-    float* s_part = s_bias + 192;                                       // [2 pipelines][2 halves][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 512);         // per pipeline: bx_full, xg_done, a1_ready, g_done, a2_ready, s_done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    float* s_part = s_bias + 192;                                       // [2 pipelines][4 column slots][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 1024);        // per pipeline: bx_full, d1_done, a1_ready, s_done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.z, pt = blockIdx.y, sg = blockIdx.x;
     const int rows_here = min(128, a.nc - pt * 128);
-    const int nq = (rows_here + 31) >> 5;                               // active TMEM lane quarters
+    const bool dup = rows_here <= 64;                                   // pairs duplicated into rows 64..127: all 16 warps stay busy
+    const int act_warps = dup ? (rows_here > 32 ? 8 : 4) : 2 * ((rows_here + 31) >> 5);   // per pipeline
     const int c_base = sg * ST_SITES;
     const int n_sites = min(ST_SITES, a.C - c_base);
 
     // ---- one-time setup
     if (tid == 0) {
         for (int p = 0; p < 2; ++p) {
-            uint64_t* pb = bars + p * 6;
-            mbar_init(pb + 0, 1); mbar_init(pb + 1, 1); mbar_init(pb + 2, 2 * nq);
-            mbar_init(pb + 3, 1); mbar_init(pb + 4, 2 * nq); mbar_init(pb + 5, 1);
+            uint64_t* pb = bars + p * 4;
+            mbar_init(pb + 0, 1); mbar_init(pb + 1, 1); mbar_init(pb + 2, act_warps); mbar_init(pb + 3, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -129,11 +200,12 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     for (int i = tid; i < 2048; i += ST_THREADS) reinterpret_cast<uint4*>(sm + ST_A0)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < 2048; i += ST_THREADS) {                      // weights -> swizzled K-major tiles
+    for (int i = tid; i < 1024; i += ST_THREADS) {                      // W_s -> swizzled K-major tiles (hi, lo)
         const int plane = i >> 9, rem = i & 511, row = rem >> 3, j = rem & 7;
-        const uint4* src = plane == 0 ? a.wgh : plane == 1 ? a.wgl : plane == 2 ? a.wsh : a.wsl;
+        const uint4* src = plane == 0 ? a.wsh : a.wsl;
         *reinterpret_cast<uint4*>(sm + ST_W + plane * 8192 + row * 128 + ((j ^ (row & 7)) << 4)) = __ldg(src + rem);
     }
+    for (int i = tid; i < 1024; i += ST_THREADS) s_part[i] = 0.f;
     if (tid < 64) { s_bias[tid] = a.bg[tid]; s_bias[64 + tid] = a.bs[tid]; s_bias[128 + tid] = a.w2[tid]; }
     __syncthreads();
     {   // alpha scattered to physical-slot order: A0[row][slot] (K-major, 64 slots = one 128 B swizzle row)
@@ -146,6 +218,10 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
             const int off = row * 128 + (((slot >> 3) ^ (row & 7)) << 4) + (slot & 7) * 2;
             *reinterpret_cast<__nv_bfloat16*>(sm + ST_A0 + off) = h;
             *reinterpret_cast<__nv_bfloat16*>(sm + ST_A0 + 16384 + off) = l;
+            if (dup) {
+                *reinterpret_cast<__nv_bfloat16*>(sm + ST_A0 + off + 8192) = h;
+                *reinterpret_cast<__nv_bfloat16*>(sm + ST_A0 + 16384 + off + 8192) = l;
+            }
         }
     }
     fence_async_smem();
@@ -155,155 +231,86 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= 16) {
-        // ================= control warp of pipeline p: TMA + MMA issue =================
+        // ================= control warp of pipeline p: TMA + MMA issue (warp-uniform, one elected lane per action) =================
         const int p = warp - 16;
-        if (lane == 0 && nq > 0) {
-            uint64_t* pb = bars + p * 6;
-            uint8_t* pipe = sm + ST_PIPE + p * ST_PIPE_BYTES;
-            const uint32_t a0h = smem_u32(sm + ST_A0), a0l = a0h + 16384;
-            const uint32_t wgh = smem_u32(sm + ST_W), wgl = wgh + 8192, wsh = wgh + 16384, wsl = wgh + 24576;
-            const uint32_t bxh = smem_u32(pipe), bxl = bxh + 8192, a1h = bxh + 16384, a1l = bxh + 32768;
-            const uint32_t t_xg = tmem_base + p * 192, t_g = t_xg + 64, t_s = t_xg + 128;
-            const uint32_t id_kk = umma_idesc_bf16(128, 64), id_mn = id_kk | (1u << 16);
-            const int ksteps = (a.S + 15) >> 4;
-            const int my_sites = (n_sites - p + 1) >> 1;
-            auto load_site = [&](int i) {
-                const int c = c_base + 2 * i + p;
-                mbar_expect_tx(pb + 0, 16384);
-                tma_load_3d(pipe, &mapXh, pb + 0, 0, 0, b * a.C + c);
-                tma_load_3d(pipe + 8192, &mapXl, pb + 0, 0, 0, b * a.C + c);
-            };
-            if (my_sites > 0) load_site(0);
-            for (int i = 0; i < my_sites; ++i) {
-                const uint32_t par = i & 1;
-                mbar_wait(pb + 0, par);
-                tc_fence_after();
-                for (int k = 0; k < ksteps; ++k) {      // x_glob = alpha . X   (B MN-major: 16 slots = 2048 B per k-step)
-                    umma_bf16(t_xg, umma_desc_k128(a0l + k * 32), umma_desc_k128(bxh + k * 2048), id_mn, k ? 1u : 0u);
-                    umma_bf16(t_xg, umma_desc_k128(a0h + k * 32), umma_desc_k128(bxl + k * 2048), id_mn, 1u);
-                    umma_bf16(t_xg, umma_desc_k128(a0h + k * 32), umma_desc_k128(bxh + k * 2048), id_mn, 1u);
+        uint64_t* pb = bars + p * 4;
+        uint8_t* pipe = sm + ST_PIPE + p * ST_PIPE_BYTES;
+        const uint32_t a0h = smem_u32(sm + ST_A0), a0l = a0h + 16384;
+        const uint32_t wsh = smem_u32(sm + ST_W), wsl = wsh + 8192;
+        const uint32_t bxh = smem_u32(pipe), bxl = bxh + 16384, a1h = bxh + 32768, a1l = bxh + 49152;
+        const uint32_t t_d1 = tmem_base + p * 192, t_s = t_d1 + 128;
+        const uint32_t id_s = umma_idesc_bf16(128, 64), id_d1 = umma_idesc_bf16(128, 128) | (1u << 16);
+        const int ksteps = (a.S + 15) >> 4;
+        const int my_sites = (n_sites - p + 1) >> 1;
+        if (my_sites > 0 && elect_one()) {
+            const int c = c_base + p;
+            mbar_expect_tx(pb + 0, 32768);
+            tma_load_3d(pipe, &mapXh, pb + 0, 0, 0, b * a.C + c);
+            tma_load_3d(pipe + 8192, &mapXh, pb + 0, 64, 0, b * a.C + c);
+            tma_load_3d(pipe + 16384, &mapXl, pb + 0, 0, 0, b * a.C + c);
+            tma_load_3d(pipe + 24576, &mapXl, pb + 0, 64, 0, b * a.C + c);
+        }
+        __syncwarp();
+        for (int i = 0; i < my_sites; ++i) {
+            const uint32_t par = i & 1;
+            mbar_wait(pb + 0, par);
+            tc_fence_after();
+            if (elect_one()) {      // [x_glob | g] = alpha . [X | W_g X]   (B MN-major: 16 slots = 2048 B per k-step, column blocks 8 KB apart)
+                for (int k = 0; k < ksteps; ++k) {
+                    umma_bf16(t_d1, umma_desc_k128(a0l + k * 32), umma_desc_lbo(bxh + k * 2048, 8192), id_d1, k ? 1u : 0u);
+                    umma_bf16(t_d1, umma_desc_k128(a0h + k * 32), umma_desc_lbo(bxl + k * 2048, 8192), id_d1, 1u);
+                    umma_bf16(t_d1, umma_desc_k128(a0h + k * 32), umma_desc_lbo(bxh + k * 2048, 8192), id_d1, 1u);
                 }
                 umma_commit(pb + 1);
-                mbar_wait(pb + 2, par);                 // epilogue has drained x_glob into the A1 operand
-                tc_fence_after();
-                for (int k = 0; k < 4; ++k) {           // g = x_glob . W_g^T
-                    umma_bf16(t_g, umma_desc_k128(a1l + k * 32), umma_desc_k128(wgh + k * 32), id_kk, k ? 1u : 0u);
-                    umma_bf16(t_g, umma_desc_k128(a1h + k * 32), umma_desc_k128(wgl + k * 32), id_kk, 1u);
-                    umma_bf16(t_g, umma_desc_k128(a1h + k * 32), umma_desc_k128(wgh + k * 32), id_kk, 1u);
+            }
+            __syncwarp();
+            mbar_wait(pb + 2, par);     // epilogue has consumed [x_glob | g] and written x' into the A1 operand
+            tc_fence_after();
+            if (elect_one()) {
+                if (i + 1 < my_sites) { // node tile buffer is free (UMMA 1 retired before a1_ready)
+                    const int c = c_base + 2 * (i + 1) + p;
+                    mbar_expect_tx(pb + 0, 32768);
+                    tma_load_3d(pipe, &mapXh, pb + 0, 0, 0, b * a.C + c);
+                    tma_load_3d(pipe + 8192, &mapXh, pb + 0, 64, 0, b * a.C + c);
+                    tma_load_3d(pipe + 16384, &mapXl, pb + 0, 0, 0, b * a.C + c);
+                    tma_load_3d(pipe + 24576, &mapXl, pb + 0, 64, 0, b * a.C + c);
+                }
+                for (int k = 0; k < 4; ++k) {   // s = x' . W_s^T
+                    umma_bf16(t_s, umma_desc_k128(a1l + k * 32), umma_desc_k128(wsh + k * 32), id_s, k ? 1u : 0u);
+                    umma_bf16(t_s, umma_desc_k128(a1h + k * 32), umma_desc_k128(wsl + k * 32), id_s, 1u);
+                    umma_bf16(t_s, umma_desc_k128(a1h + k * 32), umma_desc_k128(wsh + k * 32), id_s, 1u);
                 }
                 umma_commit(pb + 3);
-                mbar_wait(pb + 4, par);                 // epilogue has written x' over the A1 operand
-                if (i + 1 < my_sites) load_site(i + 1); // node tile buffer is free (UMMA 1 retired before a1_ready)
-                tc_fence_after();
-                for (int k = 0; k < 4; ++k) {           // s = x' . W_s^T
-                    umma_bf16(t_s, umma_desc_k128(a1l + k * 32), umma_desc_k128(wsh + k * 32), id_kk, k ? 1u : 0u);
-                    umma_bf16(t_s, umma_desc_k128(a1h + k * 32), umma_desc_k128(wsl + k * 32), id_kk, 1u);
-                    umma_bf16(t_s, umma_desc_k128(a1h + k * 32), umma_desc_k128(wsh + k * 32), id_kk, 1u);
-                }
-                umma_commit(pb + 5);
             }
+            __syncwarp();
         }
     } else {
-        // ================= epilogue warps: group p = warp / 8, TMEM lane quarter q, column half hf =================
+        // ================= epilogue warps: pipeline p = warp / 8, TMEM lane quarter q, column half hf =================
         const int p = warp >> 3, q = warp & 3, hf = (warp >> 2) & 1;
-        if (q < nq) {
-            uint64_t* pb = bars + p * 6;
+        const bool active = dup ? ((q & 1) * 32 < rows_here) : (q * 32 < rows_here);
+        if (active) {
             uint8_t* pipe = sm + ST_PIPE + p * ST_PIPE_BYTES;
-            uint8_t *a1h = pipe + 16384, *a1l = pipe + 32768;
-            const int row = q * 32 + lane;
-            const int n = pt * 128 + row;
+            EpiCtx e;
+            e.pb = bars + p * 4; e.a1h = pipe + 32768; e.a1l = pipe + 49152;
+            e.t_d1 = tmem_base + ((uint32_t)(q * 32) << 16) + p * 192; e.t_s = e.t_d1 + 128;
+            e.s_bias = s_bias; e.my_sites = (n_sites - p + 1) >> 1; e.c_base = c_base; e.p = p; e.b = b;
+            const int prow = dup ? ((q & 1) * 32 + lane) : (q * 32 + lane);
+            const int n = pt * 128 + prow;
             const bool row_ok = n < a.nc && a.pair_i[(size_t)b * a.pair_stride + a.n0 + n] >= 0;
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + p * 192 + hf * 32;
-            const float* bgv = s_bias + hf * 32;
-            const float* bsv = s_bias + 64 + hf * 32;
-            const float* w2v = s_bias + 128 + hf * 32;
-            const int my_sites = (n_sites - p + 1) >> 1;
-            float score = 0.f;
-            for (int i = 0; i < my_sites; ++i) {
-                const uint32_t par = i & 1;
-                const int c = c_base + 2 * i + p;
-                // x of this (pair, site): 32 columns as packed bf16 hi / lo words
-                uint4 xh4[4], xl4[4];
-                if (row_ok) {
-                    const size_t o = ((((size_t)b * a.pc + n) * a.C + c) * 64 + hf * 32) >> 3;
-                    for (int j = 0; j < 4; ++j) { xh4[j] = __ldg(a.xh + o + j); xl4[j] = __ldg(a.xl + o + j); }
-                } else {
-                    for (int j = 0; j < 4; ++j) { xh4[j] = make_uint4(0u, 0u, 0u, 0u); xl4[j] = xh4[j]; }
-                }
-                const uint32_t* xhw = reinterpret_cast<const uint32_t*>(xh4);
-                const uint32_t* xlw = reinterpret_cast<const uint32_t*>(xl4);
-                // ---- x_glob -> A1 operand
-                mbar_wait(pb + 1, par);
-                tc_fence_after();
-                for (int sub = 0; sub < 2; ++sub) {
-                    uint32_t v[16];
-                    tmem_ld16(t_row + sub * 16, v);
-                    for (int j = 0; j < 2; ++j) {
-                        uint4 hh, ll;
-                        split2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]), hh.x, ll.x);
-                        split2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]), hh.y, ll.y);
-                        split2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]), hh.z, ll.z);
-                        split2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]), hh.w, ll.w);
-                        const int off = row * 128 + (((hf * 4 + sub * 2 + j) ^ (row & 7)) << 4);
-                        *reinterpret_cast<uint4*>(a1h + off) = hh;
-                        *reinterpret_cast<uint4*>(a1l + off) = ll;
-                    }
-                }
-                fence_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(pb + 2);
-                // ---- gate: x' = (1-w) x + w x_glob  -> A1 operand (x_glob operand already consumed by UMMA 2)
-                mbar_wait(pb + 3, par);
-                tc_fence_after();
-                for (int sub = 0; sub < 2; ++sub) {
-                    uint32_t g[16], xg[16];
-                    tmem_ld16(t_row + 64 + sub * 16, g);
-                    tmem_ld16(t_row + sub * 16, xg);
-                    float xp[16];
-                    for (int e = 0; e < 16; e += 2) {
-                        const uint32_t wh = xhw[sub * 8 + (e >> 1)], wl = xlw[sub * 8 + (e >> 1)];
-                        const float x0 = bf_lo(wh) + bf_lo(wl), x1 = bf_hi(wh) + bf_hi(wl);
-                        const float w0 = fast_sigmoid(__uint_as_float(g[e]) + bgv[sub * 16 + e]);
-                        const float w1 = fast_sigmoid(__uint_as_float(g[e + 1]) + bgv[sub * 16 + e + 1]);
-                        xp[e] = fmaf(w0, __uint_as_float(xg[e]), (1.0f - w0) * x0);
-                        xp[e + 1] = fmaf(w1, __uint_as_float(xg[e + 1]), (1.0f - w1) * x1);
-                    }
-                    for (int j = 0; j < 2; ++j) {
-                        uint4 hh, ll;
-                        split2(xp[8 * j + 0], xp[8 * j + 1], hh.x, ll.x);
-                        split2(xp[8 * j + 2], xp[8 * j + 3], hh.y, ll.y);
-                        split2(xp[8 * j + 4], xp[8 * j + 5], hh.z, ll.z);
-                        split2(xp[8 * j + 6], xp[8 * j + 7], hh.w, ll.w);
-                        const int off = row * 128 + (((hf * 4 + sub * 2 + j) ^ (row & 7)) << 4);
-                        *reinterpret_cast<uint4*>(a1h + off) = hh;
-                        *reinterpret_cast<uint4*>(a1l + off) = ll;
-                    }
-                }
-                fence_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(pb + 4);
-                // ---- score: w2 . GELU(s + b_s) (+ b2 once per row), masked site sum
-                mbar_wait(pb + 5, par);
-                tc_fence_after();
-                float acc = 0.f;
-                for (int sub = 0; sub < 2; ++sub) {
-                    uint32_t sv[16];
-                    tmem_ld16(t_row + 128 + sub * 16, sv);
-                    for (int e = 0; e < 16; ++e) acc = fmaf(gelu_erf(__uint_as_float(sv[e]) + bsv[sub * 16 + e]), w2v[sub * 16 + e], acc);
-                }
-                tc_fence_before();
-                const bool site_ok = !(a.mask && a.mask[(size_t)b * a.C + c]);
-                if (site_ok) score += acc + (hf == 0 ? a.b2 : 0.f);
+            if (dup) {
+                const int cq = (q >> 1) * 2 + hf;
+                s_part[(p * 4 + cq) * 128 + prow] = score_epilogue<1>(a, e, prow, n, row_ok, cq * 16, true);
+            } else {
+                s_part[(p * 4 + hf) * 128 + prow] = score_epilogue<2>(a, e, prow, n, row_ok, hf * 32, false);
             }
-            s_part[(p * 2 + hf) * 128 + row] = row_ok ? score : 0.f;
         }
     }
     tc_fence_before();
     __syncthreads();
     if (tid < rows_here) {
-        const float s = (s_part[tid] + s_part[128 + tid]) + (s_part[256 + tid] + s_part[384 + tid]);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += s_part[k * 128 + tid];
         a.score_part[((size_t)b * a.alpha_pairs + pt * 128 + tid) * a.nSG + sg] = s;
     }
     if (warp == 16) {
@@ -314,7 +321,7 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
 
 // ------------------------------------------------------------------ host side
 
-// box {64, 64, 1} over site-major node planes [B*C][S][64]
+// box {64, 64, 1} over site-major node planes [B*C][S][128]  ([X | W_g X] per slot)
 static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC) {
     typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -326,8 +333,8 @@ static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC) {
             return set_error(NNJ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
         enc = reinterpret_cast<PFN>(p);
     }
-    cuuint64_t gdim[3] = {64, (cuuint64_t)S, (cuuint64_t)BC};
-    cuuint64_t gstr[2] = {128, (cuuint64_t)S * 128};
+    cuuint64_t gdim[3] = {128, (cuuint64_t)S, (cuuint64_t)BC};
+    cuuint64_t gstr[2] = {256, (cuuint64_t)S * 256};
     cuuint32_t box[3] = {64, 64, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -342,16 +349,6 @@ int launch_blend_planes(const float* X, const float* Y, size_t tree_stride, cons
     prof_begin(KC_BLEND, st);
     k_blend_planes<<<dim3((C + 15) / 16, nc, B), 256, 0, st>>>(X, Y, tree_stride, slot_of, slot_stride, C, pair_i, pair_j, pair_stride, n0, bh,
                                                                (uint2*)xh, (uint2*)xl, pc);
-    ++g_launches;
-    prof_end(st);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-    return 0;
-}
-
-int launch_pool_to_planes(const float* X, size_t tree_stride, int S, int C, int n_used, int B, void* ph, void* pl, cudaStream_t st) {
-    prof_begin(KC_MISC, st);
-    k_pool_to_planes<<<dim3(C, B), 256, 0, st>>>(X, tree_stride, S, C, n_used, (uint2*)ph, (uint2*)pl);
     ++g_launches;
     prof_end(st);
     cudaError_t e = cudaGetLastError();
@@ -377,11 +374,11 @@ int launch_score_tc(const Model* m, const void* xh, const void* xl, int pc, cons
     a.alpha = alpha; a.RP = RP; a.alpha_pairs = alpha_pairs;
     a.slot_of = slot_of; a.slot_stride = slot_stride; a.pair_i = pair_i; a.pair_stride = pair_stride; a.n0 = n0; a.nc = nc;
     a.Rp = Rp; a.S = S; a.C = C;
-    a.wgh = (const uint4*)m->nj_bf.wgh; a.wgl = (const uint4*)m->nj_bf.wgl; a.wsh = (const uint4*)m->nj_bf.wsh; a.wsl = (const uint4*)m->nj_bf.wsl;
+    a.wsh = (const uint4*)m->nj_bf.wsh; a.wsl = (const uint4*)m->nj_bf.wsl;
     a.bg = m->nj.bg; a.bs = m->nj.bs; a.w2 = m->nj.w2; a.b2 = m->nj.b2;
     a.mask = mask; a.score_part = score_part; a.nSG = nSG;
     prof_begin(KC_SCORE, st);
-    k_score_tc<<<dim3(nSG, (nc + 127) / 128, B), ST_THREADS, ST_SMEM, st>>>(mh, ml, a);
+    k_score_tc<<<dim3((C + ST_SITES - 1) / ST_SITES, (nc + 127) / 128, B), ST_THREADS, ST_SMEM, st>>>(mh, ml, a);
     ++g_launches;
     prof_end(st);
     cudaError_t e = cudaGetLastError();

@@ -62,30 +62,33 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Producer / issuer warps keep warp-uniform control flow and elect one lane per action, so descriptors and
+    // addresses stay in uniform registers (a lane==0 branch makes ptxas emit a R2UR broadcast loop per MMA).
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kk = 0; kk < nchunks; ++kk) {
-                const int s = kk % TC_STAGES, kc = kc0 + kk;
-                if (kk >= TC_STAGES) mbar_wait(&empty[s], ((kk / TC_STAGES) - 1) & 1);
-                uint8_t* st = tiles + s * STAGE;
+        for (int kk = 0; kk < nchunks; ++kk) {
+            const int s = kk % TC_STAGES, kc = kc0 + kk;
+            if (kk >= TC_STAGES) mbar_wait(&empty[s], ((kk / TC_STAGES) - 1) & 1);
+            uint8_t* st = tiles + s * STAGE;
+            if (elect_one()) {
                 mbar_expect_tx(&full[s], STAGE);
                 tma_load_3d(st, &mapAh, &full[s], kc * TC_BK, m0, z);
                 tma_load_3d(st + TC_PLANE_BYTES, &mapAl, &full[s], kc * TC_BK, m0, z);
                 tma_load_3d(st + 2 * TC_PLANE_BYTES, &mapBh, &full[s], kc * TC_BK, n0, z);
                 tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE, &mapBl, &full[s], kc * TC_BK, n0, z);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
-            for (int kk = 0; kk < nchunks; ++kk) {
-                const int s = kk % TC_STAGES, kc = kc0 + kk;
-                mbar_wait(&full[s], (kk / TC_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(tiles + s * STAGE), a_lo = a_hi + TC_PLANE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = b_hi + B_PLANE;
-                const int kvalid = min(TC_BK, g.K - kc * TC_BK);
-                const int ksteps = (kvalid + 15) / 16;
+        const uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+        for (int kk = 0; kk < nchunks; ++kk) {
+            const int s = kk % TC_STAGES, kc = kc0 + kk;
+            mbar_wait(&full[s], (kk / TC_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(tiles + s * STAGE), a_lo = a_hi + TC_PLANE_BYTES;
+            const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = b_hi + B_PLANE;
+            const int kvalid = min(TC_BK, g.K - kc * TC_BK);
+            const int ksteps = (kvalid + 15) / 16;
+            if (elect_one()) {
                 for (int k = 0; k < ksteps; ++k) {
                     const uint32_t ko = k * 32;   // 16 bf16 = 32 B inside the 128 B swizzle row
                     const uint64_t dah = umma_desc_k128(a_hi + ko), dal = umma_desc_k128(a_lo + ko);
@@ -95,9 +98,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
                     umma_bf16(tmem_base, dah, dbh, idesc, 1u);
                 }
                 umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+                if (kk == nchunks - 1) umma_commit(accum_done);   // accumulator complete
             }
-            umma_commit(accum_done);               // accumulator complete
+            __syncwarp();
         }
+        if (nchunks == 0 && elect_one()) mbar_arrive(accum_done);
     } else {
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         mbar_wait(accum_done, 0);
@@ -153,16 +158,18 @@ __global__ void k_split_bf16(const float* __restrict__ x, __nv_bfloat16* __restr
 //   A [128 x 64] K-major, written into SWIZZLE_128B shared memory by threads (not TMA), and
 //   B [64 (K) x 64 (N)] MN-major (N contiguous, one 128-byte row per k), also thread-written.
 // D [128 x 64] = (A_hi + A_lo)(B_hi + B_lo) with the 3-product split.  One CTA, 128 threads.
+template <int BN>
 __global__ void __launch_bounds__(128, 1) k_tc_unit(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ Dm) {
+    // B [64 (K) x BN (N)] MN-major: BN/64 column blocks of [64 rows x 128 B], 8 KB apart (LBO) within each plane
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *a_hi = base, *a_lo = base + 16384, *b_hi = base + 32768, *b_lo = base + 32768 + 8192;
-    uint64_t* done = reinterpret_cast<uint64_t*>(base + 49152);
+    uint8_t *a_hi = base, *a_lo = base + 16384, *b_hi = base + 32768, *b_lo = base + 32768 + 16384;
+    uint64_t* done = reinterpret_cast<uint64_t*>(base + 65536);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) { mbar_init(done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     {   // A row `tid`: 64 values -> 8 chunks of 8 bf16, chunk j stored at position j ^ (row & 7)
@@ -174,12 +181,12 @@ __global__ void __launch_bounds__(128, 1) k_tc_unit(const float* __restrict__ A,
             *reinterpret_cast<uint4*>(a_hi + off) = *reinterpret_cast<uint4*>(h);
             *reinterpret_cast<uint4*>(a_lo + off) = *reinterpret_cast<uint4*>(l);
         }
-        if (tid < 64) {   // B row k = tid: 64 n-values
-            const float* br = Bm + (size_t)tid * 64;
-            for (int j = 0; j < 8; ++j) {
+        if (tid < 64) {   // B row k = tid: BN n-values
+            const float* br = Bm + (size_t)tid * BN;
+            for (int j = 0; j < BN / 8; ++j) {
                 __align__(16) __nv_bfloat16 h[8], l[8];
                 for (int e = 0; e < 8; ++e) { float v = br[j * 8 + e]; h[e] = __float2bfloat16_rn(v); l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e])); }
-                const int off = tid * 128 + ((j ^ (tid & 7)) << 4);
+                const int off = (j >> 3) * 8192 + tid * 128 + (((j & 7) ^ (tid & 7)) << 4);
                 *reinterpret_cast<uint4*>(b_hi + off) = *reinterpret_cast<uint4*>(h);
                 *reinterpret_cast<uint4*>(b_lo + off) = *reinterpret_cast<uint4*>(l);
             }
@@ -190,33 +197,39 @@ __global__ void __launch_bounds__(128, 1) k_tc_unit(const float* __restrict__ A,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (tid == 0) {
-        const uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 16);   // B is MN-major
-        for (int k = 0; k < 4; ++k) {
-            const uint64_t dah = umma_desc_k128(smem_u32(a_hi) + k * 32), dal = umma_desc_k128(smem_u32(a_lo) + k * 32);
-            const uint64_t dbh = umma_desc_k128(smem_u32(b_hi) + k * 2048), dbl = umma_desc_k128(smem_u32(b_lo) + k * 2048);
-            umma_bf16(tmem_base, dal, dbh, idesc, k ? 1u : 0u);
-            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+    if (warp == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, BN) | (1u << 16);   // B is MN-major
+        if (elect_one()) {
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t dah = umma_desc_k128(smem_u32(a_hi) + k * 32), dal = umma_desc_k128(smem_u32(a_lo) + k * 32);
+                const uint64_t dbh = umma_desc_lbo(smem_u32(b_hi) + k * 2048, 8192), dbl = umma_desc_lbo(smem_u32(b_lo) + k * 2048, 8192);
+                umma_bf16(tmem_base, dal, dbh, idesc, k ? 1u : 0u);
+                umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+                umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+            }
+            umma_commit(done);
         }
-        umma_commit(done);
+        __syncwarp();
     }
     mbar_wait(done, 0);
     tc_fence_after();
-    for (int cb = 0; cb < 2; ++cb) {
+    for (int cb = 0; cb < BN / 32; ++cb) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
-        for (int j = 0; j < 32; ++j) Dm[(size_t)tid * 64 + cb * 32 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) Dm[(size_t)tid * BN + cb * 32 + j] = __uint_as_float(v[j]);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64)); }
+    if (warp == 0) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN)); }
 }
 
-int run_tc_unit(const float* A, const float* B, float* Dm, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_unit, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024);
+int run_tc_unit(const float* A, const float* B, float* Dm, int bn, cudaStream_t st) {
+    if (bn != 64 && bn != 128) return set_error(NNJ_ERR_INVALID, "tc_selftest: N must be 64 or 128");
+    cudaError_t e = cudaFuncSetAttribute(k_tc_unit<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_unit<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-    k_tc_unit<<<1, 128, 52 * 1024, st>>>(A, B, Dm);
+    if (bn == 64) k_tc_unit<64><<<1, 128, 68 * 1024, st>>>(A, B, Dm);
+    else k_tc_unit<128><<<1, 128, 68 * 1024, st>>>(A, B, Dm);
     ++g_launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);

@@ -47,15 +47,16 @@ def test_split_bf16_gemm_rejects_bad_k():
         _gemm(torch.randn(1, 128, 12, device="cuda"), torch.randn(1, 128, 12, device="cuda"))
 
 
-def test_thread_written_operands_and_mn_major_b():
+@pytest.mark.parametrize("N", [64, 128])
+def test_thread_written_operands_and_mn_major_b(N):
     """A K-major and B MN-major tiles staged into swizzled shared memory by threads (fused-kernel operand path)."""
     from neuralnj_b200 import _lib
     L = _lib.lib()
     g = torch.Generator(device="cuda").manual_seed(11)
     A = torch.randn(128, 64, device="cuda", generator=g)
-    B = torch.randn(64, 64, device="cuda", generator=g)
-    D = torch.full((128, 64), float("nan"), device="cuda")
-    _lib.check(L.nnj_tc_selftest(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(D.data_ptr()),
+    B = torch.randn(64, N, device="cuda", generator=g)
+    D = torch.full((128, N), float("nan"), device="cuda")
+    _lib.check(L.nnj_tc_selftest(C.c_void_p(A.data_ptr()), C.c_void_p(B.data_ptr()), C.c_void_p(D.data_ptr()), N,
                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     want = A.double() @ B.double()
