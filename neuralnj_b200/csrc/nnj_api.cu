@@ -148,7 +148,7 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
     CUDA_TRY(cudaSetDevice(device));
     nnj_model* m = new (std::nothrow) nnj_model();
     if (!m) return set_error(NNJ_ERR_NOMEM, "model_create: out of host memory");
-    m->cfg = *cfg; m->device = device; m->num_layers = Lyr; m->blob = nullptr; m->blob_bf = nullptr;
+    m->cfg = *cfg; m->device = device; m->num_layers = Lyr; m->blob = nullptr; m->blob_bf = nullptr; m->host_ws = nullptr; m->host_ws_bytes = 0;
 
     Packer pk;
     struct AttnOff { size_t ln_g, ln_b, qt, kt, vt, ot, qb, kb, vb, ob; };
@@ -233,6 +233,7 @@ void nnj_model_destroy(nnj_model* m) {
     if (!m) return;
     if (m->blob) cudaFree(m->blob);
     if (m->blob_bf) cudaFree(m->blob_bf);
+    if (m->host_ws) cudaFree(m->host_ws);
     delete m;
 }
 
@@ -317,12 +318,18 @@ int nnj_rollout_host(nnj_model* m, const int8_t* data_h, const uint8_t* mask_h, 
     const size_t ws_bytes = nj_rollout_ws_bytes(m, B, R, L);
     const size_t n_data = (size_t)B * R * L * 4, n_mask = (size_t)B * L, n_mg = (size_t)B * (R - 1) * 2;
     const size_t n_gum = gumbel_h ? (size_t)B * (R - 1) * (R * (R - 1) / 2) : 0;
-    char *ws = nullptr, *io = nullptr;
     const size_t io_bytes = ((n_data + 255) & ~(size_t)255) + ((n_mask + 255) & ~(size_t)255) + ((n_mg * 4 + 255) & ~(size_t)255) +
                             ((n_mg * 2 + 255) & ~(size_t)255) + n_gum * 4 + 256;
-    CUDA_TRY(cudaMalloc(&ws, ws_bytes));
-    cudaError_t e = cudaMalloc(&io, io_bytes);
-    if (e != cudaSuccess) { cudaFree(ws); return set_cuda_error(e, __FILE__, __LINE__); }
+    // workspace + staging buffers live in one grow-only allocation owned by the model (no cudaMalloc on the steady-state path)
+    const size_t need = ((ws_bytes + 255) & ~(size_t)255) + io_bytes;
+    if (m->host_ws_bytes < need) {
+        if (m->host_ws) { cudaFree(m->host_ws); m->host_ws = nullptr; m->host_ws_bytes = 0; }
+        CUDA_TRY(cudaMalloc(&m->host_ws, need));
+        m->host_ws_bytes = need;
+    }
+    char* ws = reinterpret_cast<char*>(m->host_ws);
+    char* io = ws + ((ws_bytes + 255) & ~(size_t)255);
+    cudaError_t e = cudaSuccess;
     int8_t* d_data = (int8_t*)io;
     uint8_t* d_mask = (uint8_t*)(io + ((n_data + 255) & ~(size_t)255));
     int32_t* d_mg = (int32_t*)((char*)d_mask + ((n_mask + 255) & ~(size_t)255));
@@ -341,8 +348,6 @@ int nnj_rollout_host(nnj_model* m, const int8_t* data_h, const uint8_t* mask_h, 
         if (selected_logp_h) { if ((e = cudaMemcpyAsync(selected_logp_h, d_slp, n_mg * 2, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break; }
         e = cudaStreamSynchronize(st);
     } while (0);
-    cudaFree(io);
-    cudaFree(ws);
     if (rc != NNJ_OK) return rc;
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     return NNJ_OK;

@@ -38,6 +38,7 @@ struct Model {
     NjW nj;
     NjBf nj_bf;
     void* blob_bf;               // device allocation behind nj_bf
+    void* host_ws; size_t host_ws_bytes;   // grow-only device workspace of nnj_rollout_host
 };
 
 // kernel classes for the optional per-class CUDA-event profiler (nnj_profile_*)

@@ -264,10 +264,9 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
                 umma_commit(pb + 1);
             }
             __syncwarp();
-            mbar_wait(pb + 2, par);     // epilogue has consumed [x_glob | g] and written x' into the A1 operand
-            tc_fence_after();
-            if (elect_one()) {
-                if (i + 1 < my_sites) { // node tile buffer is free (UMMA 1 retired before a1_ready)
+            if (i + 1 < my_sites) {     // prefetch the next node tile as soon as UMMA 1 has retired (hides the HBM/L2 latency)
+                mbar_wait(pb + 1, par);
+                if (elect_one()) {
                     const int c = c_base + 2 * (i + 1) + p;
                     mbar_expect_tx(pb + 0, 32768);
                     tma_load_3d(pipe, &mapXh, pb + 0, 0, 0, b * a.C + c);
@@ -275,6 +274,11 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
                     tma_load_3d(pipe + 16384, &mapXl, pb + 0, 0, 0, b * a.C + c);
                     tma_load_3d(pipe + 24576, &mapXl, pb + 0, 64, 0, b * a.C + c);
                 }
+                __syncwarp();
+            }
+            mbar_wait(pb + 2, par);     // epilogue has consumed [x_glob | g] and written x' into the A1 operand
+            tc_fence_after();
+            if (elect_one()) {
                 for (int k = 0; k < 4; ++k) {   // s = x' . W_s^T
                     umma_bf16(t_s, umma_desc_k128(a1l + k * 32), umma_desc_k128(wsh + k * 32), id_s, k ? 1u : 0u);
                     umma_bf16(t_s, umma_desc_k128(a1h + k * 32), umma_desc_k128(wsl + k * 32), id_s, 1u);

@@ -16,7 +16,9 @@ pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 2e-5
 STATE_TOL = 2e-4
-TIE_TOL = 1e-6      # a step whose reference top-1/top-2 gap is below TIE_TOL * max|logit| (~8 fp32 ulps) is tie-ambiguous
+# A step whose reference top-1/top-2 gap is below TIE_TOL * max|logit| is tie-ambiguous: fp32 kernels are held to
+# ~8 fp32 ulps; the split-bf16 tensor-core path carries ~16-bit operand mantissas (logit error ~5e-6) and uses the survey's 1e-5.
+TIE_TOL = {"fp32": 1e-6, "bf16x3": 1e-5}
 
 
 def _rel(a, b):
@@ -32,9 +34,9 @@ def _min_rel_gap(logits):
     return min(gaps) if gaps else 1.0
 
 
-def _assert_equivalent_trajectory(sd, data, mask, merges, trace):
+def _assert_equivalent_trajectory(sd, data, mask, merges, trace, tie_tol):
     """`merges` may leave the oracle's trajectory only at tie-ambiguous steps: replay it on the oracle
-    (teacher-forced) and require every chosen action to be an oracle argmax within TIE_TOL, logits within LOGIT_TOL."""
+    (teacher-forced) and require every chosen action to be an oracle argmax within tie_tol, logits within LOGIT_TOL."""
     import nnj_oracle as O
     ref = O.rollout(sd, data, mask, forced_merges=merges)
     off = 0
@@ -43,7 +45,7 @@ def _assert_equivalent_trajectory(sd, data, mask, merges, trace):
         assert _rel(trace[:, off:off + p], lg) < LOGIT_TOL, t
         chosen = lg.gather(1, ref["actions"][t].unsqueeze(1)).squeeze(1)
         slack = (lg.max(1).values - chosen) / lg.abs().max(1).values
-        assert float(slack.max()) < TIE_TOL, f"step {t}: chosen pair is not an oracle argmax (slack {float(slack.max()):.2e})"
+        assert float(slack.max()) < tie_tol, f"step {t}: chosen pair is not an oracle argmax (slack {float(slack.max()):.2e})"
         off += p
 
 
@@ -130,14 +132,14 @@ def test_incremental_scores_and_merge_match_oracle(golden, sd0, gpu_model):
 @pytest.mark.parametrize("case", ALL_CASES)
 def test_rollout_matches_reference_golden(case, prec, golden, sd0, gpu_models):
     """Fused device rollout vs the executed reference: identical merges / Newick (RF = 0), logits and log-probs close.
-    Only a record whose own top-1/top-2 gap falls below TIE_TOL somewhere (t100x256_a: 9.9e-8 at step 67, under one
-    fp32 ulp) is allowed the tie-aware comparison instead."""
+    Only a record whose own top-1/top-2 gap falls below TIE_TOL[prec] somewhere (t100x256_a: 9.9e-8 at step 67, under one
+    fp32 ulp; for bf16x3 also t50x512_a: 1.3e-6 at step 44) is allowed the tie-aware comparison instead."""
     from neuralnj_b200 import PhyInferEnv, inference_config, rf_distance
     g = golden(case)
     merges, slp, trace = gpu_models[prec].rollout_fused(g.data.cuda(), g.mask.cuda(), want_logits=True)
     merges, slp, trace = merges.cpu().long(), slp.cpu(), trace.cpu()
-    if not torch.equal(merges, g.merges) and _min_rel_gap(g.logits) < TIE_TOL:
-        _assert_equivalent_trajectory(sd0, g.data, g.mask, merges, trace)
+    if not torch.equal(merges, g.merges) and _min_rel_gap(g.logits) < TIE_TOL[prec]:
+        _assert_equivalent_trajectory(sd0, g.data, g.mask, merges, trace, TIE_TOL[prec])
         return
     assert torch.equal(merges, g.merges), f"first differing step: {int((merges != g.merges).any(-1).any(0).nonzero()[0])}"
     off = 0
