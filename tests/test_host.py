@@ -26,7 +26,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(raw, sym), sym
     assert L.nnj_abi_version() == 1
-    assert L.nnj_profile_classes() == 15 and L.nnj_profile_name(11) == b"pair_score"
+    assert L.nnj_profile_classes() >= 16 and L.nnj_profile_name(11) == b"pair_score"
     # argument validation happens before any CUDA call
     assert L.nnj_encode(None, None, None, 1, 2, 8, None, None, 0, None) == -1
     assert b"bad arguments" in L.nnj_last_error()
