@@ -148,10 +148,10 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
     CUDA_TRY(cudaSetDevice(device));
     nnj_model* m = new (std::nothrow) nnj_model();
     if (!m) return set_error(NNJ_ERR_NOMEM, "model_create: out of host memory");
-    m->cfg = *cfg; m->device = device; m->num_layers = Lyr; m->blob = nullptr; m->blob_bf = nullptr; m->host_ws = nullptr; m->host_ws_bytes = 0;
+    m->cfg = *cfg; m->device = device; m->num_layers = Lyr; m->blob = nullptr; m->blob_bf = nullptr; m->blob_enc = nullptr; m->host_ws = nullptr; m->host_ws_bytes = 0;
 
     Packer pk;
-    struct AttnOff { size_t ln_g, ln_b, qt, kt, vt, ot, qb, kb, vb, ob; };
+    struct AttnOff { size_t ln_g, ln_b, qt, kt, vt, ot, qb, kb, vb, ob, qkvb; };
     struct LayerOff { AttnOff a[2]; size_t fln_g, fln_b, w1t, b1, w2t, b2; };
     std::vector<LayerOff> lo(Lyr);
     int ti = 0;
@@ -164,6 +164,7 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
             a.qt = pk.add_t(tensors[ti + 4], 64, 64); a.qb = pk.add(tensors[ti + 5], 64);
             a.ot = pk.add_t(tensors[ti + 6], 64, 64); a.ob = pk.add(tensors[ti + 7], 64);
             a.ln_g = pk.add(tensors[ti + 8], 64); a.ln_b = pk.add(tensors[ti + 9], 64);
+            a.qkvb = pk.add(tensors[ti + 5], 64); pk.add(tensors[ti + 1], 64); pk.add(tensors[ti + 3], 64);   // q|k|v biases, contiguous
             ti += 10;
         }
         // fc1 [256][64] -> 4 chunks of [64 k][64 col]; fc2 [64][256] -> 4 chunks of [64 hidden][64 out]
@@ -225,6 +226,54 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
         const uint16_t* pb = reinterpret_cast<const uint16_t*>(m->blob_bf);
         m->nj_bf = NjBf{pb, pb + 4096, pb + 8192, pb + 12288};
     }
+    {   // shared-memory images of the encoder weights for the tcgen05 kernels (EncTcW)
+        constexpr size_t QKV = 2 * 192 * 64, OW = 2 * 64 * 64, W1 = 2 * 256 * 64, W2 = 2 * 64 * 256;   // bf16 elements
+        constexpr size_t PER = 2 * QKV + 2 * OW + W1 + W2;
+        std::vector<uint16_t> img((size_t)Lyr * PER, 0);
+        // W [N][ldw] rows n, K window [k0, k0+64) -> [N][64] K-major SWIZZLE_128B image, hi plane at dst_h, lo plane at dst_l
+        auto put = [&](uint16_t* dst_h, uint16_t* dst_l, const float* W, int n_rows, int ldw, int k0, int row0) {
+            for (int n = 0; n < n_rows; ++n)
+                for (int k = 0; k < 64; ++k) {
+                    const float v = W[(size_t)n * ldw + k0 + k];
+                    const __nv_bfloat16 h = __float2bfloat16_rn(v), l = __float2bfloat16_rn(v - __bfloat162float(h));
+                    const int rn = row0 + n;
+                    const size_t off = (size_t)rn * 64 + (size_t)(((k >> 3) ^ (rn & 7)) << 3) + (k & 7);
+                    dst_h[off] = __bfloat16_as_ushort(h);
+                    dst_l[off] = __bfloat16_as_ushort(l);
+                }
+        };
+        int tj = 0;
+        for (int l = 0; l < Lyr; ++l) {
+            uint16_t* base = img.data() + (size_t)l * PER;
+            uint16_t* qkv[2] = {base, base + QKV + OW};
+            uint16_t* ow[2] = {base + QKV, base + 2 * QKV + OW};
+            for (int blk = 0; blk < 2; ++blk) {   // state_dict order: k_proj, v_proj, q_proj, out_proj
+                put(qkv[blk], qkv[blk] + 192 * 64, tensors[tj + 4], 64, 64, 0, 0);     // q rows 0..63
+                put(qkv[blk], qkv[blk] + 192 * 64, tensors[tj + 0], 64, 64, 0, 64);    // k rows 64..127
+                put(qkv[blk], qkv[blk] + 192 * 64, tensors[tj + 2], 64, 64, 0, 128);   // v rows 128..191
+                put(ow[blk], ow[blk] + 64 * 64, tensors[tj + 6], 64, 64, 0, 0);
+                tj += 10;
+            }
+            uint16_t* w1 = base + 2 * QKV + 2 * OW;
+            uint16_t* w2 = w1 + W1;
+            put(w1, w1 + 256 * 64, tensors[tj], 256, 64, 0, 0);
+            for (int kc = 0; kc < 4; ++kc) put(w2 + (size_t)kc * 4096, w2 + 64 * 256 + (size_t)kc * 4096, tensors[tj + 2], 64, 256, kc * 64, 0);
+            tj += 6;
+        }
+        e = cudaMalloc(&m->blob_enc, img.size() * 2);
+        if (e == cudaSuccess) e = cudaMemcpy(m->blob_enc, img.data(), img.size() * 2, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(m->blob); cudaFree(m->blob_bf); if (m->blob_enc) cudaFree(m->blob_enc); delete m; return set_cuda_error(e, __FILE__, __LINE__); }
+        const uint16_t* pe = reinterpret_cast<const uint16_t*>(m->blob_enc);
+        m->enc_tc.resize(Lyr);
+        for (int l = 0; l < Lyr; ++l) {
+            const uint16_t* base = pe + (size_t)l * PER;
+            EncTcW& w = m->enc_tc[l];
+            w.row_qkv = (const uint4*)base; w.row_o = (const uint4*)(base + QKV);
+            w.col_qkv = (const uint4*)(base + QKV + OW); w.col_o = (const uint4*)(base + 2 * QKV + OW);
+            w.w1 = (const uint4*)(base + 2 * QKV + 2 * OW); w.w2 = (const uint4*)(base + 2 * QKV + 2 * OW + W1);
+            w.row_qkvb = B0 + lo[l].a[0].qkvb; w.col_qkvb = B0 + lo[l].a[1].qkvb;
+        }
+    }
     *out = m;
     return NNJ_OK;
 }
@@ -233,6 +282,7 @@ void nnj_model_destroy(nnj_model* m) {
     if (!m) return;
     if (m->blob) cudaFree(m->blob);
     if (m->blob_bf) cudaFree(m->blob_bf);
+    if (m->blob_enc) cudaFree(m->blob_enc);
     if (m->host_ws) cudaFree(m->host_ws);
     delete m;
 }

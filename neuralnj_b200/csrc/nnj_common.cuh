@@ -21,6 +21,25 @@ __device__ __forceinline__ float gelu_erf(float x) {            // torch.nn.GELU
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// ---- fast forms used by the tensor-core (bf16x3) kernels: MUFU ex2 / rcp (2^-22 relative), far below the ~2^-17 operand split
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+// GELU(x) = x * Phi(x), Phi(-|x|) = 0.5 erfc(|x|/sqrt 2) = poly6(u) exp(-x^2/2), u = 1/(1 + p|x|): coefficients fitted here
+// (scratch/phi_fit.py), |gelu_fast - gelu_erf| < 1e-7 absolute over the whole fp32 range (erff itself carries ~1e-7).
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x);
+    const float u = rcp_approx(fmaf(2.760034502e-01f, z, 1.0f));
+    float p = -1.134462506e-01f;
+    p = fmaf(p, u, 4.407724440e-01f);
+    p = fmaf(p, u, -3.137964904e-01f);
+    p = fmaf(p, u, 3.221081495e-01f);
+    p = fmaf(p, u, 4.673849419e-02f);
+    p = fmaf(p, u, 1.176236272e-01f);
+    const float h = p * u * ex2_approx(z * z * -0.72134752044448170f);
+    return x * (x >= 0.f ? 1.0f - h : h);
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float f4c(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }

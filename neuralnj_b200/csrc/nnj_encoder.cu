@@ -12,6 +12,7 @@
 //   k_out_proj       out_proj + residual add (:116,236; msa_modules.py:120)
 //   k_ffn            LN + fc1 + GELU + fc2 + residual (msa_modules.py:144-151)
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "nnj_internal.h"
 
@@ -25,8 +26,11 @@ __device__ __forceinline__ void tok_rc(int t, int R, int C, int& r, int& c) {
     if (CMAJOR) { c = t / R; r = t - c * R; } else { r = t / C; c = t - r * C; }
 }
 
+// element offset of token (taxon r, site c) in the residual stream: node-major [R][C][64] or site-major [C][R][64] (xsm)
+__device__ __forceinline__ size_t x_off(int r, int c, int R, int C, int xsm) { return (xsm ? (size_t)c * R + r : (size_t)r * C + c) * D; }
+
 template <bool CMAJOR>
-__device__ __forceinline__ void load_x_tile(float* __restrict__ xs, const float* __restrict__ xb, int tile, int R, int C) {
+__device__ __forceinline__ void load_x_tile(float* __restrict__ xs, const float* __restrict__ xb, int tile, int R, int C, int xsm = 0) {
     const int T = R * C;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -37,7 +41,7 @@ __device__ __forceinline__ void load_x_tile(float* __restrict__ xs, const float*
         if (t < T) {
             int r, c;
             tok_rc<CMAJOR>(t, R, C, r, c);
-            v = ld4(xb + ((size_t)r * C + c) * D + c4 * 4);
+            v = ld4(xb + x_off(r, c, R, C, xsm) + c4 * 4);
         }
         st4(xs + row * LDA + c4 * 4, v);
     }
@@ -45,7 +49,7 @@ __device__ __forceinline__ void load_x_tile(float* __restrict__ xs, const float*
 
 // ------------------------------------------------------------------ embed
 __global__ void __launch_bounds__(NTHREADS) k_embed(const int8_t* __restrict__ data, float* __restrict__ x, size_t x_tree_stride,
-                                                    int R, int L, EmbedW w) {
+                                                    int R, int L, EmbedW w, int xsm) {
     __shared__ float hbuf[16][64];
     __shared__ float lut[16][64];
     const int tid = threadIdx.x;
@@ -89,7 +93,8 @@ __global__ void __launch_bounds__(NTHREADS) k_embed(const int8_t* __restrict__ d
             }
             o = make_float4(acc[0], acc[1], acc[2], acc[3]);
         }
-        st4(xb + (size_t)t * D + c4 * 4, o);
+        const int r = t / L, c = t - r * L;
+        st4(xb + x_off(r, c, R, L, xsm) + c4 * 4, o);
     }
 }
 
@@ -99,14 +104,14 @@ __global__ void __launch_bounds__(NTHREADS) k_embed(const int8_t* __restrict__ d
 template <bool ROW>
 __global__ void __launch_bounds__(NTHREADS) k_ln_qkv(const float* __restrict__ x, size_t x_tree_stride, int R, int C,
                                                      AttnW w, float q_scale, const uint8_t* __restrict__ mask,
-                                                     float* __restrict__ q, float* __restrict__ k, float* __restrict__ v) {
+                                                     float* __restrict__ q, float* __restrict__ k, float* __restrict__ v, int xsm) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
     float* Ws = smem + TILE_ROWS * LDA;
     const int b = blockIdx.y, tile = blockIdx.x;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int T = R * C;
-    load_x_tile<ROW>(xs, x + (size_t)b * x_tree_stride, tile, R, C);
+    load_x_tile<ROW>(xs, x + (size_t)b * x_tree_stride, tile, R, C, xsm);
     __syncthreads();
     tile_layernorm(xs, w.ln_g, w.ln_b);
     __syncthreads();
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(NTHREADS) k_ln_qkv(const float* __restrict__ x
 template <bool ROW>
 __global__ void __launch_bounds__(NTHREADS) k_out_proj(float* __restrict__ x, size_t x_tree_stride, int R, int C,
                                                        const float* __restrict__ ctx, const float* __restrict__ wt,
-                                                       const float* __restrict__ bias) {
+                                                       const float* __restrict__ bias, int xsm) {
     extern __shared__ __align__(16) float smem[];
     float* as = smem;
     float* Ws = smem + TILE_ROWS * LDA;
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(NTHREADS) k_out_proj(float* __restrict__ x, si
         if (t < T) {
             int r, c;
             tok_rc<ROW>(t, R, C, r, c);
-            float* p = xb + ((size_t)r * C + c) * D + tx * 4;
+            float* p = xb + x_off(r, c, R, C, xsm) + tx * 4;
             float4 o = ld4(p);
             o.x += acc[i][0]; o.y += acc[i][1]; o.z += acc[i][2]; o.w += acc[i][3];
             st4(p, o);
@@ -413,14 +418,14 @@ __global__ void __launch_bounds__(NTHREADS) k_ln_qkv_rowtc(const float* __restri
                                                            float q_scale, const uint8_t* __restrict__ mask,
                                                            __nv_bfloat16* __restrict__ qh, __nv_bfloat16* __restrict__ ql,
                                                            __nv_bfloat16* __restrict__ kh, __nv_bfloat16* __restrict__ kl,
-                                                           __nv_bfloat16* __restrict__ vth, __nv_bfloat16* __restrict__ vtl) {
+                                                           __nv_bfloat16* __restrict__ vth, __nv_bfloat16* __restrict__ vtl, int xsm) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
     float* Ws = smem + TILE_ROWS * LDA;
     const int b = blockIdx.y, tile = blockIdx.x;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int T = R * C, KD = R * DH;
-    load_x_tile<false>(xs, x + (size_t)b * x_tree_stride, tile, R, C);
+    load_x_tile<false>(xs, x + (size_t)b * x_tree_stride, tile, R, C, xsm);
     __syncthreads();
     tile_layernorm(xs, w.ln_g, w.ln_b);
     __syncthreads();
@@ -525,14 +530,26 @@ __global__ void __launch_bounds__(NTHREADS) k_softmax_rows_split(const float* __
 // ------------------------------------------------------------------ host-side driver
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// per-tree workspace floats for the encoder
 static bool use_tc(const Model* m, int C) { return m->cfg.precision == NNJ_PREC_BF16X3 && (C % 8) == 0; }
 
+// Which per-token stages run on tcgen05 over the site-major residual stream (nnj_encoder_tc.cu): bit 0 LN1 + row q|k|v,
+// bit 1 the fused column block (at most 128 taxa), bit 2 the feed-forward block.  NNJ_ENC_TC overrides the default (all) for bisecting.
+static int enc_tc_mask(const Model* m, int R, int C) {
+    if (!use_tc(m, C)) return 0;
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("NNJ_ENC_TC"); env = e ? (atoi(e) & 7) : 7; }
+    int mk = env;
+    if (R > 128) mk &= ~2;
+    return mk;
+}
+
+// per-tree workspace floats for the encoder
 static size_t enc_tree_floats(const Model* m, int R, int C) {
     size_t act = (size_t)R * C * D;
     size_t s = (size_t)H * C * C;         // row-attention logits; also holds the column-attention context
     size_t p = use_tc(m, C) ? s : 0;      // probabilities as bf16 hi/lo planes (tensor-core path)
-    return 3 * act + (s > act ? s : act) + p; // q (row ctx), k, v, S [, P]
+    size_t xs = enc_tc_mask(m, R, C) ? act : 0;   // site-major residual stream
+    return 3 * act + (s > act ? s : act) + p + xs; // q (row ctx), k, v, S [, P] [, xs]
 }
 
 int encoder_chunk(const Model* m, int B, int R, int C) {
@@ -568,8 +585,11 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
     float* v = k + act * chunk;
     float* S = v + act * chunk;   // region of chunk * max(H*C*C, act) floats
     const bool tc = use_tc(m, C);
+    const int mk = enc_tc_mask(m, R, C);
+    const int xsm = mk ? 1 : 0;
     const size_t s_floats = (size_t)H * C * C > act ? (size_t)H * C * C : act;
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(S + s_floats * chunk);   // [2 planes][chunk*H][C][C] (tensor-core path only)
+    float* xs_ws = S + s_floats * chunk + (tc ? (size_t)H * C * C * chunk : 0);  // site-major residual stream [chunk][C][R][64]
     const int T = R * C;
     const int tiles = (T + TILE_ROWS - 1) / TILE_ROWS;
     const size_t smem_qkv = (TILE_ROWS * LDA + 4096) * sizeof(float);
@@ -586,39 +606,51 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
         cudaFuncSetAttribute(k_col_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
-    if (smem_col > 200 * 1024) return set_error(NNJ_ERR_INVALID, "encode: too many taxa for the column-attention kernel (max 400)");
+    if (!(mk & 2) && smem_col > 200 * 1024) return set_error(NNJ_ERR_INVALID, "encode: too many taxa for the column-attention kernel (max 400)");
+    if (R == 1) return set_error(NNJ_ERR_INVALID, "encode: R == 1 is not supported");
     const float row_scale = (1.0f / sqrtf((float)DH)) / sqrtf((float)R);   // align_scaling, axial_attention.py:31-33
     const float col_scale = 1.0f / sqrtf((float)DH);
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
-        float* xb = x + (size_t)b0 * x_tree_stride;
+        float* xout = x + (size_t)b0 * x_tree_stride;
+        float* xb = xsm ? xs_ws : xout;                       // the residual stream the layers work on
+        const size_t xstr = xsm ? act : x_tree_stride;
         const int8_t* db = data + (size_t)b0 * R * L * 4;
         const uint8_t* mb = mask ? mask + (size_t)b0 * C : nullptr;
         prof_begin(KC_EMBED, st);
-        k_embed<<<dim3((T + 1023) / 1024, nb), NTHREADS, 0, st>>>(db, xb, x_tree_stride, R, L, m->embed);
+        k_embed<<<dim3((T + 1023) / 1024, nb), NTHREADS, 0, st>>>(db, xb, xstr, R, L, m->embed, xsm);
         LAUNCH_CHECK();
         for (int l = 0; l < m->num_layers; ++l) {
             const LayerW& lw = m->layers[l];
             // --- tied row attention
             if (tc) {
-                const size_t pl = act * chunk;                 // elements per bf16 plane of q / k / v^T
+                const size_t pl = act * chunk;                 // elements per bf16 plane of q / k / v
                 __nv_bfloat16 *qh = reinterpret_cast<__nv_bfloat16*>(q), *ql = qh + pl;
                 __nv_bfloat16 *kh = reinterpret_cast<__nv_bfloat16*>(k), *kl = kh + pl;
                 __nv_bfloat16 *vh = reinterpret_cast<__nv_bfloat16*>(v), *vl = vh + pl;
                 const size_t pp = (size_t)chunk * H * C * C;   // elements per plane of P
                 const int KD = R * DH;
-                prof_begin(KC_LN_QKV, st);
-                k_ln_qkv_rowtc<<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, lw.row, row_scale, mb, qh, ql, kh, kl, vh, vl);
-                LAUNCH_CHECK();
+                if (mk & 1) {      // V as [B,H,C,R*8]: the MN-major B operand of ctx = P V
+                    if (int e = launch_enc_rowqkv_tc(m, l, xb, xstr, nb, R, C, row_scale, mb, qh, ql, kh, kl, vh, vl, st)) return e;
+                } else {           // V^T as [B,H,R*8,C]
+                    prof_begin(KC_LN_QKV, st);
+                    k_ln_qkv_rowtc<<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, xstr, R, C, lw.row, row_scale, mb, qh, ql, kh, kl, vh, vl, xsm);
+                    LAUNCH_CHECK();
+                }
                 if (int e = launch_tc_gemm(KC_ROW_QK, qh, ql, kh, kl, S, nb * H, C, C, KD, KD, (size_t)C * KD, KD, (size_t)C * KD, C, (size_t)C * C, st)) return e;
                 prof_begin(KC_ROW_SOFTMAX, st);
                 k_softmax_rows_split<<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, P + pp, C, mb);
                 LAUNCH_CHECK();
-                if (int e = launch_tc_gemm(KC_ROW_PV, P, P + pp, vh, vl, q /*ctx fp32 [B,H,C,R*8]*/, nb * H, C, KD, C, C, (size_t)C * C, C,
-                                           (size_t)KD * C, KD, (size_t)C * KD, st)) return e;
+                if (mk & 1) {
+                    if (int e = launch_tc_gemm_bmn(KC_ROW_PV, P, P + pp, vh, vl, q /*ctx fp32 [B,H,C,R*8]*/, nb * H, C, KD, C, C, (size_t)C * C, KD,
+                                                   (size_t)C * KD, KD, (size_t)C * KD, st)) return e;
+                } else {
+                    if (int e = launch_tc_gemm(KC_ROW_PV, P, P + pp, vh, vl, q /*ctx fp32 [B,H,C,R*8]*/, nb * H, C, KD, C, C, (size_t)C * C, C,
+                                               (size_t)KD * C, KD, (size_t)C * KD, st)) return e;
+                }
             } else {
                 prof_begin(KC_LN_QKV, st);
-                k_ln_qkv<true><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, lw.row, row_scale, mb, q, k, v);
+                k_ln_qkv<true><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, xstr, R, C, lw.row, row_scale, mb, q, k, v, xsm);
                 LAUNCH_CHECK();
                 prof_begin(KC_ROW_QK, st);
                 k_gemm<true><<<dim3((C + 127) / 128, (C + 127) / 128, nb * H), NTHREADS, 0, st>>>(
@@ -632,24 +664,35 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
                     S, v, q /*ctx*/, C, R * DH, C, (size_t)C * C, (size_t)C * R * DH, (size_t)C * R * DH, C, R * DH, R * DH);
                 LAUNCH_CHECK();
             }
-            prof_begin(KC_OUT_PROJ, st);
-            k_out_proj<true><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, q, lw.row.ot, lw.row.ob);
-            LAUNCH_CHECK();
-            // --- column attention
-            if (R == 1) return set_error(NNJ_ERR_INVALID, "encode: R == 1 is not supported");
-            prof_begin(KC_LN_QKV, st);
-            k_ln_qkv<false><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, lw.col, col_scale, mb, q, k, v);
-            LAUNCH_CHECK();
-            prof_begin(KC_COL_ATTN, st);
-            k_col_attn<<<dim3(C, nb), NTHREADS, smem_col, st>>>(q, k, v, S /*ctx [B,R,C,64]*/, R, C, mb);
-            LAUNCH_CHECK();
-            prof_begin(KC_OUT_PROJ, st);
-            k_out_proj<false><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, x_tree_stride, R, C, S, lw.col.ot, lw.col.ob);
-            LAUNCH_CHECK();
-            // --- feed forward
-            prof_begin(KC_FFN, st);
-            k_ffn<<<dim3(tiles, nb), NTHREADS, smem_ffn, st>>>(xb, x_tree_stride, R, C, lw.ffn);
-            LAUNCH_CHECK();
+            if (mk & 2) {
+                // --- row out_proj + residual, LN2, column attention, column out_proj + residual: one kernel
+                if (int e = launch_enc_colblock_tc(m, l, xb, xstr, q, nb, R, C, mb, st)) return e;
+            } else {
+                prof_begin(KC_OUT_PROJ, st);
+                k_out_proj<true><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, xstr, R, C, q, lw.row.ot, lw.row.ob, xsm);
+                LAUNCH_CHECK();
+                // --- column attention
+                prof_begin(KC_LN_QKV, st);
+                k_ln_qkv<false><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, xstr, R, C, lw.col, col_scale, mb, q, k, v, xsm);
+                LAUNCH_CHECK();
+                prof_begin(KC_COL_ATTN, st);
+                k_col_attn<<<dim3(C, nb), NTHREADS, smem_col, st>>>(q, k, v, S /*ctx [B,R,C,64]*/, R, C, mb);
+                LAUNCH_CHECK();
+                prof_begin(KC_OUT_PROJ, st);
+                k_out_proj<false><<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, xstr, R, C, S, lw.col.ot, lw.col.ob, xsm);
+                LAUNCH_CHECK();
+            }
+            // --- feed forward (per token: the memory order of the stream does not matter)
+            if (mk & 4) {
+                if (int e = launch_enc_ffn_tc(m, l, xb, xstr, nb, R, C, st)) return e;
+            } else {
+                prof_begin(KC_FFN, st);
+                k_ffn<<<dim3(tiles, nb), NTHREADS, smem_ffn, st>>>(xb, xstr, R, C, lw.ffn);
+                LAUNCH_CHECK();
+            }
+        }
+        if (xsm) {
+            if (int e = launch_sm_to_nm(xb, xstr, xout, x_tree_stride, nb, R, C, st)) return e;
         }
     }
     return NNJ_OK;

@@ -1,0 +1,598 @@
+// nnj_encoder_tc.cu — the MSA encoder's per-token work on tcgen05 (precision bf16x3).
+//
+// The residual stream is kept SITE-MAJOR inside the encoder, xs [B][C][R][64] fp32, so that a tile of 128 consecutive tokens
+// (site c, taxon r -> t = c*R + r) is one contiguous 32 KB block and the head-major row-attention planes [B,H,C,R*8] are
+// written in 16-byte pieces that are contiguous across the lanes of a warp.  Between two tied row attentions everything is
+// per token or per site, so one layer is three fused kernels (msa_modules.py:62-125):
+//   k_enc_rowqkv_tc   LN1 + q|k|v projection of the tied row attention (axial_attention.py:75-82) -> bf16 hi/lo planes
+//   k_enc_colblock_tc row out_proj + residual (:116), LN2 + column q|k|v (:211-214), per-site attention over taxa (:216-234),
+//                     column out_proj + residual (:236) — x is read once and written once
+//   k_enc_ffn_tc      LN3 + fc1 + GELU + fc2 + residual (msa_modules.py:144-151), hidden activations never leave the SM
+// Every contraction is a split-bf16 UMMA (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM); weights sit in shared memory as
+// ready-made SWIZZLE_128B images (EncTcW); A operands are written by the threads that produced them (LayerNorm output, the
+// attention context, the GELU output).  256 threads: warp w owns TMEM lane quarter w & 3 (row = 32*(w&3) + lane) and column
+// half w >> 2, so a token row is handled by two threads that exchange only the LayerNorm statistics.
+#include "nnj_internal.h"
+#include "nnj_tc.cuh"
+
+namespace nnj {
+
+constexpr int ET_THREADS = 256;
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); }
+
+__device__ __forceinline__ void copy_img(uint8_t* dst, const uint4* __restrict__ src, int bytes) {
+    for (int i = threadIdx.x; i < (bytes >> 4); i += ET_THREADS) reinterpret_cast<uint4*>(dst)[i] = __ldg(src + i);
+}
+
+// LayerNorm(64) (eps 1e-5, biased variance) of a row held as two 32-value halves by threads (row, hf = 0/1).  The halves are
+// combined with the pairwise (Chan) update, so the result has two-pass quality.  Contains one __syncthreads.
+__device__ __forceinline__ void ln_half(float (&v)[32], float2* part, int row, int hf, const float* __restrict__ g, const float* __restrict__ bta) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s += v[k];
+    const float mh = s * (1.0f / 32.0f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { const float d = v[k] - mh; m2 = fmaf(d, d, m2); }
+    part[hf * 128 + row] = make_float2(mh, m2);
+    __syncthreads();
+    const float2 o = part[(hf ^ 1) * 128 + row];
+    const float mean = 0.5f * (mh + o.x), dm = mh - o.x;
+    const float var = (m2 + o.y + dm * dm * 16.0f) * (1.0f / 64.0f);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(g + hf * 32 + k), b4 = *reinterpret_cast<const float4*>(bta + hf * 32 + k);
+        v[k] = (v[k] - mean) * rstd * g4.x + b4.x;
+        v[k + 1] = (v[k + 1] - mean) * rstd * g4.y + b4.y;
+        v[k + 2] = (v[k + 2] - mean) * rstd * g4.z + b4.z;
+        v[k + 3] = (v[k + 3] - mean) * rstd * g4.w + b4.w;
+    }
+}
+
+// this thread's 32 values -> chunks hf*4 .. hf*4+3 of row `row` of the A operand
+__device__ __forceinline__ void a_store32(uint8_t* a_hi, uint8_t* a_lo, int row, int hf, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a_store8(a_hi, a_lo, row, hf * 4 + j, &v[j * 8]);
+}
+
+// all threads: make the freshly written A operand visible to the tensor core, then one elected lane of warp 0 issues
+#define ET_PUBLISH_A()      \
+    do {                    \
+        fence_async_smem(); \
+        tc_fence_before();  \
+        __syncthreads();    \
+    } while (0)
+
+// ------------------------------------------------------------------ K1: LN1 + row q|k|v -> planes
+struct RowQkvArgs {
+    const float* x; size_t x_tree_stride;      // site-major [B][C][R][64]
+    int R, C, B, tiles_per_tree;
+    const uint4* w_img;                         // EncTcW::row_qkv (48 KB)
+    const float *ln_g, *ln_b, *qkvb;
+    float q_scale; const uint8_t* mask;
+    __nv_bfloat16 *qh, *ql, *kh, *kl, *vh, *vl; // [B,H,C,R*8]
+};
+
+constexpr int K1_W = 49152;
+constexpr int K1_SMEM = 1024 + K1_W + 32768 + (192 + 128) * 4 + 2048 + 64;
+
+__global__ void __launch_bounds__(ET_THREADS, 2) k_enc_rowqkv_tc(const RowQkvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = align1024(smem_raw);
+    uint8_t* w_s = sm;
+    uint8_t* a_hi = sm + K1_W;
+    uint8_t* a_lo = a_hi + 16384;
+    float* s_bias = reinterpret_cast<float*>(a_lo + 16384);   // q|k|v biases [192]
+    float* s_g = s_bias + 192;
+    float* s_b = s_g + 64;
+    float2* part = reinterpret_cast<float2*>(s_b + 64);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(part + 256);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane;
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    copy_img(w_s, a.w_img, K1_W);
+    if (tid < 192) s_bias[tid] = a.qkvb[tid];
+    if (tid < 64) { s_g[tid] = a.ln_g[tid]; s_b[tid] = a.ln_b[tid]; }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t idesc = umma_idesc_bf16(128, 192);
+    const int T = a.R * a.C, KD = a.R * DH;
+    const int n_work = a.B * a.tiles_per_tree;
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const int b = w / a.tiles_per_tree, tile = w - b * a.tiles_per_tree;
+        const int t = tile * 128 + row;
+        const bool valid = t < T;
+        float v[32];
+        if (valid) {
+            const float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + hf * 32;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const float4 f = ld4(xp + k * 4); v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = 0.f;
+        }
+        ln_half(v, part, row, hf, s_g, s_b);
+        a_store32(a_hi, a_lo, row, hf, v);
+        ET_PUBLISH_A();
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                umma_split_k64(tmem_base, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_s), smem_u32(w_s) + K1_W / 2, idesc, 0u);
+                umma_commit(bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar, it & 1);
+        tc_fence_after();
+        const int c = valid ? t / a.R : 0, r = t - c * a.R;
+        const float qs = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale;   // axial_attention.py:81-82
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            uint32_t acc[32];
+            tmem_ld32(t_row + p * 64 + hf * 32, acc);
+            if (valid) {
+                __nv_bfloat16* ph = p == 0 ? a.qh : (p == 1 ? a.kh : a.vh);
+                __nv_bfloat16* pl = p == 0 ? a.ql : (p == 1 ? a.kl : a.vl);
+                const float s = p == 0 ? qs : 1.0f;
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                    float o[8];
+#pragma unroll
+                    for (int d = 0; d < 8; ++d) o[d] = (__uint_as_float(acc[hh * 8 + d]) + s_bias[p * 64 + hf * 32 + hh * 8 + d]) * s;
+                    uint4 hi4, lo4;
+                    split2(o[0], o[1], hi4.x, lo4.x);
+                    split2(o[2], o[3], hi4.y, lo4.y);
+                    split2(o[4], o[5], hi4.z, lo4.z);
+                    split2(o[6], o[7], hi4.w, lo4.w);
+                    const size_t off = (((size_t)b * H + hf * 4 + hh) * a.C + c) * KD + (size_t)r * DH;
+                    *reinterpret_cast<uint4*>(ph + off) = hi4;
+                    *reinterpret_cast<uint4*>(pl + off) = lo4;
+                }
+            }
+        }
+        tc_fence_before();   // TMEM reads of this tile are ordered before the next tile's UMMA by the __syncthreads in between
+    }
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// ------------------------------------------------------------------ K3: LN3 + fc1 + GELU + fc2 + residual
+struct FfnTcArgs {
+    float* x; size_t x_tree_stride;             // site-major, updated in place
+    int T, B, tiles_per_tree;
+    const uint4 *w1, *w2;                       // EncTcW images (64 KB each)
+    const float *ln_g, *ln_b, *b1, *b2;
+};
+
+constexpr int K3_SMEM = 1024 + 2 * 65536 + 2 * 32768 + (256 + 64 + 128) * 4 + 2048 + 64;
+
+__global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = align1024(smem_raw);
+    uint8_t* w1_s = sm;                       // hi 32 KB | lo 32 KB   ([256][64])
+    uint8_t* w2_s = sm + 65536;               // hi: 4 K-chunks of 8 KB | lo: 4 K-chunks
+    uint8_t* const abuf0 = sm + 131072;       // two operand buffers, each: hi 16 KB | lo 16 KB
+    float* s_b1 = reinterpret_cast<float*>(sm + 196608);
+    float* s_b2 = s_b1 + 256;
+    float* s_g = s_b2 + 64;
+    float* s_b = s_g + 64;
+    float2* part = reinterpret_cast<float2*>(s_b + 64);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 256);   // d1_done, c0_done, c1_done, d2_done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane;
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    copy_img(w1_s, a.w1, 65536);
+    copy_img(w2_s, a.w2, 65536);
+    s_b1[tid] = a.b1[tid];
+    if (tid < 64) { s_b2[tid] = a.b2[tid]; s_g[tid] = a.ln_g[tid]; s_b[tid] = a.ln_b[tid]; }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 256;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t id_d1 = umma_idesc_bf16(128, 256), id_d2 = umma_idesc_bf16(128, 64);
+    const int n_work = a.B * a.tiles_per_tree;
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const uint32_t par = it & 1;
+        const int b = w / a.tiles_per_tree, tile = w - b * a.tiles_per_tree;
+        const int t = tile * 128 + row;
+        const bool valid = t < a.T;
+        float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + hf * 32;
+        float xr[32], v[32];
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const float4 f = ld4(xp + k * 4); xr[4 * k] = f.x; xr[4 * k + 1] = f.y; xr[4 * k + 2] = f.z; xr[4 * k + 3] = f.w; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) xr[k] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = xr[k];
+        ln_half(v, part, row, hf, s_g, s_b);
+        a_store32(abuf0, abuf0 + 16384, row, hf, v);
+        ET_PUBLISH_A();
+        if (warp == 0) {   // hidden pre-activations D1 [128 x 256] = LN3(x) . fc1^T
+            tc_fence_after();
+            if (elect_one()) {
+                umma_split_k64(t_d1, smem_u32(abuf0), smem_u32(abuf0) + 16384, smem_u32(w1_s), smem_u32(w1_s) + 32768, id_d1, 0u);
+                umma_commit(bars + 0);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bars + 0, par);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            // the operand buffer of chunk ch was last read by the fc2 UMMA of chunk ch-2
+            if (ch >= 2) { mbar_wait(bars + 1 + (ch - 2), par); tc_fence_after(); }
+            uint32_t acc[32];
+            tmem_ld32(t_d1 + lane_off + ch * 64 + hf * 32, acc);
+            float hdn[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) hdn[k] = gelu_fast(__uint_as_float(acc[k]) + s_b1[ch * 64 + hf * 32 + k]);
+            uint8_t* ab = abuf0 + (ch & 1) * 32768;
+            a_store32(ab, ab + 16384, row, hf, hdn);
+            ET_PUBLISH_A();
+            if (warp == 0) {   // D2 [128 x 64] += GELU chunk . fc2[:, 64 ch .. 64 ch + 63]^T
+                tc_fence_after();
+                if (elect_one()) {
+                    umma_split_k64(t_d2, smem_u32(ab), smem_u32(ab) + 16384, smem_u32(w2_s) + ch * 8192, smem_u32(w2_s) + 32768 + ch * 8192, id_d2,
+                                   ch ? 1u : 0u);
+                    if (ch == 0) umma_commit(bars + 1);
+                    else if (ch == 1) umma_commit(bars + 2);
+                    else if (ch == 3) umma_commit(bars + 3);
+                }
+                __syncwarp();
+            }
+        }
+        mbar_wait(bars + 3, par);
+        tc_fence_after();
+        {
+            uint32_t acc[32];
+            tmem_ld32(t_d2 + lane_off + hf * 32, acc);
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    st4(xp + k * 4, make_float4(xr[4 * k] + __uint_as_float(acc[4 * k]) + s_b2[hf * 32 + 4 * k],
+                                                xr[4 * k + 1] + __uint_as_float(acc[4 * k + 1]) + s_b2[hf * 32 + 4 * k + 1],
+                                                xr[4 * k + 2] + __uint_as_float(acc[4 * k + 2]) + s_b2[hf * 32 + 4 * k + 2],
+                                                xr[4 * k + 3] + __uint_as_float(acc[4 * k + 3]) + s_b2[hf * 32 + 4 * k + 3]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------ K2: row out_proj + residual, LN2, column attention block
+struct ColBlkArgs {
+    float* x; size_t x_tree_stride;             // site-major, updated in place
+    int R, C, B, s, groups_per_tree;            // s = 128 / R whole sites per tile
+    const float* ctx;                            // tied row-attention context fp32 [B,H,C,R*8]
+    const uint4* w_img;                          // EncTcW::row_o | col_qkv | col_o, contiguous (80 KB)
+    const float *rob, *ln_g, *ln_b, *qkvb, *cob;
+    float q_scale_log2e; const uint8_t* mask;
+};
+
+constexpr int K2_W = 81920;
+constexpr int K2_SMEM = 1024 + K2_W + 32768 + 2 * 32768 + (64 + 192 + 64 + 128) * 4 + 2048 + 64;
+
+__global__ void __launch_bounds__(ET_THREADS, 1) k_enc_colblock_tc(const ColBlkArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = align1024(smem_raw);
+    uint8_t* w_ro = sm;                        // row out_proj   hi 8 KB | lo 8 KB
+    uint8_t* w_qkv = sm + 16384;               // column q|k|v   hi 24 KB | lo 24 KB
+    uint8_t* w_co = sm + 65536;                // column out_proj
+    uint8_t* a_hi = sm + K2_W;
+    uint8_t* a_lo = a_hi + 16384;
+    float* ks = reinterpret_cast<float*>(a_lo + 16384);   // [128][64]
+    float* vs = ks + 128 * 64;
+    float* s_rob = vs + 128 * 64;
+    float* s_qkvb = s_rob + 64;
+    float* s_cob = s_qkvb + 192;
+    float* s_g = s_cob + 64;
+    float* s_b = s_g + 64;
+    float2* part = reinterpret_cast<float2*>(s_b + 64);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(part + 256);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane;
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    copy_img(sm, a.w_img, K2_W);
+    if (tid < 192) s_qkvb[tid] = a.qkvb[tid];
+    if (tid < 64) { s_rob[tid] = a.rob[tid]; s_cob[tid] = a.cob[tid]; s_g[tid] = a.ln_g[tid]; s_b[tid] = a.ln_b[tid]; }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_o = tmem_base, t_qkv = tmem_base + 64;          // [128 x 64] projections | [128 x 192] q|k|v
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t id64 = umma_idesc_bf16(128, 64), id192 = umma_idesc_bf16(128, 192);
+    const int R = a.R, KD = a.R * DH;
+    const int si = row / R, r = row - si * R;
+    const int n_work = a.B * a.groups_per_tree;
+    uint32_t ph = 0;   // completions of `bar` so far
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int b = w / a.groups_per_tree, grp = w - b * a.groups_per_tree;
+        const int c = grp * a.s + si;
+        const bool valid = si < a.s && c < a.C;
+        float* xp = a.x + (size_t)b * a.x_tree_stride + ((size_t)c * R + r) * D + hf * 32;
+        float xr[32], v[32];
+        // ---- stage 1: x += ctx_row . W_o^T + b_o
+        if (valid) {
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+                const float* cp = a.ctx + (((size_t)b * H + hf * 4 + hh) * a.C + c) * KD + (size_t)r * DH;
+                const float4 f0 = ld4(cp), f1 = ld4(cp + 4);
+                v[hh * 8] = f0.x; v[hh * 8 + 1] = f0.y; v[hh * 8 + 2] = f0.z; v[hh * 8 + 3] = f0.w;
+                v[hh * 8 + 4] = f1.x; v[hh * 8 + 5] = f1.y; v[hh * 8 + 6] = f1.z; v[hh * 8 + 7] = f1.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const float4 f = ld4(xp + k * 4); xr[4 * k] = f.x; xr[4 * k + 1] = f.y; xr[4 * k + 2] = f.z; xr[4 * k + 3] = f.w; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) { v[k] = 0.f; xr[k] = 0.f; }
+        }
+        a_store32(a_hi, a_lo, row, hf, v);
+        ET_PUBLISH_A();
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                umma_split_k64(t_o, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_ro), smem_u32(w_ro) + 8192, id64, 0u);
+                umma_commit(bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar, ph & 1); ++ph;
+        tc_fence_after();
+        {
+            uint32_t acc[32];
+            tmem_ld32(t_o + lane_off + hf * 32, acc);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) xr[k] += __uint_as_float(acc[k]) + s_rob[hf * 32 + k];
+        }
+        // ---- stage 2: q|k|v = LN2(x) . W^T + b
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = xr[k];
+        tc_fence_before();
+        ln_half(v, part, row, hf, s_g, s_b);
+        a_store32(a_hi, a_lo, row, hf, v);
+        ET_PUBLISH_A();
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                umma_split_k64(t_qkv, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_qkv), smem_u32(w_qkv) + 24576, id192, 0u);
+                umma_commit(bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar, ph & 1); ++ph;
+        tc_fence_after();
+        float qv[32];
+        {
+            uint32_t acc[32];
+            tmem_ld32(t_qkv + lane_off + hf * 32, acc);
+            // all keys of a padded site get the same logit (-10000, axial_attention.py:220-224): softmax is uniform, i.e. q = 0
+            const float qs = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale_log2e;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) qv[k] = (__uint_as_float(acc[k]) + s_qkvb[hf * 32 + k]) * qs;
+            tmem_ld32(t_qkv + lane_off + 64 + hf * 32, acc);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                st4(ks + row * 64 + hf * 32 + k * 4, make_float4(__uint_as_float(acc[4 * k]) + s_qkvb[64 + hf * 32 + 4 * k], __uint_as_float(acc[4 * k + 1]) + s_qkvb[64 + hf * 32 + 4 * k + 1],
+                                                                 __uint_as_float(acc[4 * k + 2]) + s_qkvb[64 + hf * 32 + 4 * k + 2], __uint_as_float(acc[4 * k + 3]) + s_qkvb[64 + hf * 32 + 4 * k + 3]));
+            tmem_ld32(t_qkv + lane_off + 128 + hf * 32, acc);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                st4(vs + row * 64 + hf * 32 + k * 4, make_float4(__uint_as_float(acc[4 * k]) + s_qkvb[128 + hf * 32 + 4 * k], __uint_as_float(acc[4 * k + 1]) + s_qkvb[128 + hf * 32 + 4 * k + 1],
+                                                                 __uint_as_float(acc[4 * k + 2]) + s_qkvb[128 + hf * 32 + 4 * k + 2], __uint_as_float(acc[4 * k + 3]) + s_qkvb[128 + hf * 32 + 4 * k + 3]));
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- stage 3: attention of token (site si, taxon r) over the R taxa of its site, heads hf*4 .. hf*4+3 (logits carry log2 e)
+        if (valid) {
+            const float* kb = ks + (size_t)si * R * 64 + hf * 32;
+            const float* vb = vs + (size_t)si * R * 64 + hf * 32;
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 2
+            for (int j = 0; j < R; ++j) {
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                    const float4 k0 = ld4(kb + j * 64 + hh * 8), k1 = ld4(kb + j * 64 + hh * 8 + 4);
+                    float s0 = qv[hh * 8] * k0.x, s1 = qv[hh * 8 + 4] * k1.x;
+                    s0 = fmaf(qv[hh * 8 + 1], k0.y, s0); s1 = fmaf(qv[hh * 8 + 5], k1.y, s1);
+                    s0 = fmaf(qv[hh * 8 + 2], k0.z, s0); s1 = fmaf(qv[hh * 8 + 6], k1.z, s1);
+                    s0 = fmaf(qv[hh * 8 + 3], k0.w, s0); s1 = fmaf(qv[hh * 8 + 7], k1.w, s1);
+                    mx[hh] = fmaxf(mx[hh], s0 + s1);
+                }
+            }
+            float l[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll 2
+            for (int j = 0; j < R; ++j) {
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                    const float4 k0 = ld4(kb + j * 64 + hh * 8), k1 = ld4(kb + j * 64 + hh * 8 + 4);
+                    float s0 = qv[hh * 8] * k0.x, s1 = qv[hh * 8 + 4] * k1.x;
+                    s0 = fmaf(qv[hh * 8 + 1], k0.y, s0); s1 = fmaf(qv[hh * 8 + 5], k1.y, s1);
+                    s0 = fmaf(qv[hh * 8 + 2], k0.z, s0); s1 = fmaf(qv[hh * 8 + 6], k1.z, s1);
+                    s0 = fmaf(qv[hh * 8 + 3], k0.w, s0); s1 = fmaf(qv[hh * 8 + 7], k1.w, s1);
+                    const float p = ex2_approx((s0 + s1) - mx[hh]);
+                    l[hh] += p;
+                    const float4 v0 = ld4(vb + j * 64 + hh * 8), v1 = ld4(vb + j * 64 + hh * 8 + 4);
+                    v[hh * 8] = fmaf(p, v0.x, v[hh * 8]); v[hh * 8 + 1] = fmaf(p, v0.y, v[hh * 8 + 1]);
+                    v[hh * 8 + 2] = fmaf(p, v0.z, v[hh * 8 + 2]); v[hh * 8 + 3] = fmaf(p, v0.w, v[hh * 8 + 3]);
+                    v[hh * 8 + 4] = fmaf(p, v1.x, v[hh * 8 + 4]); v[hh * 8 + 5] = fmaf(p, v1.y, v[hh * 8 + 5]);
+                    v[hh * 8 + 6] = fmaf(p, v1.z, v[hh * 8 + 6]); v[hh * 8 + 7] = fmaf(p, v1.w, v[hh * 8 + 7]);
+                }
+            }
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+                const float inv = 1.0f / l[hh];
+#pragma unroll
+                for (int d = 0; d < 8; ++d) v[hh * 8 + d] *= inv;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = 0.f;
+        }
+        // ---- stage 4: x += ctx_col . W_o^T + b_o
+        a_store32(a_hi, a_lo, row, hf, v);
+        ET_PUBLISH_A();
+        if (warp == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+                umma_split_k64(t_o, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_co), smem_u32(w_co) + 8192, id64, 0u);
+                umma_commit(bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar, ph & 1); ++ph;
+        tc_fence_after();
+        {
+            uint32_t acc[32];
+            tmem_ld32(t_o + lane_off + hf * 32, acc);
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    st4(xp + k * 4, make_float4(xr[4 * k] + __uint_as_float(acc[4 * k]) + s_cob[hf * 32 + 4 * k],
+                                                xr[4 * k + 1] + __uint_as_float(acc[4 * k + 1]) + s_cob[hf * 32 + 4 * k + 1],
+                                                xr[4 * k + 2] + __uint_as_float(acc[4 * k + 2]) + s_cob[hf * 32 + 4 * k + 2],
+                                                xr[4 * k + 3] + __uint_as_float(acc[4 * k + 3]) + s_cob[hf * 32 + 4 * k + 3]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// ------------------------------------------------------------------ site-major -> node-major (the NJ pool / public layout [B,R,C,64])
+__global__ void __launch_bounds__(256) k_sm_to_nm(const float* __restrict__ xs, size_t xs_tree_stride, float* __restrict__ out, size_t out_tree_stride,
+                                                  int R, int C) {
+    const int b = blockIdx.y;
+    const size_t n4 = (size_t)R * C * 16;
+    const float4* src = reinterpret_cast<const float4*>(xs + (size_t)b * xs_tree_stride);
+    float* dst = out + (size_t)b * out_tree_stride;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t tok = i >> 4;
+        const int c4 = (int)(i & 15);
+        const int c = (int)(tok / R), r = (int)(tok - (size_t)c * R);
+        st4(dst + ((size_t)r * C + c) * D + c4 * 4, src[i]);
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+static int g_sms = 0;
+static int sm_count() {
+    if (!g_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sms <= 0) g_sms = 148;
+    }
+    return g_sms;
+}
+
+static int enc_tc_attrs() {
+    static bool done = false;
+    if (done) return 0;
+    cudaError_t e = cudaFuncSetAttribute(k_enc_rowqkv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_ffn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM);
+    if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    done = true;
+    return 0;
+}
+
+#define ETC_DONE()                                                             \
+    do {                                                                       \
+        ++g_launches;                                                          \
+        prof_end(st);                                                          \
+        cudaError_t e_ = cudaGetLastError();                                   \
+        if (e_ != cudaSuccess) return set_cuda_error(e_, __FILE__, __LINE__);  \
+    } while (0)
+
+int launch_enc_rowqkv_tc(const Model* m, int layer, const float* xs, size_t xs_tree_stride, int B, int R, int C, float q_scale, const uint8_t* mask,
+                         void* qh, void* ql, void* kh, void* kl, void* vh, void* vl, cudaStream_t st) {
+    if (int e = enc_tc_attrs()) return e;
+    const LayerW& lw = m->layers[layer];
+    const EncTcW& tw = m->enc_tc[layer];
+    RowQkvArgs a;
+    a.x = xs; a.x_tree_stride = xs_tree_stride; a.R = R; a.C = C; a.B = B; a.tiles_per_tree = (R * C + 127) / 128;
+    a.w_img = tw.row_qkv; a.ln_g = lw.row.ln_g; a.ln_b = lw.row.ln_b; a.qkvb = tw.row_qkvb; a.q_scale = q_scale; a.mask = mask;
+    a.qh = (__nv_bfloat16*)qh; a.ql = (__nv_bfloat16*)ql; a.kh = (__nv_bfloat16*)kh; a.kl = (__nv_bfloat16*)kl;
+    a.vh = (__nv_bfloat16*)vh; a.vl = (__nv_bfloat16*)vl;
+    const int work = B * a.tiles_per_tree;
+    const int grid = work < 2 * sm_count() ? work : 2 * sm_count();
+    prof_begin(KC_LN_QKV, st);
+    k_enc_rowqkv_tc<<<grid, ET_THREADS, K1_SMEM, st>>>(a);
+    ETC_DONE();
+    return 0;
+}
+
+int launch_enc_colblock_tc(const Model* m, int layer, float* xs, size_t xs_tree_stride, const float* ctx, int B, int R, int C, const uint8_t* mask,
+                           cudaStream_t st) {
+    if (int e = enc_tc_attrs()) return e;
+    if (R > 128) return set_error(NNJ_ERR_INVALID, "encode: the fused column block handles at most 128 taxa");
+    const LayerW& lw = m->layers[layer];
+    const EncTcW& tw = m->enc_tc[layer];
+    ColBlkArgs a;
+    a.x = xs; a.x_tree_stride = xs_tree_stride; a.R = R; a.C = C; a.B = B; a.s = 128 / R; a.groups_per_tree = (C + a.s - 1) / a.s;
+    a.ctx = ctx; a.w_img = tw.row_o; a.rob = lw.row.ob; a.ln_g = lw.col.ln_g; a.ln_b = lw.col.ln_b; a.qkvb = tw.col_qkvb; a.cob = lw.col.ob;
+    a.q_scale_log2e = (1.0f / sqrtf((float)DH)) * 1.4426950408889634f; a.mask = mask;
+    const int work = B * a.groups_per_tree;
+    const int grid = work < sm_count() ? work : sm_count();
+    prof_begin(KC_COL_ATTN, st);
+    k_enc_colblock_tc<<<grid, ET_THREADS, K2_SMEM, st>>>(a);
+    ETC_DONE();
+    return 0;
+}
+
+int launch_enc_ffn_tc(const Model* m, int layer, float* xs, size_t xs_tree_stride, int B, int R, int C, cudaStream_t st) {
+    if (int e = enc_tc_attrs()) return e;
+    const LayerW& lw = m->layers[layer];
+    const EncTcW& tw = m->enc_tc[layer];
+    FfnTcArgs a;
+    a.x = xs; a.x_tree_stride = xs_tree_stride; a.T = R * C; a.B = B; a.tiles_per_tree = (R * C + 127) / 128;
+    a.w1 = tw.w1; a.w2 = tw.w2; a.ln_g = lw.ffn.ln_g; a.ln_b = lw.ffn.ln_b; a.b1 = lw.ffn.b1; a.b2 = lw.ffn.b2;
+    const int work = B * a.tiles_per_tree;
+    const int grid = work < sm_count() ? work : sm_count();
+    prof_begin(KC_FFN, st);
+    k_enc_ffn_tc<<<grid, ET_THREADS, K3_SMEM, st>>>(a);
+    ETC_DONE();
+    return 0;
+}
+
+int launch_sm_to_nm(const float* xs, size_t xs_tree_stride, float* out, size_t out_tree_stride, int B, int R, int C, cudaStream_t st) {
+    prof_begin(KC_MISC, st);
+    k_sm_to_nm<<<dim3(64, B), 256, 0, st>>>(xs, xs_tree_stride, out, out_tree_stride, R, C);
+    ETC_DONE();
+    return 0;
+}
+
+}  // namespace nnj

@@ -26,7 +26,14 @@ struct NjW {                                                        // model.py:
     float b2;                   // s_out.2 bias
 };
 
-struct NjBf { const void *wgh, *wgl, *wsh, *wsl; };   // g_linear_last / s_out.0 weights [out][in] as bf16 hi/lo planes
+struct NjBf { const void *wgh, *wgl, *wsh, *wsl; };
+// Encoder weights for the tcgen05 kernels: ready-to-copy shared-memory images (bf16 hi plane, then lo plane; every [N][64]
+// block K-major SWIZZLE_128B), one set per layer, plus the stacked q|k|v biases.
+struct EncTcW {
+    const uint4 *row_qkv, *row_o, *col_qkv, *col_o;   // 48 KB, 16 KB, 48 KB, 16 KB
+    const uint4 *w1, *w2;                              // fc1 [256][64]: 64 KB; fc2 [64][256]: 4 K-chunks of [64][64] per plane, 64 KB
+    const float *row_qkvb, *col_qkvb;                  // [192]
+};   // g_linear_last / s_out.0 weights [out][in] as bf16 hi/lo planes
 
 struct Model {
     nnj_config cfg;
@@ -38,6 +45,8 @@ struct Model {
     NjW nj;
     NjBf nj_bf;
     void* blob_bf;               // device allocation behind nj_bf
+    std::vector<EncTcW> enc_tc;  // per layer
+    void* blob_enc;              // device allocation behind enc_tc
     void* host_ws; size_t host_ws_bytes;   // grow-only device workspace of nnj_rollout_host
 };
 
@@ -78,12 +87,24 @@ int launch_tc_gemm(int cls, const void* Ah, const void* Al, const void* Bh, cons
 int launch_blend_planes(const float* X, const float* Y, size_t tree_stride, const int32_t* slot_of, int slot_stride, int C, const int32_t* pair_i,
                         const int32_t* pair_j, int pair_stride, int n0, int nc, int B, const float* bh, void* xh, void* xl, int pc,
                         cudaStream_t st);
+int launch_alpha_tc(const Model* m, const float* X, const float* Y, size_t tree_stride, const int32_t* slot_of, int slot_stride, const int32_t* pair_i,
+                    const int32_t* pair_j, int pair_stride, int n0, int nc, int S, int C, int B, const void* kp_h, const void* kp_l, void* xh,
+                    void* xl, int pc, float* alpha_part, int alpha_pairs, int nSG, int RP, cudaStream_t st);
 int launch_score_tc(const Model* m, const void* xh, const void* xl, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
                     int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,
                     int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, cudaStream_t st);
 int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, int bn, int nsplit, int chunks_per_split, size_t split_stride,
                       cudaStream_t st);
+int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
+                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st);
+// tcgen05 encoder kernels over the site-major residual stream (nnj_encoder_tc.cu)
+int launch_enc_rowqkv_tc(const Model* m, int layer, const float* xs, size_t xs_tree_stride, int B, int R, int C, float q_scale, const uint8_t* mask,
+                         void* qh, void* ql, void* kh, void* kl, void* vh, void* vl, cudaStream_t st);
+int launch_enc_colblock_tc(const Model* m, int layer, float* xs, size_t xs_tree_stride, const float* ctx, int B, int R, int C, const uint8_t* mask,
+                           cudaStream_t st);
+int launch_enc_ffn_tc(const Model* m, int layer, float* xs, size_t xs_tree_stride, int B, int R, int C, cudaStream_t st);
+int launch_sm_to_nm(const float* xs, size_t xs_tree_stride, float* out, size_t out_tree_stride, int B, int R, int C, cudaStream_t st);
 int run_tc_unit(const float* A, const float* B, float* Dm, int bn, cudaStream_t st);
 int run_gemm_split_bf16(const float* A, const float* B, float* Cm, int Z, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t st);
 

@@ -28,7 +28,9 @@ struct TcGemmArgs {
     int nsplit, chunks_per_split; size_t split_stride;
 };
 
-template <int BN>
+// BMN: B is given MN-major, [Z][K][N] with N contiguous (e.g. V of the row attention, [key site][taxon*8+d]); its tiles are loaded
+// as 64 x 64 boxes (64 N values = one 128-byte swizzle row per K index), the 64-column blocks of an N tile 8 KB apart.
+template <int BN, bool BMN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
           const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcGemmArgs g) {
@@ -73,13 +75,21 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
                 mbar_expect_tx(&full[s], STAGE);
                 tma_load_3d(st, &mapAh, &full[s], kc * TC_BK, m0, z);
                 tma_load_3d(st + TC_PLANE_BYTES, &mapAl, &full[s], kc * TC_BK, m0, z);
-                tma_load_3d(st + 2 * TC_PLANE_BYTES, &mapBh, &full[s], kc * TC_BK, n0, z);
-                tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE, &mapBl, &full[s], kc * TC_BK, n0, z);
+                if (BMN) {
+#pragma unroll
+                    for (int nb = 0; nb < BN / 64; ++nb) {
+                        tma_load_3d(st + 2 * TC_PLANE_BYTES + nb * 8192, &mapBh, &full[s], n0 + nb * 64, kc * TC_BK, z);
+                        tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE + nb * 8192, &mapBl, &full[s], n0 + nb * 64, kc * TC_BK, z);
+                    }
+                } else {
+                    tma_load_3d(st + 2 * TC_PLANE_BYTES, &mapBh, &full[s], kc * TC_BK, n0, z);
+                    tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE, &mapBl, &full[s], kc * TC_BK, n0, z);
+                }
             }
             __syncwarp();
         }
     } else if (warp == 1) {
-        const uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+        const uint32_t idesc = umma_idesc_bf16(TC_BM, BN) | (BMN ? (1u << 16) : 0u);
         for (int kk = 0; kk < nchunks; ++kk) {
             const int s = kk % TC_STAGES, kc = kc0 + kk;
             mbar_wait(&full[s], (kk / TC_STAGES) & 1);
@@ -92,7 +102,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
                 for (int k = 0; k < ksteps; ++k) {
                     const uint32_t ko = k * 32;   // 16 bf16 = 32 B inside the 128 B swizzle row
                     const uint64_t dah = umma_desc_k128(a_hi + ko), dal = umma_desc_k128(a_lo + ko);
-                    const uint64_t dbh = umma_desc_k128(b_hi + ko), dbl = umma_desc_k128(b_lo + ko);
+                    const uint64_t dbh = BMN ? umma_desc_lbo(b_hi + k * 2048, 8192) : umma_desc_k128(b_hi + ko);   // MN-major: 16 K rows = 2 KB per step
+                    const uint64_t dbl = BMN ? umma_desc_lbo(b_lo + k * 2048, 8192) : umma_desc_k128(b_lo + ko);
                     umma_bf16(tmem_base, dal, dbh, idesc, (kk | k) ? 1u : 0u);   // small terms first
                     umma_bf16(tmem_base, dah, dbl, idesc, 1u);
                     umma_bf16(tmem_base, dah, dbh, idesc, 1u);
@@ -272,6 +283,48 @@ int make_tmap_k_major(CUtensorMap* map, const void* base, int K, int rows, int Z
     return 0;
 }
 
+// 3-D bf16 tensor [Z][K][N] (N contiguous, pitch ld elements), box 64 (N) x 64 (K) x 1, SWIZZLE_128B: MN-major B operand tiles.
+static int make_tmap_mn_major(CUtensorMap* map, const void* base, int N, int K, int Z, size_t ld, size_t sz) {
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return set_error(NNJ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    if ((ld * 2) % 16 != 0 || (sz * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15))
+        return set_error(NNJ_ERR_INVALID, "tensor-core path: operand rows must be 16-byte aligned");
+    cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)K, (cuuint64_t)Z};
+    cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)sz * 2};
+    cuuint32_t box[3] = {64, 64, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(NNJ_ERR_CUDA, "cuTensorMapEncodeTiled failed (MN-major operand)");
+    return 0;
+}
+
+// C[z] = (Ah+Al)[z] * (Bh+Bl)[z] with B MN-major: B planes [Z][K][N] (N contiguous, pitch ldb).  128 x 128 tiles.
+int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
+                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st) {
+    static bool attr = false;
+    constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
+        if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+        attr = true;
+    }
+    CUtensorMap mAh, mAl, mBh, mBl;
+    if (int e = make_tmap_k_major(&mAh, Ah, K, M, Z, lda, sA, TC_BM)) return e;
+    if (int e = make_tmap_k_major(&mAl, Al, K, M, Z, lda, sA, TC_BM)) return e;
+    if (int e = make_tmap_mn_major(&mBh, Bh, N, K, Z, ldb, sB)) return e;
+    if (int e = make_tmap_mn_major(&mBl, Bl, N, K, Z, ldb, sB)) return e;
+    TcGemmArgs g{Cm, M, N, K, ldc, sC, 1, (K + TC_BK - 1) / TC_BK, 0};
+    const dim3 grid((N + 127) / 128, (M + TC_BM - 1) / TC_BM, Z);
+    prof_begin(cls, st);
+    k_tc_gemm<128, true><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g);
+    ++g_launches;
+    prof_end(st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    return 0;
+}
+
 // C[z] = (Ah+Al)[z] * (Bh+Bl)[z]^T.  A planes [Z][M][K] (pitch lda, batch stride sA), B planes [Z][N][K].
 // bn = 128 or 64 (N tile); nsplit > 1 splits K into nsplit ranges of chunks_per_split 64-element chunks, split s writing
 // its partial tile at C + s*split_stride.
@@ -282,8 +335,8 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
     constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256;
     constexpr int SMEM64 = TC_STAGES * (3 * TC_PLANE_BYTES) + 1024 + 256;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64);
+        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
         attr = true;
     }
@@ -295,8 +348,8 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
     TcGemmArgs g{Cm, M, N, K, ldc, sC, nsplit, chunks_per_split, split_stride};
     const dim3 grid(((N + bn - 1) / bn) * nsplit, (M + TC_BM - 1) / TC_BM, Z);
     prof_begin(cls, st);
-    if (bn == 128) k_tc_gemm<128><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g);
-    else k_tc_gemm<64><<<grid, TC_THREADS, SMEM64, st>>>(mAh, mAl, mBh, mBl, g);
+    if (bn == 128) k_tc_gemm<128, false><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g);
+    else k_tc_gemm<64, false><<<grid, TC_THREADS, SMEM64, st>>>(mAh, mAl, mBh, mBl, g);
     ++g_launches;
     prof_end(st);
     cudaError_t e = cudaGetLastError();

@@ -100,14 +100,72 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// two floats -> bf16x2 word (element 0 = a in the low half), round to nearest even: one cvt.rn.bf16x2.f32
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
 // pack (hi, lo) bf16 split of two floats: returns hi pair / lo pair as bf16x2 words (element 0 in the low half)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }          // element 0 of a bf16x2 word
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }  // element 1
+
+// ---- TMEM allocation (one warp, converged) and wider loads
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols));
+}
+// tcgen05.ld without the trailing wait: issue several, then tmem_ld_wait() once
+__device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- operand staging by threads: K-major SWIZZLE_128B tiles [rows][64 bf16] (128 B per row, 16-byte chunk j stored at j ^ (row & 7))
+// 8 consecutive K elements (chunk j) of one row, split into the hi / lo planes.
+__device__ __forceinline__ void a_store8(uint8_t* hi, uint8_t* lo, int row, int j, const float* v) {
+    uint4 hh, ll;
+    split2(v[0], v[1], hh.x, ll.x);
+    split2(v[2], v[3], hh.y, ll.y);
+    split2(v[4], v[5], hh.z, ll.z);
+    split2(v[6], v[7], hh.w, ll.w);
+    const int off = row * 128 + ((j ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(hi + off) = hh;
+    *reinterpret_cast<uint4*>(lo + off) = ll;
+}
+
+// D[128 x N] (+)= A[128 x 64] * W[N x 64]^T with the 3-product bf16 split; all four operands are K-major SWIZZLE_128B tiles
+// (A planes 16 KB, W planes N*128 B).  Call from ONE elected lane.  first_acc = 0 starts a fresh accumulator.
+__device__ __forceinline__ void umma_split_k64(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, uint32_t idesc,
+                                               uint32_t first_acc) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t ko = k * 32;   // 16 bf16 = 32 B inside the 128 B swizzle row
+        umma_bf16(tmem_d, umma_desc_k128(a_lo + ko), umma_desc_k128(w_hi + ko), idesc, (k | first_acc) ? 1u : 0u);   // small terms first
+        umma_bf16(tmem_d, umma_desc_k128(a_hi + ko), umma_desc_k128(w_lo + ko), idesc, 1u);
+        umma_bf16(tmem_d, umma_desc_k128(a_hi + ko), umma_desc_k128(w_hi + ko), idesc, 1u);
+    }
+}
 
 }  // namespace nnj
