@@ -19,8 +19,6 @@ namespace nnj {
 
 constexpr int ET_THREADS = 256;
 
-__device__ __forceinline__ uint8_t* align1024(uint8_t* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); }
-
 __device__ __forceinline__ void copy_img(uint8_t* dst, const uint4* __restrict__ src, int bytes) {
     for (int i = threadIdx.x; i < (bytes >> 4); i += ET_THREADS) reinterpret_cast<uint4*>(dst)[i] = __ldg(src + i);
 }
@@ -80,7 +78,7 @@ constexpr int K1_SMEM = 1024 + K1_W + 32768 + (192 + 128) * 4 + 2048 + 64;
 
 __global__ void __launch_bounds__(ET_THREADS, 2) k_enc_rowqkv_tc(const RowQkvArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = align1024(smem_raw);
+    uint8_t* sm = smem_align1024(smem_raw);
     uint8_t* w_s = sm;
     uint8_t* a_hi = sm + K1_W;
     uint8_t* a_lo = a_hi + 16384;
@@ -178,7 +176,7 @@ constexpr int K3_SMEM = 1024 + 2 * 65536 + 2 * 32768 + (256 + 64 + 128) * 4 + 20
 
 __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = align1024(smem_raw);
+    uint8_t* sm = smem_align1024(smem_raw);
     uint8_t* w1_s = sm;                       // hi 32 KB | lo 32 KB   ([256][64])
     uint8_t* w2_s = sm + 65536;               // hi: 4 K-chunks of 8 KB | lo: 4 K-chunks
     uint8_t* const abuf0 = sm + 131072;       // two operand buffers, each: hi 16 KB | lo 16 KB
@@ -285,21 +283,81 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
 }
 
 // ------------------------------------------------------------------ K2: row out_proj + residual, LN2, column attention block
+// 512 threads: warp w owns TMEM lane quarter w & 3 (row = 32*(w&3) + lane) and column quarter cq = w >> 2 (16 columns = heads
+// 2cq, 2cq+1), i.e. four threads per token row.  A tile holds s = 128 / rb whole sites, each in a block of rb = 32 / 64 / 128 rows
+// (the power of two >= R), so the 32 rows of a warp belong to one site and every key / value read is a single broadcast.
 struct ColBlkArgs {
     float* x; size_t x_tree_stride;             // site-major, updated in place
-    int R, C, B, s, groups_per_tree;            // s = 128 / R whole sites per tile
+    int R, C, B, rb_shift, groups_per_tree;     // rb = 1 << rb_shift rows per site block, s = 128 >> rb_shift sites per tile
     const float* ctx;                            // tied row-attention context fp32 [B,H,C,R*8]
     const uint4* w_img;                          // EncTcW::row_o | col_qkv | col_o, contiguous (80 KB)
     const float *rob, *ln_g, *ln_b, *qkvb, *cob;
     float q_scale_log2e; const uint8_t* mask;
 };
 
+constexpr int K2_THREADS = 512;
 constexpr int K2_W = 81920;
-constexpr int K2_SMEM = 1024 + K2_W + 32768 + 2 * 32768 + (64 + 192 + 64 + 128) * 4 + 2048 + 64;
+constexpr int K2_SMEM = 1024 + K2_W + 32768 + 2 * 32768 + (64 + 192 + 64 + 128) * 4 + 4096 + 64;
 
-__global__ void __launch_bounds__(ET_THREADS, 1) k_enc_colblock_tc(const ColBlkArgs a) {
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): one issue slot for two lanes of work
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float dot8(const float2 (&q)[4], float4 k0, float4 k1) {
+    float2 acc = fmul2(q[0], make_float2(k0.x, k0.y));
+    acc = ffma2(q[1], make_float2(k0.z, k0.w), acc);
+    acc = ffma2(q[2], make_float2(k1.x, k1.y), acc);
+    acc = ffma2(q[3], make_float2(k1.z, k1.w), acc);
+    return acc.x + acc.y;
+}
+
+// LayerNorm(64) of a row held as four 16-value quarters by threads (row, cq = 0..3); quarters combined pairwise (Chan), in the
+// same fixed order by all four threads.  Contains one __syncthreads.
+__device__ __forceinline__ void ln_quarter(float (&v)[16], float2* part, int row, int cq, const float* __restrict__ g, const float* __restrict__ bta) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += v[k];
+    const float mq = s * (1.0f / 16.0f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const float d = v[k] - mq; m2 = fmaf(d, d, m2); }
+    part[cq * 128 + row] = make_float2(mq, m2);
+    __syncthreads();
+    const float2 p0 = part[row], p1 = part[128 + row], p2 = part[256 + row], p3 = part[384 + row];
+    const float d01 = p0.x - p1.x, d23 = p2.x - p3.x;
+    const float m01 = 0.5f * (p0.x + p1.x), m23 = 0.5f * (p2.x + p3.x);
+    const float s01 = p0.y + p1.y + d01 * d01 * 8.0f, s23 = p2.y + p3.y + d23 * d23 * 8.0f;
+    const float mean = 0.5f * (m01 + m23), dm = m01 - m23;
+    const float var = (s01 + s23 + dm * dm * 16.0f) * (1.0f / 64.0f);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(g + cq * 16 + k), b4 = *reinterpret_cast<const float4*>(bta + cq * 16 + k);
+        v[k] = (v[k] - mean) * rstd * g4.x + b4.x;
+        v[k + 1] = (v[k + 1] - mean) * rstd * g4.y + b4.y;
+        v[k + 2] = (v[k + 2] - mean) * rstd * g4.z + b4.z;
+        v[k + 3] = (v[k + 3] - mean) * rstd * g4.w + b4.w;
+    }
+}
+
+__device__ __forceinline__ void a_store16(uint8_t* a_hi, uint8_t* a_lo, int row, int cq, const float (&v)[16]) {
+    a_store8(a_hi, a_lo, row, cq * 2, &v[0]);
+    a_store8(a_hi, a_lo, row, cq * 2 + 1, &v[8]);
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = align1024(smem_raw);
+    uint8_t* sm = smem_align1024(smem_raw);
     uint8_t* w_ro = sm;                        // row out_proj   hi 8 KB | lo 8 KB
     uint8_t* w_qkv = sm + 16384;               // column q|k|v   hi 24 KB | lo 24 KB
     uint8_t* w_co = sm + 65536;                // column out_proj
@@ -312,15 +370,15 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_colblock_tc(const ColBlkA
     float* s_cob = s_qkvb + 192;
     float* s_g = s_cob + 64;
     float* s_b = s_g + 64;
-    float2* part = reinterpret_cast<float2*>(s_b + 64);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(part + 256);
+    float2* part = reinterpret_cast<float2*>(s_b + 64);   // [4][128]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(part + 512);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane;
+    const int q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
     if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) tmem_alloc(tmem_slot, 256);
-    copy_img(sm, a.w_img, K2_W);
+    for (int i = tid; i < (K2_W >> 4); i += K2_THREADS) reinterpret_cast<uint4*>(sm)[i] = __ldg(a.w_img + i);
     if (tid < 192) s_qkvb[tid] = a.qkvb[tid];
     if (tid < 64) { s_rob[tid] = a.rob[tid]; s_cob[tid] = a.cob[tid]; s_g[tid] = a.ln_g[tid]; s_b[tid] = a.ln_b[tid]; }
     fence_async_smem();
@@ -332,31 +390,32 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_colblock_tc(const ColBlkA
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t id64 = umma_idesc_bf16(128, 64), id192 = umma_idesc_bf16(128, 192);
     const int R = a.R, KD = a.R * DH;
-    const int si = row / R, r = row - si * R;
+    const int rb = 1 << a.rb_shift, s_tile = 128 >> a.rb_shift;
+    const int si = row >> a.rb_shift, r = row & (rb - 1);
     const int n_work = a.B * a.groups_per_tree;
     uint32_t ph = 0;   // completions of `bar` so far
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int b = w / a.groups_per_tree, grp = w - b * a.groups_per_tree;
-        const int c = grp * a.s + si;
-        const bool valid = si < a.s && c < a.C;
-        float* xp = a.x + (size_t)b * a.x_tree_stride + ((size_t)c * R + r) * D + hf * 32;
-        float xr[32], v[32];
+        const int c = grp * s_tile + si;
+        const bool valid = r < R && c < a.C;
+        float* xp = a.x + (size_t)b * a.x_tree_stride + ((size_t)c * R + r) * D + cq * 16;
+        float xr[16], v[16];
         // ---- stage 1: x += ctx_row . W_o^T + b_o
         if (valid) {
 #pragma unroll
-            for (int hh = 0; hh < 4; ++hh) {
-                const float* cp = a.ctx + (((size_t)b * H + hf * 4 + hh) * a.C + c) * KD + (size_t)r * DH;
+            for (int hh = 0; hh < 2; ++hh) {
+                const float* cp = a.ctx + (((size_t)b * H + cq * 2 + hh) * a.C + c) * KD + (size_t)r * DH;
                 const float4 f0 = ld4(cp), f1 = ld4(cp + 4);
                 v[hh * 8] = f0.x; v[hh * 8 + 1] = f0.y; v[hh * 8 + 2] = f0.z; v[hh * 8 + 3] = f0.w;
                 v[hh * 8 + 4] = f1.x; v[hh * 8 + 5] = f1.y; v[hh * 8 + 6] = f1.z; v[hh * 8 + 7] = f1.w;
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const float4 f = ld4(xp + k * 4); xr[4 * k] = f.x; xr[4 * k + 1] = f.y; xr[4 * k + 2] = f.z; xr[4 * k + 3] = f.w; }
+            for (int k = 0; k < 4; ++k) { const float4 f = ld4(xp + k * 4); xr[4 * k] = f.x; xr[4 * k + 1] = f.y; xr[4 * k + 2] = f.z; xr[4 * k + 3] = f.w; }
         } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) { v[k] = 0.f; xr[k] = 0.f; }
+            for (int k = 0; k < 16; ++k) { v[k] = 0.f; xr[k] = 0.f; }
         }
-        a_store32(a_hi, a_lo, row, hf, v);
+        a_store16(a_hi, a_lo, row, cq, v);
         ET_PUBLISH_A();
         if (warp == 0) {
             tc_fence_after();
@@ -369,17 +428,18 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         mbar_wait(bar, ph & 1); ++ph;
         tc_fence_after();
         {
-            uint32_t acc[32];
-            tmem_ld32(t_o + lane_off + hf * 32, acc);
+            uint32_t acc[16];
+            tmem_ld16_nw(t_o + lane_off + cq * 16, acc);
+            tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) xr[k] += __uint_as_float(acc[k]) + s_rob[hf * 32 + k];
+            for (int k = 0; k < 16; ++k) xr[k] += __uint_as_float(acc[k]) + s_rob[cq * 16 + k];
         }
         // ---- stage 2: q|k|v = LN2(x) . W^T + b
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = xr[k];
+        for (int k = 0; k < 16; ++k) v[k] = xr[k];
         tc_fence_before();
-        ln_half(v, part, row, hf, s_g, s_b);
-        a_store32(a_hi, a_lo, row, hf, v);
+        ln_quarter(v, part, row, cq, s_g, s_b);
+        a_store16(a_hi, a_lo, row, cq, v);
         ET_PUBLISH_A();
         if (warp == 0) {
             tc_fence_after();
@@ -391,77 +451,81 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         }
         mbar_wait(bar, ph & 1); ++ph;
         tc_fence_after();
-        float qv[32];
+        float2 q0[4], q1[4];   // heads 2cq, 2cq+1 (scaled by dh^-0.5 log2 e)
         {
-            uint32_t acc[32];
-            tmem_ld32(t_qkv + lane_off + hf * 32, acc);
+            uint32_t aq[16], ak[16], av[16];
+            tmem_ld16_nw(t_qkv + lane_off + cq * 16, aq);
+            tmem_ld16_nw(t_qkv + lane_off + 64 + cq * 16, ak);
+            tmem_ld16_nw(t_qkv + lane_off + 128 + cq * 16, av);
+            tmem_ld_wait();
             // all keys of a padded site get the same logit (-10000, axial_attention.py:220-224): softmax is uniform, i.e. q = 0
             const float qs = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale_log2e;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) qv[k] = (__uint_as_float(acc[k]) + s_qkvb[hf * 32 + k]) * qs;
-            tmem_ld32(t_qkv + lane_off + 64 + hf * 32, acc);
+            for (int k = 0; k < 4; ++k) {
+                q0[k] = make_float2((__uint_as_float(aq[2 * k]) + s_qkvb[cq * 16 + 2 * k]) * qs, (__uint_as_float(aq[2 * k + 1]) + s_qkvb[cq * 16 + 2 * k + 1]) * qs);
+                q1[k] = make_float2((__uint_as_float(aq[8 + 2 * k]) + s_qkvb[cq * 16 + 8 + 2 * k]) * qs, (__uint_as_float(aq[8 + 2 * k + 1]) + s_qkvb[cq * 16 + 8 + 2 * k + 1]) * qs);
+            }
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                st4(ks + row * 64 + hf * 32 + k * 4, make_float4(__uint_as_float(acc[4 * k]) + s_qkvb[64 + hf * 32 + 4 * k], __uint_as_float(acc[4 * k + 1]) + s_qkvb[64 + hf * 32 + 4 * k + 1],
-                                                                 __uint_as_float(acc[4 * k + 2]) + s_qkvb[64 + hf * 32 + 4 * k + 2], __uint_as_float(acc[4 * k + 3]) + s_qkvb[64 + hf * 32 + 4 * k + 3]));
-            tmem_ld32(t_qkv + lane_off + 128 + hf * 32, acc);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                st4(vs + row * 64 + hf * 32 + k * 4, make_float4(__uint_as_float(acc[4 * k]) + s_qkvb[128 + hf * 32 + 4 * k], __uint_as_float(acc[4 * k + 1]) + s_qkvb[128 + hf * 32 + 4 * k + 1],
-                                                                 __uint_as_float(acc[4 * k + 2]) + s_qkvb[128 + hf * 32 + 4 * k + 2], __uint_as_float(acc[4 * k + 3]) + s_qkvb[128 + hf * 32 + 4 * k + 3]));
+            for (int k = 0; k < 4; ++k) {
+                st4(ks + row * 64 + cq * 16 + k * 4, make_float4(__uint_as_float(ak[4 * k]) + s_qkvb[64 + cq * 16 + 4 * k], __uint_as_float(ak[4 * k + 1]) + s_qkvb[64 + cq * 16 + 4 * k + 1],
+                                                                 __uint_as_float(ak[4 * k + 2]) + s_qkvb[64 + cq * 16 + 4 * k + 2], __uint_as_float(ak[4 * k + 3]) + s_qkvb[64 + cq * 16 + 4 * k + 3]));
+                st4(vs + row * 64 + cq * 16 + k * 4, make_float4(__uint_as_float(av[4 * k]) + s_qkvb[128 + cq * 16 + 4 * k], __uint_as_float(av[4 * k + 1]) + s_qkvb[128 + cq * 16 + 4 * k + 1],
+                                                                 __uint_as_float(av[4 * k + 2]) + s_qkvb[128 + cq * 16 + 4 * k + 2], __uint_as_float(av[4 * k + 3]) + s_qkvb[128 + cq * 16 + 4 * k + 3]));
+            }
         }
         tc_fence_before();
         __syncthreads();
-        // ---- stage 3: attention of token (site si, taxon r) over the R taxa of its site, heads hf*4 .. hf*4+3 (logits carry log2 e)
+        // ---- stage 3: attention of token (site si, taxon r) over the R taxa of its site; online softmax, rescaling only when the
+        //      running maximum moves (logits carry log2 e, probabilities are exp2)
         if (valid) {
-            const float* kb = ks + (size_t)si * R * 64 + hf * 32;
-            const float* vb = vs + (size_t)si * R * 64 + hf * 32;
-            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 2
-            for (int j = 0; j < R; ++j) {
-#pragma unroll
-                for (int hh = 0; hh < 4; ++hh) {
-                    const float4 k0 = ld4(kb + j * 64 + hh * 8), k1 = ld4(kb + j * 64 + hh * 8 + 4);
-                    float s0 = qv[hh * 8] * k0.x, s1 = qv[hh * 8 + 4] * k1.x;
-                    s0 = fmaf(qv[hh * 8 + 1], k0.y, s0); s1 = fmaf(qv[hh * 8 + 5], k1.y, s1);
-                    s0 = fmaf(qv[hh * 8 + 2], k0.z, s0); s1 = fmaf(qv[hh * 8 + 6], k1.z, s1);
-                    s0 = fmaf(qv[hh * 8 + 3], k0.w, s0); s1 = fmaf(qv[hh * 8 + 7], k1.w, s1);
-                    mx[hh] = fmaxf(mx[hh], s0 + s1);
-                }
+            const float* kb = ks + ((size_t)si << a.rb_shift) * 64 + cq * 16;
+            const float* vb = vs + ((size_t)si << a.rb_shift) * 64 + cq * 16;
+            float m0 = dot8(q0, ld4(kb), ld4(kb + 4)), m1 = dot8(q1, ld4(kb + 8), ld4(kb + 12));
+            float l0 = 1.0f, l1 = 1.0f;
+            float2 o0[4], o1[4];
+            {
+                const float4 v0 = ld4(vb), v1 = ld4(vb + 4), v2 = ld4(vb + 8), v3 = ld4(vb + 12);
+                o0[0] = make_float2(v0.x, v0.y); o0[1] = make_float2(v0.z, v0.w); o0[2] = make_float2(v1.x, v1.y); o0[3] = make_float2(v1.z, v1.w);
+                o1[0] = make_float2(v2.x, v2.y); o1[1] = make_float2(v2.z, v2.w); o1[2] = make_float2(v3.x, v3.y); o1[3] = make_float2(v3.z, v3.w);
             }
-            float l[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = 0.f;
 #pragma unroll 2
-            for (int j = 0; j < R; ++j) {
-#pragma unroll
-                for (int hh = 0; hh < 4; ++hh) {
-                    const float4 k0 = ld4(kb + j * 64 + hh * 8), k1 = ld4(kb + j * 64 + hh * 8 + 4);
-                    float s0 = qv[hh * 8] * k0.x, s1 = qv[hh * 8 + 4] * k1.x;
-                    s0 = fmaf(qv[hh * 8 + 1], k0.y, s0); s1 = fmaf(qv[hh * 8 + 5], k1.y, s1);
-                    s0 = fmaf(qv[hh * 8 + 2], k0.z, s0); s1 = fmaf(qv[hh * 8 + 6], k1.z, s1);
-                    s0 = fmaf(qv[hh * 8 + 3], k0.w, s0); s1 = fmaf(qv[hh * 8 + 7], k1.w, s1);
-                    const float p = ex2_approx((s0 + s1) - mx[hh]);
-                    l[hh] += p;
-                    const float4 v0 = ld4(vb + j * 64 + hh * 8), v1 = ld4(vb + j * 64 + hh * 8 + 4);
-                    v[hh * 8] = fmaf(p, v0.x, v[hh * 8]); v[hh * 8 + 1] = fmaf(p, v0.y, v[hh * 8 + 1]);
-                    v[hh * 8 + 2] = fmaf(p, v0.z, v[hh * 8 + 2]); v[hh * 8 + 3] = fmaf(p, v0.w, v[hh * 8 + 3]);
-                    v[hh * 8 + 4] = fmaf(p, v1.x, v[hh * 8 + 4]); v[hh * 8 + 5] = fmaf(p, v1.y, v[hh * 8 + 5]);
-                    v[hh * 8 + 6] = fmaf(p, v1.z, v[hh * 8 + 6]); v[hh * 8 + 7] = fmaf(p, v1.w, v[hh * 8 + 7]);
+            for (int j = 1; j < R; ++j) {
+                const float* kj = kb + j * 64;
+                const float* vj = vb + j * 64;
+                const float s0 = dot8(q0, ld4(kj), ld4(kj + 4)), s1 = dot8(q1, ld4(kj + 8), ld4(kj + 12));
+                const float4 v0 = ld4(vj), v1 = ld4(vj + 4), v2 = ld4(vj + 8), v3 = ld4(vj + 12);
+                if (s0 > m0) {
+                    const float f = ex2_approx(m0 - s0);
+                    const float2 ff = make_float2(f, f);
+                    l0 *= f; m0 = s0;
+                    o0[0] = fmul2(o0[0], ff); o0[1] = fmul2(o0[1], ff); o0[2] = fmul2(o0[2], ff); o0[3] = fmul2(o0[3], ff);
                 }
+                if (s1 > m1) {
+                    const float f = ex2_approx(m1 - s1);
+                    const float2 ff = make_float2(f, f);
+                    l1 *= f; m1 = s1;
+                    o1[0] = fmul2(o1[0], ff); o1[1] = fmul2(o1[1], ff); o1[2] = fmul2(o1[2], ff); o1[3] = fmul2(o1[3], ff);
+                }
+                const float p0 = ex2_approx(s0 - m0), p1 = ex2_approx(s1 - m1);
+                const float2 pp0 = make_float2(p0, p0), pp1 = make_float2(p1, p1);
+                l0 += p0; l1 += p1;
+                o0[0] = ffma2(pp0, make_float2(v0.x, v0.y), o0[0]); o0[1] = ffma2(pp0, make_float2(v0.z, v0.w), o0[1]);
+                o0[2] = ffma2(pp0, make_float2(v1.x, v1.y), o0[2]); o0[3] = ffma2(pp0, make_float2(v1.z, v1.w), o0[3]);
+                o1[0] = ffma2(pp1, make_float2(v2.x, v2.y), o1[0]); o1[1] = ffma2(pp1, make_float2(v2.z, v2.w), o1[1]);
+                o1[2] = ffma2(pp1, make_float2(v3.x, v3.y), o1[2]); o1[3] = ffma2(pp1, make_float2(v3.z, v3.w), o1[3]);
             }
+            const float i0 = 1.0f / l0, i1 = 1.0f / l1;
 #pragma unroll
-            for (int hh = 0; hh < 4; ++hh) {
-                const float inv = 1.0f / l[hh];
-#pragma unroll
-                for (int d = 0; d < 8; ++d) v[hh * 8 + d] *= inv;
+            for (int k = 0; k < 4; ++k) {
+                v[2 * k] = o0[k].x * i0; v[2 * k + 1] = o0[k].y * i0;
+                v[8 + 2 * k] = o1[k].x * i1; v[8 + 2 * k + 1] = o1[k].y * i1;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = 0.f;
+            for (int k = 0; k < 16; ++k) v[k] = 0.f;
         }
         // ---- stage 4: x += ctx_col . W_o^T + b_o
-        a_store32(a_hi, a_lo, row, hf, v);
+        a_store16(a_hi, a_lo, row, cq, v);
         ET_PUBLISH_A();
         if (warp == 0) {
             tc_fence_after();
@@ -474,15 +538,16 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         mbar_wait(bar, ph & 1); ++ph;
         tc_fence_after();
         {
-            uint32_t acc[32];
-            tmem_ld32(t_o + lane_off + hf * 32, acc);
+            uint32_t acc[16];
+            tmem_ld16_nw(t_o + lane_off + cq * 16, acc);
+            tmem_ld_wait();
             if (valid) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    st4(xp + k * 4, make_float4(xr[4 * k] + __uint_as_float(acc[4 * k]) + s_cob[hf * 32 + 4 * k],
-                                                xr[4 * k + 1] + __uint_as_float(acc[4 * k + 1]) + s_cob[hf * 32 + 4 * k + 1],
-                                                xr[4 * k + 2] + __uint_as_float(acc[4 * k + 2]) + s_cob[hf * 32 + 4 * k + 2],
-                                                xr[4 * k + 3] + __uint_as_float(acc[4 * k + 3]) + s_cob[hf * 32 + 4 * k + 3]));
+                for (int k = 0; k < 4; ++k)
+                    st4(xp + k * 4, make_float4(xr[4 * k] + __uint_as_float(acc[4 * k]) + s_cob[cq * 16 + 4 * k],
+                                                xr[4 * k + 1] + __uint_as_float(acc[4 * k + 1]) + s_cob[cq * 16 + 4 * k + 1],
+                                                xr[4 * k + 2] + __uint_as_float(acc[4 * k + 2]) + s_cob[cq * 16 + 4 * k + 2],
+                                                xr[4 * k + 3] + __uint_as_float(acc[4 * k + 3]) + s_cob[cq * 16 + 4 * k + 3]));
             }
         }
         tc_fence_before();
@@ -562,13 +627,15 @@ int launch_enc_colblock_tc(const Model* m, int layer, float* xs, size_t xs_tree_
     const LayerW& lw = m->layers[layer];
     const EncTcW& tw = m->enc_tc[layer];
     ColBlkArgs a;
-    a.x = xs; a.x_tree_stride = xs_tree_stride; a.R = R; a.C = C; a.B = B; a.s = 128 / R; a.groups_per_tree = (C + a.s - 1) / a.s;
+    a.rb_shift = R <= 32 ? 5 : (R <= 64 ? 6 : 7);
+    const int s_tile = 128 >> a.rb_shift;
+    a.x = xs; a.x_tree_stride = xs_tree_stride; a.R = R; a.C = C; a.B = B; a.groups_per_tree = (C + s_tile - 1) / s_tile;
     a.ctx = ctx; a.w_img = tw.row_o; a.rob = lw.row.ob; a.ln_g = lw.col.ln_g; a.ln_b = lw.col.ln_b; a.qkvb = tw.col_qkvb; a.cob = lw.col.ob;
     a.q_scale_log2e = (1.0f / sqrtf((float)DH)) * 1.4426950408889634f; a.mask = mask;
     const int work = B * a.groups_per_tree;
     const int grid = work < sm_count() ? work : sm_count();
     prof_begin(KC_COL_ATTN, st);
-    k_enc_colblock_tc<<<grid, ET_THREADS, K2_SMEM, st>>>(a);
+    k_enc_colblock_tc<<<grid, K2_THREADS, K2_SMEM, st>>>(a);
     ETC_DONE();
     return 0;
 }

@@ -12,6 +12,8 @@
 // new node into a free slot ("slot i <- new, slot j removed" becomes a table update).
 // All cross-CTA reductions go through partial buffers summed in a fixed order: results are
 // run-to-run deterministic.
+#include <cstdlib>
+
 #include "nnj_internal.h"
 #include "nnj_tc.cuh"
 
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(NTHREADS) k_alpha_softmax(const float* __restr
                                                             const int32_t* __restrict__ slot_of, int slot_stride, int S, int nCT,
                                                             int Rp, const int32_t* __restrict__ pair_i, const int32_t* __restrict__ pair_j,
                                                             int pair_stride, int n0, int nc, int nSB, int RP, float inv_scale,
-                                                            float* __restrict__ alpha, int by_slot) {
+                                                            float* __restrict__ alpha, int by_slot, int n_part) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * 8 + warp, b = blockIdx.y;
     if (n >= nc) return;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(NTHREADS) k_alpha_softmax(const float* __restr
     for (int r = lane; r < Rp; r += 32) {
         float s = 0.f;
         const int col = by_slot ? so[r] : r;   // tensor-core alpha partials are indexed by physical slot
-        for (int k = 0; k < nSB; ++k) s += ap[(size_t)k * RP + col];
+        for (int k = 0; k < n_part; ++k) s += ap[(size_t)k * RP + col];   // n_part <= nSB partials, fixed order
         const float* kp = kap + ((size_t)b * S + so[r]) * nCT;
         float kk = 0.f;
         for (int k = 0; k < nCT; ++k) kk += kp[k];
@@ -828,16 +830,26 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
     for (int n0 = 0; n0 < N; n0 += step) {
         const int nc = (N - n0 < step) ? (N - n0) : step;
         if (glob && tc) {
-            // x planes -> alpha partials on tcgen05 (split-K over site blocks, indexed by physical slot) -> softmax -> fused score kernel
-            if (int e = launch_blend_planes(pool.X, pool.Y, pool.tree_stride, slot, nb.S, C, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, B,
-                                            m->nj.bh, nb.xh, nb.xl, TC_PAIRS, st)) return e;
-            const size_t KK = (size_t)C * D;
-            if (int e = launch_tc_gemm_ex(KC_ALPHA, nb.xh, nb.xl, nb.kp_h, nb.kp_l, nb.alpha_part, B, nc, nb.S, (int)KK, KK, (size_t)TC_PAIRS * KK, KK,
-                                          (size_t)nb.S * KK, nb.nSB * nb.RP, (size_t)PAIR_CHUNK * nb.nSB * nb.RP, 64, nb.nSB, SB_SITES, nb.RP, st))
-                return e;
+            // blend + alpha partials in one tcgen05 kernel (x planes written on the way, partials per 64-site group, indexed by
+            // physical slot) -> softmax -> fused score kernel.  NNJ_ALPHA_FUSED=1 selects it; the default is the two-kernel form (blend, split-K GEMM), measured faster.
+            static int fused = -1;
+            if (fused < 0) { const char* ev = getenv("NNJ_ALPHA_FUSED"); fused = ev ? atoi(ev) : 0; }
+            int n_part = nb.nSB;
+            if (fused) {
+                n_part = (C + 63) / 64;
+                if (int e = launch_alpha_tc(m, pool.X, pool.Y, pool.tree_stride, slot, nb.S, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, nb.S, C, B,
+                                            nb.kp_h, nb.kp_l, nb.xh, nb.xl, TC_PAIRS, nb.alpha_part, PAIR_CHUNK, nb.nSB, nb.RP, st)) return e;
+            } else {
+                if (int e = launch_blend_planes(pool.X, pool.Y, pool.tree_stride, slot, nb.S, C, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, B,
+                                                m->nj.bh, nb.xh, nb.xl, TC_PAIRS, st)) return e;
+                const size_t KK = (size_t)C * D;
+                if (int e = launch_tc_gemm_ex(KC_ALPHA, nb.xh, nb.xl, nb.kp_h, nb.kp_l, nb.alpha_part, B, nc, nb.S, (int)KK, KK, (size_t)TC_PAIRS * KK, KK,
+                                              (size_t)nb.S * KK, nb.nSB * nb.RP, (size_t)PAIR_CHUNK * nb.nSB * nb.RP, 64, nb.nSB, SB_SITES, nb.RP, st))
+                    return e;
+            }
             prof_begin(KC_ALPHA_SOFTMAX, st);
             k_alpha_softmax<<<dim3((nc + 7) / 8, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
-                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha, 1);
+                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha, 1, n_part);
             LAUNCH_CHECK();
             if (int e = launch_score_tc(m, nb.xh, nb.xl, TC_PAIRS, nb.nodes_h, nb.nodes_l, nb.alpha, nb.RP, PAIR_CHUNK, slot, nb.S, nb.pair_i,
                                         nb.pair_stride, n0, nc, Rp, nb.S, C, B, mask, nb.score_part, nb.nSB, st)) return e;
@@ -849,7 +861,7 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
             LAUNCH_CHECK();
             prof_begin(KC_ALPHA_SOFTMAX, st);
             k_alpha_softmax<<<dim3((nc + 7) / 8, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
-                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha, 0);
+                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha, 0, nb.nSB);
             LAUNCH_CHECK();
             prof_begin(KC_SCORE, st);
             k_score<true><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
@@ -881,7 +893,7 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
         // pair list for the softmax kernel: reuse it with one pair per tree = ij itself
         prof_begin(KC_ALPHA_SOFTMAX, st);
         k_alpha_softmax<<<dim3(1, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, ij, ij + 1, ij_stride, 0, 1,
-                                                         nb.nSB, nb.RP, inv_scale, nb.alpha, 0);
+                                                         nb.nSB, nb.RP, inv_scale, nb.alpha, 0, nb.nSB);
         LAUNCH_CHECK();
         prof_begin(KC_MERGE, st);
         k_merge<true><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,

@@ -95,16 +95,14 @@ template <int NCOL>
 __device__ __forceinline__ void blend_site(const AlphaTcArgs& a, const float* __restrict__ xi_p, const float* __restrict__ xj_p,
                                            const float* __restrict__ yi_p, const float* __restrict__ yj_p, const float* __restrict__ s_bh,
                                            uint8_t* a_hi, uint8_t* a_lo, int row, int col0, uint4* __restrict__ gxh, uint4* __restrict__ gxl) {
-    float4 xi[NCOL / 4], xj[NCOL / 4], yi[NCOL / 4], yj[NCOL / 4];
-#pragma unroll
-    for (int e = 0; e < NCOL / 4; ++e) { xi[e] = ld4(xi_p + 4 * e); xj[e] = ld4(xj_p + 4 * e); yi[e] = ld4(yi_p + 4 * e); yj[e] = ld4(yj_p + 4 * e); }
 #pragma unroll
     for (int e = 0; e < NCOL / 8; ++e) {
         float v[8];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bh + col0 + 8 * e + 4 * h2);
-            const float4 xa = xi[2 * e + h2], xb = xj[2 * e + h2], ya = yi[2 * e + h2], yb = yj[2 * e + h2];
+            const int o = 8 * e + 4 * h2;
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bh + col0 + o);
+            const float4 xa = ld4(xi_p + o), xb = ld4(xj_p + o), ya = ld4(yi_p + o), yb = ld4(yj_p + o);
             v[4 * h2 + 0] = fmaf(sigmoid_fast(ya.x - yb.x + b4.x), xa.x - xb.x, xb.x);   // z x_i + (1-z) x_j
             v[4 * h2 + 1] = fmaf(sigmoid_fast(ya.y - yb.y + b4.y), xa.y - xb.y, xb.y);
             v[4 * h2 + 2] = fmaf(sigmoid_fast(ya.z - yb.z + b4.z), xa.z - xb.z, xb.z);
@@ -126,7 +124,7 @@ __device__ __forceinline__ void blend_site(const AlphaTcArgs& a, const float* __
 __global__ void __launch_bounds__(AT_THREADS, 2)
 k_alpha_tc(const __grid_constant__ CUtensorMap mapKh, const __grid_constant__ CUtensorMap mapKl, const AlphaTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sm = smem_align1024(smem_raw);
     int* s_pi = reinterpret_cast<int*>(sm + AT_MISC);      // physical slots of the pair rows (-1: no pair)
     int* s_pj = s_pi + 128;
     float* s_bh = reinterpret_cast<float*>(s_pj + 128);
@@ -349,7 +347,7 @@ __device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiC
 __global__ void __launch_bounds__(ST_THREADS, 1)
 k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl, const ScoreTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sm = smem_align1024(smem_raw);
     float* s_bias = reinterpret_cast<float*>(sm + ST_MISC);            // bg[64] | bs[64] | w2[64]
     float* s_part = s_bias + 192;                                       // [2 pipelines][4 column slots][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 1024);        // per pipeline: bx_full, d1_done, a1_ready, s_done

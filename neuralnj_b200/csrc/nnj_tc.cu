@@ -37,7 +37,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     constexpr int B_PLANE = BN * TC_BK * 2;
     constexpr int STAGE = 2 * TC_PLANE_BYTES + 2 * B_PLANE;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* tiles = smem_align1024(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * STAGE);
     uint64_t* empty = full + TC_STAGES;
     uint64_t* accum_done = empty + TC_STAGES;
@@ -173,7 +173,7 @@ template <int BN>
 __global__ void __launch_bounds__(128, 1) k_tc_unit(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ Dm) {
     // B [64 (K) x BN (N)] MN-major: BN/64 column blocks of [64 rows x 128 B], 8 KB apart (LBO) within each plane
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* base = smem_align1024(smem_raw);
     uint8_t *a_hi = base, *a_lo = base + 16384, *b_hi = base + 32768, *b_lo = base + 32768 + 16384;
     uint64_t* done = reinterpret_cast<uint64_t*>(base + 65536);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);

@@ -8,6 +8,10 @@ namespace nnj {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 1024-byte aligned start inside the dynamic shared-memory window.  Pure pointer arithmetic on the __shared__ array (no integer
+// round trip), so the compiler keeps the shared address space and emits LDS / STS instead of generic LD / ST.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

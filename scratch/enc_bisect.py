@@ -20,7 +20,7 @@ for nl in (1, 6):
         err = float((got - want).abs().max())
         print(f"  layers={nl} B={B} R={R} L={L} pad={pad}: max|err|={err:.3e} {'OK' if err < 2e-4 else 'FAIL'}", flush=True)
 ''' % (ROOT, ROOT)
-for mk in (0, 1, 4, 2, 7):
+for mk in [int(v) for v in (sys.argv[1:] or ["0", "1", "4", "2", "7"])]:
     print(f"== NNJ_ENC_TC={mk}", flush=True)
     env = dict(os.environ, NNJ_ENC_TC=str(mk))
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=600)
