@@ -12,8 +12,6 @@
 // new node into a free slot ("slot i <- new, slot j removed" becomes a table update).
 // All cross-CTA reductions go through partial buffers summed in a fixed order: results are
 // run-to-run deterministic.
-#include <cstdlib>
-
 #include "nnj_internal.h"
 #include "nnj_tc.cuh"
 
@@ -745,11 +743,11 @@ struct NjBuffers {
     float *Y, *K, *kap, *alpha_part, *alpha, *score_part, *new_scores, *logits[2], *newx;
     int32_t *slot[2], *free_slot, *new_slot, *pair_i, *pair_j;
     float* X;         // pool X when owned by the workspace (rollout), else null
-    void *xh, *xl;            // tensor-core path: x planes of the current pair chunk [B][TC_PAIRS][C][64] bf16
+    float* xf;                // tensor-core path: x planes of the current pair chunk [B][TC_PAIRS][C][64] fp32
     void *nodes_h, *nodes_l;  // tensor-core path: site-major node planes [B][C][S][128] bf16 = [X | W_g X]
     void *kp_h, *kp_l;        // tensor-core path: K' planes [B][S][C][64] bf16 (B operand of the alpha GEMM)
     bool tc;
-    int S, nCT, nSB, RP, pair_stride, P0;
+    int S, nCT, nSB, nAP, RP, pair_stride, P0;   // nSB: 32-site groups (fp32 kernels); nAP: alpha partials allocated per pair (stride)
     size_t total;
 };
 
@@ -761,6 +759,7 @@ static bool nj_use_tc(const Model* m, int S) { return m->cfg.precision == NNJ_PR
 static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws, bool need_newx, bool tc) {
     NjBuffers nb{};
     nb.S = S; nb.nCT = (C + TILE_ROWS - 1) / TILE_ROWS; nb.nSB = (C + SB_SITES - 1) / SB_SITES;
+    nb.nAP = nb.nSB > 2 * ((C + 63) / 64) ? nb.nSB : 2 * ((C + 63) / 64);   // tensor-core alpha: up to two partials per 64-site group
     nb.RP = (S + 3) & ~3;     // >= S: tensor-core alpha partials are indexed by physical slot
     nb.P0 = R * (R - 1) / 2;
     nb.pair_stride = nb.P0 > R ? nb.P0 : R;
@@ -771,7 +770,7 @@ static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws,
     nb.Y = (float*)take(pool);
     nb.K = (float*)take(pool);
     nb.kap = (float*)take((size_t)B * S * nb.nCT * sizeof(float));
-    nb.alpha_part = (float*)take((size_t)B * PAIR_CHUNK * nb.nSB * nb.RP * sizeof(float));
+    nb.alpha_part = (float*)take((size_t)B * PAIR_CHUNK * nb.nAP * nb.RP * sizeof(float));
     nb.alpha = (float*)take((size_t)B * PAIR_CHUNK * nb.RP * sizeof(float));
     nb.score_part = (float*)take((size_t)B * PAIR_CHUNK * nb.nSB * sizeof(float));
     nb.new_scores = (float*)take((size_t)B * nb.pair_stride * sizeof(float));
@@ -786,8 +785,8 @@ static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws,
     nb.pair_j = (int32_t*)take((size_t)B * nb.pair_stride * sizeof(int32_t));
     nb.tc = tc;
     if (tc) {
-        const size_t xp = (size_t)B * TC_PAIRS * C * D * 2, np = (size_t)B * C * S * D * 2;
-        nb.xh = take(xp); nb.xl = take(xp); nb.nodes_h = take(2 * np); nb.nodes_l = take(2 * np); nb.kp_h = take(np); nb.kp_l = take(np);
+        const size_t xp = (size_t)B * TC_PAIRS * C * D * 4, np = (size_t)B * C * S * D * 2;
+        nb.xf = (float*)take(xp); nb.nodes_h = take(2 * np); nb.nodes_l = take(2 * np); nb.kp_h = take(np); nb.kp_l = take(np);
     }
     nb.total = off + 256;
     return nb;
@@ -830,38 +829,26 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
     for (int n0 = 0; n0 < N; n0 += step) {
         const int nc = (N - n0 < step) ? (N - n0) : step;
         if (glob && tc) {
-            // blend + alpha partials in one tcgen05 kernel (x planes written on the way, partials per 64-site group, indexed by
-            // physical slot) -> softmax -> fused score kernel.  NNJ_ALPHA_FUSED=1 selects it; the default is the two-kernel form (blend, split-K GEMM), measured faster.
-            static int fused = -1;
-            if (fused < 0) { const char* ev = getenv("NNJ_ALPHA_FUSED"); fused = ev ? atoi(ev) : 0; }
-            int n_part = nb.nSB;
-            if (fused) {
-                n_part = (C + 63) / 64;
-                if (int e = launch_alpha_tc(m, pool.X, pool.Y, pool.tree_stride, slot, nb.S, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, nb.S, C, B,
-                                            nb.kp_h, nb.kp_l, nb.xh, nb.xl, TC_PAIRS, nb.alpha_part, PAIR_CHUNK, nb.nSB, nb.RP, st)) return e;
-            } else {
-                if (int e = launch_blend_planes(pool.X, pool.Y, pool.tree_stride, slot, nb.S, C, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, B,
-                                                m->nj.bh, nb.xh, nb.xl, TC_PAIRS, st)) return e;
-                const size_t KK = (size_t)C * D;
-                if (int e = launch_tc_gemm_ex(KC_ALPHA, nb.xh, nb.xl, nb.kp_h, nb.kp_l, nb.alpha_part, B, nc, nb.S, (int)KK, KK, (size_t)TC_PAIRS * KK, KK,
-                                              (size_t)nb.S * KK, nb.nSB * nb.RP, (size_t)PAIR_CHUNK * nb.nSB * nb.RP, 64, nb.nSB, SB_SITES, nb.RP, st))
-                    return e;
-            }
+            // blend + alpha partials in one tcgen05 kernel (fp32 x planes written on the way, partials per 64-site group - two when the
+            // tile is split by site parity - indexed by physical slot) -> softmax -> fused score kernel
+            int n_part = 0;
+            if (int e = launch_alpha_tc(m, pool.X, pool.Y, pool.tree_stride, slot, nb.S, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, nb.S, C, B,
+                                        nb.kp_h, nb.kp_l, nb.xf, TC_PAIRS, nb.alpha_part, PAIR_CHUNK, nb.nAP, nb.RP, &n_part, st)) return e;
             prof_begin(KC_ALPHA_SOFTMAX, st);
             k_alpha_softmax<<<dim3((nc + 7) / 8, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
-                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha, 1, n_part);
+                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nAP, nb.RP, inv_scale, nb.alpha, 1, n_part);
             LAUNCH_CHECK();
-            if (int e = launch_score_tc(m, nb.xh, nb.xl, TC_PAIRS, nb.nodes_h, nb.nodes_l, nb.alpha, nb.RP, PAIR_CHUNK, slot, nb.S, nb.pair_i,
+            if (int e = launch_score_tc(m, nb.xf, TC_PAIRS, nb.nodes_h, nb.nodes_l, nb.alpha, nb.RP, PAIR_CHUNK, slot, nb.S, nb.pair_i,
                                         nb.pair_stride, n0, nc, Rp, nb.S, C, B, mask, nb.score_part, nb.nSB, st)) return e;
         } else if (glob) {
             const int node_tiles = (Rp + 63) / 64, pair_tiles = (nc + 63) / 64;
             prof_begin(KC_ALPHA, st);
             k_alpha<<<dim3(nb.nSB, pair_tiles * node_tiles, B), NTHREADS, 0, st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j, nb.pair_stride,
-                                                                                   n0, nc, node_tiles, m->nj.bh, nb.alpha_part, nb.nSB, nb.RP);
+                                                                                   n0, nc, node_tiles, m->nj.bh, nb.alpha_part, nb.nAP, nb.RP);
             LAUNCH_CHECK();
             prof_begin(KC_ALPHA_SOFTMAX, st);
             k_alpha_softmax<<<dim3((nc + 7) / 8, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
-                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nSB, nb.RP, inv_scale, nb.alpha, 0, nb.nSB);
+                                                                        nb.pair_j, nb.pair_stride, n0, nc, nb.nAP, nb.RP, inv_scale, nb.alpha, 0, nb.nSB);
             LAUNCH_CHECK();
             prof_begin(KC_SCORE, st);
             k_score<true><<<dim3(nb.nSB, (nc + 31) / 32, B), NTHREADS, smem_score(Rp), st>>>(pool, slot, nb.S, Rp, C, nb.pair_i, nb.pair_j,
@@ -888,12 +875,12 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
     const float inv_scale = 1.0f / sqrtf((float)D * (float)C);
     if (Rp > 2) {
         prof_begin(KC_ALPHA, st);
-        k_alpha1<<<dim3(nb.nSB, B), NTHREADS, 0, st>>>(pool, slot, nb.S, Rp, C, ij, ij_stride, m->nj.bh, nb.alpha_part, nb.nSB, nb.RP);
+        k_alpha1<<<dim3(nb.nSB, B), NTHREADS, 0, st>>>(pool, slot, nb.S, Rp, C, ij, ij_stride, m->nj.bh, nb.alpha_part, nb.nAP, nb.RP);
         LAUNCH_CHECK();
         // pair list for the softmax kernel: reuse it with one pair per tree = ij itself
         prof_begin(KC_ALPHA_SOFTMAX, st);
         k_alpha_softmax<<<dim3(1, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, ij, ij + 1, ij_stride, 0, 1,
-                                                         nb.nSB, nb.RP, inv_scale, nb.alpha, 0, nb.nSB);
+                                                         nb.nAP, nb.RP, inv_scale, nb.alpha, 0, nb.nSB);
         LAUNCH_CHECK();
         prof_begin(KC_MERGE, st);
         k_merge<true><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,

@@ -234,8 +234,82 @@ __global__ void __launch_bounds__(128, 1) k_tc_unit(const float* __restrict__ A,
     if (warp == 0) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN)); }
 }
 
+
+// Unit-test kernel for the A-from-TMEM operand form: A [128 x 64] is split into bf16 hi / lo by its row's thread and stored into
+// tensor memory with tcgen05.st (row = TMEM lane, two bf16 per 32-bit column, K ascending), W [64 n x 64 k] is a thread-written
+// K-major SWIZZLE_128B tile.  D [128 x 64] = A W^T with the 3-product split.  One CTA, 128 threads.
+// TMEM columns: D [0,64) | A_hi [64,96) | A_lo [96,128).
+__global__ void __launch_bounds__(128, 1) k_tc_unit_ta(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ Dm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_align1024(smem_raw);
+    uint8_t *w_hi = base, *w_lo = base + 8192;
+    uint64_t* done = reinterpret_cast<uint64_t*>(base + 16384);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(tmem_slot, 128);
+    if (tid < 64) {
+        const float* wr = W + (size_t)tid * 64;
+        for (int j = 0; j < 8; ++j) {
+            float v[8];
+            for (int e = 0; e < 8; ++e) v[e] = wr[j * 8 + e];
+            a_store8(w_hi, w_lo, tid, j, v);
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    {
+        const float* ar = A + (size_t)tid * 64;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < 2; ++c) {           // 32 K values -> 16 columns per plane
+            uint32_t hh[16], ll[16];
+            for (int e = 0; e < 16; ++e) split2(ar[c * 32 + 2 * e], ar[c * 32 + 2 * e + 1], hh[e], ll[e]);
+            tmem_st16(lane_base + 64 + c * 16, hh);
+            tmem_st16(lane_base + 96 + c * 16, ll);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, 64);
+        if (elect_one()) {
+            for (int k = 0; k < 4; ++k) {
+                umma_bf16_ta(tmem_base, tmem_base + 96 + k * 8, umma_desc_k128(smem_u32(w_hi) + k * 32), idesc, k ? 1u : 0u);
+                umma_bf16_ta(tmem_base, tmem_base + 64 + k * 8, umma_desc_k128(smem_u32(w_lo) + k * 32), idesc, 1u);
+                umma_bf16_ta(tmem_base, tmem_base + 64 + k * 8, umma_desc_k128(smem_u32(w_hi) + k * 32), idesc, 1u);
+            }
+            umma_commit(done);
+        }
+        __syncwarp();
+    }
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int cb = 0; cb < 2; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+        for (int j = 0; j < 32; ++j) Dm[(size_t)tid * 64 + cb * 32 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+}
+
 int run_tc_unit(const float* A, const float* B, float* Dm, int bn, cudaStream_t st) {
-    if (bn != 64 && bn != 128) return set_error(NNJ_ERR_INVALID, "tc_selftest: N must be 64 or 128");
+    if (bn == 1064) {   // A from tensor memory, W [64 n][64 k] K-major
+        cudaError_t e0 = cudaFuncSetAttribute(k_tc_unit_ta, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * 1024);
+        if (e0 != cudaSuccess) return set_cuda_error(e0, __FILE__, __LINE__);
+        k_tc_unit_ta<<<1, 128, 20 * 1024, st>>>(A, B, Dm);
+        ++g_launches;
+        e0 = cudaGetLastError();
+        if (e0 != cudaSuccess) return set_cuda_error(e0, __FILE__, __LINE__);
+        return 0;
+    }
+    if (bn != 64 && bn != 128) return set_error(NNJ_ERR_INVALID, "tc_selftest: N must be 64, 128 or 1064 (A from TMEM)");
     cudaError_t e = cudaFuncSetAttribute(k_tc_unit<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_unit<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);

@@ -61,3 +61,18 @@ def test_thread_written_operands_and_mn_major_b(N):
     torch.cuda.synchronize()
     want = A.double() @ B.double()
     assert float((D.double() - want).abs().max() / want.abs().max()) < 3e-5
+
+
+def test_a_operand_from_tensor_memory():
+    """A written to TMEM by tcgen05.st (row = lane, two bf16 per column), W K-major in shared memory: D = A W^T."""
+    from neuralnj_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(12)
+    A = torch.randn(128, 64, device="cuda", generator=g)
+    W = torch.randn(64, 64, device="cuda", generator=g)
+    D = torch.full((128, 64), float("nan"), device="cuda")
+    _lib.check(L.nnj_tc_selftest(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(D.data_ptr()), 1064,
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    want = A.double() @ W.double().T
+    assert float((D.double() - want).abs().max() / want.abs().max()) < 3e-5
