@@ -3,6 +3,9 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#ifdef NNJ_MBAR_DEBUG
+#include <cstdio>
+#endif
 
 namespace nnj {
 
@@ -33,7 +36,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 1.9 GHz: protocol error, fail loudly instead of hanging
+        if (clock64() - t0 > 4000000000LL) {   // ~2 s at 1.9 GHz: protocol error, fail loudly instead of hanging
+#ifdef NNJ_MBAR_DEBUG
+            printf("mbar timeout: block (%d,%d,%d) thread %d bar smem+%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x,
+                   smem_u32(bar), parity);
+#endif
+            __trap();
+        }
     }
 }
 
@@ -49,6 +58,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
