@@ -27,7 +27,8 @@ constexpr int ST_A0 = 0;                   // alpha operand   hi 16 KB | lo 16 K
 constexpr int ST_W = 32768;                // Ws_h, Ws_l: 2 x 8 KB
 constexpr int ST_PIPE = 49152;             // per pipeline: [X|G]_h 16K | [X|G]_l 16K | A1_h 16K | A1_l 16K = 64 KB
 constexpr int ST_PIPE_BYTES = 65536;
-constexpr int ST_MISC = ST_PIPE + 2 * ST_PIPE_BYTES;   // biases (768 B) | part (4 KB) | barriers | tmem slot
+constexpr int ST_XT = ST_PIPE + 2 * ST_PIPE_BYTES;     // <= 64 pairs: per pipeline the site's x tile [64 pairs][64 ch] fp32 by TMA (2 x 8 KB halves)
+constexpr int ST_MISC = ST_XT + 2 * 16384;             // biases (768 B) | part (4 KB) | barriers | tmem slot
 constexpr int ST_SMEM = ST_MISC + 768 + 4096 + 256 + 1024;
 
 struct ScoreTcArgs {
@@ -45,7 +46,7 @@ struct ScoreTcArgs {
 };
 
 struct EpiCtx {
-    uint64_t* pb; uint8_t* a1h; uint8_t* a1l; uint32_t t_d1; uint32_t t_s;
+    uint64_t* pb; uint8_t* a1h; uint8_t* a1l; uint32_t t_d1; uint32_t t_s; const uint8_t* xt; uint64_t* x_full;
     const float* s_bias; int my_sites; int c_base; int p; int b;
 };
 
@@ -61,7 +62,13 @@ __device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiC
         const uint32_t par = i & 1;
         const int c = e.c_base + 2 * i + e.p;
         float4 x4[4 * NSUB];
-        if (row_ok) {
+        if (dup) {
+            // x tile of the site in shared memory (TMA, SWIZZLE_128B): row prow, channels [col0, col0 + 16)
+            mbar_wait(e.x_full, par);
+            const uint8_t* xr = e.xt + (col0 >> 5) * 8192 + prow * 128;
+#pragma unroll
+            for (int j = 0; j < 4 * NSUB; ++j) x4[j] = *reinterpret_cast<const float4*>(xr + (((((col0 & 31) >> 2) + j) ^ (prow & 7)) << 4));
+        } else if (row_ok) {
             const size_t o = ((((size_t)e.b * a.pc + n) * a.C + c) * 64 + col0) >> 2;
 #pragma unroll
             for (int j = 0; j < 4 * NSUB; ++j) x4[j] = __ldg(a.xf + o + j);
@@ -131,13 +138,14 @@ __device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiC
 }
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
-k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl, const ScoreTcArgs a) {
+k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl, const __grid_constant__ CUtensorMap mapXf,
+           const ScoreTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_align1024(smem_raw);
     float* s_bias = reinterpret_cast<float*>(sm + ST_MISC);            // bg[64] | bs[64] | w2[64]
     float* s_part = s_bias + 192;                                       // [2 pipelines][4 column slots][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 1024);        // per pipeline: bx_full, d1_done, a1_ready, s_done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 1024);        // per pipeline: bx_full, d1_done, a1_ready, s_done; then x_full[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.z, pt = blockIdx.y, sg = blockIdx.x;
@@ -151,7 +159,7 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
     if (tid == 0) {
         for (int p = 0; p < 2; ++p) {
             uint64_t* pb = bars + p * 4;
-            mbar_init(pb + 0, 1); mbar_init(pb + 1, 1); mbar_init(pb + 2, act_warps); mbar_init(pb + 3, 1);
+            mbar_init(pb + 0, 1); mbar_init(pb + 1, 1); mbar_init(pb + 2, act_warps); mbar_init(pb + 3, 1); mbar_init(bars + 8 + p, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -202,6 +210,12 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
         const uint32_t id_s = umma_idesc_bf16(128, 64), id_d1 = umma_idesc_bf16(128, 128) | (1u << 16);
         const int ksteps = (a.S + 15) >> 4;
         const int my_sites = (n_sites - p + 1) >> 1;
+        uint8_t* xt = sm + ST_XT + p * 16384;
+        if (dup && my_sites > 0 && elect_one()) {
+            mbar_expect_tx(bars + 8 + p, 16384);
+            tma_load_4d(xt, &mapXf, bars + 8 + p, 0, c_base + p, pt * 128, b);
+            tma_load_4d(xt + 8192, &mapXf, bars + 8 + p, 32, c_base + p, pt * 128, b);
+        }
         if (my_sites > 0 && elect_one()) {
             const int c = c_base + p;
             mbar_expect_tx(pb + 0, 32768);
@@ -236,8 +250,14 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
                 }
                 __syncwarp();
             }
-            mbar_wait(pb + 2, par);     // epilogue has consumed [x_glob | g] and written x' into the A1 operand
+            mbar_wait(pb + 2, par);     // epilogue has consumed [x_glob | g] and the x tile, and written x' into the A1 operand
             tc_fence_after();
+            if (dup && i + 1 < my_sites && elect_one()) {   // next x tile of this pipeline
+                const int c = c_base + 2 * (i + 1) + p;
+                mbar_expect_tx(bars + 8 + p, 16384);
+                tma_load_4d(xt, &mapXf, bars + 8 + p, 0, c, pt * 128, b);
+                tma_load_4d(xt + 8192, &mapXf, bars + 8 + p, 32, c, pt * 128, b);
+            }
             if (elect_one()) {
                 for (int k = 0; k < 4; ++k) {   // s = x' . W_s^T
                     umma_bf16(t_s, umma_desc_k128(a1l + k * 32), umma_desc_k128(wsh + k * 32), id_s, k ? 1u : 0u);
@@ -255,7 +275,7 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
         if (active) {
             uint8_t* pipe = sm + ST_PIPE + p * ST_PIPE_BYTES;
             EpiCtx e;
-            e.pb = bars + p * 4; e.a1h = pipe + 32768; e.a1l = pipe + 49152;
+            e.pb = bars + p * 4; e.a1h = pipe + 32768; e.a1l = pipe + 49152; e.xt = sm + ST_XT + p * 16384; e.x_full = bars + 8 + p;
             e.t_d1 = tmem_base + ((uint32_t)(q * 32) << 16) + p * 192; e.t_s = e.t_d1 + 128;
             e.s_bias = s_bias; e.my_sites = (n_sites - p + 1) >> 1; e.c_base = c_base; e.p = p; e.b = b;
             const int prow = dup ? ((q & 1) * 32 + lane) : (q * 32 + lane);
@@ -307,6 +327,25 @@ static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC) {
     return 0;
 }
 
+// x planes [B][pc][C][64] fp32 as a 4-D tensor (d, site, pair, tree); box = 32 channels of 64 pairs at one site (pairs >= nc read as 0)
+static int make_tmap_xtile(CUtensorMap* map, const float* base, int pc, int nrows, int C, int B) {
+    typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                            const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+        return set_error(NNJ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[4] = {64, (cuuint64_t)C, (cuuint64_t)nrows, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {256, (cuuint64_t)C * 256, (cuuint64_t)pc * C * 256};
+    cuuint32_t box[4] = {32, 1, 64, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = reinterpret_cast<PFN>(p)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(NNJ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the x tiles");
+    return 0;
+}
+
 int launch_score_tc(const Model* m, const float* xf, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
                     int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,
                     int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, cudaStream_t st) {
@@ -317,7 +356,8 @@ int launch_score_tc(const Model* m, const float* xf, int pc, const void* nodes_h
         attr = true;
     }
     if (S > 64) return set_error(NNJ_ERR_INVALID, "score_tc: at most 63 taxa on the tensor-core pair-score path");
-    CUtensorMap mh, ml;
+    CUtensorMap mh, ml, mx;
+    if (int e = make_tmap_xtile(&mx, xf, pc, nc, C, B)) return e;
     if (int e = make_tmap_nodes(&mh, nodes_h, S, B * C)) return e;
     if (int e = make_tmap_nodes(&ml, nodes_l, S, B * C)) return e;
     ScoreTcArgs a;
@@ -329,7 +369,7 @@ int launch_score_tc(const Model* m, const float* xf, int pc, const void* nodes_h
     a.bg = m->nj.bg; a.bs = m->nj.bs; a.w2 = m->nj.w2; a.b2 = m->nj.b2;
     a.mask = mask; a.score_part = score_part; a.nSG = nSG;
     prof_begin(KC_SCORE, st);
-    k_score_tc<<<dim3((C + ST_SITES - 1) / ST_SITES, (nc + 127) / 128, B), ST_THREADS, ST_SMEM, st>>>(mh, ml, a);
+    k_score_tc<<<dim3((C + ST_SITES - 1) / ST_SITES, (nc + 127) / 128, B), ST_THREADS, ST_SMEM, st>>>(mh, ml, mx, a);
     ++g_launches;
     prof_end(st);
     cudaError_t e = cudaGetLastError();
