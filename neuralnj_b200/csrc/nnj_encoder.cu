@@ -554,11 +554,12 @@ static size_t enc_tree_floats(const Model* m, int R, int C) {
 
 int encoder_chunk(const Model* m, int B, int R, int C) {
     size_t per = enc_tree_floats(m, R, C) * sizeof(float);
-    size_t budget = (size_t)6 << 30;
+    size_t budget = (size_t)16 << 30;
     int ch = (int)(budget / per);
     if (ch < 1) ch = 1;
     if (ch > B) ch = B;
-    return ch;
+    const int n = (B + ch - 1) / ch;     // equal-sized chunks: no small tail launch
+    return (B + n - 1) / n;
 }
 
 size_t encoder_ws_bytes(const Model* m, int B, int R, int C) {

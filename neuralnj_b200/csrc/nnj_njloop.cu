@@ -995,12 +995,13 @@ int run_merge(Model* m, const float* state_in, int B, int Rp, int C, const int32
 // ---- fused rollout
 int nj_rollout_chunk(const Model* m, int B, int R, int C) {
     size_t per = nj_layout(nullptr, 1, R + 1, R, C, true, false, nj_use_tc(m, R + 1)).total + encoder_ws_bytes(m, 1, R, C);
-    size_t budget = (size_t)16 << 30;
+    size_t budget = (size_t)48 << 30;     // of 180 GB HBM3e
     int ch = (int)(budget / per);
     if (ch < 1) ch = 1;
     if (ch > 128) ch = 128;
     if (ch > B) ch = B;
-    return ch;
+    const int n = (B + ch - 1) / ch;      // equal-sized chunks: no small tail launch
+    return (B + n - 1) / n;
 }
 
 size_t nj_rollout_ws_bytes(const Model* m, int B, int R, int C) {

@@ -46,7 +46,7 @@ struct ScoreTcArgs {
 };
 
 struct EpiCtx {
-    uint64_t* pb; uint8_t* a1h; uint8_t* a1l; uint32_t t_d1; uint32_t t_s; const uint8_t* xt; uint64_t* x_full;
+    uint64_t* pb; uint8_t* a1h; uint8_t* a1l; uint32_t t_d1; uint32_t t_s; uint32_t t_a1; const uint8_t* xt; uint64_t* x_full;
     const float* s_bias; int my_sites; int c_base; int p; int b;
 };
 
@@ -62,19 +62,13 @@ __device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiC
         const uint32_t par = i & 1;
         const int c = e.c_base + 2 * i + e.p;
         float4 x4[4 * NSUB];
-        if (dup) {
-            // x tile of the site in shared memory (TMA, SWIZZLE_128B): row prow, channels [col0, col0 + 16)
+        {
+            // x tile of the site in shared memory (TMA, SWIZZLE_128B; 32-channel halves of [rows][128 B]): row prow, channels
+            // [col0, col0 + 16 NSUB); rows without a pair were written as zeros / are zero-filled by the map
             mbar_wait(e.x_full, par);
-            const uint8_t* xr = e.xt + (col0 >> 5) * 8192 + prow * 128;
+            const uint8_t* xr = e.xt + (col0 >> 5) * (dup ? 8192 : 16384) + prow * 128;
 #pragma unroll
             for (int j = 0; j < 4 * NSUB; ++j) x4[j] = *reinterpret_cast<const float4*>(xr + (((((col0 & 31) >> 2) + j) ^ (prow & 7)) << 4));
-        } else if (row_ok) {
-            const size_t o = ((((size_t)e.b * a.pc + n) * a.C + c) * 64 + col0) >> 2;
-#pragma unroll
-            for (int j = 0; j < 4 * NSUB; ++j) x4[j] = __ldg(a.xf + o + j);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4 * NSUB; ++j) x4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const float* xv = reinterpret_cast<const float*>(x4);
         // ---- gate: w = sigmoid(g + b_g), x' = (1-w) x + w x_glob  -> A1 operand of the s_out GEMM
@@ -95,22 +89,30 @@ __device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiC
                 xp[k] = fmaf(w0, __uint_as_float(xg[k]) - x0, x0);       // (1-w) x + w x_glob
                 xp[k + 1] = fmaf(w1, __uint_as_float(xg[k + 1]) - x1, x1);
             }
+            if (dup) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                uint4 hh, ll;
-                split2(xp[8 * j + 0], xp[8 * j + 1], hh.x, ll.x);
-                split2(xp[8 * j + 2], xp[8 * j + 3], hh.y, ll.y);
-                split2(xp[8 * j + 4], xp[8 * j + 5], hh.z, ll.z);
-                split2(xp[8 * j + 6], xp[8 * j + 7], hh.w, ll.w);
-                const int off = prow * 128 + (((((col0 + sub * 16) >> 3) + j) ^ (prow & 7)) << 4);
-                *reinterpret_cast<uint4*>(e.a1h + off) = hh;
-                *reinterpret_cast<uint4*>(e.a1l + off) = ll;
-                if (dup) {
-                    *reinterpret_cast<uint4*>(e.a1h + off + 8192) = hh;
+                for (int j = 0; j < 2; ++j) {
+                    uint4 hh, ll;
+                    split2(xp[8 * j + 0], xp[8 * j + 1], hh.x, ll.x);
+                    split2(xp[8 * j + 2], xp[8 * j + 3], hh.y, ll.y);
+                    split2(xp[8 * j + 4], xp[8 * j + 5], hh.z, ll.z);
+                    split2(xp[8 * j + 6], xp[8 * j + 7], hh.w, ll.w);
+                    const int off = prow * 128 + (((((col0 + sub * 16) >> 3) + j) ^ (prow & 7)) << 4);
+                    *reinterpret_cast<uint4*>(e.a1h + off) = hh;
+                    *reinterpret_cast<uint4*>(e.a1l + off) = ll;
+                    *reinterpret_cast<uint4*>(e.a1h + off + 8192) = hh;      // rows 64..127 repeat the pairs
                     *reinterpret_cast<uint4*>(e.a1l + off + 8192) = ll;
                 }
+            } else {
+                // a full tile keeps the A1 operand in tensor memory (row = this thread's TMEM lane, two bf16 per column)
+                uint32_t hh[8], ll[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) split2(xp[2 * j], xp[2 * j + 1], hh[j], ll[j]);
+                tmem_st8(e.t_a1 + ((col0 + sub * 16) >> 1), hh);
+                tmem_st8(e.t_a1 + 32 + ((col0 + sub * 16) >> 1), ll);
             }
         }
+        if (!dup) tmem_st_wait();
         fence_async_smem();
         tc_fence_before();
         __syncwarp();
@@ -206,16 +208,25 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
         const uint32_t a0h = smem_u32(sm + ST_A0), a0l = a0h + 16384;
         const uint32_t wsh = smem_u32(sm + ST_W), wsl = wsh + 8192;
         const uint32_t bxh = smem_u32(pipe), bxl = bxh + 16384, a1h = bxh + 32768, a1l = bxh + 49152;
-        const uint32_t t_d1 = tmem_base + p * 192, t_s = t_d1 + 128;
+        const uint32_t t_d1 = tmem_base + p * 256, t_s = t_d1 + 128, t_a1 = t_d1 + 192;   // [x_glob | g] 128 | s 64 | A1 hi 32 | A1 lo 32
         const uint32_t id_s = umma_idesc_bf16(128, 64), id_d1 = umma_idesc_bf16(128, 128) | (1u << 16);
         const int ksteps = (a.S + 15) >> 4;
         const int my_sites = (n_sites - p + 1) >> 1;
-        uint8_t* xt = sm + ST_XT + p * 16384;
-        if (dup && my_sites > 0 && elect_one()) {
-            mbar_expect_tx(bars + 8 + p, 16384);
-            tma_load_4d(xt, &mapXf, bars + 8 + p, 0, c_base + p, pt * 128, b);
-            tma_load_4d(xt + 8192, &mapXf, bars + 8 + p, 32, c_base + p, pt * 128, b);
-        }
+        uint8_t* xt = dup ? sm + ST_XT + p * 16384 : pipe + 32768;   // a full tile has its A1 operand in TMEM: the x tile takes that space
+        auto load_x = [&](int c) {      // one elected lane
+            if (dup) {
+                mbar_expect_tx(bars + 8 + p, 16384);
+                tma_load_4d(xt, &mapXf, bars + 8 + p, 0, c, pt * 128, b);
+                tma_load_4d(xt + 8192, &mapXf, bars + 8 + p, 32, c, pt * 128, b);
+            } else {
+                mbar_expect_tx(bars + 8 + p, 32768);
+                tma_load_4d(xt, &mapXf, bars + 8 + p, 0, c, pt * 128, b);
+                tma_load_4d(xt + 8192, &mapXf, bars + 8 + p, 0, c, pt * 128 + 64, b);
+                tma_load_4d(xt + 16384, &mapXf, bars + 8 + p, 32, c, pt * 128, b);
+                tma_load_4d(xt + 24576, &mapXf, bars + 8 + p, 32, c, pt * 128 + 64, b);
+            }
+        };
+        if (my_sites > 0 && elect_one()) load_x(c_base + p);
         if (my_sites > 0 && elect_one()) {
             const int c = c_base + p;
             mbar_expect_tx(pb + 0, 32768);
@@ -252,17 +263,20 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
             }
             mbar_wait(pb + 2, par);     // epilogue has consumed [x_glob | g] and the x tile, and written x' into the A1 operand
             tc_fence_after();
-            if (dup && i + 1 < my_sites && elect_one()) {   // next x tile of this pipeline
-                const int c = c_base + 2 * (i + 1) + p;
-                mbar_expect_tx(bars + 8 + p, 16384);
-                tma_load_4d(xt, &mapXf, bars + 8 + p, 0, c, pt * 128, b);
-                tma_load_4d(xt + 8192, &mapXf, bars + 8 + p, 32, c, pt * 128, b);
-            }
+            if (i + 1 < my_sites && elect_one()) load_x(c_base + 2 * (i + 1) + p);   // next x tile of this pipeline
             if (elect_one()) {
-                for (int k = 0; k < 4; ++k) {   // s = x' . W_s^T
-                    umma_bf16(t_s, umma_desc_k128(a1l + k * 32), umma_desc_k128(wsh + k * 32), id_s, k ? 1u : 0u);
-                    umma_bf16(t_s, umma_desc_k128(a1h + k * 32), umma_desc_k128(wsl + k * 32), id_s, 1u);
-                    umma_bf16(t_s, umma_desc_k128(a1h + k * 32), umma_desc_k128(wsh + k * 32), id_s, 1u);
+                if (dup) {
+                    for (int k = 0; k < 4; ++k) {   // s = x' . W_s^T
+                        umma_bf16(t_s, umma_desc_k128(a1l + k * 32), umma_desc_k128(wsh + k * 32), id_s, k ? 1u : 0u);
+                        umma_bf16(t_s, umma_desc_k128(a1h + k * 32), umma_desc_k128(wsl + k * 32), id_s, 1u);
+                        umma_bf16(t_s, umma_desc_k128(a1h + k * 32), umma_desc_k128(wsh + k * 32), id_s, 1u);
+                    }
+                } else {
+                    for (int k = 0; k < 4; ++k) {   // the same with x' read from tensor memory
+                        umma_bf16_ta(t_s, t_a1 + 32 + k * 8, umma_desc_k128(wsh + k * 32), id_s, k ? 1u : 0u);
+                        umma_bf16_ta(t_s, t_a1 + k * 8, umma_desc_k128(wsl + k * 32), id_s, 1u);
+                        umma_bf16_ta(t_s, t_a1 + k * 8, umma_desc_k128(wsh + k * 32), id_s, 1u);
+                    }
                 }
                 umma_commit(pb + 3);
             }
@@ -275,8 +289,8 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
         if (active) {
             uint8_t* pipe = sm + ST_PIPE + p * ST_PIPE_BYTES;
             EpiCtx e;
-            e.pb = bars + p * 4; e.a1h = pipe + 32768; e.a1l = pipe + 49152; e.xt = sm + ST_XT + p * 16384; e.x_full = bars + 8 + p;
-            e.t_d1 = tmem_base + ((uint32_t)(q * 32) << 16) + p * 192; e.t_s = e.t_d1 + 128;
+            e.pb = bars + p * 4; e.a1h = pipe + 32768; e.a1l = pipe + 49152; e.xt = dup ? sm + ST_XT + p * 16384 : pipe + 32768; e.x_full = bars + 8 + p;
+            e.t_d1 = tmem_base + ((uint32_t)(q * 32) << 16) + p * 256; e.t_s = e.t_d1 + 128; e.t_a1 = e.t_d1 + 192;
             e.s_bias = s_bias; e.my_sites = (n_sites - p + 1) >> 1; e.c_base = c_base; e.p = p; e.b = b;
             const int prow = dup ? ((q & 1) * 32 + lane) : (q * 32 + lane);
             const int n = pt * 128 + prow;
