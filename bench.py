@@ -57,9 +57,9 @@ def algorithmic_flops(R, Cc, layers=6):
         "row_pv_gemm": layers * 2 * Cc * Cc * R * D,
         "col_attn": layers * 4 * Cc * R * R * D,
         "ffn": layers * 4 * R * Cc * D * F,
-        "alpha": sum(p * 2 * n * Cc * D for p, n in pair_evals if n > 2) + sum(2 * n * Cc * D for n in range(R, 2, -1)),
+        "alpha": sum(p * 2 * n * Cc * D for p, n in pair_evals if n > 2),
         "pair_score": sum(p * ((2 * n * Cc * D + 2 * Cc * D * D if n > 2 else 0) + 2 * Cc * D * D + 2 * Cc * D) for p, n in pair_evals),
-        "merge": sum(2 * n * Cc * D + 2 * Cc * D * D + 3 * 2 * Cc * D * D for n in range(R, 2, -1)),
+        "merge": sum(2 * 2 * n * Cc * D + 2 * Cc * D * D + 3 * 2 * Cc * D * D for n in range(R, 2, -1)),   # incl. the merge pair's alpha
         "node_derive": R * 3 * 2 * Cc * D * D,
     }
     return fl

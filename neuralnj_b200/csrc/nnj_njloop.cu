@@ -874,7 +874,7 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
                       const int32_t* ij, int ij_stride, int B, float* out_x, size_t out_stride, bool derive, cudaStream_t st) {
     const float inv_scale = 1.0f / sqrtf((float)D * (float)C);
     if (Rp > 2) {
-        prof_begin(KC_ALPHA, st);
+        prof_begin(KC_MERGE, st);     // the merge pair's own attention logits: counted with the merge
         k_alpha1<<<dim3(nb.nSB, B), NTHREADS, 0, st>>>(pool, slot, nb.S, Rp, C, ij, ij_stride, m->nj.bh, nb.alpha_part, nb.nAP, nb.RP);
         LAUNCH_CHECK();
         // pair list for the softmax kernel: reuse it with one pair per tree = ij itself
