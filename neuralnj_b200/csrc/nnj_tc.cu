@@ -24,12 +24,16 @@ constexpr int TC_THREADS = 192;
 // grid (N tiles * nsplit, M tiles, Z).  C row-major with leading dimension ldc, batch stride sC (elements).
 // Split-K: split s = blockIdx.x % nsplit handles K chunks [s*cps, (s+1)*cps) and writes to C + s*split_stride.
 struct TcGemmArgs {
-    float* C; int M, N, K, ldc; size_t sC;
+    float* C; int M, N, K, ldc; size_t sC; int Z;
     int nsplit, chunks_per_split; size_t split_stride;
 };
 
 // BMN: B is given MN-major, [Z][K][N] with N contiguous (e.g. V of the row attention, [key site][taxon*8+d]); its tiles are loaded
 // as 64 x 64 boxes (64 N values = one 128-byte swizzle row per K index), the 64-column blocks of an N tile 8 KB apart.
+//
+// Persistent: grid = min(tiles, SMs); every role walks the same static tile list (t = blockIdx.x, += gridDim.x; N tiles fastest
+// so that neighbouring CTAs share the A rows in L2).  The TMA ring and its barriers run on across tiles, and the accumulator
+// is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i drains while the tensor core works on tile i+1.
 template <int BN, bool BMN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
@@ -40,25 +44,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     uint8_t* tiles = smem_align1024(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * STAGE);
     uint64_t* empty = full + TC_STAGES;
-    uint64_t* accum_done = empty + TC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_done + 1);
+    uint64_t* acc_full = empty + TC_STAGES;      // [2]
+    uint64_t* acc_free = acc_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = blockIdx.x % g.nsplit, ntile = blockIdx.x / g.nsplit;
-    const int n0 = ntile * BN, m0 = blockIdx.y * TC_BM, z = blockIdx.z;
     const int total_chunks = (g.K + TC_BK - 1) / TC_BK;
-    const int kc0 = split * g.chunks_per_split;
-    const int nchunks = max(0, min(total_chunks - kc0, g.chunks_per_split));
+    const int nt = ((g.N + BN - 1) / BN) * g.nsplit, mt = (g.M + TC_BM - 1) / TC_BM;
+    const int n_tiles = g.Z * mt * nt;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(accum_done, 1);
+        mbar_init(acc_full, 1); mbar_init(acc_full + 1, 1);
+        mbar_init(acc_free, 4); mbar_init(acc_free + 1, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // TMEM: BN fp32 columns for the 128 x BN accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);   // two 128 x BN fp32 accumulators
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -67,88 +68,113 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     // Producer / issuer warps keep warp-uniform control flow and elect one lane per action, so descriptors and
     // addresses stay in uniform registers (a lane==0 branch makes ptxas emit a R2UR broadcast loop per MMA).
     if (warp == 0) {
-        for (int kk = 0; kk < nchunks; ++kk) {
-            const int s = kk % TC_STAGES, kc = kc0 + kk;
-            if (kk >= TC_STAGES) mbar_wait(&empty[s], ((kk / TC_STAGES) - 1) & 1);
-            uint8_t* st = tiles + s * STAGE;
-            if (elect_one()) {
-                mbar_expect_tx(&full[s], STAGE);
-                tma_load_3d(st, &mapAh, &full[s], kc * TC_BK, m0, z);
-                tma_load_3d(st + TC_PLANE_BYTES, &mapAl, &full[s], kc * TC_BK, m0, z);
-                if (BMN) {
+        int gc = 0;     // chunks issued so far (ring position)
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int xi = t % nt, r0 = t / nt, z = r0 / mt;
+            const int split = xi % g.nsplit, n0 = (xi / g.nsplit) * BN, m0 = (r0 - z * mt) * TC_BM;
+            const int kc0 = split * g.chunks_per_split;
+            const int nchunks = max(0, min(total_chunks - kc0, g.chunks_per_split));
+            for (int kk = 0; kk < nchunks; ++kk, ++gc) {
+                const int s = gc % TC_STAGES, kc = kc0 + kk;
+                if (gc >= TC_STAGES) mbar_wait(&empty[s], ((gc / TC_STAGES) - 1) & 1);
+                uint8_t* st = tiles + s * STAGE;
+                if (elect_one()) {
+                    mbar_expect_tx(&full[s], STAGE);
+                    tma_load_3d(st, &mapAh, &full[s], kc * TC_BK, m0, z);
+                    tma_load_3d(st + TC_PLANE_BYTES, &mapAl, &full[s], kc * TC_BK, m0, z);
+                    if (BMN) {
 #pragma unroll
-                    for (int nb = 0; nb < BN / 64; ++nb) {
-                        tma_load_3d(st + 2 * TC_PLANE_BYTES + nb * 8192, &mapBh, &full[s], n0 + nb * 64, kc * TC_BK, z);
-                        tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE + nb * 8192, &mapBl, &full[s], n0 + nb * 64, kc * TC_BK, z);
+                        for (int nb = 0; nb < BN / 64; ++nb) {
+                            tma_load_3d(st + 2 * TC_PLANE_BYTES + nb * 8192, &mapBh, &full[s], n0 + nb * 64, kc * TC_BK, z);
+                            tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE + nb * 8192, &mapBl, &full[s], n0 + nb * 64, kc * TC_BK, z);
+                        }
+                    } else {
+                        tma_load_3d(st + 2 * TC_PLANE_BYTES, &mapBh, &full[s], kc * TC_BK, n0, z);
+                        tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE, &mapBl, &full[s], kc * TC_BK, n0, z);
                     }
-                } else {
-                    tma_load_3d(st + 2 * TC_PLANE_BYTES, &mapBh, &full[s], kc * TC_BK, n0, z);
-                    tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE, &mapBl, &full[s], kc * TC_BK, n0, z);
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         const uint32_t idesc = umma_idesc_bf16(TC_BM, BN) | (BMN ? (1u << 16) : 0u);
-        for (int kk = 0; kk < nchunks; ++kk) {
-            const int s = kk % TC_STAGES, kc = kc0 + kk;
-            mbar_wait(&full[s], (kk / TC_STAGES) & 1);
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(tiles + s * STAGE), a_lo = a_hi + TC_PLANE_BYTES;
-            const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = b_hi + B_PLANE;
-            const int kvalid = min(TC_BK, g.K - kc * TC_BK);
-            const int ksteps = (kvalid + 15) / 16;
-            if (elect_one()) {
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t ko = k * 32;   // 16 bf16 = 32 B inside the 128 B swizzle row
-                    const uint64_t dah = umma_desc_k128(a_hi + ko), dal = umma_desc_k128(a_lo + ko);
-                    const uint64_t dbh = BMN ? umma_desc_lbo(b_hi + k * 2048, 8192) : umma_desc_k128(b_hi + ko);   // MN-major: 16 K rows = 2 KB per step
-                    const uint64_t dbl = BMN ? umma_desc_lbo(b_lo + k * 2048, 8192) : umma_desc_k128(b_lo + ko);
-                    umma_bf16(tmem_base, dal, dbh, idesc, (kk | k) ? 1u : 0u);   // small terms first
-                    umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-                    umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+        int gc = 0, ti = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+            const int split = (t % nt) % g.nsplit;
+            const int kc0 = split * g.chunks_per_split;
+            const int nchunks = max(0, min(total_chunks - kc0, g.chunks_per_split));
+            const int ab = ti & 1;
+            const uint32_t t_acc = tmem_base + ab * BN;
+            if (ti >= 2) { mbar_wait(acc_free + ab, ((ti >> 1) - 1) & 1); tc_fence_after(); }   // the epilogue has drained this accumulator
+            for (int kk = 0; kk < nchunks; ++kk, ++gc) {
+                const int s = gc % TC_STAGES, kc = kc0 + kk;
+                mbar_wait(&full[s], (gc / TC_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(tiles + s * STAGE), a_lo = a_hi + TC_PLANE_BYTES;
+                const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = b_hi + B_PLANE;
+                const int kvalid = min(TC_BK, g.K - kc * TC_BK);
+                const int ksteps = (kvalid + 15) / 16;
+                if (elect_one()) {
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint32_t ko = k * 32;   // 16 bf16 = 32 B inside the 128 B swizzle row
+                        const uint64_t dah = umma_desc_k128(a_hi + ko), dal = umma_desc_k128(a_lo + ko);
+                        const uint64_t dbh = BMN ? umma_desc_lbo(b_hi + k * 2048, 8192) : umma_desc_k128(b_hi + ko);   // MN-major: 16 K rows = 2 KB per step
+                        const uint64_t dbl = BMN ? umma_desc_lbo(b_lo + k * 2048, 8192) : umma_desc_k128(b_lo + ko);
+                        umma_bf16(t_acc, dal, dbh, idesc, (kk | k) ? 1u : 0u);   // small terms first
+                        umma_bf16(t_acc, dah, dbl, idesc, 1u);
+                        umma_bf16(t_acc, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+                    if (kk == nchunks - 1) umma_commit(acc_full + ab);   // accumulator complete
                 }
-                umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
-                if (kk == nchunks - 1) umma_commit(accum_done);   // accumulator complete
+                __syncwarp();
             }
+            if (nchunks == 0 && elect_one()) mbar_arrive(acc_full + ab);
             __syncwarp();
         }
-        if (nchunks == 0 && elect_one()) mbar_arrive(accum_done);
     } else {
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
-        mbar_wait(accum_done, 0);
-        tc_fence_after();
-        const int m = m0 + q * 32 + lane;
-        float* crow = g.C + (size_t)z * g.sC + (size_t)m * g.ldc + (size_t)split * g.split_stride;
+        int ti = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+            const int xi = t % nt, r0 = t / nt, z = r0 / mt;
+            const int split = xi % g.nsplit, n0 = (xi / g.nsplit) * BN, m0 = (r0 - z * mt) * TC_BM;
+            const int kc0 = split * g.chunks_per_split;
+            const int nchunks = max(0, min(total_chunks - kc0, g.chunks_per_split));
+            const int ab = ti & 1;
+            mbar_wait(acc_full + ab, (ti >> 1) & 1);
+            tc_fence_after();
+            const int m = m0 + q * 32 + lane;
+            float* crow = g.C + (size_t)z * g.sC + (size_t)m * g.ldc + (size_t)split * g.split_stride;
 #pragma unroll 1
-        for (int cb = 0; cb < BN / 32; ++cb) {
-            uint32_t v[32];
-            if (nchunks > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cb * 32, v);
-            else {
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                uint32_t v[32];
+                if (nchunks > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + cb * 32, v);
+                else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0u;
-            }
-            const int n = n0 + cb * 32;
-            if (m < g.M) {
-                if (n + 31 < g.N && (g.ldc & 3) == 0 && (g.split_stride & 3) == 0) {
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                const int n = n0 + cb * 32;
+                if (m < g.M) {
+                    if (n + 31 < g.N && (g.ldc & 3) == 0 && (g.split_stride & 3) == 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        st4(crow + n + j * 4, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-                } else {
+                        for (int j = 0; j < 8; ++j)
+                            st4(crow + n + j * 4, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n + j < g.N) crow[n + j] = __uint_as_float(v[j]);
+                        for (int j = 0; j < 32; ++j)
+                            if (n + j < g.N) crow[n + j] = __uint_as_float(v[j]);
+                    }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free + ab);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
-    }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
 }
 
 // fp32 -> (hi, lo) bf16 planes: hi = bf16(x), lo = bf16(x - hi)
@@ -373,6 +399,16 @@ static int make_tmap_mn_major(CUtensorMap* map, const void* base, int N, int K, 
     return 0;
 }
 
+static int tc_sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 // C[z] = (Ah+Al)[z] * (Bh+Bl)[z] with B MN-major: B planes [Z][K][N] (N contiguous, pitch ldb).  128 x 128 tiles.
 int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                        size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st) {
@@ -388,8 +424,9 @@ int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, 
     if (int e = make_tmap_k_major(&mAl, Al, K, M, Z, lda, sA, TC_BM)) return e;
     if (int e = make_tmap_mn_major(&mBh, Bh, N, K, Z, ldb, sB)) return e;
     if (int e = make_tmap_mn_major(&mBl, Bl, N, K, Z, ldb, sB)) return e;
-    TcGemmArgs g{Cm, M, N, K, ldc, sC, 1, (K + TC_BK - 1) / TC_BK, 0};
-    const dim3 grid((N + 127) / 128, (M + TC_BM - 1) / TC_BM, Z);
+    TcGemmArgs g{Cm, M, N, K, ldc, sC, Z, 1, (K + TC_BK - 1) / TC_BK, 0};
+    const int n_tiles = ((N + 127) / 128) * ((M + TC_BM - 1) / TC_BM) * Z;
+    const dim3 grid(n_tiles < tc_sm_count() ? n_tiles : tc_sm_count());
     prof_begin(cls, st);
     k_tc_gemm<128, true><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g);
     ++g_launches;
@@ -419,8 +456,9 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
     if (int e = make_tmap_k_major(&mAl, Al, K, M, Z, lda, sA, TC_BM)) return e;
     if (int e = make_tmap_k_major(&mBh, Bh, K, N, Z, ldb, sB, bn)) return e;
     if (int e = make_tmap_k_major(&mBl, Bl, K, N, Z, ldb, sB, bn)) return e;
-    TcGemmArgs g{Cm, M, N, K, ldc, sC, nsplit, chunks_per_split, split_stride};
-    const dim3 grid(((N + bn - 1) / bn) * nsplit, (M + TC_BM - 1) / TC_BM, Z);
+    TcGemmArgs g{Cm, M, N, K, ldc, sC, Z, nsplit, chunks_per_split, split_stride};
+    const int n_tiles = ((N + bn - 1) / bn) * nsplit * ((M + TC_BM - 1) / TC_BM) * Z;
+    const dim3 grid(n_tiles < tc_sm_count() ? n_tiles : tc_sm_count());
     prof_begin(cls, st);
     if (bn == 128) k_tc_gemm<128, false><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g);
     else k_tc_gemm<64, false><<<grid, TC_THREADS, SMEM64, st>>>(mAh, mAl, mBh, mBl, g);
