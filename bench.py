@@ -255,6 +255,32 @@ def main():
     for n in kernels:
         if n in fl:
             kernels[n]["tflops"] = round(fl[n] * B / (kernels[n]["ms"] * 1e-3) / 1e12, 3)
+    # DRAM traffic per launch from the committed `ncu --set full` captures of the same workload (128-tree chunks):
+    # launch-count-weighted mean of the step-0 launch (256 pairs / tree) and an incremental launch (35 pairs / tree)
+    roofline_hbm = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic_b128.json")) as f:
+            tr = json.load(f)
+        chunks = max(1, kernels["node_derive"]["launches"])
+        per_chunk = {"pair_score": ("score_step0", "score_incr", 5, 48), "alpha": ("alpha_step0", "alpha_incr", 5, 47)}
+        scale = (B / chunks) / 128.0
+
+        def mean_traffic(cls):
+            k0, k1, n0, n1 = per_chunk[cls]
+            return scale * (n0 * tr[k0]["dram_bytes"] + n1 * tr[k1]["dram_bytes"]) / (n0 + n1)
+        if top in per_chunk:
+            roofline["traffic"] = round(mean_traffic(top))
+            roofline["traffic_source"] = "ncu dram__bytes_read+write.sum, profiles/r01_traffic_b128.json (launch-weighted mean of a step-0 and an incremental launch)"
+        if "alpha" in kernels:
+            hbm_peak = peaks.get("hbm_gbs", 6554.2)
+            a_ms = kernels["alpha"]["ms"] / kernels["alpha"]["launches"]
+            a_bytes = mean_traffic("alpha")
+            roofline_hbm = {"bound": "hbm", "kernel": "alpha", "achieved": round(a_bytes / (a_ms * 1e-3) / 1e9, 1), "peak": hbm_peak,
+                            "unit": "GB/s", "frac": round(a_bytes / (a_ms * 1e-3) / 1e9 / hbm_peak, 4), "traffic": round(a_bytes),
+                            "ms_per_launch": round(a_ms, 4),
+                            "note": "k_alpha_v3: bytes per launch = ncu dram bytes (equal to the algorithmic bytes: node pool X, Y, K' once + x planes); time live"}
+    except (OSError, KeyError, ValueError):
+        pass
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -276,6 +302,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
+            "roofline_hbm": roofline_hbm,
             "kernels": kernels,
             "cpu_baseline": cpu_baseline,
         }
