@@ -16,6 +16,9 @@
 // accumulate); operands produced on the fly are written by the epilogue threads straight into SWIZZLE_128B shared
 // memory (validated by nnj_tc_selftest).  Node state for UMMA 1 comes from site-major bf16 planes [B][C][S][128]
 // [X | W_g X], indexed by PHYSICAL slot, so alpha is scattered to slot order and dead / free slots simply get weight 0.
+#include <cstdio>
+#include <cstdlib>
+
 #include "nnj_internal.h"
 #include "nnj_tc.cuh"
 
@@ -317,10 +320,341 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
     }
 }
 
+// ------------------------------------------------------------------ incremental steps: <= 64 pairs per tree
+// Every NJ step after the first scores only the pairs of the new node (<= R-1 <= 63 rows), and the 48 of them dominate the loop.
+// k_score_inc is the pair-score kernel for that regime, persistent over work items (tree, 64-site group):
+//   * the 128-row tile is split by site parity like k_alpha_v3: lanes 0..63 = the pairs at site 2k, lanes 64..127 = the same
+//     pairs at site 2k+1.  UMMA 1 runs once per site into its own accumulator ([x_glob | g] of site 2k in D1a rows 0..63,
+//     of site 2k+1 in D1b rows 64..127; the other halves are ignored); UMMA 2 (x' . W_s^T) runs ONCE for both sites, its A
+//     operand x' written by the epilogue threads straight into tensor memory (no shared-memory staging, no row duplication);
+//   * a producer warp streams the node tiles ([X | W_g X] bf16 hi/lo) and the x tiles of the sites through a ring sized from
+//     the slot / pair counts (4 sites at 51 slots), running ahead across work items, so the kernel can follow HBM;
+//   * the issue warp queues UMMA 1 of the next site pair right behind UMMA 2 of the current one, so the tensor core works on
+//     the next [x_glob | g] while the 16 epilogue warps run the GELU / site-sum epilogue.
+// The alpha operand (A of UMMA 1) is rebuilt per work item from alpha[b] scattered to physical-slot order.
+constexpr int SI_THREADS = 608;            // 16 epilogue warps + issue warp + node-tile producer + x-tile producer
+constexpr int SI_SITES = 64;
+constexpr int SI_A0 = 0;                   // staging of alpha by physical slot, fp32 [64 pairs][68] (the operand itself lives in tensor memory)
+constexpr int SI_A0_LD = 68;
+constexpr int SI_W = 32768;                // W_s hi 8 KB | lo 8 KB
+constexpr int SI_RING = 49152;
+constexpr int SI_MAXST = 6;
+constexpr int SI_MISC_BYTES = 768 + 2048 + 512;   // biases | score partials [4][128] | barriers (4 x 6 + 5), tmem slot
+constexpr int SI_SMEM_MAX = 232448;
+constexpr uint32_t SI_TM_D1 = 0, SI_TM_S = 256, SI_TM_A1 = 320, SI_TM_S1 = 384, SI_TM_A0 = 448;   // TMEM: D1a 128 | D1b 128 | s[0] 64 | x' hi/lo 64 | s[1] 64 | alpha hi/lo 64
+
+#define SI_TRACE(tag, item) do { if (a.trace && blockIdx.x == 0 && lane == 0 && (item) < 600) { const int ti_ = atomicAdd(reinterpret_cast<int*>(a.trace), 1); if (ti_ < 20000) { a.trace[1 + 3 * ti_] = (tag); a.trace[2 + 3 * ti_] = (item); a.trace[3 + 3 * ti_] = clock64(); } } } while (0)
+
+struct ScoreIncArgs {
+    const float* alpha; int RP; int alpha_pairs;
+    const int32_t* slot_of; int slot_stride;
+    const int32_t* pair_i; int pair_stride; int n0; int nc;
+    int Rp, S, C, B, groups;
+    int pf;                                  // L2 prefetch distance in sites (0: off)
+    long long* trace;                        // NNJ_SCORE_TRACE: clock64 stamps of CTA 0 (tag, item, clock) triples, else null
+    int dbg;                                 // timing experiments only (NNJ_SCORE_DBG): 1 = one UMMA-1 product of three, 2 = no gate math, 4 = no GELU math
+    int node_rows, x_rows, nst;              // ring geometry: node blocks [node_rows][128 B] x 4, x halves [x_rows][128 B] x 2
+    const uint4* wsh; const uint4* wsl;
+    const float* bg; const float* bs; const float* w2; float b2;
+    const uint8_t* mask;
+    float* score_part; int nSG;
+};
+
+__global__ void __launch_bounds__(SI_THREADS, 1)
+k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl, const __grid_constant__ CUtensorMap mapXf,
+            const ScoreIncArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = smem_align1024(smem_raw);
+    const int NB = a.node_rows * 128, XB = a.x_rows * 128;      // bytes of one node column block / one x half
+    const int STG = 4 * NB + 2 * XB, NST = a.nst;               // per site: node blocks X_h | G_h | X_l | G_l, x halves ch 0-31 | ch 32-63
+    // Ring layout: [NST][4 node blocks] | 1 KB of zeros | [NST][2 x halves].  UMMA 1 reads 16 slot rows per k-step, up to 64, from
+    // blocks of node_rows (>= slots, multiple of 8) rows: what lies behind a block must be finite bf16 (0 x NaN would poison
+    // the accumulator) - the next node block, or the zero pad behind the last one; never the fp32 x tiles.
+    uint8_t* ring = sm + SI_RING;
+    uint8_t* xring = ring + NST * 4 * NB + 1024;
+    float* s_bias = reinterpret_cast<float*>(ring + NST * STG + 1024);
+    float* s_part = s_bias + 192;                                          // [4 column groups][128 rows]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 512);
+    // the node tiles (freed by UMMA 1) and the x tiles (freed by the gate epilogue) run as two rings with their own barriers, so a
+    // node stage is refilled as soon as its UMMA 1 has retired, one item earlier than the x tile of the same site
+    uint64_t *full = bars, *stage_free = bars + SI_MAXST, *x_full = bars + 2 * SI_MAXST, *x_free = bars + 3 * SI_MAXST,
+             *a0_ready = bars + 4 * SI_MAXST, *d1_done = a0_ready + 1, *a1_ready = d1_done + 1, *s_done = a1_ready + 1;   // s_done[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_done + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_work = a.B * a.groups;
+
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(full + i, 1); mbar_init(stage_free + i, 1); mbar_init(x_full + i, 1); mbar_init(x_free + i, 8); }
+        mbar_init(a0_ready, 16); mbar_init(d1_done, 1); mbar_init(a1_ready, 16); mbar_init(s_done, 1); mbar_init(s_done + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) tmem_alloc(tmem_slot, 512);
+    // the ring (and the pad behind it) starts as zeros: slot rows past the tile read by UMMA 1 must be finite
+    for (int i = tid; i < (NST * STG + 1024) >> 4; i += SI_THREADS) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 1024; i += SI_THREADS) {                      // W_s -> swizzled K-major tiles (hi, lo)
+        const int plane = i >> 9, rem = i & 511, row = rem >> 3, j = rem & 7;
+        const uint4* src = plane == 0 ? a.wsh : a.wsl;
+        *reinterpret_cast<uint4*>(sm + SI_W + plane * 8192 + row * 128 + ((j ^ (row & 7)) << 4)) = __ldg(src + rem);
+    }
+    if (tid < 64) { s_bias[tid] = a.bg[tid]; s_bias[64 + tid] = a.bs[tid]; s_bias[128 + tid] = a.w2[tid]; }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 17) {
+        // ================= producer warps: 17 streams the node tiles, 18 the x tiles, one site per ring stage =================
+        const bool nodes = warp == 17;
+        uint64_t* fullb = nodes ? full : x_full;
+        uint64_t* freeb = nodes ? stage_free : x_free;
+        int st = 0; uint32_t ph = 0; int gs = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int b = w / a.groups, sg = w - b * a.groups;
+            const int c_base = sg * SI_SITES, n_sites = min(SI_SITES, a.C - c_base);
+            for (int s = 0; s < n_sites; ++s, ++gs) {
+                if (gs >= NST) mbar_wait(freeb + st, ph ^ 1u);
+                SI_TRACE(nodes ? 1 : 2, gs);
+                if (elect_one()) {
+                    const int c = c_base + s;
+                    if (nodes) {
+                        uint8_t* stg = ring + st * 4 * NB;
+                        mbar_expect_tx(full + st, 4 * NB);
+                        tma_load_3d(stg, &mapXh, full + st, 0, 0, b * a.C + c);
+                        tma_load_3d(stg + NB, &mapXh, full + st, 64, 0, b * a.C + c);
+                        tma_load_3d(stg + 2 * NB, &mapXl, full + st, 0, 0, b * a.C + c);
+                        tma_load_3d(stg + 3 * NB, &mapXl, full + st, 64, 0, b * a.C + c);
+                    } else {
+                        uint8_t* xt = xring + st * 2 * XB;
+                        mbar_expect_tx(x_full + st, 2 * XB);
+                        tma_load_4d(xt, &mapXf, x_full + st, 0, c, 0, b);
+                        tma_load_4d(xt + XB, &mapXf, x_full + st, 32, c, 0, b);
+                    }
+                }
+                __syncwarp();
+                if (++st == NST) { st = 0; ph ^= 1u; }
+            }
+        }
+        (void)fullb;
+    } else if (warp == 16) {
+        // ================= issue warp =================
+        const uint32_t wsh = smem_u32(sm + SI_W), wsl = wsh + 8192;
+        const uint32_t id_s = umma_idesc_bf16(128, 64), id_d1 = umma_idesc_bf16(128, 128) | (1u << 16);
+        const int ksteps = (a.S + 15) >> 4;
+        int st = 0; uint32_t ph = 0;
+        uint32_t gi = 0, wi = 0;        // items / work items so far (phases of a1_ready, a0_ready)
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
+            const int sg = w % a.groups;
+            const int n_sites = min(SI_SITES, a.C - sg * SI_SITES);
+            const int n_items = (n_sites + 1) >> 1;
+            mbar_wait(a0_ready, wi & 1u);
+            for (int k = 0; k < n_items; ++k, ++gi) {
+                // [x_glob | g] of site 2k+h = alpha . [X | W_g X]: the alpha operand is read from TENSOR MEMORY (a 128 x 128 x 16 UMMA
+                // costs ~75 clk with A in TMEM against ~107 clk with A in shared memory, measured), B MN-major from the node ring
+                for (int h = 0; h < 2; ++h) {
+                    if (2 * k + h >= n_sites) break;
+                    mbar_wait(full + st, ph);
+                    SI_TRACE(10 + h, (int)gi);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        // 16 slots = 2048 B per k-step, column blocks NB apart; descriptor low words advance by plain adds
+                        const uint32_t bh = umma_desc_lo(smem_u32(ring + st * 4 * NB), NB), bl = umma_desc_lo(smem_u32(ring + st * 4 * NB + 2 * NB), NB);
+                        const uint32_t ta0 = tmem_base + SI_TM_A0;
+                        const uint32_t td = tmem_base + SI_TM_D1 + h * 128;
+                        umma_ts<false>(td, ta0 + 32, bh, id_d1);
+                        umma_ts<true>(td, ta0, bl, id_d1);
+                        umma_ts<true>(td, ta0, bh, id_d1);
+#pragma unroll
+                        for (int kk = 1; kk < 4; ++kk) {
+                            if (kk < ksteps) {
+                                umma_ts<true>(td, ta0 + 32 + kk * 8, bh + kk * 128, id_d1);
+                                umma_ts<true>(td, ta0 + kk * 8, bl + kk * 128, id_d1);
+                                umma_ts<true>(td, ta0 + kk * 8, bh + kk * 128, id_d1);
+                            }
+                        }
+                        umma_commit(stage_free + st);
+                    }
+                    __syncwarp();
+                    if (++st == NST) { st = 0; ph ^= 1u; }
+                }
+                if (elect_one()) umma_commit(d1_done);
+                __syncwarp();
+                mbar_wait(a1_ready, gi & 1u);       // the epilogue has read D1 and written x' (tensor memory)
+                SI_TRACE(12, (int)gi);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t ta = tmem_base + SI_TM_A1, ts = tmem_base + ((gi & 1u) ? SI_TM_S1 : SI_TM_S);
+                    const uint32_t wh = umma_desc_lo(wsh), wl = umma_desc_lo(wsl);
+                    umma_ts<false>(ts, ta + 32, wh, id_s);          // s = x' . W_s^T for both sites at once; small terms first
+                    umma_ts<true>(ts, ta, wl, id_s);
+                    umma_ts<true>(ts, ta, wh, id_s);
+#pragma unroll
+                    for (int kk = 1; kk < 4; ++kk) {
+                        umma_ts<true>(ts, ta + 32 + kk * 8, wh + kk * 2, id_s);
+                        umma_ts<true>(ts, ta + kk * 8, wl + kk * 2, id_s);
+                        umma_ts<true>(ts, ta + kk * 8, wh + kk * 2, id_s);
+                    }
+                    umma_commit(s_done + (gi & 1u));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= epilogue warps: TMEM lane quarter q (lanes < 64: site 2k, else site 2k+1), 16 columns cg =================
+        const int q = warp & 3, cg = warp >> 2, h = q >> 1;
+        const int prow = (q & 1) * 32 + lane;                       // pair row
+        const bool warp_rows = (q & 1) * 32 < a.nc;                 // this warp's rows hold listed pairs
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float* bgv = s_bias + cg * 16;
+        const float* bsv = s_bias + 64 + cg * 16;
+        const float* w2v = s_bias + 128 + cg * 16;
+        int st = 0; uint32_t ph = 0;
+        uint32_t gi = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int b = w / a.groups, sg = w - b * a.groups;
+            const int c_base = sg * SI_SITES, n_sites = min(SI_SITES, a.C - c_base);
+            const int n_items = (n_sites + 1) >> 1;
+            // ---- alpha operand of this tree: alpha[b][pair][r] scattered to physical-slot order through a shared-memory table, then
+            //      split into bf16 hi / lo and stored to tensor memory by the row's own threads (lanes 64.. repeat the pairs)
+            {
+                float* tab = reinterpret_cast<float*>(sm + SI_A0);
+                for (int i = tid; i < 64 * SI_A0_LD / 4; i += 512) reinterpret_cast<float4*>(tab)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                const int32_t* so = a.slot_of + (size_t)b * a.slot_stride;
+                for (int idx = tid; idx < a.nc * a.Rp; idx += 512) {
+                    const int row = idx / a.Rp, r = idx - row * a.Rp;
+                    tab[row * SI_A0_LD + so[r]] = a.alpha[((size_t)b * a.alpha_pairs + row) * a.RP + r];
+                }
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                uint32_t hh[8], ll[8];
+                const float* tr = tab + prow * SI_A0_LD + cg * 16;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 v = *reinterpret_cast<const float4*>(tr + 4 * e);
+                    split2(v.x, v.y, hh[2 * e], ll[2 * e]);
+                    split2(v.z, v.w, hh[2 * e + 1], ll[2 * e + 1]);
+                }
+                tmem_st8(lane_base + SI_TM_A0 + cg * 8, hh);
+                tmem_st8(lane_base + SI_TM_A0 + 32 + cg * 8, ll);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a0_ready);
+            const bool row_ok = prow < a.nc && a.pair_i[(size_t)b * a.pair_stride + a.n0 + prow] >= 0;
+            float score = 0.f;
+            // w2 . GELU(s + b_s) (+ b2 once per row), masked site sum, for item `it` (global count) whose site of this thread is `site`
+            auto ep2 = [&](uint32_t it, int site) {
+                mbar_wait(s_done + (it & 1u), (it >> 1) & 1u);
+                if (warp == 0) SI_TRACE(23, (int)it);
+                tc_fence_after();
+                if (warp_rows && !(a.dbg & 4)) {
+                    uint32_t sv[16];
+                    tmem_ld16_nw(lane_base + ((it & 1u) ? SI_TM_S1 : SI_TM_S) + cg * 16, sv);
+                    tmem_ld_wait();
+                    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        acc0 = fmaf(gelu_fast(__uint_as_float(sv[e]) + bsv[e]), w2v[e], acc0);
+                        acc1 = fmaf(gelu_fast(__uint_as_float(sv[e + 1]) + bsv[e + 1]), w2v[e + 1], acc1);
+                    }
+                    const bool unmasked = site < n_sites && !(a.mask && a.mask[(size_t)b * a.C + c_base + site]);
+                    if (unmasked) score += (acc0 + acc1) + (cg == 0 ? a.b2 : 0.f);
+                }
+                tc_fence_before();
+                if (warp == 0) SI_TRACE(24, (int)it);
+            };
+            for (int k = 0; k < n_items; ++k, ++gi) {
+                // every warp observes every phase of every ring stage (both sites of the item, in order)
+                int st1 = st; uint32_t ph1 = ph;
+                if (++st1 == NST) { st1 = 0; ph1 ^= 1u; }
+                const bool two = 2 * k + 1 < n_sites;
+                mbar_wait(x_full + st, ph);
+                if (two) mbar_wait(x_full + st1, ph1);
+                const int site = 2 * k + h;
+                const bool site_ok = site < n_sites;
+                const int my_st = h ? st1 : st;
+                if (++st == NST) { st = 0; ph ^= 1u; }
+                if (two) { if (++st == NST) { st = 0; ph ^= 1u; } }
+                // ---- gate: w = sigmoid(g + b_g), x' = (1-w) x + w x_glob  -> A operand of the s_out GEMM (tensor memory)
+                float4 x4[4];
+                if (site_ok && prow < a.x_rows) {
+                    const uint8_t* xr = xring + my_st * 2 * XB + (cg >> 1) * XB + prow * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x4[j] = *reinterpret_cast<const float4*>(xr + ((((cg & 1) * 4 + j) ^ (prow & 7)) << 4));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const float* xv = reinterpret_cast<const float*>(x4);
+                if (warp == 0) SI_TRACE(20, (int)gi);
+                mbar_wait(d1_done, gi & 1u);
+                if (warp == 0) SI_TRACE(21, (int)gi);
+                tc_fence_after();
+                if (!warp_rows || (a.dbg & 2)) {          // no listed pair in this warp's 32 rows: x' = 0 (keeps UMMA 2's operand finite), nothing to score
+                    uint32_t z[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) z[e] = 0u;
+                    if (gi < 2 || k == 0) {
+                        tmem_st8(lane_base + SI_TM_A1 + cg * 8, z);
+                        tmem_st8(lane_base + SI_TM_A1 + 32 + cg * 8, z);
+                        tmem_st_wait();
+                    }
+                } else {
+                    uint32_t g[16], xg[16];
+                    tmem_ld16_nw(lane_base + SI_TM_D1 + h * 128 + 64 + cg * 16, g);
+                    tmem_ld16_nw(lane_base + SI_TM_D1 + h * 128 + cg * 16, xg);
+                    tmem_ld_wait();
+                    uint32_t hh[8], ll[8];
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        float p0 = 0.f, p1 = 0.f;
+                        if (site_ok) {
+                            const float x0 = xv[e], x1 = xv[e + 1];
+                            const float w0 = sigmoid_fast(__uint_as_float(g[e]) + bgv[e]);
+                            const float w1 = sigmoid_fast(__uint_as_float(g[e + 1]) + bgv[e + 1]);
+                            p0 = fmaf(w0, __uint_as_float(xg[e]) - x0, x0);       // (1-w) x + w x_glob
+                            p1 = fmaf(w1, __uint_as_float(xg[e + 1]) - x1, x1);
+                        }
+                        split2(p0, p1, hh[e >> 1], ll[e >> 1]);
+                    }
+                    tmem_st8(lane_base + SI_TM_A1 + cg * 8, hh);
+                    tmem_st8(lane_base + SI_TM_A1 + 32 + cg * 8, ll);
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(a1_ready);
+                    if (site_ok) mbar_arrive(x_free + my_st);           // x tile consumed
+                }
+                if (warp == 0) SI_TRACE(22, (int)gi);
+                // ---- score of the PREVIOUS item (its s = x' W_s^T has had the whole gate epilogue to finish): the tensor core runs
+                //      UMMA 2 of this item and UMMA 1 of the next while the GELU / site-sum epilogue of item k-1 executes
+                if (k > 0) ep2(gi - 1, 2 * (k - 1) + h);
+            }
+            ep2(gi - 1, 2 * (n_items - 1) + h);
+            // ---- partial score of this site group: column groups, then the two site halves, in fixed order
+            s_part[cg * 128 + q * 32 + lane] = row_ok ? score : 0.f;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (tid < a.nc) {
+                const float sa = (s_part[tid] + s_part[128 + tid]) + (s_part[256 + tid] + s_part[384 + tid]);
+                const float sb = (s_part[64 + tid] + s_part[192 + tid]) + (s_part[320 + tid] + s_part[448 + tid]);
+                a.score_part[((size_t)b * a.alpha_pairs + tid) * a.nSG + sg] = sa + sb;
+            }
+            // s_part and the alpha operand are rewritten by the next work item only after this barrier and the next one
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ------------------------------------------------------------------ host side
 
 // box {64, 64, 1} over site-major node planes [B*C][S][128]  ([X | W_g X] per slot)
-static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC) {
+static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC, int box_rows = 64) {
     typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static PFN enc = nullptr;
@@ -333,7 +667,7 @@ static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC) {
     }
     cuuint64_t gdim[3] = {128, (cuuint64_t)S, (cuuint64_t)BC};
     cuuint64_t gstr[2] = {256, (cuuint64_t)S * 256};
-    cuuint32_t box[3] = {64, 64, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -342,7 +676,7 @@ static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC) {
 }
 
 // x planes [B][pc][C][64] fp32 as a 4-D tensor (d, site, pair, tree); box = 32 channels of 64 pairs at one site (pairs >= nc read as 0)
-static int make_tmap_xtile(CUtensorMap* map, const float* base, int pc, int nrows, int C, int B) {
+static int make_tmap_xtile(CUtensorMap* map, const float* base, int pc, int nrows, int C, int B, int box_rows = 64) {
     typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     void* p = nullptr;
@@ -351,12 +685,67 @@ static int make_tmap_xtile(CUtensorMap* map, const float* base, int pc, int nrow
         return set_error(NNJ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[4] = {64, (cuuint64_t)C, (cuuint64_t)nrows, (cuuint64_t)B};
     cuuint64_t gstr[3] = {256, (cuuint64_t)C * 256, (cuuint64_t)pc * C * 256};
-    cuuint32_t box[4] = {32, 1, 64, 1};
+    cuuint32_t box[4] = {32, 1, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = reinterpret_cast<PFN>(p)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(NNJ_ERR_CUDA, "cuTensorMapEncodeTiled failed for the x tiles");
+    return 0;
+}
+
+// <= 64 pairs per tree: the persistent site-parity kernel
+static int launch_score_inc(const Model* m, const float* xf, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
+                            int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,
+                            int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, cudaStream_t st) {
+    static int n_sm = 0;
+    if (!n_sm) {
+        cudaError_t e = cudaFuncSetAttribute(k_score_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_SMEM_MAX);
+        if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess || n_sm <= 0) { n_sm = 0; return set_cuda_error(e, __FILE__, __LINE__); }
+    }
+    ScoreIncArgs a;
+    a.trace = nullptr;
+    static long long* trace_buf = nullptr; static int trace_state = -1;
+    if (trace_state < 0) { const char* ev = getenv("NNJ_SCORE_TRACE"); trace_state = ev ? atoi(ev) : 0; }
+    if (trace_state > 0 && nc == trace_state) { if (!trace_buf) cudaMalloc(&trace_buf, (1 + 3 * 20000) * 8); cudaMemsetAsync(trace_buf, 0, 8, st); a.trace = trace_buf; }
+    { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("NNJ_SCORE_DBG"); dbg = ev ? atoi(ev) : 0; } a.dbg = dbg; }
+    { static int pf = -1; if (pf < 0) { const char* ev = getenv("NNJ_SCORE_PF"); pf = ev ? atoi(ev) : 0; } a.pf = pf; }
+    a.node_rows = (S + 7) & ~7; a.x_rows = (nc + 7) & ~7;
+    const int stage = 4 * a.node_rows * 128 + 2 * a.x_rows * 128;
+    a.nst = (SI_SMEM_MAX - 1024 - SI_RING - 1024 - SI_MISC_BYTES) / stage;
+    if (a.nst > SI_MAXST) a.nst = SI_MAXST;
+    if (a.nst < 3) return set_error(NNJ_ERR_INVALID, "score_inc: ring does not fit");
+    CUtensorMap mh, ml, mx;
+    if (int e = make_tmap_xtile(&mx, xf + (size_t)0, pc, nc, C, B, a.x_rows)) return e;
+    if (int e = make_tmap_nodes(&mh, nodes_h, S, B * C, a.node_rows)) return e;
+    if (int e = make_tmap_nodes(&ml, nodes_l, S, B * C, a.node_rows)) return e;
+    a.alpha = alpha; a.RP = RP; a.alpha_pairs = alpha_pairs;
+    a.slot_of = slot_of; a.slot_stride = slot_stride; a.pair_i = pair_i; a.pair_stride = pair_stride; a.n0 = n0; a.nc = nc;
+    a.Rp = Rp; a.S = S; a.C = C; a.B = B; a.groups = (C + SI_SITES - 1) / SI_SITES;
+    a.wsh = (const uint4*)m->nj_bf.wsh; a.wsl = (const uint4*)m->nj_bf.wsl;
+    a.bg = m->nj.bg; a.bs = m->nj.bs; a.w2 = m->nj.w2; a.b2 = m->nj.b2;
+    a.mask = mask; a.score_part = score_part; a.nSG = nSG;
+    const int n_work = B * a.groups;
+    const size_t smem = 1024 + SI_RING + (size_t)a.nst * stage + 1024 + SI_MISC_BYTES;
+    prof_begin(KC_SCORE, st);
+    k_score_inc<<<n_work < n_sm ? n_work : n_sm, SI_THREADS, smem, st>>>(mh, ml, mx, a);
+    ++g_launches;
+    prof_end(st);
+    if (a.trace) {
+        cudaStreamSynchronize(st);
+        std::vector<long long> h(1 + 3 * 20000);
+        cudaMemcpy(h.data(), trace_buf, h.size() * 8, cudaMemcpyDeviceToHost);
+        const int n = (int)(h[0] & 0xffffffff) < 20000 ? (int)(h[0] & 0xffffffff) : 20000;
+        FILE* f = fopen("gpurun_out/score_trace.txt", "w");
+        if (f) { for (int i = 0; i < n; ++i) fprintf(f, "%lld %lld %lld\n", h[1 + 3 * i], h[2 + 3 * i], h[3 + 3 * i]); fclose(f); }
+        trace_state = 0;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     return 0;
 }
 
@@ -370,6 +759,13 @@ int launch_score_tc(const Model* m, const float* xf, int pc, const void* nodes_h
         attr = true;
     }
     if (S > 64) return set_error(NNJ_ERR_INVALID, "score_tc: at most 63 taxa on the tensor-core pair-score path");
+    {
+        static int inc = -1;
+        if (inc < 0) { const char* ev = getenv("NNJ_SCORE_INC"); inc = ev ? atoi(ev) : 1; }
+        if (inc && nc <= 64)
+            return launch_score_inc(m, xf, pc, nodes_h, nodes_l, alpha, RP, alpha_pairs, slot_of, slot_stride, pair_i, pair_stride, n0, nc, Rp, S, C, B,
+                                    mask, score_part, nSG, st);
+    }
     CUtensorMap mh, ml, mx;
     if (int e = make_tmap_xtile(&mx, xf, pc, nc, C, B)) return e;
     if (int e = make_tmap_nodes(&mh, nodes_h, S, B * C)) return e;

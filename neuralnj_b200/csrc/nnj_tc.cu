@@ -325,7 +325,68 @@ __global__ void __launch_bounds__(128, 1) k_tc_unit_ta(const float* __restrict__
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
+// Micro-benchmark (not on any product path): cycles per tcgen05.mma for the shapes the kernels use.  variant bits:
+//   [0..1] N: 0 = 64, 1 = 128, 2 = 256, 3 = 32      [2] A from tensor memory      [3] B MN-major      [4] two independent accumulators, alternating
+// Issues 512 UMMAs (operands = whatever is in shared / tensor memory, zero-initialised) from one thread and times issue-to-retire
+// with clock64.  Dm[0] = cycles per UMMA, Dm[1] = cycles the issuing thread spent in the issue loop per UMMA.
+__global__ void __launch_bounds__(128, 1) k_tc_mma_bench(float* __restrict__ Dm, int variant) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_align1024(smem_raw);
+    uint64_t* done = reinterpret_cast<uint64_t*>(base + 98304);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 98304 / 16; i += 128) reinterpret_cast<uint4*>(base)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) { mbar_init(done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    {   // zero the TMEM columns used as A operand
+        uint32_t z[16];
+        for (int e = 0; e < 16; ++e) z[e] = 0u;
+        for (int c = 448; c < 512; c += 16) tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + c, z);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const int nsel = variant & 3, N = nsel == 0 ? 64 : (nsel == 1 ? 128 : (nsel == 2 ? 256 : 32));
+    const bool ta = variant & 4, bmn = variant & 8, two = variant & 16;
+    if (warp == 0 && elect_one()) {
+        const uint32_t idesc = umma_idesc_bf16(128, N) | (bmn ? (1u << 16) : 0u);
+        const uint32_t a_lo = umma_desc_lo(smem_u32(base)), b_lo = umma_desc_lo(smem_u32(base) + 32768, bmn ? 8192 : 0);
+        const long long t0 = clock64();
+        for (int i = 0; i < 128; ++i) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t td = tmem_base + ((two && (kk & 1)) ? 256 - (N > 128 ? 64 : 0) : 0);
+                if (ta) umma_ts<true>(td, tmem_base + 448 + kk * 8, b_lo + (bmn ? kk * 128 : kk * 2), idesc);
+                else umma_ss<true>(td, a_lo + kk * 2, b_lo + (bmn ? kk * 128 : kk * 2), idesc);
+            }
+        }
+        const long long t1 = clock64();
+        umma_commit(done);
+        mbar_wait(done, 0);
+        const long long t2 = clock64();
+        Dm[0] = (float)(t2 - t0) / 512.0f;
+        Dm[1] = (float)(t1 - t0) / 512.0f;
+    }
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 int run_tc_unit(const float* A, const float* B, float* Dm, int bn, cudaStream_t st) {
+    if (bn >= 2000 && bn < 2032) {   // UMMA throughput micro-benchmark
+        cudaError_t e0 = cudaFuncSetAttribute(k_tc_mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e0 != cudaSuccess) return set_cuda_error(e0, __FILE__, __LINE__);
+        k_tc_mma_bench<<<1, 128, 100 * 1024, st>>>(Dm, bn - 2000);
+        ++g_launches;
+        e0 = cudaGetLastError();
+        if (e0 != cudaSuccess) return set_cuda_error(e0, __FILE__, __LINE__);
+        return 0;
+    }
     if (bn == 1064) {   // A from tensor memory, W [64 n][64 k] K-major
         cudaError_t e0 = cudaFuncSetAttribute(k_tc_unit_ta, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * 1024);
         if (e0 != cudaSuccess) return set_cuda_error(e0, __FILE__, __LINE__);

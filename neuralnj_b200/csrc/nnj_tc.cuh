@@ -118,6 +118,32 @@ __device__ __forceinline__ void umma_bf16_ta(uint32_t tmem_d, uint32_t tmem_a, u
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- cheap-issue forms.  One thread issues every UMMA of a CTA, and with 128 x 64..128 x 16 instructions and the 3-product
+// split the tensor core finishes one in 32-64 clk: building two 64-bit descriptors per instruction (shifts, masks, ors) made the
+// ISSUING THREAD the bottleneck (~125 clk per UMMA measured).  Here the descriptors are split into a constant high word and a
+// low word (start address >> 4 | LBO >> 4 << 16) that advances by a plain 32-bit add per k-step; `ACC` is a template constant.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes = 0) { return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+constexpr uint32_t UMMA_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B, version 1, SWIZZLE_128B
+template <bool ACC>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(ACC ? 1 : 0), "r"(UMMA_DESC_HI)
+        : "memory");
+}
+template <bool ACC>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(idesc), "n"(ACC ? 1 : 0), "r"(UMMA_DESC_HI)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
