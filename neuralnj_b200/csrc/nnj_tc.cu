@@ -40,11 +40,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
           const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcGemmArgs g) {
     constexpr int B_PLANE = BN * TC_BK * 2;
     constexpr int STAGE = 2 * TC_PLANE_BYTES + 2 * B_PLANE;
+    constexpr int NSTG = BN == 256 ? 2 : TC_STAGES;    // 128 x 256 tiles: 96 KB per stage (a 128 x 256 x 16 UMMA runs at 75 % of the tensor peak, 128 x 128 at 60 %)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = smem_align1024(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * STAGE);
-    uint64_t* empty = full + TC_STAGES;
-    uint64_t* acc_full = empty + TC_STAGES;      // [2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTG * STAGE);
+    uint64_t* empty = full + NSTG;
+    uint64_t* acc_full = empty + NSTG;      // [2]
     uint64_t* acc_free = acc_full + 2;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
 
@@ -54,7 +55,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     const int n_tiles = g.Z * mt * nt;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1); mbar_init(acc_full + 1, 1);
         mbar_init(acc_free, 4); mbar_init(acc_free + 1, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -75,8 +76,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
             const int kc0 = split * g.chunks_per_split;
             const int nchunks = max(0, min(total_chunks - kc0, g.chunks_per_split));
             for (int kk = 0; kk < nchunks; ++kk, ++gc) {
-                const int s = gc % TC_STAGES, kc = kc0 + kk;
-                if (gc >= TC_STAGES) mbar_wait(&empty[s], ((gc / TC_STAGES) - 1) & 1);
+                const int s = gc % NSTG, kc = kc0 + kk;
+                if (gc >= NSTG) mbar_wait(&empty[s], ((gc / NSTG) - 1) & 1);
                 uint8_t* st = tiles + s * STAGE;
                 if (elect_one()) {
                     mbar_expect_tx(&full[s], STAGE);
@@ -107,22 +108,28 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
             const uint32_t t_acc = tmem_base + ab * BN;
             if (ti >= 2) { mbar_wait(acc_free + ab, ((ti >> 1) - 1) & 1); tc_fence_after(); }   // the epilogue has drained this accumulator
             for (int kk = 0; kk < nchunks; ++kk, ++gc) {
-                const int s = gc % TC_STAGES, kc = kc0 + kk;
-                mbar_wait(&full[s], (gc / TC_STAGES) & 1);
+                const int s = gc % NSTG, kc = kc0 + kk;
+                mbar_wait(&full[s], (gc / NSTG) & 1);
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(tiles + s * STAGE), a_lo = a_hi + TC_PLANE_BYTES;
                 const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = b_hi + B_PLANE;
                 const int kvalid = min(TC_BK, g.K - kc * TC_BK);
                 const int ksteps = (kvalid + 15) / 16;
                 if (elect_one()) {
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint32_t ko = k * 32;   // 16 bf16 = 32 B inside the 128 B swizzle row
-                        const uint64_t dah = umma_desc_k128(a_hi + ko), dal = umma_desc_k128(a_lo + ko);
-                        const uint64_t dbh = BMN ? umma_desc_lbo(b_hi + k * 2048, 8192) : umma_desc_k128(b_hi + ko);   // MN-major: 16 K rows = 2 KB per step
-                        const uint64_t dbl = BMN ? umma_desc_lbo(b_lo + k * 2048, 8192) : umma_desc_k128(b_lo + ko);
-                        umma_bf16(t_acc, dal, dbh, idesc, (kk | k) ? 1u : 0u);   // small terms first
-                        umma_bf16(t_acc, dah, dbl, idesc, 1u);
-                        umma_bf16(t_acc, dah, dbh, idesc, 1u);
+                    // descriptor low words advance by plain adds: K-major 16 bf16 = 32 B (>> 4 = 2) per k-step; MN-major 16 K rows = 2 KB (128)
+                    const uint32_t dah = umma_desc_lo(a_hi), dal = umma_desc_lo(a_lo);
+                    const uint32_t dbh = BMN ? umma_desc_lo(b_hi, 8192) : umma_desc_lo(b_hi), dbl = BMN ? umma_desc_lo(b_lo, 8192) : umma_desc_lo(b_lo);
+                    constexpr uint32_t BSTEP = BMN ? 128u : 2u;
+                    if (kk == 0) umma_ss<false>(t_acc, dal, dbh, idesc); else umma_ss<true>(t_acc, dal, dbh, idesc);   // small terms first
+                    umma_ss<true>(t_acc, dah, dbl, idesc);
+                    umma_ss<true>(t_acc, dah, dbh, idesc);
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) {
+                        if (k < ksteps) {
+                            umma_ss<true>(t_acc, dal + k * 2, dbh + k * BSTEP, idesc);
+                            umma_ss<true>(t_acc, dah + k * 2, dbl + k * BSTEP, idesc);
+                            umma_ss<true>(t_acc, dah + k * 2, dbh + k * BSTEP, idesc);
+                        }
                     }
                     umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
                     if (kk == nchunks - 1) umma_commit(acc_full + ab);   // accumulator complete
@@ -506,9 +513,11 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
     static bool attr = false;
     constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256;
     constexpr int SMEM64 = TC_STAGES * (3 * TC_PLANE_BYTES) + 1024 + 256;
+    constexpr int SMEM256 = 2 * (6 * TC_PLANE_BYTES) + 1024 + 256;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM256);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
         attr = true;
     }
@@ -521,7 +530,8 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
     const int n_tiles = ((N + bn - 1) / bn) * nsplit * ((M + TC_BM - 1) / TC_BM) * Z;
     const dim3 grid(n_tiles < tc_sm_count() ? n_tiles : tc_sm_count());
     prof_begin(cls, st);
-    if (bn == 128) k_tc_gemm<128, false><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g);
+    if (bn == 256) k_tc_gemm<256, false><<<grid, TC_THREADS, SMEM256, st>>>(mAh, mAl, mBh, mBl, g);
+    else if (bn == 128) k_tc_gemm<128, false><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g);
     else k_tc_gemm<64, false><<<grid, TC_THREADS, SMEM64, st>>>(mAh, mAl, mBh, mBl, g);
     ++g_launches;
     prof_end(st);
@@ -532,7 +542,8 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
 
 int launch_tc_gemm(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                    size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st) {
-    return launch_tc_gemm_ex(cls, Ah, Al, Bh, Bl, Cm, Z, M, N, K, lda, sA, ldb, sB, ldc, sC, 128, 1, (K + TC_BK - 1) / TC_BK, 0, st);
+    const int bn = (N >= 256 && N % 256 == 0) ? 256 : 128;     // 128 x 256 tiles when they divide N (row-attention logits)
+    return launch_tc_gemm_ex(cls, Ah, Al, Bh, Bl, Cm, Z, M, N, K, lda, sA, ldb, sB, ldc, sC, bn, 1, (K + TC_BK - 1) / TC_BK, 0, st);
 }
 
 // Stand-alone building block (also the unit-test entry): fp32 A [Z][M][K], B [Z][N][K] -> C [Z][M][N].
