@@ -339,7 +339,7 @@ constexpr int SI_A0_LD = 68;
 constexpr int SI_W = 32768;                // W_s hi 8 KB | lo 8 KB
 constexpr int SI_RING = 49152;
 constexpr int SI_MAXST = 6;
-constexpr int SI_MISC_BYTES = 768 + 2048 + 512;   // biases | score partials [4][128] | barriers (4 x 6 + 5), tmem slot
+constexpr int SI_MISC_BYTES = 768 + 2048 + 512;   // biases | score partials [4][128] | barriers (4 x 6 + 7), tmem slot
 constexpr int SI_SMEM_MAX = 232448;
 constexpr uint32_t SI_TM_D1 = 0, SI_TM_S = 256, SI_TM_A1 = 320, SI_TM_S1 = 384, SI_TM_A0 = 448;   // TMEM: D1a 128 | D1b 128 | s[0] 64 | x' hi/lo 64 | s[1] 64 | alpha hi/lo 64
 
@@ -378,7 +378,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
     // the node tiles (freed by UMMA 1) and the x tiles (freed by the gate epilogue) run as two rings with their own barriers, so a
     // node stage is refilled as soon as its UMMA 1 has retired, one item earlier than the x tile of the same site
     uint64_t *full = bars, *stage_free = bars + SI_MAXST, *x_full = bars + 2 * SI_MAXST, *x_free = bars + 3 * SI_MAXST,
-             *a0_ready = bars + 4 * SI_MAXST, *d1_done = a0_ready + 1, *a1_ready = d1_done + 1, *s_done = a1_ready + 1;   // s_done[2]
+             *a0_ready = bars + 4 * SI_MAXST, *d1_done = a0_ready + 1, *a1_ready = d1_done + 2, *s_done = a1_ready + 2;   // d1_done[2] a1_ready[2] s_done[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_done + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -386,7 +386,8 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
 
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(full + i, 1); mbar_init(stage_free + i, 1); mbar_init(x_full + i, 1); mbar_init(x_free + i, 8); }
-        mbar_init(a0_ready, 16); mbar_init(d1_done, 1); mbar_init(a1_ready, 16); mbar_init(s_done, 1); mbar_init(s_done + 1, 1);
+        mbar_init(a0_ready, 16); mbar_init(d1_done, 1); mbar_init(d1_done + 1, 1); mbar_init(a1_ready, 8); mbar_init(a1_ready + 1, 8);
+        mbar_init(s_done, 1); mbar_init(s_done + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(tmem_slot, 512);
@@ -449,39 +450,42 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
             const int n_sites = min(SI_SITES, a.C - sg * SI_SITES);
             const int n_items = (n_sites + 1) >> 1;
             mbar_wait(a0_ready, wi & 1u);
-            for (int k = 0; k < n_items; ++k, ++gi) {
-                // [x_glob | g] of site 2k+h = alpha . [X | W_g X]: the alpha operand is read from TENSOR MEMORY (a 128 x 128 x 16 UMMA
-                // costs ~75 clk with A in TMEM against ~107 clk with A in shared memory, measured), B MN-major from the node ring
-                for (int h = 0; h < 2; ++h) {
-                    if (2 * k + h >= n_sites) break;
-                    mbar_wait(full + st, ph);
-                    SI_TRACE(10 + h, (int)gi);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        // 16 slots = 2048 B per k-step, column blocks NB apart; descriptor low words advance by plain adds
-                        const uint32_t bh = umma_desc_lo(smem_u32(ring + st * 4 * NB), NB), bl = umma_desc_lo(smem_u32(ring + st * 4 * NB + 2 * NB), NB);
-                        const uint32_t ta0 = tmem_base + SI_TM_A0;
-                        const uint32_t td = tmem_base + SI_TM_D1 + h * 128;
-                        umma_ts<false>(td, ta0 + 32, bh, id_d1);
-                        umma_ts<true>(td, ta0, bl, id_d1);
-                        umma_ts<true>(td, ta0, bh, id_d1);
+            // The two sites of an item are two half-pipelines: while the 8 epilogue warps of one half run the gate epilogue on their
+            // accumulator (D1a / D1b), the tensor core refills the other one.  Issue order: U1a(0) U1b(0), then per item k:
+            //   [half A done with D1a(k)] U1a(k+1)   [half B done with D1b(k)] U2(k) U1b(k+1)
+            // (sites stay in ring order A(k) B(k) A(k+1) ...).  [x_glob | g] = alpha . [X | W_g X]: alpha from TENSOR MEMORY (a 128 x 128
+            // x 16 UMMA costs ~75 clk with A in TMEM against ~107 clk from shared memory), B MN-major from the node ring.
+            auto issue_u1 = [&](int h) {
+                mbar_wait(full + st, ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    // 16 slots = 2048 B per k-step, column blocks NB apart; descriptor low words advance by plain adds
+                    const uint32_t bh = umma_desc_lo(smem_u32(ring + st * 4 * NB), NB), bl = umma_desc_lo(smem_u32(ring + st * 4 * NB + 2 * NB), NB);
+                    const uint32_t ta0 = tmem_base + SI_TM_A0;
+                    const uint32_t td = tmem_base + SI_TM_D1 + h * 128;
+                    umma_ts<false>(td, ta0 + 32, bh, id_d1);
+                    umma_ts<true>(td, ta0, bl, id_d1);
+                    umma_ts<true>(td, ta0, bh, id_d1);
 #pragma unroll
-                        for (int kk = 1; kk < 4; ++kk) {
-                            if (kk < ksteps) {
-                                umma_ts<true>(td, ta0 + 32 + kk * 8, bh + kk * 128, id_d1);
-                                umma_ts<true>(td, ta0 + kk * 8, bl + kk * 128, id_d1);
-                                umma_ts<true>(td, ta0 + kk * 8, bh + kk * 128, id_d1);
-                            }
+                    for (int kk = 1; kk < 4; ++kk) {
+                        if (kk < ksteps) {
+                            umma_ts<true>(td, ta0 + 32 + kk * 8, bh + kk * 128, id_d1);
+                            umma_ts<true>(td, ta0 + kk * 8, bl + kk * 128, id_d1);
+                            umma_ts<true>(td, ta0 + kk * 8, bh + kk * 128, id_d1);
                         }
-                        umma_commit(stage_free + st);
                     }
-                    __syncwarp();
-                    if (++st == NST) { st = 0; ph ^= 1u; }
+                    umma_commit(stage_free + st);
+                    umma_commit(d1_done + h);
                 }
-                if (elect_one()) umma_commit(d1_done);
                 __syncwarp();
-                mbar_wait(a1_ready, gi & 1u);       // the epilogue has read D1 and written x' (tensor memory)
-                SI_TRACE(12, (int)gi);
+                if (++st == NST) { st = 0; ph ^= 1u; }
+            };
+            issue_u1(0);
+            if (n_sites > 1) issue_u1(1);
+            for (int k = 0; k < n_items; ++k, ++gi) {
+                mbar_wait(a1_ready, gi & 1u);           // half A has read D1a and written its x' rows
+                if (2 * (k + 1) < n_sites) issue_u1(0);
+                mbar_wait(a1_ready + 1, gi & 1u);       // half B likewise (it arrives with zeros when the item has no second site)
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t ta = tmem_base + SI_TM_A1, ts = tmem_base + ((gi & 1u) ? SI_TM_S1 : SI_TM_S);
@@ -498,6 +502,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                     umma_commit(s_done + (gi & 1u));
                 }
                 __syncwarp();
+                if (2 * (k + 1) + 1 < n_sites) issue_u1(1);
             }
         }
     } else {
@@ -510,7 +515,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
         const float* bsv = s_bias + 64 + cg * 16;
         const float* w2v = s_bias + 128 + cg * 16;
         int st = 0; uint32_t ph = 0;
-        uint32_t gi = 0;
+        uint32_t gi = 0, c_d1 = 0;      // items so far; UMMA-1 completions of this half so far (phase of d1_done[h])
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int b = w / a.groups, sg = w - b * a.groups;
             const int c_base = sg * SI_SITES, n_sites = min(SI_SITES, a.C - c_base);
@@ -589,7 +594,8 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                 }
                 const float* xv = reinterpret_cast<const float*>(x4);
                 if (warp == 0) SI_TRACE(20, (int)gi);
-                mbar_wait(d1_done, gi & 1u);
+                if (site_ok) { mbar_wait(d1_done + h, c_d1 & 1u); ++c_d1; }      // this half's [x_glob | g]
+                if (gi >= 1) mbar_wait(s_done + ((gi - 1) & 1u), ((gi - 1) >> 1) & 1u);   // UMMA 2 of the previous item has read the x' operand
                 if (warp == 0) SI_TRACE(21, (int)gi);
                 tc_fence_after();
                 if (!warp_rows || (a.dbg & 2)) {          // no listed pair in this warp's 32 rows: x' = 0 (keeps UMMA 2's operand finite), nothing to score
@@ -626,7 +632,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(a1_ready);
+                    mbar_arrive(a1_ready + h);
                     if (site_ok) mbar_arrive(x_free + my_st);           // x tile consumed
                 }
                 if (warp == 0) SI_TRACE(22, (int)gi);
