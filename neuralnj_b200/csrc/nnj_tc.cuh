@@ -240,14 +240,18 @@ __device__ __forceinline__ void a_store8(uint8_t* hi, uint8_t* lo, int row, int 
 
 // D[128 x N] (+)= A[128 x 64] * W[N x 64]^T with the 3-product bf16 split; all four operands are K-major SWIZZLE_128B tiles
 // (A planes 16 KB, W planes N*128 B).  Call from ONE elected lane.  first_acc = 0 starts a fresh accumulator.
+// Descriptor low words advance by 2 (32 B >> 4) per 16-element k-step (cheap-issue forms above).
 __device__ __forceinline__ void umma_split_k64(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, uint32_t idesc,
                                                uint32_t first_acc) {
+    const uint32_t dah = umma_desc_lo(a_hi), dal = umma_desc_lo(a_lo), dwh = umma_desc_lo(w_hi), dwl = umma_desc_lo(w_lo);
+    if (first_acc) umma_ss<true>(tmem_d, dal, dwh, idesc); else umma_ss<false>(tmem_d, dal, dwh, idesc);   // small terms first
+    umma_ss<true>(tmem_d, dah, dwl, idesc);
+    umma_ss<true>(tmem_d, dah, dwh, idesc);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t ko = k * 32;   // 16 bf16 = 32 B inside the 128 B swizzle row
-        umma_bf16(tmem_d, umma_desc_k128(a_lo + ko), umma_desc_k128(w_hi + ko), idesc, (k | first_acc) ? 1u : 0u);   // small terms first
-        umma_bf16(tmem_d, umma_desc_k128(a_hi + ko), umma_desc_k128(w_lo + ko), idesc, 1u);
-        umma_bf16(tmem_d, umma_desc_k128(a_hi + ko), umma_desc_k128(w_hi + ko), idesc, 1u);
+    for (int k = 1; k < 4; ++k) {
+        umma_ss<true>(tmem_d, dal + 2 * k, dwh + 2 * k, idesc);
+        umma_ss<true>(tmem_d, dah + 2 * k, dwl + 2 * k, idesc);
+        umma_ss<true>(tmem_d, dah + 2 * k, dwh + 2 * k, idesc);
     }
 }
 
