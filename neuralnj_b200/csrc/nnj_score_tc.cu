@@ -571,15 +571,16 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                 if (warp == 0) SI_TRACE(24, (int)it);
             };
             for (int k = 0; k < n_items; ++k, ++gi) {
-                // every warp observes every phase of every ring stage (both sites of the item, in order)
+                // The halves run decoupled (ping-pong), so a warp may wait only on the x stages its own half releases: the ring depth is
+                // even and every work item starts on an even ring position, hence even stages always hold the first site of an item
+                // (half A) and odd stages the second (half B), and a warp sees every phase of the stages it looks at.
                 int st1 = st; uint32_t ph1 = ph;
                 if (++st1 == NST) { st1 = 0; ph1 ^= 1u; }
                 const bool two = 2 * k + 1 < n_sites;
-                mbar_wait(x_full + st, ph);
-                if (two) mbar_wait(x_full + st1, ph1);
                 const int site = 2 * k + h;
                 const bool site_ok = site < n_sites;
                 const int my_st = h ? st1 : st;
+                if (site_ok) mbar_wait(x_full + my_st, h ? ph1 : ph);
                 if (++st == NST) { st = 0; ph ^= 1u; }
                 if (two) { if (++st == NST) { st = 0; ph ^= 1u; } }
                 // ---- gate: w = sigmoid(g + b_g), x' = (1-w) x + w x_glob  -> A operand of the s_out GEMM (tensor memory)
@@ -724,7 +725,9 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
     const int stage = 4 * a.node_rows * 128 + 2 * a.x_rows * 128;
     a.nst = (SI_SMEM_MAX - 1024 - SI_RING - 1024 - SI_MISC_BYTES) / stage;
     if (a.nst > SI_MAXST) a.nst = SI_MAXST;
-    if (a.nst < 3) return set_error(NNJ_ERR_INVALID, "score_inc: ring does not fit");
+    a.nst &= ~1;                      // even: the two half-pipelines own the even / odd ring stages (see the kernel)
+    if (a.nst < 2) return set_error(NNJ_ERR_INVALID, "score_inc: ring does not fit");
+    if ((C % SI_SITES) & 1) return set_error(NNJ_ERR_INVALID, "score_inc: odd site count");   // unreachable: the tensor-core path needs C % 8 == 0
     CUtensorMap mh, ml, mx;
     if (int e = make_tmap_xtile(&mx, xf + (size_t)0, pc, nc, C, B, a.x_rows)) return e;
     if (int e = make_tmap_nodes(&mh, nodes_h, S, B * C, a.node_rows)) return e;
