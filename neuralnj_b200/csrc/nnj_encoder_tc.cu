@@ -185,13 +185,14 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
     float* s_g = s_b2 + 64;
     float* s_b = s_g + 64;
     float2* part = reinterpret_cast<float2*>(s_b + 64);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 256);   // d1_done, c0_done, c1_done, d2_done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 256);   // d1_done, c0_done, c1_done, d2_done, a_ready[2], a0_ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane;
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+        mbar_init(bars + 4, ET_THREADS / 32); mbar_init(bars + 5, ET_THREADS / 32); mbar_init(bars + 6, ET_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 256;
+    const uint32_t t_d1 = tmem_base, t_d2 = tmem_base + 256, t_a = tmem_base + 320, t_a0 = tmem_base + 448;   // D1 256 | D2 64 | GELU chunk operand 2 x (hi 32 | lo 32) | LN3(x) operand (hi 32 | lo 32)
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t id_d1 = umma_idesc_bf16(128, 256), id_d2 = umma_idesc_bf16(128, 64);
     const int n_work = a.B * a.tiles_per_tree;
@@ -226,12 +227,31 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = xr[k];
         ln_half(v, part, row, hf, s_g, s_b);
-        a_store32(abuf0, abuf0 + 16384, row, hf, v);
-        ET_PUBLISH_A();
+        {   // LN3(x) -> bf16 hi / lo in tensor memory: A operand of fc1
+            uint32_t hh[16], ll[16];
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) split2(v[k], v[k + 1], hh[k >> 1], ll[k >> 1]);
+            tmem_st16(t_a0 + lane_off + hf * 16, hh);
+            tmem_st16(t_a0 + lane_off + 32 + hf * 16, ll);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 6);
+        }
         if (warp == 0) {   // hidden pre-activations D1 [128 x 256] = LN3(x) . fc1^T
+            mbar_wait(bars + 6, par);
             tc_fence_after();
             if (elect_one()) {
-                umma_split_k64(t_d1, smem_u32(abuf0), smem_u32(abuf0) + 16384, smem_u32(w1_s), smem_u32(w1_s) + 32768, id_d1, 0u);
+                const uint32_t wh = umma_desc_lo(smem_u32(w1_s)), wl = umma_desc_lo(smem_u32(w1_s) + 32768);
+                umma_ts<false>(t_d1, t_a0 + 32, wh, id_d1);      // small terms first
+                umma_ts<true>(t_d1, t_a0, wl, id_d1);
+                umma_ts<true>(t_d1, t_a0, wh, id_d1);
+#pragma unroll
+                for (int kk = 1; kk < 4; ++kk) {
+                    umma_ts<true>(t_d1, t_a0 + 32 + kk * 8, wh + kk * 2, id_d1);
+                    umma_ts<true>(t_d1, t_a0 + kk * 8, wl + kk * 2, id_d1);
+                    umma_ts<true>(t_d1, t_a0 + kk * 8, wh + kk * 2, id_d1);
+                }
                 umma_commit(bars + 0);
             }
             __syncwarp();
@@ -240,21 +260,38 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
         tc_fence_after();
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
-            // the operand buffer of chunk ch was last read by the fc2 UMMA of chunk ch-2
+            // GELU chunk ch -> bf16 hi / lo straight into TENSOR MEMORY (row = this thread's lane, two bf16 per column): the fc2 UMMA
+            // reads its A operand from there (42 clk per 128 x 64 x 16 instead of 75 from shared memory) and the hand-off is an
+            // mbarrier arrive per warp, not a block-wide barrier.  The operand buffer of chunk ch was last read by the UMMA of chunk ch-2.
             if (ch >= 2) { mbar_wait(bars + 1 + (ch - 2), par); tc_fence_after(); }
             uint32_t acc[32];
             tmem_ld32(t_d1 + lane_off + ch * 64 + hf * 32, acc);
-            float hdn[32];
+            uint32_t hh[16], ll[16];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) hdn[k] = gelu_fast(__uint_as_float(acc[k]) + s_b1[ch * 64 + hf * 32 + k]);
-            uint8_t* ab = abuf0 + (ch & 1) * 32768;
-            a_store32(ab, ab + 16384, row, hf, hdn);
-            ET_PUBLISH_A();
+            for (int k = 0; k < 32; k += 2)
+                split2(gelu_fast(__uint_as_float(acc[k]) + s_b1[ch * 64 + hf * 32 + k]), gelu_fast(__uint_as_float(acc[k + 1]) + s_b1[ch * 64 + hf * 32 + k + 1]),
+                       hh[k >> 1], ll[k >> 1]);
+            const uint32_t ta = t_a + (ch & 1) * 64;
+            tmem_st16(ta + lane_off + hf * 16, hh);
+            tmem_st16(ta + lane_off + 32 + hf * 16, ll);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 4 + (ch & 1));
             if (warp == 0) {   // D2 [128 x 64] += GELU chunk . fc2[:, 64 ch .. 64 ch + 63]^T
+                mbar_wait(bars + 4 + (ch & 1), (2 * it + (ch >> 1)) & 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    umma_split_k64(t_d2, smem_u32(ab), smem_u32(ab) + 16384, smem_u32(w2_s) + ch * 8192, smem_u32(w2_s) + 32768 + ch * 8192, id_d2,
-                                   ch ? 1u : 0u);
+                    const uint32_t wh = umma_desc_lo(smem_u32(w2_s) + ch * 8192), wl = umma_desc_lo(smem_u32(w2_s) + 32768 + ch * 8192);
+                    if (ch == 0) umma_ts<false>(t_d2, ta + 32, wh, id_d2); else umma_ts<true>(t_d2, ta + 32, wh, id_d2);   // small terms first
+                    umma_ts<true>(t_d2, ta, wl, id_d2);
+                    umma_ts<true>(t_d2, ta, wh, id_d2);
+#pragma unroll
+                    for (int kk = 1; kk < 4; ++kk) {
+                        umma_ts<true>(t_d2, ta + 32 + kk * 8, wh + kk * 2, id_d2);
+                        umma_ts<true>(t_d2, ta + kk * 8, wl + kk * 2, id_d2);
+                        umma_ts<true>(t_d2, ta + kk * 8, wh + kk * 2, id_d2);
+                    }
                     if (ch == 0) umma_commit(bars + 1);
                     else if (ch == 1) umma_commit(bars + 2);
                     else if (ch == 3) umma_commit(bars + 3);
