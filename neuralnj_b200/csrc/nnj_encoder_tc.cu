@@ -210,6 +210,21 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
     const uint32_t id_d1 = umma_idesc_bf16(128, 256), id_d2 = umma_idesc_bf16(128, 64);
     const int n_work = a.B * a.tiles_per_tree;
     uint32_t it = 0;
+    // this thread's 32 values of its token row, loaded one tile ahead (the global-load latency hides behind the previous tile's GEMMs)
+    auto load_row = [&](int w, float4 (&dst)[8]) {
+        const int b = w / a.tiles_per_tree, tile = w - b * a.tiles_per_tree;
+        const int t = tile * 128 + row;
+        if (w < n_work && t < a.T) {
+            const float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + hf * 32;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[k] = ld4(xp + k * 4);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    float4 xnext[8];
+    load_row(blockIdx.x, xnext);
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
         const uint32_t par = it & 1;
         const int b = w / a.tiles_per_tree, tile = w - b * a.tiles_per_tree;
@@ -217,13 +232,9 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
         const bool valid = t < a.T;
         float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + hf * 32;
         float xr[32], v[32];
-        if (valid) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const float4 f = ld4(xp + k * 4); xr[4 * k] = f.x; xr[4 * k + 1] = f.y; xr[4 * k + 2] = f.z; xr[4 * k + 3] = f.w; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) xr[k] = 0.f;
-        }
+        for (int k = 0; k < 8; ++k) { xr[4 * k] = xnext[k].x; xr[4 * k + 1] = xnext[k].y; xr[4 * k + 2] = xnext[k].z; xr[4 * k + 3] = xnext[k].w; }
+        load_row(w + gridDim.x, xnext);
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = xr[k];
         ln_half(v, part, row, hf, s_g, s_b);
