@@ -104,3 +104,24 @@ def test_full_size_properties_tensor_core(gpu_models):
     assert torch.equal(m1, m2) and torch.equal(s1, s2) and torch.equal(t1, t2)
     m3, s3, t3 = model.rollout_fused(data[3:4].cuda(), mask[3:4].cuda(), want_logits=True)
     assert torch.equal(m3, m1[3:4]) and torch.equal(t3, t1[3:4])
+
+
+def test_large_alignment_200x4096(gpu_models):
+    """BASELINE config 4 (200 taxa x 4096 sites, Argmax): above 63 taxa the NJ loop runs on the fp32 CUDA-core kernels, the encoder
+    stays on tcgen05.  The CPU oracle needs minutes at this size, so the check is by properties: valid merge lists, finite
+    log-probabilities, bit-exact rerun, and batch independence (B = 2 against its own B = 1 halves)."""
+    import nnj_oracle as O
+    model = gpu_models["bf16x3"]
+    R, L = 200, 4096
+    data = O.synthetic_msa(2, R, L, seed=7)
+    mask = torch.zeros(2, L, dtype=torch.bool)
+    m2, s2, _ = model.rollout_fused(data.cuda(), mask.cuda())
+    m1, s1, _ = model.rollout_fused(data[:1].cuda(), mask[:1].cuda())
+    m1b, _, _ = model.rollout_fused(data[:1].cuda(), mask[:1].cuda())
+    assert torch.equal(m1, m1b)
+    assert torch.equal(m2[:1], m1) and torch.equal(s2[:1], s1)
+    mm = m2.cpu()
+    for t in range(R - 1):
+        n = R - t
+        assert bool(((0 <= mm[:, t, 0]) & (mm[:, t, 0] < mm[:, t, 1]) & (mm[:, t, 1] < n)).all())
+    assert bool(torch.isfinite(s2).all())
