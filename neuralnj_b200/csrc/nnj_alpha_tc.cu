@@ -39,7 +39,8 @@ struct AlphaV3Args {
     const float* bh;
     float* alpha_part; int alpha_pairs; int nSG; int RP;
     int dup;                                   // nc <= 64: tile split by site parity, two partials per site group
-    int tile_bytes, nst;                       // ring geometry: [round8(slots)][128 B] tiles, 6 per stage, nst stages
+    int tile_bytes, nst;                       // ring geometry: [round8(live slots)][128 B] tiles, 6 per stage, nst stages
+    int nmma;                                  // UMMA N = round16(live slots)
 };
 
 struct RingPos {                               // position in the node ring / its phase bit
@@ -130,7 +131,7 @@ k_alpha_v3(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         }
     } else if (warp == AV_BLEND_WARPS) {
         // ================= issue warp: acc (+)= A (tensor memory) . K'^T =================
-        const uint32_t idesc = umma_idesc_bf16(128, 64);
+        const uint32_t idesc = umma_idesc_bf16(128, a.nmma);
         RingPos rp{0, 0u};
         int gk = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -359,10 +360,10 @@ static int make_tmap_xplanes(CUtensorMap* map, float* base, int pc, int nrows, i
 }
 
 // K' planes [B][S][C][64] bf16 as a 4-D tensor (d, site, slot, tree); box = all slots of one site: [64 slots][64 d]
-static int make_tmap_kprime(CUtensorMap* map, const void* base, int S, int C, int B, int box_rows) {
+static int make_tmap_kprime(CUtensorMap* map, const void* base, int S, int n_live, int C, int B, int box_rows) {
     PFN_enc enc = get_enc();
     if (!enc) return set_error(NNJ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t gdim[4] = {64, (cuuint64_t)C, (cuuint64_t)S, (cuuint64_t)B};
+    cuuint64_t gdim[4] = {64, (cuuint64_t)C, (cuuint64_t)n_live, (cuuint64_t)B};   // slots >= n_live are dead: never loaded (zero-filled)
     cuuint64_t gstr[3] = {128, (cuuint64_t)C * 128, (cuuint64_t)S * C * 128};
     cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -374,7 +375,7 @@ static int make_tmap_kprime(CUtensorMap* map, const void* base, int S, int C, in
 
 // writes the x planes of pairs [n0, n0+nc) and alpha_part[b][n][partial][slot]; returns the number of partials per pair in *n_part
 int launch_alpha_tc(const Model* m, const float* X, const float* Y, size_t tree_stride, const int32_t* slot_of, int slot_stride, const int32_t* pair_i,
-                    const int32_t* pair_j, int pair_stride, int n0, int nc, int S, int C, int B, const void* kp_h, const void* kp_l, float* xf,
+                    const int32_t* pair_j, int pair_stride, int n0, int nc, int S, int n_live, int C, int B, const void* kp_h, const void* kp_l, float* xf,
                     int pc, float* alpha_part, int alpha_pairs, int nSG, int RP, int* n_part, cudaStream_t st) {
     static int n_sm = 0;
     if (!n_sm) {
@@ -391,17 +392,19 @@ int launch_alpha_tc(const Model* m, const float* X, const float* Y, size_t tree_
     const bool dup = nc <= 64;
     *n_part = dup ? 2 * groups : groups;
     if (*n_part > nSG) return set_error(NNJ_ERR_INVALID, "alpha_tc: partial buffer too small");
-    const int rows8 = (S + 7) & ~7;
+    // the live nodes occupy physical slots [0, n_live) (k_select keeps them compact): only those rows are streamed
+    const int rows8 = (n_live + 7) & ~7;
     AlphaV3Args a;
     a.tile_bytes = rows8 * 128;
+    a.nmma = (rows8 + 15) & ~15;
     a.nst = (AV_SMEM_MAX - 1024 - AV_XS_BYTES - AV_MISC_BYTES) / (6 * a.tile_bytes);
     if (a.nst > AV_MAXST) a.nst = AV_MAXST;
     CUtensorMap mx, my, mh, ml, mo;
     if (int e = make_tmap_xplanes(&mo, xf, pc, nc, C, B)) return e;
-    if (int e = make_tmap_pool_f32(&mx, X, tree_stride, S, C, B, rows8)) return e;
-    if (int e = make_tmap_pool_f32(&my, Y, tree_stride, S, C, B, rows8)) return e;
-    if (int e = make_tmap_kprime(&mh, kp_h, S, C, B, rows8)) return e;
-    if (int e = make_tmap_kprime(&ml, kp_l, S, C, B, rows8)) return e;
+    if (int e = make_tmap_pool_f32(&mx, X, tree_stride, n_live, C, B, rows8)) return e;
+    if (int e = make_tmap_pool_f32(&my, Y, tree_stride, n_live, C, B, rows8)) return e;
+    if (int e = make_tmap_kprime(&mh, kp_h, S, n_live, C, B, rows8)) return e;
+    if (int e = make_tmap_kprime(&ml, kp_l, S, n_live, C, B, rows8)) return e;
     a.slot_of = slot_of; a.slot_stride = slot_stride;
     a.pair_i = pair_i; a.pair_j = pair_j; a.pair_stride = pair_stride; a.n0 = n0; a.nc = nc; a.C = C; a.B = B; a.groups = groups; a.bh = m->nj.bh;
     a.dup = dup ? 1 : 0;

@@ -85,7 +85,7 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
 int launch_tc_gemm(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                    size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st);
 int launch_alpha_tc(const Model* m, const float* X, const float* Y, size_t tree_stride, const int32_t* slot_of, int slot_stride, const int32_t* pair_i,
-                    const int32_t* pair_j, int pair_stride, int n0, int nc, int S, int C, int B, const void* kp_h, const void* kp_l, float* xf,
+                    const int32_t* pair_j, int pair_stride, int n0, int nc, int S, int n_live, int C, int B, const void* kp_h, const void* kp_l, float* xf,
                     int pc, float* alpha_part, int alpha_pairs, int nSG, int RP, int* n_part, cudaStream_t st);
 int launch_score_tc(const Model* m, const float* xf, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
                     int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,

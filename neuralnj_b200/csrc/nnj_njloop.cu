@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
                                                     const float* __restrict__ alpha, int RP, NjW w, float* __restrict__ out_x,
                                                     size_t out_stride, const int32_t* __restrict__ new_slot, int derive,
                                                     uint2* __restrict__ nodes_h, uint2* __restrict__ nodes_l, uint2* __restrict__ kp_h,
-                                                    uint2* __restrict__ kp_l) {
+                                                    uint2* __restrict__ kp_l, const int32_t* __restrict__ move_dst) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
     float* xg = xs + TILE_ROWS * LDA;
@@ -583,6 +583,34 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
         derive_tile(xs, xg, Ws, w, Yw + nb, Kw + nb, kapw + ((size_t)b * pool.S + ns) * pool.nCT + ct, row0, C, red,
                     kp_h ? kp_h + nb / 4 : nullptr, kp_l ? kp_l + nb / 4 : nullptr, nodes_h ? nodes_h + (size_t)b * C * pool.S * 32 : nullptr,
                     nodes_l ? nodes_l + (size_t)b * C * pool.S * 32 : nullptr, pool.S, ns);
+        // ---- compaction: this tile's rows of the last live node (slot Rp-1) -> the freed slot move_dst[b] (k_select).  Everything this
+        //      CTA read from the destination slot (the pair's x, Y) was consumed above; other CTAs own other sites.
+        const int dst = move_dst ? move_dst[b] : -1;
+        if (dst >= 0) {
+            const int src = Rp - 1;
+            const int rows = min(TILE_ROWS, C - row0);
+            const size_t so_ = tb + ((size_t)src * C + row0) * D, do_ = tb + ((size_t)dst * C + row0) * D;
+            for (int k = tid; k < rows * 16; k += NTHREADS) {
+                st4(Xw + do_ + k * 4, ld4(Xw + so_ + k * 4));
+                st4(Yw + do_ + k * 4, ld4(Yw + so_ + k * 4));
+                st4(Kw + do_ + k * 4, ld4(Kw + so_ + k * 4));
+            }
+            if (kp_h) {
+                const uint4* sh = reinterpret_cast<const uint4*>(kp_h) + so_ / 8; uint4* dh = reinterpret_cast<uint4*>(kp_h) + do_ / 8;
+                const uint4* sl = reinterpret_cast<const uint4*>(kp_l) + so_ / 8; uint4* dl = reinterpret_cast<uint4*>(kp_l) + do_ / 8;
+                for (int k = tid; k < rows * 8; k += NTHREADS) { dh[k] = sh[k]; dl[k] = sl[k]; }
+            }
+            if (nodes_h) {     // site-major planes [C][S][128 bf16]: one 256-byte row per (site, slot)
+                uint4* nh = reinterpret_cast<uint4*>(nodes_h) + (size_t)b * C * pool.S * 16;
+                uint4* nl = reinterpret_cast<uint4*>(nodes_l) + (size_t)b * C * pool.S * 16;
+                for (int k = tid; k < rows * 16; k += NTHREADS) {
+                    const size_t c = row0 + (k >> 4);
+                    const size_t os = (c * pool.S + src) * 16 + (k & 15), od = (c * pool.S + dst) * 16 + (k & 15);
+                    nh[od] = nh[os]; nl[od] = nl[os];
+                }
+            }
+            if (tid == 0) kapw[((size_t)b * pool.S + dst) * pool.nCT + ct] = kapw[((size_t)b * pool.S + src) * pool.nCT + ct];
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -702,18 +730,23 @@ __global__ void __launch_bounds__(NTHREADS) k_select(int t, int n, int R, const 
         if (selected_logp) selected_logp[(size_t)b * (R - 1) + t] = (cur[act] - gmax) - logf(s_red[0]);
     }
     if (n > 2) {
+        // Physical slots stay COMPACT: the n live nodes occupy slots [0, n).  The merged node is written in place into the lower of
+        // the pair's two slots, and the node in the last live slot (n-1) moves into the higher one (k_merge does both), so every
+        // kernel that streams "all nodes of a site" reads n slots, not the R+1 the pool was allocated with.
         const int32_t* sc = slot_cur + (size_t)b * slot_stride;
         int32_t* sn = slot_next + (size_t)b * slot_stride;
-        const int ns = free_slot[b];
-        const int pj_phys = sc[j];
+        const int pi_phys = sc[i], pj_phys = sc[j];
+        const int lo = min(pi_phys, pj_phys), hi = max(pi_phys, pj_phys), last = n - 1;
         __syncthreads();
         for (int r = tid; r < n - 1; r += NTHREADS) {
             int src = r + (r >= j ? 1 : 0);
-            sn[r] = (r == i) ? ns : sc[src];
+            int p = (r == i) ? lo : sc[src];
+            if (r != i && p == last) p = hi;           // the moved node (never i or j: then hi == last and nothing moves)
+            sn[r] = p;
             pair_i[(size_t)b * pair_stride + r] = (r == i) ? -1 : min(i, r);
             pair_j[(size_t)b * pair_stride + r] = (r == i) ? -1 : max(i, r);
         }
-        if (tid == 0) { new_slot[b] = ns; free_slot[b] = pj_phys; }
+        if (tid == 0) { new_slot[b] = lo; free_slot[b] = (hi != last) ? hi : -1; }   // free_slot: destination of the moved node, -1: none
     }
 }
 
@@ -832,7 +865,7 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
             // blend + alpha partials in one tcgen05 kernel (fp32 x planes written on the way, partials per 64-site group - two when the
             // tile is split by site parity - indexed by physical slot) -> softmax -> fused score kernel
             int n_part = 0;
-            if (int e = launch_alpha_tc(m, pool.X, pool.Y, pool.tree_stride, slot, nb.S, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, nb.S, C, B,
+            if (int e = launch_alpha_tc(m, pool.X, pool.Y, pool.tree_stride, slot, nb.S, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, nb.S, Rp, C, B,
                                         nb.kp_h, nb.kp_l, nb.xf, TC_PAIRS, nb.alpha_part, PAIR_CHUNK, nb.nAP, nb.RP, &n_part, st)) return e;
             prof_begin(KC_ALPHA_SOFTMAX, st);
             k_alpha_softmax<<<dim3((nc + 7) / 8, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
@@ -886,14 +919,14 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
         k_merge<true><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
                                                                          nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0,
                                                                          (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr, (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr,
-                                                                         (derive && nb.tc) ? (uint2*)nb.kp_h : nullptr, (derive && nb.tc) ? (uint2*)nb.kp_l : nullptr);
+                                                                         (derive && nb.tc) ? (uint2*)nb.kp_h : nullptr, (derive && nb.tc) ? (uint2*)nb.kp_l : nullptr, derive ? nb.free_slot : nullptr);
         LAUNCH_CHECK();
     } else {
         prof_begin(KC_MERGE, st);
         k_merge<false><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
                                                                           nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0,
                                                                          (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr, (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr,
-                                                                         (derive && nb.tc) ? (uint2*)nb.kp_h : nullptr, (derive && nb.tc) ? (uint2*)nb.kp_l : nullptr);
+                                                                         (derive && nb.tc) ? (uint2*)nb.kp_h : nullptr, (derive && nb.tc) ? (uint2*)nb.kp_l : nullptr, derive ? nb.free_slot : nullptr);
         LAUNCH_CHECK();
     }
     return 0;

@@ -661,7 +661,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
 // ------------------------------------------------------------------ host side
 
 // box {64, 64, 1} over site-major node planes [B*C][S][128]  ([X | W_g X] per slot)
-static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC, int box_rows = 64) {
+static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC, int box_rows = 64, int n_live = -1) {
     typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static PFN enc = nullptr;
@@ -672,7 +672,7 @@ static int make_tmap_nodes(CUtensorMap* map, const void* base, int S, int BC, in
             return set_error(NNJ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
         enc = reinterpret_cast<PFN>(p);
     }
-    cuuint64_t gdim[3] = {128, (cuuint64_t)S, (cuuint64_t)BC};
+    cuuint64_t gdim[3] = {128, (cuuint64_t)(n_live > 0 ? n_live : S), (cuuint64_t)BC};   // slots >= n_live are dead: zero-filled, never loaded
     cuuint64_t gstr[2] = {256, (cuuint64_t)S * 256};
     cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -721,7 +721,8 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
     if (trace_state > 0 && nc == trace_state) { if (!trace_buf) cudaMalloc(&trace_buf, (1 + 3 * 20000) * 8); cudaMemsetAsync(trace_buf, 0, 8, st); a.trace = trace_buf; }
     { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("NNJ_SCORE_DBG"); dbg = ev ? atoi(ev) : 0; } a.dbg = dbg; }
     { static int pf = -1; if (pf < 0) { const char* ev = getenv("NNJ_SCORE_PF"); pf = ev ? atoi(ev) : 0; } a.pf = pf; }
-    a.node_rows = (S + 7) & ~7; a.x_rows = (nc + 7) & ~7;
+    // the live nodes occupy physical slots [0, Rp) (k_select keeps them compact): only those rows are streamed / contracted
+    a.node_rows = (Rp + 7) & ~7; a.x_rows = (nc + 7) & ~7;
     const int stage = 4 * a.node_rows * 128 + 2 * a.x_rows * 128;
     a.nst = (SI_SMEM_MAX - 1024 - SI_RING - 1024 - SI_MISC_BYTES) / stage;
     if (a.nst > SI_MAXST) a.nst = SI_MAXST;
@@ -730,11 +731,11 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
     if ((C % SI_SITES) & 1) return set_error(NNJ_ERR_INVALID, "score_inc: odd site count");   // unreachable: the tensor-core path needs C % 8 == 0
     CUtensorMap mh, ml, mx;
     if (int e = make_tmap_xtile(&mx, xf + (size_t)0, pc, nc, C, B, a.x_rows)) return e;
-    if (int e = make_tmap_nodes(&mh, nodes_h, S, B * C, a.node_rows)) return e;
-    if (int e = make_tmap_nodes(&ml, nodes_l, S, B * C, a.node_rows)) return e;
+    if (int e = make_tmap_nodes(&mh, nodes_h, S, B * C, a.node_rows, Rp)) return e;
+    if (int e = make_tmap_nodes(&ml, nodes_l, S, B * C, a.node_rows, Rp)) return e;
     a.alpha = alpha; a.RP = RP; a.alpha_pairs = alpha_pairs;
     a.slot_of = slot_of; a.slot_stride = slot_stride; a.pair_i = pair_i; a.pair_stride = pair_stride; a.n0 = n0; a.nc = nc;
-    a.Rp = Rp; a.S = S; a.C = C; a.B = B; a.groups = (C + SI_SITES - 1) / SI_SITES;
+    a.Rp = Rp; a.S = Rp; a.C = C; a.B = B; a.groups = (C + SI_SITES - 1) / SI_SITES;   // a.S: slots contracted by UMMA 1
     a.wsh = (const uint4*)m->nj_bf.wsh; a.wsl = (const uint4*)m->nj_bf.wsl;
     a.bg = m->nj.bg; a.bs = m->nj.bs; a.w2 = m->nj.w2; a.b2 = m->nj.b2;
     a.mask = mask; a.score_part = score_part; a.nSG = nSG;
