@@ -343,7 +343,8 @@ constexpr int SI_MISC_BYTES = 768 + 2048 + 512;   // biases | score partials [4]
 constexpr int SI_SMEM_MAX = 232448;
 constexpr uint32_t SI_TM_D1 = 0, SI_TM_S = 256, SI_TM_A1 = 320, SI_TM_S1 = 384, SI_TM_A0 = 448;   // TMEM: D1a 128 | D1b 128 | s[0] 64 | x' hi/lo 64 | s[1] 64 | alpha hi/lo 64
 
-#define SI_TRACE(tag, item) do { if (a.trace && blockIdx.x == 0 && lane == 0 && (item) < 600) { const int ti_ = atomicAdd(reinterpret_cast<int*>(a.trace), 1); if (ti_ < 20000) { a.trace[1 + 3 * ti_] = (tag); a.trace[2 + 3 * ti_] = (item); a.trace[3 + 3 * ti_] = clock64(); } } } while (0)
+// timeline trace of CTA 0 (NNJ_SCORE_TRACE=<pair count>): one clock64 stamp per (tag, item), no atomics on the traced path
+#define SI_TRACE(tag, item) do { if (a.trace && blockIdx.x == 0 && lane == 0 && (item) < 600) a.trace[(tag) * 600 + (item)] = clock64(); } while (0)
 
 struct ScoreIncArgs {
     const float* alpha; int RP; int alpha_pairs;
@@ -484,8 +485,10 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
             if (n_sites > 1) issue_u1(1);
             for (int k = 0; k < n_items; ++k, ++gi) {
                 mbar_wait(a1_ready, gi & 1u);           // half A has read D1a and written its x' rows
+                SI_TRACE(4, (int)gi);
                 if (2 * (k + 1) < n_sites) issue_u1(0);
                 mbar_wait(a1_ready + 1, gi & 1u);       // half B likewise (it arrives with zeros when the item has no second site)
+                SI_TRACE(5, (int)gi);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t ta = tmem_base + SI_TM_A1, ts = tmem_base + ((gi & 1u) ? SI_TM_S1 : SI_TM_S);
@@ -502,7 +505,9 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                     umma_commit(s_done + (gi & 1u));
                 }
                 __syncwarp();
+                SI_TRACE(6, (int)gi);
                 if (2 * (k + 1) + 1 < n_sites) issue_u1(1);
+                SI_TRACE(7, (int)gi);
             }
         }
     } else {
@@ -552,7 +557,6 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
             // w2 . GELU(s + b_s) (+ b2 once per row), masked site sum, for item `it` (global count) whose site of this thread is `site`
             auto ep2 = [&](uint32_t it, int site) {
                 mbar_wait(s_done + (it & 1u), (it >> 1) & 1u);
-                if (warp == 0) SI_TRACE(23, (int)it);
                 tc_fence_after();
                 if (warp_rows && !(a.dbg & 4)) {
                     uint32_t sv[16];
@@ -568,7 +572,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                     if (unmasked) score += (acc0 + acc1) + (cg == 0 ? a.b2 : 0.f);
                 }
                 tc_fence_before();
-                if (warp == 0) SI_TRACE(24, (int)it);
+                if (warp == 0 || warp == 2) SI_TRACE(14 + 5 * warp, (int)it);
             };
             for (int k = 0; k < n_items; ++k, ++gi) {
                 // The halves run decoupled (ping-pong), so a warp may wait only on the x stages its own half releases: the ring depth is
@@ -594,10 +598,11 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                     for (int j = 0; j < 4; ++j) x4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 const float* xv = reinterpret_cast<const float*>(x4);
-                if (warp == 0) SI_TRACE(20, (int)gi);
+                if (warp == 0 || warp == 2) SI_TRACE(10 + 5 * warp, (int)gi);
                 if (site_ok) { mbar_wait(d1_done + h, c_d1 & 1u); ++c_d1; }      // this half's [x_glob | g]
+                if (warp == 0 || warp == 2) SI_TRACE(11 + 5 * warp, (int)gi);
                 if (gi >= 1) mbar_wait(s_done + ((gi - 1) & 1u), ((gi - 1) >> 1) & 1u);   // UMMA 2 of the previous item has read the x' operand
-                if (warp == 0) SI_TRACE(21, (int)gi);
+                if (warp == 0 || warp == 2) SI_TRACE(12 + 5 * warp, (int)gi);
                 tc_fence_after();
                 if (!warp_rows || (a.dbg & 2)) {          // no listed pair in this warp's 32 rows: x' = 0 (keeps UMMA 2's operand finite), nothing to score
                     uint32_t z[8];
@@ -636,7 +641,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                     mbar_arrive(a1_ready + h);
                     if (site_ok) mbar_arrive(x_free + my_st);           // x tile consumed
                 }
-                if (warp == 0) SI_TRACE(22, (int)gi);
+                if (warp == 0 || warp == 2) SI_TRACE(13 + 5 * warp, (int)gi);
                 // ---- score of the PREVIOUS item (its s = x' W_s^T has had the whole gate epilogue to finish): the tensor core runs
                 //      UMMA 2 of this item and UMMA 1 of the next while the GELU / site-sum epilogue of item k-1 executes
                 if (k > 0) ep2(gi - 1, 2 * (k - 1) + h);
@@ -718,7 +723,7 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
     a.trace = nullptr;
     static long long* trace_buf = nullptr; static int trace_state = -1;
     if (trace_state < 0) { const char* ev = getenv("NNJ_SCORE_TRACE"); trace_state = ev ? atoi(ev) : 0; }
-    if (trace_state > 0 && nc == trace_state) { if (!trace_buf) cudaMalloc(&trace_buf, (1 + 3 * 20000) * 8); cudaMemsetAsync(trace_buf, 0, 8, st); a.trace = trace_buf; }
+    if (trace_state > 0 && nc == trace_state) { if (!trace_buf) cudaMalloc(&trace_buf, 32 * 600 * 8); cudaMemsetAsync(trace_buf, 0, 32 * 600 * 8, st); a.trace = trace_buf; }
     { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("NNJ_SCORE_DBG"); dbg = ev ? atoi(ev) : 0; } a.dbg = dbg; }
     { static int pf = -1; if (pf < 0) { const char* ev = getenv("NNJ_SCORE_PF"); pf = ev ? atoi(ev) : 0; } a.pf = pf; }
     // the live nodes occupy physical slots [0, Rp) (k_select keeps them compact): only those rows are streamed / contracted
@@ -747,11 +752,10 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
     prof_end(st);
     if (a.trace) {
         cudaStreamSynchronize(st);
-        std::vector<long long> h(1 + 3 * 20000);
+        std::vector<long long> h(32 * 600);
         cudaMemcpy(h.data(), trace_buf, h.size() * 8, cudaMemcpyDeviceToHost);
-        const int n = (int)(h[0] & 0xffffffff) < 20000 ? (int)(h[0] & 0xffffffff) : 20000;
         FILE* f = fopen("gpurun_out/score_trace.txt", "w");
-        if (f) { for (int i = 0; i < n; ++i) fprintf(f, "%lld %lld %lld\n", h[1 + 3 * i], h[2 + 3 * i], h[3 + 3 * i]); fclose(f); }
+        if (f) { for (int t = 0; t < 32; ++t) for (int i = 0; i < 600; ++i) if (h[t * 600 + i]) fprintf(f, "%d %d %lld\n", t, i, h[t * 600 + i]); fclose(f); }
         trace_state = 0;
     }
     cudaError_t e = cudaGetLastError();
