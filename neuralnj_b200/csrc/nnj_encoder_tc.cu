@@ -344,8 +344,10 @@ struct ColBlkArgs {
 };
 
 constexpr int K2_THREADS = 512;
+constexpr int CB_CH = 5;                       // keys per online-softmax chunk of the column attention
 constexpr int K2_W = 81920;
-constexpr int K2_SMEM = 1024 + K2_W + 32768 + 2 * 32768 + (64 + 192 + 64 + 128) * 4 + 4096 + 64;
+constexpr int CB_LDK = 68;                     // fp32 row pitch of the K / V tiles: lanes = consecutive rows store 16 B each without bank conflicts
+constexpr int K2_SMEM = 1024 + K2_W + 32768 + 2 * 128 * CB_LDK * 4 + (64 + 192 + 64 + 128) * 4 + 4096 + 64;
 
 // packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): one issue slot for two lanes of work
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -411,9 +413,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
     uint8_t* w_co = sm + 65536;                // column out_proj
     uint8_t* a_hi = sm + K2_W;
     uint8_t* a_lo = a_hi + 16384;
-    float* ks = reinterpret_cast<float*>(a_lo + 16384);   // [128][64]
-    float* vs = ks + 128 * 64;
-    float* s_rob = vs + 128 * 64;
+    float* ks = reinterpret_cast<float*>(a_lo + 16384);   // [128][CB_LDK]
+    float* vs = ks + 128 * CB_LDK;
+    float* s_rob = vs + 128 * CB_LDK;
     float* s_qkvb = s_rob + 64;
     float* s_cob = s_qkvb + 192;
     float* s_g = s_cob + 64;
@@ -448,6 +450,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         const bool valid = r < R && c < a.C;
         float* xp = a.x + (size_t)b * a.x_tree_stride + ((size_t)c * R + r) * D + cq * 16;
         float xr[16], v[16];
+        // all keys of a padded site get the same logit (-10000, axial_attention.py:220-224): softmax is uniform, i.e. q = 0
+        const float qs = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale_log2e;   // loaded with the tile, used in stage 2
         // ---- stage 1: x += ctx_row . W_o^T + b_o
         if (valid) {
 #pragma unroll
@@ -506,8 +510,6 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
             tmem_ld16_nw(t_qkv + lane_off + 64 + cq * 16, ak);
             tmem_ld16_nw(t_qkv + lane_off + 128 + cq * 16, av);
             tmem_ld_wait();
-            // all keys of a padded site get the same logit (-10000, axial_attention.py:220-224): softmax is uniform, i.e. q = 0
-            const float qs = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale_log2e;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 q0[k] = make_float2((__uint_as_float(aq[2 * k]) + s_qkvb[cq * 16 + 2 * k]) * qs, (__uint_as_float(aq[2 * k + 1]) + s_qkvb[cq * 16 + 2 * k + 1]) * qs);
@@ -515,52 +517,73 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                st4(ks + row * 64 + cq * 16 + k * 4, make_float4(__uint_as_float(ak[4 * k]) + s_qkvb[64 + cq * 16 + 4 * k], __uint_as_float(ak[4 * k + 1]) + s_qkvb[64 + cq * 16 + 4 * k + 1],
+                st4(ks + row * CB_LDK + cq * 16 + k * 4, make_float4(__uint_as_float(ak[4 * k]) + s_qkvb[64 + cq * 16 + 4 * k], __uint_as_float(ak[4 * k + 1]) + s_qkvb[64 + cq * 16 + 4 * k + 1],
                                                                  __uint_as_float(ak[4 * k + 2]) + s_qkvb[64 + cq * 16 + 4 * k + 2], __uint_as_float(ak[4 * k + 3]) + s_qkvb[64 + cq * 16 + 4 * k + 3]));
-                st4(vs + row * 64 + cq * 16 + k * 4, make_float4(__uint_as_float(av[4 * k]) + s_qkvb[128 + cq * 16 + 4 * k], __uint_as_float(av[4 * k + 1]) + s_qkvb[128 + cq * 16 + 4 * k + 1],
+                st4(vs + row * CB_LDK + cq * 16 + k * 4, make_float4(__uint_as_float(av[4 * k]) + s_qkvb[128 + cq * 16 + 4 * k], __uint_as_float(av[4 * k + 1]) + s_qkvb[128 + cq * 16 + 4 * k + 1],
                                                                  __uint_as_float(av[4 * k + 2]) + s_qkvb[128 + cq * 16 + 4 * k + 2], __uint_as_float(av[4 * k + 3]) + s_qkvb[128 + cq * 16 + 4 * k + 3]));
             }
         }
         tc_fence_before();
         __syncthreads();
-        // ---- stage 3: attention of token (site si, taxon r) over the R taxa of its site; online softmax, rescaling only when the
-        //      running maximum moves (logits carry log2 e, probabilities are exp2)
+        // ---- stage 3: attention of token (site si, taxon r) over the R taxa of its site; chunked online softmax
+        //      (logits carry log2 e, probabilities are exp2)
         if (valid) {
-            const float* kb = ks + ((size_t)si << a.rb_shift) * 64 + cq * 16;
-            const float* vb = vs + ((size_t)si << a.rb_shift) * 64 + cq * 16;
-            float m0 = dot8(q0, ld4(kb), ld4(kb + 4)), m1 = dot8(q1, ld4(kb + 8), ld4(kb + 12));
-            float l0 = 1.0f, l1 = 1.0f;
+            const float* kb = ks + (si << a.rb_shift) * CB_LDK + cq * 16;
+            const float* vb = vs + (si << a.rb_shift) * CB_LDK + cq * 16;
+            // keys in chunks of CB_CH: the running maximum moves (and the accumulators are rescaled) once per chunk, not per key
+            float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
             float2 o0[4], o1[4];
-            {
-                const float4 v0 = ld4(vb), v1 = ld4(vb + 4), v2 = ld4(vb + 8), v3 = ld4(vb + 12);
-                o0[0] = make_float2(v0.x, v0.y); o0[1] = make_float2(v0.z, v0.w); o0[2] = make_float2(v1.x, v1.y); o0[3] = make_float2(v1.z, v1.w);
-                o1[0] = make_float2(v2.x, v2.y); o1[1] = make_float2(v2.z, v2.w); o1[2] = make_float2(v3.x, v3.y); o1[3] = make_float2(v3.z, v3.w);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { o0[k] = make_float2(0.f, 0.f); o1[k] = make_float2(0.f, 0.f); }
+            int j0 = 0;
+            for (; j0 + CB_CH <= R; j0 += CB_CH) {
+                const float* kc = kb + j0 * CB_LDK;
+                const float* vc = vb + j0 * CB_LDK;
+                float s0[CB_CH], s1[CB_CH];
+#pragma unroll
+                for (int u = 0; u < CB_CH; ++u) {
+                    s0[u] = dot8(q0, ld4(kc + u * CB_LDK), ld4(kc + u * CB_LDK + 4));
+                    s1[u] = dot8(q1, ld4(kc + u * CB_LDK + 8), ld4(kc + u * CB_LDK + 12));
+                }
+                float n0 = m0, n1 = m1;
+#pragma unroll
+                for (int u = 0; u < CB_CH; ++u) { n0 = fmaxf(n0, s0[u]); n1 = fmaxf(n1, s1[u]); }
+                {
+                    const float f0 = ex2_approx(m0 - n0), f1 = ex2_approx(m1 - n1);   // 0 on the first chunk (m = -inf), 1 when the maximum stays
+                    const float2 ff0 = make_float2(f0, f0), ff1 = make_float2(f1, f1);
+                    l0 *= f0; l1 *= f1; m0 = n0; m1 = n1;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { o0[k] = fmul2(o0[k], ff0); o1[k] = fmul2(o1[k], ff1); }
+                }
+#pragma unroll
+                for (int u = 0; u < CB_CH; ++u) {
+                    const float* vj = vc + u * CB_LDK;
+                    const float4 v0 = ld4(vj), v1 = ld4(vj + 4), v2 = ld4(vj + 8), v3 = ld4(vj + 12);
+                    const float p0 = ex2_approx(s0[u] - m0), p1 = ex2_approx(s1[u] - m1);
+                    const float2 pp0 = make_float2(p0, p0), pp1 = make_float2(p1, p1);
+                    l0 += p0; l1 += p1;
+                    o0[0] = ffma2(pp0, make_float2(v0.x, v0.y), o0[0]); o0[1] = ffma2(pp0, make_float2(v0.z, v0.w), o0[1]);
+                    o0[2] = ffma2(pp0, make_float2(v1.x, v1.y), o0[2]); o0[3] = ffma2(pp0, make_float2(v1.z, v1.w), o0[3]);
+                    o1[0] = ffma2(pp1, make_float2(v2.x, v2.y), o1[0]); o1[1] = ffma2(pp1, make_float2(v2.z, v2.w), o1[1]);
+                    o1[2] = ffma2(pp1, make_float2(v3.x, v3.y), o1[2]); o1[3] = ffma2(pp1, make_float2(v3.z, v3.w), o1[3]);
+                }
             }
-#pragma unroll 2
-            for (int j = 1; j < R; ++j) {
-                const float* kj = kb + j * 64;
-                const float* vj = vb + j * 64;
+#pragma unroll 1
+            for (; j0 < R; ++j0) {                               // the R % CB_CH last keys, one at a time
+                const float* kj = kb + j0 * CB_LDK;
+                const float* vj = vb + j0 * CB_LDK;
                 const float s0 = dot8(q0, ld4(kj), ld4(kj + 4)), s1 = dot8(q1, ld4(kj + 8), ld4(kj + 12));
                 const float4 v0 = ld4(vj), v1 = ld4(vj + 4), v2 = ld4(vj + 8), v3 = ld4(vj + 12);
-                if (s0 > m0) {
-                    const float f = ex2_approx(m0 - s0);
-                    const float2 ff = make_float2(f, f);
-                    l0 *= f; m0 = s0;
-                    o0[0] = fmul2(o0[0], ff); o0[1] = fmul2(o0[1], ff); o0[2] = fmul2(o0[2], ff); o0[3] = fmul2(o0[3], ff);
-                }
-                if (s1 > m1) {
-                    const float f = ex2_approx(m1 - s1);
-                    const float2 ff = make_float2(f, f);
-                    l1 *= f; m1 = s1;
-                    o1[0] = fmul2(o1[0], ff); o1[1] = fmul2(o1[1], ff); o1[2] = fmul2(o1[2], ff); o1[3] = fmul2(o1[3], ff);
-                }
-                const float p0 = ex2_approx(s0 - m0), p1 = ex2_approx(s1 - m1);
-                const float2 pp0 = make_float2(p0, p0), pp1 = make_float2(p1, p1);
-                l0 += p0; l1 += p1;
-                o0[0] = ffma2(pp0, make_float2(v0.x, v0.y), o0[0]); o0[1] = ffma2(pp0, make_float2(v0.z, v0.w), o0[1]);
-                o0[2] = ffma2(pp0, make_float2(v1.x, v1.y), o0[2]); o0[3] = ffma2(pp0, make_float2(v1.z, v1.w), o0[3]);
-                o1[0] = ffma2(pp1, make_float2(v2.x, v2.y), o1[0]); o1[1] = ffma2(pp1, make_float2(v2.z, v2.w), o1[1]);
-                o1[2] = ffma2(pp1, make_float2(v3.x, v3.y), o1[2]); o1[3] = ffma2(pp1, make_float2(v3.z, v3.w), o1[3]);
+                const float n0 = fmaxf(m0, s0), n1 = fmaxf(m1, s1);
+                const float f0 = ex2_approx(m0 - n0), f1 = ex2_approx(m1 - n1);
+                const float p0 = ex2_approx(s0 - n0), p1 = ex2_approx(s1 - n1);
+                const float2 ff0 = make_float2(f0, f0), ff1 = make_float2(f1, f1), pp0 = make_float2(p0, p0), pp1 = make_float2(p1, p1);
+                m0 = n0; m1 = n1;
+                l0 = fmaf(l0, f0, p0); l1 = fmaf(l1, f1, p1);
+                o0[0] = ffma2(pp0, make_float2(v0.x, v0.y), fmul2(o0[0], ff0)); o0[1] = ffma2(pp0, make_float2(v0.z, v0.w), fmul2(o0[1], ff0));
+                o0[2] = ffma2(pp0, make_float2(v1.x, v1.y), fmul2(o0[2], ff0)); o0[3] = ffma2(pp0, make_float2(v1.z, v1.w), fmul2(o0[3], ff0));
+                o1[0] = ffma2(pp1, make_float2(v2.x, v2.y), fmul2(o1[0], ff1)); o1[1] = ffma2(pp1, make_float2(v2.z, v2.w), fmul2(o1[1], ff1));
+                o1[2] = ffma2(pp1, make_float2(v3.x, v3.y), fmul2(o1[2], ff1)); o1[3] = ffma2(pp1, make_float2(v3.z, v3.w), fmul2(o1[3], ff1));
             }
             const float i0 = 1.0f / l0, i1 = 1.0f / l1;
 #pragma unroll
