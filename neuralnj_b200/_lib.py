@@ -61,10 +61,11 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise NnjError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("NNJ_LIB_PATH") or LIB_PATH       # override: A/B runs against another build of the same sources
+    if not os.path.exists(path):
+        raise NnjError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(there is no CPU fallback for the NeuralNJ hot path)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
     L.nnj_last_error.restype = C.c_char_p
     L.nnj_abi_version.restype = i32

@@ -24,7 +24,7 @@ namespace nnj {
 constexpr int AV_BLEND_WARPS = 16;
 constexpr int AV_THREADS = (AV_BLEND_WARPS + 2) * 32;   // + UMMA issue warp + TMA producer warp
 constexpr int AV_SITES = 64;                            // sites per work item
-constexpr int AV_MAXST = 6;                             // node-ring depth (runtime, 3..6 by the slot count)
+constexpr int AV_MAXST = 12;                            // node-ring depth (runtime, 3..12 by the slot count)
 constexpr int AV_MAXT = 4;                              // pair tiles per work item
 constexpr int AV_XS_BYTES = AV_BLEND_WARPS * 2048;      // x staging for the TMA stores: 16 warps x [32 rows][64 B] (SWIZZLE_64B)
 constexpr int AV_TAB_BYTES = 2 * 2 * AV_MAXT * 128 * 4; // pair tables: 2 buffers x (slot_i, slot_j) x 512 rows
@@ -39,6 +39,7 @@ struct AlphaV3Args {
     const float* bh;
     float* alpha_part; int alpha_pairs; int nSG; int RP;
     int dup;                                   // nc <= 64: tile split by site parity, two partials per site group
+    int ways;                                  // sites per 128-lane tile: 1, 2 (dup, nc <= 64) or 4 (nc <= 32: lane quarter q = site 4k+q)
     int tile_bytes, nst;                       // ring geometry: [round8(live slots)][128 B] tiles, 6 per stage, nst stages
     int nmma;                                  // UMMA N = round16(live slots)
 };
@@ -69,10 +70,12 @@ k_alpha_v3(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     const int rows_cta = a.nc;
     const int NT = (rows_cta + 127) >> 7;
     const bool dup = a.dup != 0;                                          // site-parity split of a half-empty tile
+    const int WAYS = a.ways;                                              // 2 or 4 sites per item when dup
+    const bool quad = WAYS == 4;
     const int n_work = a.B * a.groups;
 
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(full + i, 1); mbar_init(stage_free + i, (dup ? AV_BLEND_WARPS / 2 : AV_BLEND_WARPS) + 1); }
+        for (int i = 0; i < NST; ++i) { mbar_init(full + i, 1); mbar_init(stage_free + i, AV_BLEND_WARPS / WAYS + 1); }
         mbar_init(a_ready, AV_BLEND_WARPS); mbar_init(a_ready + 1, AV_BLEND_WARPS);
         mbar_init(a_free, 1); mbar_init(a_free + 1, 1);
         mbar_init(done, 1);
@@ -161,12 +164,12 @@ k_alpha_v3(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     rp.next(NST);
                 }
             } else {
-                const int n_items = (n_sites + 1) >> 1;
+                const int n_items = (n_sites + WAYS - 1) / WAYS;
                 for (int k = 0; k < n_items; ++k, ++gk) {
                     const int buf = gk & 1;
                     mbar_wait(a_ready + buf, (gk >> 1) & 1);
-                    for (int h = 0; h < 2; ++h) {
-                        if (2 * k + h >= n_sites) break;
+                    for (int h = 0; h < WAYS; ++h) {
+                        if (WAYS * k + h >= n_sites) break;
                         mbar_wait(full + rp.st, rp.ph);
                         tc_fence_after();
                         if (elect_one()) {
@@ -204,7 +207,7 @@ k_alpha_v3(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++wi) {
             const int b = w / a.groups, sg = w - b * a.groups;
             const int c_base = sg * AV_SITES, n_sites = min(AV_SITES, a.C - c_base);
-            const int n_items = dup ? (n_sites + 1) >> 1 : n_sites * NT;
+            const int n_items = dup ? (n_sites + WAYS - 1) / WAYS : n_sites * NT;
             const int* tpi = s_tab + (wi & 1) * (2 * AV_MAXT * 128);
             const int* tpj = tpi + AV_MAXT * 128;
             mbar_wait(tab_full + (wi & 1), (wi >> 1) & 1);
@@ -216,13 +219,16 @@ k_alpha_v3(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 if (dup) {
                     // every warp observes every phase of every ring stage (both sites of the item, in order): a warp that skipped
                     // the other parity's phases could otherwise pass a later wait on a stale phase bit
-                    const int h = q >> 1;
-                    RingPos r1 = rp; r1.next(NST);
-                    mbar_wait(full + rp.st, rp.ph);
-                    if (2 * k + 1 < n_sites) mbar_wait(full + r1.st, r1.ph);
-                    site = 2 * k + h; site_ok = site < n_sites; st = h ? r1.st : rp.st;
-                    row = (q & 1) * 32 + lane; last_use = true;
-                    rp.next(NST); if (2 * k + 1 < n_sites) rp.next(NST);
+                    const int h = quad ? q : q >> 1;
+                    st = rp.st;
+                    for (int i = 0; i < WAYS; ++i) {
+                        if (WAYS * k + i >= n_sites) break;
+                        mbar_wait(full + rp.st, rp.ph);
+                        if (i == h) st = rp.st;
+                        rp.next(NST);
+                    }
+                    site = WAYS * k + h; site_ok = site < n_sites;
+                    row = quad ? lane : (q & 1) * 32 + lane; last_use = true;
                 } else {
                     mbar_wait(full + rp.st, rp.ph);
                     site = s; st = rp.st; row = t * 128 + q * 32 + lane; last_use = (t == NT - 1);
@@ -242,11 +248,13 @@ k_alpha_v3(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                         const int ci = ((j0 + e) ^ (pi & 7)) << 4, cj = ((j0 + e) ^ (pj & 7)) << 4;
                         const float4 xa = *reinterpret_cast<const float4*>(xi_r + ci), xc = *reinterpret_cast<const float4*>(xj_r + cj);
                         const float4 ya = *reinterpret_cast<const float4*>(xi_r + 2 * T + ci), yc = *reinterpret_cast<const float4*>(xj_r + 2 * T + cj);
-                        float4 v;
-                        v.x = fmaf(sigmoid_fast(ya.x - yc.x + bh[4 * e + 0]), xa.x - xc.x, xc.x);   // z x_i + (1-z) x_j
-                        v.y = fmaf(sigmoid_fast(ya.y - yc.y + bh[4 * e + 1]), xa.y - xc.y, xc.y);
-                        v.z = fmaf(sigmoid_fast(ya.z - yc.z + bh[4 * e + 2]), xa.z - xc.z, xc.z);
-                        v.w = fmaf(sigmoid_fast(ya.w - yc.w + bh[4 * e + 3]), xa.w - xc.w, xc.w);
+                        // z x_i + (1-z) x_j in packed fp32x2 math (channel pairs share every FMA-pipe instruction; same operations and
+                        // order as the scalar form)
+                        const float2 z0 = sigmoid_fast2(fadd2(fsub2(make_float2(ya.x, ya.y), make_float2(yc.x, yc.y)), make_float2(bh[4 * e + 0], bh[4 * e + 1])));
+                        const float2 z1 = sigmoid_fast2(fadd2(fsub2(make_float2(ya.z, ya.w), make_float2(yc.z, yc.w)), make_float2(bh[4 * e + 2], bh[4 * e + 3])));
+                        const float2 v0 = ffma2(z0, fsub2(make_float2(xa.x, xa.y), make_float2(xc.x, xc.y)), make_float2(xc.x, xc.y));
+                        const float2 v1 = ffma2(z1, fsub2(make_float2(xa.z, xa.w), make_float2(xc.z, xc.w)), make_float2(xc.z, xc.w));
+                        const float4 v = make_float4(v0.x, v0.y, v1.x, v1.y);
                         split2(v.x, v.y, hh[2 * e], ll[2 * e]);
                         split2(v.z, v.w, hh[2 * e + 1], ll[2 * e + 1]);
                         *reinterpret_cast<float4*>(xs + ((e ^ ((lane >> 1) & 3)) << 4)) = v;
@@ -291,13 +299,13 @@ k_alpha_v3(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                         }
                     }
                 } else {
-                    const int h = q >> 1, row = (q & 1) * 32 + lane;
+                    const int h = quad ? q : q >> 1, row = quad ? lane : (q & 1) * 32 + lane;
                     uint32_t acc[16];
                     tmem_ld16_nw(lane_base + h * 64 + cg * 16, acc);
                     tmem_ld_wait();
                     const bool have = h < n_sites;             // the odd-site accumulator is never written when the group has one site
                     if (row < rows_cta) {
-                        float* o = a.alpha_part + (((size_t)b * a.alpha_pairs + row) * a.nSG + 2 * sg + h) * a.RP + cg * 16;
+                        float* o = a.alpha_part + (((size_t)b * a.alpha_pairs + row) * a.nSG + WAYS * sg + h) * a.RP + cg * 16;
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             if (cg * 16 + 4 * e < a.RP)
@@ -390,7 +398,9 @@ int launch_alpha_tc(const Model* m, const float* X, const float* Y, size_t tree_
     if (nc > AV_MAXT * 128 || nc > pc) return set_error(NNJ_ERR_INVALID, "alpha_tc: at most 512 pairs per launch");
     const int groups = (C + AV_SITES - 1) / AV_SITES;
     const bool dup = nc <= 64;
-    *n_part = dup ? 2 * groups : groups;
+    static const int quad_on = getenv("NNJ_ALPHA_QUAD") ? atoi(getenv("NNJ_ALPHA_QUAD")) : 1;
+    const int ways = !dup ? 1 : (nc <= 32 && quad_on && 4 * groups <= nSG) ? 4 : 2;
+    *n_part = ways * groups;
     if (*n_part > nSG) return set_error(NNJ_ERR_INVALID, "alpha_tc: partial buffer too small");
     // the live nodes occupy physical slots [0, n_live) (k_select keeps them compact): only those rows are streamed
     const int rows8 = (n_live + 7) & ~7;
@@ -407,7 +417,7 @@ int launch_alpha_tc(const Model* m, const float* X, const float* Y, size_t tree_
     if (int e = make_tmap_kprime(&ml, kp_l, S, n_live, C, B, rows8)) return e;
     a.slot_of = slot_of; a.slot_stride = slot_stride;
     a.pair_i = pair_i; a.pair_j = pair_j; a.pair_stride = pair_stride; a.n0 = n0; a.nc = nc; a.C = C; a.B = B; a.groups = groups; a.bh = m->nj.bh;
-    a.dup = dup ? 1 : 0;
+    a.dup = dup ? 1 : 0; a.ways = ways;
     a.alpha_part = alpha_part; a.alpha_pairs = alpha_pairs; a.nSG = nSG; a.RP = RP;
     const int n_work = B * groups;
     const size_t smem = 1024 + (size_t)a.nst * 6 * a.tile_bytes + AV_XS_BYTES + AV_MISC_BYTES;

@@ -40,6 +40,56 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return x * (x >= 0.f ? 1.0f - h : h);
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): one issue slot for two lanes of work, each lane rounded exactly
+//      like the scalar instruction (the packed forms below are bit-identical to their scalar counterparts)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+// sigmoid_fast / gelu_fast on two values: the same operations in the same order as the scalar forms
+__device__ __forceinline__ float2 sigmoid_fast2(float2 x) {
+    const float2 t = fmul2(splat2(-1.4426950408889634f), x);
+    const float2 d = fadd2(splat2(1.0f), make_float2(ex2_approx(t.x), ex2_approx(t.y)));
+    return make_float2(rcp_approx(d.x), rcp_approx(d.y));
+}
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+    const float2 z = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 d = ffma2(splat2(2.760034502e-01f), z, splat2(1.0f));
+    const float2 u = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+    float2 p = splat2(-1.134462506e-01f);
+    p = ffma2(p, u, splat2(4.407724440e-01f));
+    p = ffma2(p, u, splat2(-3.137964904e-01f));
+    p = ffma2(p, u, splat2(3.221081495e-01f));
+    p = ffma2(p, u, splat2(4.673849419e-02f));
+    p = ffma2(p, u, splat2(1.176236272e-01f));
+    const float2 t = fmul2(fmul2(z, z), splat2(-0.72134752044448170f));
+    const float2 h = fmul2(fmul2(p, u), make_float2(ex2_approx(t.x), ex2_approx(t.y)));
+    const float2 g = fsub2(splat2(1.0f), h);
+    return fmul2(x, make_float2(x.x >= 0.f ? g.x : h.x, x.y >= 0.f ? g.y : h.y));
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float f4c(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }

@@ -279,9 +279,11 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
             tmem_ld32(t_d1 + lane_off + ch * 64 + hf * 32, acc);
             uint32_t hh[16], ll[16];
 #pragma unroll
-            for (int k = 0; k < 32; k += 2)
-                split2(gelu_fast(__uint_as_float(acc[k]) + s_b1[ch * 64 + hf * 32 + k]), gelu_fast(__uint_as_float(acc[k + 1]) + s_b1[ch * 64 + hf * 32 + k + 1]),
-                       hh[k >> 1], ll[k >> 1]);
+            for (int k = 0; k < 32; k += 2) {      // packed fp32x2 math: hidden units (k, k+1) share every FMA-pipe instruction
+                const float2 gl = gelu_fast2(fadd2(make_float2(__uint_as_float(acc[k]), __uint_as_float(acc[k + 1])),
+                                                   *reinterpret_cast<const float2*>(s_b1 + ch * 64 + hf * 32 + k)));
+                split2(gl.x, gl.y, hh[k >> 1], ll[k >> 1]);
+            }
             const uint32_t ta = t_a + (ch & 1) * 64;
             tmem_st16(ta + lane_off + hf * 16, hh);
             tmem_st16(ta + lane_off + 32 + hf * 16, ll);
@@ -349,20 +351,6 @@ constexpr int K2_W = 81920;
 constexpr int CB_LDK = 68;                     // fp32 row pitch of the K / V tiles: lanes = consecutive rows store 16 B each without bank conflicts
 constexpr int K2_SMEM = 1024 + K2_W + 32768 + 2 * 128 * CB_LDK * 4 + (64 + 192 + 64 + 128) * 4 + 4096 + 64;
 
-// packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): one issue slot for two lanes of work
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return d;
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-    float2 d;
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
 __device__ __forceinline__ float dot8(const float2 (&q)[4], float4 k0, float4 k1) {
     float2 acc = fmul2(q[0], make_float2(k0.x, k0.y));
     acc = ffma2(q[1], make_float2(k0.z, k0.w), acc);

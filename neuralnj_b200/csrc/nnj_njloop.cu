@@ -792,7 +792,8 @@ static bool nj_use_tc(const Model* m, int S) { return m->cfg.precision == NNJ_PR
 static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws, bool need_newx, bool tc) {
     NjBuffers nb{};
     nb.S = S; nb.nCT = (C + TILE_ROWS - 1) / TILE_ROWS; nb.nSB = (C + SB_SITES - 1) / SB_SITES;
-    nb.nAP = nb.nSB > 2 * ((C + 63) / 64) ? nb.nSB : 2 * ((C + 63) / 64);   // tensor-core alpha: up to two partials per 64-site group
+    const int tc_parts = tc ? 4 * ((C + 63) / 64) : 0;                       // tensor-core alpha: up to four partials per 64-site group
+    nb.nAP = nb.nSB > tc_parts ? nb.nSB : tc_parts;
     nb.RP = (S + 3) & ~3;     // >= S: tensor-core alpha partials are indexed by physical slot
     nb.P0 = R * (R - 1) / 2;
     nb.pair_stride = nb.P0 > R ? nb.P0 : R;

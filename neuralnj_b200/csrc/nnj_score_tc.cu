@@ -86,11 +86,10 @@ __device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiC
             float xp[16];
 #pragma unroll
             for (int k = 0; k < 16; k += 2) {
-                const float x0 = xv[sub * 16 + k], x1 = xv[sub * 16 + k + 1];
-                const float w0 = sigmoid_fast(__uint_as_float(g[k]) + bgv[sub * 16 + k]);
-                const float w1 = sigmoid_fast(__uint_as_float(g[k + 1]) + bgv[sub * 16 + k + 1]);
-                xp[k] = fmaf(w0, __uint_as_float(xg[k]) - x0, x0);       // (1-w) x + w x_glob
-                xp[k + 1] = fmaf(w1, __uint_as_float(xg[k + 1]) - x1, x1);
+                const float2 x2 = make_float2(xv[sub * 16 + k], xv[sub * 16 + k + 1]);
+                const float2 w = sigmoid_fast2(fadd2(make_float2(__uint_as_float(g[k]), __uint_as_float(g[k + 1])), *reinterpret_cast<const float2*>(bgv + sub * 16 + k)));
+                const float2 pp = ffma2(w, fsub2(make_float2(__uint_as_float(xg[k]), __uint_as_float(xg[k + 1])), x2), x2);   // (1-w) x + w x_glob
+                xp[k] = pp.x; xp[k + 1] = pp.y;
             }
             if (dup) {
 #pragma unroll
@@ -123,7 +122,7 @@ __device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiC
         // ---- score: w2 . GELU(s + b_s) (+ b2 once per row), masked site sum
         mbar_wait(e.pb + 3, par);
         tc_fence_after();
-        float acc0 = 0.f, acc1 = 0.f;
+        float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int sub = 0; sub < NSUB; ++sub) {
             uint32_t sv[16];
@@ -131,13 +130,13 @@ __device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiC
             tmem_ld_wait();
 #pragma unroll
             for (int k = 0; k < 16; k += 2) {
-                acc0 = fmaf(gelu_fast(__uint_as_float(sv[k]) + bsv[sub * 16 + k]), w2v[sub * 16 + k], acc0);
-                acc1 = fmaf(gelu_fast(__uint_as_float(sv[k + 1]) + bsv[sub * 16 + k + 1]), w2v[sub * 16 + k + 1], acc1);
+                const float2 sb = fadd2(make_float2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), *reinterpret_cast<const float2*>(bsv + sub * 16 + k));
+                acc = ffma2(gelu_fast2(sb), *reinterpret_cast<const float2*>(w2v + sub * 16 + k), acc);
             }
         }
         tc_fence_before();
         const bool site_ok = !(a.mask && a.mask[(size_t)e.b * a.C + c]);
-        if (site_ok) score += (acc0 + acc1) + (col0 == 0 ? a.b2 : 0.f);
+        if (site_ok) score += (acc.x + acc.y) + (col0 == 0 ? a.b2 : 0.f);
     }
     return row_ok ? score : 0.f;
 }
@@ -562,14 +561,14 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                     uint32_t sv[16];
                     tmem_ld16_nw(lane_base + ((it & 1u) ? SI_TM_S1 : SI_TM_S) + cg * 16, sv);
                     tmem_ld_wait();
-                    float acc0 = 0.f, acc1 = 0.f;
+                    float2 acc = make_float2(0.f, 0.f);          // packed fp32x2 math: channel pairs (e, e+1) share every FMA-pipe instruction
 #pragma unroll
                     for (int e = 0; e < 16; e += 2) {
-                        acc0 = fmaf(gelu_fast(__uint_as_float(sv[e]) + bsv[e]), w2v[e], acc0);
-                        acc1 = fmaf(gelu_fast(__uint_as_float(sv[e + 1]) + bsv[e + 1]), w2v[e + 1], acc1);
+                        const float2 sb = fadd2(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), *reinterpret_cast<const float2*>(bsv + e));
+                        acc = ffma2(gelu_fast2(sb), *reinterpret_cast<const float2*>(w2v + e), acc);
                     }
                     const bool unmasked = site < n_sites && !(a.mask && a.mask[(size_t)b * a.C + c_base + site]);
-                    if (unmasked) score += (acc0 + acc1) + (cg == 0 ? a.b2 : 0.f);
+                    if (unmasked) score += (acc.x + acc.y) + (cg == 0 ? a.b2 : 0.f);
                 }
                 tc_fence_before();
                 if (warp == 0 || warp == 2) SI_TRACE(14 + 5 * warp, (int)it);
@@ -619,17 +618,17 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                     tmem_ld16_nw(lane_base + SI_TM_D1 + h * 128 + cg * 16, xg);
                     tmem_ld_wait();
                     uint32_t hh[8], ll[8];
+                    if (site_ok) {                   // packed fp32x2 math: channel pairs (e, e+1) share every FMA-pipe instruction
 #pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        float p0 = 0.f, p1 = 0.f;
-                        if (site_ok) {
-                            const float x0 = xv[e], x1 = xv[e + 1];
-                            const float w0 = sigmoid_fast(__uint_as_float(g[e]) + bgv[e]);
-                            const float w1 = sigmoid_fast(__uint_as_float(g[e + 1]) + bgv[e + 1]);
-                            p0 = fmaf(w0, __uint_as_float(xg[e]) - x0, x0);       // (1-w) x + w x_glob
-                            p1 = fmaf(w1, __uint_as_float(xg[e + 1]) - x1, x1);
+                        for (int e = 0; e < 16; e += 2) {
+                            const float2 x2 = make_float2(xv[e], xv[e + 1]);
+                            const float2 w = sigmoid_fast2(fadd2(make_float2(__uint_as_float(g[e]), __uint_as_float(g[e + 1])), *reinterpret_cast<const float2*>(bgv + e)));
+                            const float2 pp = ffma2(w, fsub2(make_float2(__uint_as_float(xg[e]), __uint_as_float(xg[e + 1])), x2), x2);       // (1-w) x + w x_glob
+                            split2(pp.x, pp.y, hh[e >> 1], ll[e >> 1]);
                         }
-                        split2(p0, p1, hh[e >> 1], ll[e >> 1]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { hh[e] = 0u; ll[e] = 0u; }
                     }
                     tmem_st8(lane_base + SI_TM_A1 + cg * 8, hh);
                     tmem_st8(lane_base + SI_TM_A1 + 32 + cg * 8, ll);

@@ -179,7 +179,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // pack (hi, lo) bf16 split of two floats: returns hi pair / lo pair as bf16x2 words (element 0 in the low half)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     hi = pack_bf16x2(a, b);
-    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+    const float2 r = fsub2(make_float2(a, b), make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)));   // one FADD2
+    lo = pack_bf16x2(r.x, r.y);
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }          // element 0 of a bf16x2 word
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }  // element 1
