@@ -15,6 +15,7 @@
 #include <cstdlib>
 
 #include "nnj_internal.h"
+#include "nnj_tc.cuh"
 
 namespace nnj {
 
@@ -527,6 +528,64 @@ __global__ void __launch_bounds__(NTHREADS) k_softmax_rows_split(const float* __
     }
 }
 
+// The same for rows of at most 256 NCH sites (C % 8 == 0): the row stays in registers (one read of S instead of three), 32-byte loads and
+// 16-byte stores per lane, MUFU ex2 on log2-scaled logits (2^-22 relative, far below the bf16 hi/lo split of P).
+template <int NCH>
+__global__ void __launch_bounds__(NTHREADS) k_softmax_rows_split_reg(const float* __restrict__ S, __nv_bfloat16* __restrict__ Ph,
+                                                                     __nv_bfloat16* __restrict__ Pl, int C, const uint8_t* __restrict__ mask) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= C) return;
+    const int z = blockIdx.y, b = z / H;
+    const size_t base = ((size_t)z * C + row) * C;
+    const uint8_t* mk = mask ? mask + (size_t)b * C : nullptr;
+    float v[NCH][8];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int j = c * 256 + lane * 8;
+        if (j < C) {
+            const float4 a0 = __ldcs(reinterpret_cast<const float4*>(S + base + j)), a1 = __ldcs(reinterpret_cast<const float4*>(S + base + j + 4));
+            v[c][0] = a0.x; v[c][1] = a0.y; v[c][2] = a0.z; v[c][3] = a0.w; v[c][4] = a1.x; v[c][5] = a1.y; v[c][6] = a1.z; v[c][7] = a1.w;
+            if (mk) {
+                const uint2 mm = *reinterpret_cast<const uint2*>(mk + j);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (((e < 4 ? mm.x : mm.y) >> (8 * (e & 3))) & 0xffu) v[c][e] = -10000.0f;      // axial_attention.py:81-82
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m = fmaxf(m, v[c][e]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[c][e] = -INFINITY;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float ms = -m * 1.4426950408889634f;
+    float l = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { v[c][e] = ex2_approx(fmaf(v[c][e], 1.4426950408889634f, ms)); l += v[c][e]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int j = c * 256 + lane * 8;
+        if (j < C) {
+            uint4 hh, ll;
+            split2(v[c][0] * inv, v[c][1] * inv, hh.x, ll.x);
+            split2(v[c][2] * inv, v[c][3] * inv, hh.y, ll.y);
+            split2(v[c][4] * inv, v[c][5] * inv, hh.z, ll.z);
+            split2(v[c][6] * inv, v[c][7] * inv, hh.w, ll.w);
+            *reinterpret_cast<uint4*>(Ph + base + j) = hh;
+            *reinterpret_cast<uint4*>(Pl + base + j) = ll;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host-side driver
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -640,7 +699,9 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
                 }
                 if (int e = launch_tc_gemm(KC_ROW_QK, qh, ql, kh, kl, S, nb * H, C, C, KD, KD, (size_t)C * KD, KD, (size_t)C * KD, C, (size_t)C * C, st)) return e;
                 prof_begin(KC_ROW_SOFTMAX, st);
-                k_softmax_rows_split<<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, P + pp, C, mb);
+                if (C <= 512) k_softmax_rows_split_reg<2><<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, P + pp, C, mb);
+                else if (C <= 1024) k_softmax_rows_split_reg<4><<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, P + pp, C, mb);
+                else k_softmax_rows_split<<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, P + pp, C, mb);
                 LAUNCH_CHECK();
                 if (mk & 1) {
                     if (int e = launch_tc_gemm_bmn(KC_ROW_PV, P, P + pp, vh, vl, q /*ctx fp32 [B,H,C,R*8]*/, nb * H, C, KD, C, C, (size_t)C * C, KD,

@@ -335,6 +335,7 @@ constexpr int SI_THREADS = 608;            // 16 epilogue warps + issue warp + n
 constexpr int SI_SITES = 64;
 constexpr int SI_A0 = 0;                   // staging of alpha by physical slot, fp32 [64 pairs][68] (the operand itself lives in tensor memory)
 constexpr int SI_A0_LD = 68;
+constexpr int SI_XCH = 9216;               // narrow mode (<= 32 pairs): x' word exchange between the two warps of a (half, column group), 16 KB behind the 32-row alpha staging
 constexpr int SI_W = 32768;                // W_s hi 8 KB | lo 8 KB
 constexpr int SI_RING = 49152;
 constexpr int SI_MAXST = 6;
@@ -353,6 +354,7 @@ struct ScoreIncArgs {
     int pf;                                  // L2 prefetch distance in sites (0: off)
     long long* trace;                        // NNJ_SCORE_TRACE: clock64 stamps of CTA 0 (tag, item, clock) triples, else null
     int dbg;                                 // timing experiments only (NNJ_SCORE_DBG): 1 = one UMMA-1 product of three, 2 = no gate math, 4 = no GELU math
+    int narrow;                              // nc <= 32: lanes 32..63 of a half repeat the pairs; the two warps of a (half, column group) split its 16 channels
     int node_rows, x_rows, nst;              // ring geometry: node blocks [node_rows][128 B] x 4, x halves [x_rows][128 B] x 2
     const uint4* wsh; const uint4* wsl;
     const float* bg; const float* bs; const float* w2; float b2;
@@ -512,8 +514,16 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
     } else {
         // ================= epilogue warps: TMEM lane quarter q (lanes < 64: site 2k, else site 2k+1), 16 columns cg =================
         const int q = warp & 3, cg = warp >> 2, h = q >> 1;
-        const int prow = (q & 1) * 32 + lane;                       // pair row
-        const bool warp_rows = (q & 1) * 32 < a.nc;                 // this warp's rows hold listed pairs
+        // narrow mode (<= 32 pairs): rows 32..63 of a half would idle, and with them two of the four SM sub-partitions.  Instead they
+        // repeat rows 0..31 (same alpha rows, same x rows), and the two warps (q even / odd) of a (half, column group) each take 8 of the
+        // group's 16 channels in both epilogues; the packed x' words are swapped through shared memory so that both lanes of a pair
+        // carry the complete x' row into UMMA 2.
+        const bool narrow = a.narrow != 0;
+        const int sub = q & 1;
+        const int prow = narrow ? lane : (q & 1) * 32 + lane;       // pair row
+        const bool warp_rows = narrow || (q & 1) * 32 < a.nc;       // this warp's rows hold listed pairs
+        uint4* xch = reinterpret_cast<uint4*>(sm + SI_XCH) + (h * 4 + cg) * 128;      // [sub][hi | lo][32 lanes]
+        const int xch_bar = 2 + h * 4 + cg;                         // named barrier of the warp pair
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const float* bgv = s_bias + cg * 16;
         const float* bsv = s_bias + 64 + cg * 16;
@@ -528,7 +538,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
             //      split into bf16 hi / lo and stored to tensor memory by the row's own threads (lanes 64.. repeat the pairs)
             {
                 float* tab = reinterpret_cast<float*>(sm + SI_A0);
-                for (int i = tid; i < 64 * SI_A0_LD / 4; i += 512) reinterpret_cast<float4*>(tab)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = tid; i < (narrow ? 32 : 64) * SI_A0_LD / 4; i += 512) reinterpret_cast<float4*>(tab)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 asm volatile("bar.sync 1, 512;" ::: "memory");
                 const int32_t* so = a.slot_of + (size_t)b * a.slot_stride;
                 for (int idx = tid; idx < a.nc * a.Rp; idx += 512) {
@@ -557,7 +567,19 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
             auto ep2 = [&](uint32_t it, int site) {
                 mbar_wait(s_done + (it & 1u), (it >> 1) & 1u);
                 tc_fence_after();
-                if (warp_rows && !(a.dbg & 4)) {
+                if (narrow && !(a.dbg & 4)) {
+                    uint32_t sv[8];
+                    tmem_ld8_nw(lane_base + ((it & 1u) ? SI_TM_S1 : SI_TM_S) + cg * 16 + sub * 8, sv);
+                    tmem_ld_wait();
+                    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const float2 sb = fadd2(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), *reinterpret_cast<const float2*>(bsv + sub * 8 + e));
+                        acc = ffma2(gelu_fast2(sb), *reinterpret_cast<const float2*>(w2v + sub * 8 + e), acc);
+                    }
+                    const bool unmasked = site < n_sites && !(a.mask && a.mask[(size_t)b * a.C + c_base + site]);
+                    if (unmasked) score += (acc.x + acc.y) + ((cg | sub) == 0 ? a.b2 : 0.f);
+                } else if (warp_rows && !(a.dbg & 4)) {
                     uint32_t sv[16];
                     tmem_ld16_nw(lane_base + ((it & 1u) ? SI_TM_S1 : SI_TM_S) + cg * 16, sv);
                     tmem_ld_wait();
@@ -590,8 +612,13 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                 float4 x4[4];
                 if (site_ok && prow < a.x_rows) {
                     const uint8_t* xr = xring + my_st * 2 * XB + (cg >> 1) * XB + prow * 128;
+                    if (narrow) {              // this warp's 8 channels only
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) x4[j] = *reinterpret_cast<const float4*>(xr + ((((cg & 1) * 4 + j) ^ (prow & 7)) << 4));
+                        for (int j = 0; j < 2; ++j) x4[j] = *reinterpret_cast<const float4*>(xr + ((((cg & 1) * 4 + sub * 2 + j) ^ (prow & 7)) << 4));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) x4[j] = *reinterpret_cast<const float4*>(xr + ((((cg & 1) * 4 + j) ^ (prow & 7)) << 4));
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) x4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -612,6 +639,35 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                         tmem_st8(lane_base + SI_TM_A1 + 32 + cg * 8, z);
                         tmem_st_wait();
                     }
+                } else if (narrow && site_ok) {
+                    uint32_t g[8], xg[8];
+                    tmem_ld8_nw(lane_base + SI_TM_D1 + h * 128 + 64 + cg * 16 + sub * 8, g);
+                    tmem_ld8_nw(lane_base + SI_TM_D1 + h * 128 + cg * 16 + sub * 8, xg);
+                    tmem_ld_wait();
+                    uint4 oh, ol;
+                    {
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) {
+                            const float2 x2 = make_float2(xv[e], xv[e + 1]);
+                            const float2 w = sigmoid_fast2(fadd2(make_float2(__uint_as_float(g[e]), __uint_as_float(g[e + 1])), *reinterpret_cast<const float2*>(bgv + sub * 8 + e)));
+                            const float2 pp = ffma2(w, fsub2(make_float2(__uint_as_float(xg[e]), __uint_as_float(xg[e + 1])), x2), x2);
+                            split2(pp.x, pp.y, hw[e >> 1], lw[e >> 1]);
+                        }
+                        oh = make_uint4(hw[0], hw[1], hw[2], hw[3]); ol = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                    // swap the packed words with the partner warp (same half, same column group, other 8 channels).  The first barrier
+                    // orders this write behind the partner's read of the previous item, the second publishes it.
+                    asm volatile("bar.sync %0, 64;" ::"r"(xch_bar) : "memory");
+                    xch[(sub * 2) * 32 + lane] = oh;
+                    xch[(sub * 2 + 1) * 32 + lane] = ol;
+                    asm volatile("bar.sync %0, 64;" ::"r"(xch_bar) : "memory");
+                    const uint4 ph_ = xch[((sub ^ 1) * 2) * 32 + lane], pl_ = xch[((sub ^ 1) * 2 + 1) * 32 + lane];
+                    tmem_st4(lane_base + SI_TM_A1 + cg * 8 + sub * 4, oh.x, oh.y, oh.z, oh.w);
+                    tmem_st4(lane_base + SI_TM_A1 + cg * 8 + (sub ^ 1) * 4, ph_.x, ph_.y, ph_.z, ph_.w);
+                    tmem_st4(lane_base + SI_TM_A1 + 32 + cg * 8 + sub * 4, ol.x, ol.y, ol.z, ol.w);
+                    tmem_st4(lane_base + SI_TM_A1 + 32 + cg * 8 + (sub ^ 1) * 4, pl_.x, pl_.y, pl_.z, pl_.w);
+                    tmem_st_wait();
                 } else {
                     uint32_t g[16], xg[16];
                     tmem_ld16_nw(lane_base + SI_TM_D1 + h * 128 + 64 + cg * 16, g);
@@ -650,8 +706,12 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
             s_part[cg * 128 + q * 32 + lane] = row_ok ? score : 0.f;
             asm volatile("bar.sync 1, 512;" ::: "memory");
             if (tid < a.nc) {
-                const float sa = (s_part[tid] + s_part[128 + tid]) + (s_part[256 + tid] + s_part[384 + tid]);
-                const float sb = (s_part[64 + tid] + s_part[192 + tid]) + (s_part[320 + tid] + s_part[448 + tid]);
+                float sa = (s_part[tid] + s_part[128 + tid]) + (s_part[256 + tid] + s_part[384 + tid]);
+                float sb = (s_part[64 + tid] + s_part[192 + tid]) + (s_part[320 + tid] + s_part[448 + tid]);
+                if (narrow) {      // the other 8 channels of every column group live in rows 32..63 / 96..127
+                    sa += (s_part[32 + tid] + s_part[160 + tid]) + (s_part[288 + tid] + s_part[416 + tid]);
+                    sb += (s_part[96 + tid] + s_part[224 + tid]) + (s_part[352 + tid] + s_part[480 + tid]);
+                }
                 a.score_part[((size_t)b * a.alpha_pairs + tid) * a.nSG + sg] = sa + sb;
             }
             // s_part and the alpha operand are rewritten by the next work item only after this barrier and the next one
@@ -726,6 +786,7 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
     { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("NNJ_SCORE_DBG"); dbg = ev ? atoi(ev) : 0; } a.dbg = dbg; }
     { static int pf = -1; if (pf < 0) { const char* ev = getenv("NNJ_SCORE_PF"); pf = ev ? atoi(ev) : 0; } a.pf = pf; }
     // the live nodes occupy physical slots [0, Rp) (k_select keeps them compact): only those rows are streamed / contracted
+    { static int nw = -1; if (nw < 0) { const char* ev = getenv("NNJ_SCORE_NARROW"); nw = ev ? atoi(ev) : 1; } a.narrow = (nw && nc <= 32) ? 1 : 0; }
     a.node_rows = (Rp + 7) & ~7; a.x_rows = (nc + 7) & ~7;
     const int stage = 4 * a.node_rows * 128 + 2 * a.x_rows * 128;
     a.nst = (SI_SMEM_MAX - 1024 - SI_RING - 1024 - SI_MISC_BYTES) / stage;
