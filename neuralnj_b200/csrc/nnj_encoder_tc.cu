@@ -20,7 +20,7 @@ namespace nnj {
 constexpr int ET_THREADS = 256;
 
 __device__ __forceinline__ void copy_img(uint8_t* dst, const uint4* __restrict__ src, int bytes) {
-    for (int i = threadIdx.x; i < (bytes >> 4); i += ET_THREADS) reinterpret_cast<uint4*>(dst)[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < (bytes >> 4); i += blockDim.x) reinterpret_cast<uint4*>(dst)[i] = __ldg(src + i);
 }
 
 // LayerNorm(64) (eps 1e-5, biased variance) of a row held as two 32-value halves by threads (row, hf = 0/1).  The halves are
@@ -172,33 +172,35 @@ struct FfnTcArgs {
     const float *ln_g, *ln_b, *b1, *b2;
 };
 
-constexpr int K3_SMEM = 1024 + 2 * 65536 + 2 * 32768 + (256 + 64 + 128) * 4 + 2048 + 64;
+constexpr int K3_THREADS = 512;             // 16 warps: TMEM lane quarter q = warp & 3 (row = 32 q + lane), column quarter cq = warp >> 2 (16 of every 64 columns)
+constexpr int K3_SMEM = 1024 + 2 * 65536 + (256 + 64 + 128) * 4 + 4096 + 64;
+__device__ __forceinline__ void ln_quarter(float (&v)[16], float2* part, int row, int cq, const float* __restrict__ g, const float* __restrict__ bta);
 
-__global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a) {
+
+__global__ void __launch_bounds__(K3_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_align1024(smem_raw);
     uint8_t* w1_s = sm;                       // hi 32 KB | lo 32 KB   ([256][64])
     uint8_t* w2_s = sm + 65536;               // hi: 4 K-chunks of 8 KB | lo: 4 K-chunks
-    uint8_t* const abuf0 = sm + 131072;       // two operand buffers, each: hi 16 KB | lo 16 KB
-    float* s_b1 = reinterpret_cast<float*>(sm + 196608);
+    float* s_b1 = reinterpret_cast<float*>(sm + 131072);
     float* s_b2 = s_b1 + 256;
     float* s_g = s_b2 + 64;
     float* s_b = s_g + 64;
-    float2* part = reinterpret_cast<float2*>(s_b + 64);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 256);   // d1_done, c0_done, c1_done, d2_done, a_ready[2], a0_ready
+    float2* part = reinterpret_cast<float2*>(s_b + 64);            // [4][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 512);   // d1_done, c0_done, c1_done, d2_done, a_ready[2], a0_ready
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane;
+    const int q = warp & 3, cq = warp >> 2, row = q * 32 + lane;
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
-        mbar_init(bars + 4, ET_THREADS / 32); mbar_init(bars + 5, ET_THREADS / 32); mbar_init(bars + 6, ET_THREADS / 32);
+        mbar_init(bars + 4, K3_THREADS / 32); mbar_init(bars + 5, K3_THREADS / 32); mbar_init(bars + 6, K3_THREADS / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     copy_img(w1_s, a.w1, 65536);
     copy_img(w2_s, a.w2, 65536);
-    s_b1[tid] = a.b1[tid];
+    if (tid < 256) s_b1[tid] = a.b1[tid];
     if (tid < 64) { s_b2[tid] = a.b2[tid]; s_g[tid] = a.ln_g[tid]; s_b[tid] = a.ln_b[tid]; }
     fence_async_smem();
     tc_fence_before();
@@ -210,40 +212,40 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
     const uint32_t id_d1 = umma_idesc_bf16(128, 256), id_d2 = umma_idesc_bf16(128, 64);
     const int n_work = a.B * a.tiles_per_tree;
     uint32_t it = 0;
-    // this thread's 32 values of its token row, loaded one tile ahead (the global-load latency hides behind the previous tile's GEMMs)
-    auto load_row = [&](int w, float4 (&dst)[8]) {
+    // this thread's 16 values of its token row, loaded one tile ahead (the global-load latency hides behind the previous tile's GEMMs)
+    auto load_row = [&](int w, float4 (&dst)[4]) {
         const int b = w / a.tiles_per_tree, tile = w - b * a.tiles_per_tree;
         const int t = tile * 128 + row;
         if (w < n_work && t < a.T) {
-            const float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + hf * 32;
+            const float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + cq * 16;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) dst[k] = ld4(xp + k * 4);
+            for (int k = 0; k < 4; ++k) dst[k] = ld4(xp + k * 4);
         } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < 4; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    float4 xnext[8];
+    float4 xnext[4];
     load_row(blockIdx.x, xnext);
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
         const uint32_t par = it & 1;
         const int b = w / a.tiles_per_tree, tile = w - b * a.tiles_per_tree;
         const int t = tile * 128 + row;
         const bool valid = t < a.T;
-        float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + hf * 32;
-        float xr[32], v[32];
+        float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + cq * 16;
+        float xr[16], v[16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { xr[4 * k] = xnext[k].x; xr[4 * k + 1] = xnext[k].y; xr[4 * k + 2] = xnext[k].z; xr[4 * k + 3] = xnext[k].w; }
+        for (int k = 0; k < 4; ++k) { xr[4 * k] = xnext[k].x; xr[4 * k + 1] = xnext[k].y; xr[4 * k + 2] = xnext[k].z; xr[4 * k + 3] = xnext[k].w; }
         load_row(w + gridDim.x, xnext);
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = xr[k];
-        ln_half(v, part, row, hf, s_g, s_b);
+        for (int k = 0; k < 16; ++k) v[k] = xr[k];
+        ln_quarter(v, part, row, cq, s_g, s_b);
         {   // LN3(x) -> bf16 hi / lo in tensor memory: A operand of fc1
-            uint32_t hh[16], ll[16];
+            uint32_t hh[8], ll[8];
 #pragma unroll
-            for (int k = 0; k < 32; k += 2) split2(v[k], v[k + 1], hh[k >> 1], ll[k >> 1]);
-            tmem_st16(t_a0 + lane_off + hf * 16, hh);
-            tmem_st16(t_a0 + lane_off + 32 + hf * 16, ll);
+            for (int k = 0; k < 16; k += 2) split2(v[k], v[k + 1], hh[k >> 1], ll[k >> 1]);
+            tmem_st8(t_a0 + lane_off + cq * 8, hh);
+            tmem_st8(t_a0 + lane_off + 32 + cq * 8, ll);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -275,18 +277,19 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
             // reads its A operand from there (42 clk per 128 x 64 x 16 instead of 75 from shared memory) and the hand-off is an
             // mbarrier arrive per warp, not a block-wide barrier.  The operand buffer of chunk ch was last read by the UMMA of chunk ch-2.
             if (ch >= 2) { mbar_wait(bars + 1 + (ch - 2), par); tc_fence_after(); }
-            uint32_t acc[32];
-            tmem_ld32(t_d1 + lane_off + ch * 64 + hf * 32, acc);
-            uint32_t hh[16], ll[16];
+            uint32_t acc[16];
+            tmem_ld16_nw(t_d1 + lane_off + ch * 64 + cq * 16, acc);
+            tmem_ld_wait();
+            uint32_t hh[8], ll[8];
 #pragma unroll
-            for (int k = 0; k < 32; k += 2) {      // packed fp32x2 math: hidden units (k, k+1) share every FMA-pipe instruction
+            for (int k = 0; k < 16; k += 2) {      // packed fp32x2 math: hidden units (k, k+1) share every FMA-pipe instruction
                 const float2 gl = gelu_fast2(fadd2(make_float2(__uint_as_float(acc[k]), __uint_as_float(acc[k + 1])),
-                                                   *reinterpret_cast<const float2*>(s_b1 + ch * 64 + hf * 32 + k)));
+                                                   *reinterpret_cast<const float2*>(s_b1 + ch * 64 + cq * 16 + k)));
                 split2(gl.x, gl.y, hh[k >> 1], ll[k >> 1]);
             }
             const uint32_t ta = t_a + (ch & 1) * 64;
-            tmem_st16(ta + lane_off + hf * 16, hh);
-            tmem_st16(ta + lane_off + 32 + hf * 16, ll);
+            tmem_st8(ta + lane_off + cq * 8, hh);
+            tmem_st8(ta + lane_off + 32 + cq * 8, ll);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -315,15 +318,16 @@ __global__ void __launch_bounds__(ET_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
         mbar_wait(bars + 3, par);
         tc_fence_after();
         {
-            uint32_t acc[32];
-            tmem_ld32(t_d2 + lane_off + hf * 32, acc);
+            uint32_t acc[16];
+            tmem_ld16_nw(t_d2 + lane_off + cq * 16, acc);
+            tmem_ld_wait();
             if (valid) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    st4(xp + k * 4, make_float4(xr[4 * k] + __uint_as_float(acc[4 * k]) + s_b2[hf * 32 + 4 * k],
-                                                xr[4 * k + 1] + __uint_as_float(acc[4 * k + 1]) + s_b2[hf * 32 + 4 * k + 1],
-                                                xr[4 * k + 2] + __uint_as_float(acc[4 * k + 2]) + s_b2[hf * 32 + 4 * k + 2],
-                                                xr[4 * k + 3] + __uint_as_float(acc[4 * k + 3]) + s_b2[hf * 32 + 4 * k + 3]));
+                for (int k = 0; k < 4; ++k)
+                    st4(xp + k * 4, make_float4(xr[4 * k] + __uint_as_float(acc[4 * k]) + s_b2[cq * 16 + 4 * k],
+                                                xr[4 * k + 1] + __uint_as_float(acc[4 * k + 1]) + s_b2[cq * 16 + 4 * k + 1],
+                                                xr[4 * k + 2] + __uint_as_float(acc[4 * k + 2]) + s_b2[cq * 16 + 4 * k + 2],
+                                                xr[4 * k + 3] + __uint_as_float(acc[4 * k + 3]) + s_b2[cq * 16 + 4 * k + 3]));
             }
         }
         tc_fence_before();
@@ -709,7 +713,7 @@ int launch_enc_ffn_tc(const Model* m, int layer, float* xs, size_t xs_tree_strid
     const int work = B * a.tiles_per_tree;
     const int grid = work < sm_count() ? work : sm_count();
     prof_begin(KC_FFN, st);
-    k_enc_ffn_tc<<<grid, ET_THREADS, K3_SMEM, st>>>(a);
+    k_enc_ffn_tc<<<grid, K3_THREADS, K3_SMEM, st>>>(a);
     ETC_DONE();
     return 0;
 }
