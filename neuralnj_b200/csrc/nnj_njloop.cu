@@ -1102,7 +1102,10 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
             if (t == 0) {
                 if (int e = score_pairs(m, pool, nb, slot, n, C, P0, mk, nbt, nb.logits[0], P0, st)) return e;
             } else {
-                if (int e = score_pairs(m, pool, nb, slot, n, C, n, mk, nbt, nb.new_scores, nb.pair_stride, st)) return e;
+                // the last step has a single candidate pair: its log-probability is 0 whatever its score (any finite value left in new_scores
+                // does), so the score is computed only when the caller records the logits
+                if (n > 2 || ltr || R <= 3)      // R = 3: no earlier incremental step has filled new_scores
+                    if (int e = score_pairs(m, pool, nb, slot, n, C, n, mk, nbt, nb.new_scores, nb.pair_stride, st)) return e;
                 cur ^= 1;
             }
             prof_begin(KC_SELECT, st);

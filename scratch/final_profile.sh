@@ -11,11 +11,12 @@ cap() {  # name regex skip
   ncu -i gpurun_out/${tag}_$1.ncu-rep --page source --csv > gpurun_out/${tag}_$1.source.csv
 }
 cap score_incr k_score_inc 15
+cap score_late k_score_inc 36
 cap score_step0 k_score_tc 0
 cap alpha_incr k_alpha_v3 20
+cap alpha_late k_alpha_v3 41
 cap alpha_step0 k_alpha_v3 0
 cap colblock k_enc_colblock 2
-cap rowqk "k_tc_gemm<256" 2
-cap rowpv "k_tc_gemm<128" 2
 cap ffn k_enc_ffn 2
+cap softmax k_softmax_rows 2
 ls -la gpurun_out | tail -30

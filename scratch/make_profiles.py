@@ -11,7 +11,7 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
-names = ["score_incr", "score_step0", "alpha_incr", "alpha_step0", "colblock", "rowqk", "rowpv", "ffn"]
+names = ["score_incr", "score_late", "score_step0", "alpha_incr", "alpha_late", "alpha_step0", "colblock", "rowqk", "rowpv", "ffn", "softmax"]
 out, tr = [], {}
 def gb(v, u): return f(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
 for name in names:
@@ -35,7 +35,7 @@ for name in names:
     T = sum(f(x[si]) for x in data) or 1
     out.append("   warp-state samples: " + "  ".join(f"{h2[i][6:]}={100 * sum(f(x[i]) for x in data) / T:.1f}%" for i in st if sum(f(x[i]) for x in data) / T > 0.02))
 head = ("ncu --set full --import-source on --clock-control none, python scratch/prof_rollout.py 128 1 (one 128-alignment chunk, 50 x 1024, bf16x3); one launch per kernel\n"
-        "score_incr = k_score_inc launch #15 (NJ step 15/16, 34-35 pairs per tree); alpha_incr = k_alpha_v3 launch #20 (step 15); step0 = first launch, 256 pairs per tree\n")
+        "score_incr = k_score_inc launch #15 (NJ step 16, 33 pairs per tree); score_late = launch #36 (step 37, 12 pairs: narrow mode); alpha_incr = k_alpha_v3 launch #20 (step 16);\nalpha_late = launch #41 (step 37: 4-way site split); step0 = first launch, 256 pairs per tree\n")
 open("profiles/r01_ncu_full_summary_b128.txt", "w").write(head + "\n".join(out) + "\n")
 json.dump(tr, open("profiles/r01_traffic_b128.json", "w"), indent=1)
 # launch list
@@ -47,7 +47,7 @@ for r in rows[1:]:
     a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += f(r[vi])
 tot = sum(a[1] for a in agg.values())
 cls = {"k_score_tc": "pair_score", "k_score_inc": "pair_score", "k_score<0>": "pair_score", "k_alpha_v3": "alpha", "k_enc_colblock_tc": "col_attn", "k_tc_gemm<256, 0>": "row_qk_gemm",
-       "k_tc_gemm<256, 1>": "row_pv_gemm", "k_tc_gemm<128, 1>": "row_pv_gemm", "k_tc_gemm<128, 0>": "row_qk_gemm", "k_softmax_rows_split": "row_softmax", "k_enc_ffn_tc": "ffn",
+       "k_tc_gemm<256, 1>": "row_pv_gemm", "k_tc_gemm<128, 1>": "row_pv_gemm", "k_tc_gemm<128, 0>": "row_qk_gemm", "k_softmax_rows_split": "row_softmax", "k_softmax_rows_split_reg<4>": "row_softmax", "k_softmax_rows_split_reg<2>": "row_softmax", "k_enc_ffn_tc": "ffn",
        "k_enc_rowqkv_tc": "ln_qkv", "k_alpha1": "merge", "k_merge<1>": "merge", "k_merge<0>": "merge", "k_node_derive": "node_derive",
        "k_alpha_softmax": "alpha_softmax", "k_select": "select", "k_embed": "embed"}
 lines = ["ncu --metrics gpu__time_duration.sum --clock-control none python scratch/prof_rollout.py 128 1   (one chunk of 128 alignments, 50 x 1024, bf16x3)",
