@@ -523,10 +523,20 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
         float* dst = xs + row * LDA + half * 32;
         if (c < C) {
             size_t oi = tb + ((size_t)pi * C + c) * D + half * 32, oj = tb + ((size_t)pj * C + c) * D + half * 32;
+            // loads first, in two batches of 16 (the shared-memory stores below may alias them for the compiler: without the explicit
+            // batches every 16-byte group waited for its own DRAM round trip)
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                st4(dst + e * 4, blend4(ld4(pool.X + oi + e * 4), ld4(pool.X + oj + e * 4), ld4(pool.Y + oi + e * 4),
-                                        ld4(pool.Y + oj + e * 4), __ldg(reinterpret_cast<const float4*>(w.bh) + half * 8 + e)));
+            for (int e0 = 0; e0 < 8; e0 += 4) {
+                float4 xi[4], xj[4], yi[4], yj[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    xi[e] = ld4(pool.X + oi + (e0 + e) * 4); xj[e] = ld4(pool.X + oj + (e0 + e) * 4);
+                    yi[e] = ld4(pool.Y + oi + (e0 + e) * 4); yj[e] = ld4(pool.Y + oj + (e0 + e) * 4);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    st4(dst + (e0 + e) * 4, blend4(xi[e], xj[e], yi[e], yj[e], __ldg(reinterpret_cast<const float4*>(w.bh) + half * 8 + e0 + e)));
+            }
         } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) st4(dst + e * 4, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -538,13 +548,37 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
         float acc[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
-        for (int r = 0; r < Rp; ++r) {
-            if (r == li || r == lj) continue;   // alpha is exactly 0 there (softmax of -inf)
+        // alpha is exactly 0 at r = li, lj (softmax of -inf), so those nodes add nothing and the loop needs no branch; two nodes per
+        // iteration keep 16 independent 16-byte loads in flight per thread (rows past C: clamped to the last row, weight 0 below)
+        const int rclamp = C - 1 - row0 - ty * 8;           // last valid row offset of this thread's 8 rows (may be negative: tile past C)
+        auto node_ptr = [&](int r) { return pool.X + tb + ((size_t)s_slot[r] * C + row0 + ty * 8) * D + tx * 4; };
+        int r = 0;
+        if (rclamp >= 7) {
+            for (; r + 1 < Rp; r += 2) {
+                const float a0 = al[r], a1 = al[r + 1];
+                const float* v0p = node_ptr(r);
+                const float* v1p = node_ptr(r + 1);
+                float4 v0[8], v1[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { v0[i] = ld4(v0p + (size_t)i * D); v1[i] = ld4(v1p + (size_t)i * D); }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc[i][0] = fmaf(a0, v0[i].x, acc[i][0]); acc[i][1] = fmaf(a0, v0[i].y, acc[i][1]);
+                    acc[i][2] = fmaf(a0, v0[i].z, acc[i][2]); acc[i][3] = fmaf(a0, v0[i].w, acc[i][3]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc[i][0] = fmaf(a1, v1[i].x, acc[i][0]); acc[i][1] = fmaf(a1, v1[i].y, acc[i][1]);
+                    acc[i][2] = fmaf(a1, v1[i].z, acc[i][2]); acc[i][3] = fmaf(a1, v1[i].w, acc[i][3]);
+                }
+            }
+        }
+        for (; r < Rp; ++r) {
             const float a = al[r];
-            const float* vp = pool.X + tb + ((size_t)s_slot[r] * C + row0 + ty * 8) * D + tx * 4;
+            const float* vp = node_ptr(r);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (row0 + ty * 8 + i < C) {
+                if (i <= rclamp) {
                     float4 v = ld4(vp + (size_t)i * D);
                     acc[i][0] = fmaf(a, v.x, acc[i][0]); acc[i][1] = fmaf(a, v.y, acc[i][1]);
                     acc[i][2] = fmaf(a, v.z, acc[i][2]); acc[i][3] = fmaf(a, v.w, acc[i][3]);
@@ -590,23 +624,36 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
             const int src = Rp - 1;
             const int rows = min(TILE_ROWS, C - row0);
             const size_t so_ = tb + ((size_t)src * C + row0) * D, do_ = tb + ((size_t)dst * C + row0) * D;
-            for (int k = tid; k < rows * 16; k += NTHREADS) {
-                st4(Xw + do_ + k * 4, ld4(Xw + so_ + k * 4));
-                st4(Yw + do_ + k * 4, ld4(Yw + so_ + k * 4));
-                st4(Kw + do_ + k * 4, ld4(Kw + so_ + k * 4));
-            }
+            // Source and destination slots never overlap, but they live in the same arrays, so the compiler keeps every load behind
+            // the previous store: a plain copy loop makes one DRAM round trip per 16 bytes and thread.  Each plane is therefore copied
+            // as "all loads of this thread, then all stores" (TILE_ROWS * 16 / NTHREADS = 8 uint4 per thread and plane).
+            auto copy8 = [&](const uint4* __restrict__ sp, uint4* __restrict__ dp, int n16) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int k = tid + u * NTHREADS; if (k < n16) v[u] = sp[k]; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int k = tid + u * NTHREADS; if (k < n16) dp[k] = v[u]; }
+            };
+            copy8(reinterpret_cast<const uint4*>(Xw + so_), reinterpret_cast<uint4*>(Xw + do_), rows * 16);
+            copy8(reinterpret_cast<const uint4*>(Yw + so_), reinterpret_cast<uint4*>(Yw + do_), rows * 16);
+            copy8(reinterpret_cast<const uint4*>(Kw + so_), reinterpret_cast<uint4*>(Kw + do_), rows * 16);
             if (kp_h) {
-                const uint4* sh = reinterpret_cast<const uint4*>(kp_h) + so_ / 8; uint4* dh = reinterpret_cast<uint4*>(kp_h) + do_ / 8;
-                const uint4* sl = reinterpret_cast<const uint4*>(kp_l) + so_ / 8; uint4* dl = reinterpret_cast<uint4*>(kp_l) + do_ / 8;
-                for (int k = tid; k < rows * 8; k += NTHREADS) { dh[k] = sh[k]; dl[k] = sl[k]; }
+                copy8(reinterpret_cast<const uint4*>(kp_h) + so_ / 8, reinterpret_cast<uint4*>(kp_h) + do_ / 8, rows * 8);
+                copy8(reinterpret_cast<const uint4*>(kp_l) + so_ / 8, reinterpret_cast<uint4*>(kp_l) + do_ / 8, rows * 8);
             }
             if (nodes_h) {     // site-major planes [C][S][128 bf16]: one 256-byte row per (site, slot)
                 uint4* nh = reinterpret_cast<uint4*>(nodes_h) + (size_t)b * C * pool.S * 16;
                 uint4* nl = reinterpret_cast<uint4*>(nodes_l) + (size_t)b * C * pool.S * 16;
-                for (int k = tid; k < rows * 16; k += NTHREADS) {
-                    const size_t c = row0 + (k >> 4);
-                    const size_t os = (c * pool.S + src) * 16 + (k & 15), od = (c * pool.S + dst) * 16 + (k & 15);
-                    nh[od] = nh[os]; nl[od] = nl[os];
+                uint4 vh[8], vl[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = tid + u * NTHREADS;
+                    if (k < rows * 16) { const size_t os = (((size_t)row0 + (k >> 4)) * pool.S + src) * 16 + (k & 15); vh[u] = nh[os]; vl[u] = nl[os]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = tid + u * NTHREADS;
+                    if (k < rows * 16) { const size_t od = (((size_t)row0 + (k >> 4)) * pool.S + dst) * 16 + (k & 15); nh[od] = vh[u]; nl[od] = vl[u]; }
                 }
             }
             if (tid == 0) kapw[((size_t)b * pool.S + dst) * pool.nCT + ct] = kapw[((size_t)b * pool.S + src) * pool.nCT + ct];
