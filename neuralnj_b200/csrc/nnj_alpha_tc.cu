@@ -23,7 +23,7 @@ namespace nnj {
 
 constexpr int AV_BLEND_WARPS = 16;
 constexpr int AV_THREADS = (AV_BLEND_WARPS + 2) * 32;   // + UMMA issue warp + TMA producer warp
-constexpr int AV_SITES = 64;                            // sites per work item
+constexpr int AV_SITES = 128;                           // sites per work item (accumulators are read out and the roles resynchronise at every boundary)
 constexpr int AV_MAXST = 12;                            // node-ring depth (runtime, 3..12 by the slot count)
 constexpr int AV_MAXT = 4;                              // pair tiles per work item
 constexpr int AV_XS_BYTES = AV_BLEND_WARPS * 2048;      // x staging for the TMA stores: 16 warps x [32 rows][64 B] (SWIZZLE_64B)

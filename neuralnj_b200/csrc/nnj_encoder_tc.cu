@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(ET_THREADS, 2) k_enc_rowqkv_tc(const RowQkvArg
         const int b = w / a.tiles_per_tree, tile = w - b * a.tiles_per_tree;
         const int t = tile * 128 + row;
         const bool valid = t < T;
+        const int c = valid ? t / a.R : 0, r = t - c * a.R;
+        const float qs = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale;   // axial_attention.py:81-82 (loaded with the tile, used after the UMMA)
         float v[32];
         if (valid) {
             const float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + hf * 32;
@@ -132,8 +134,6 @@ __global__ void __launch_bounds__(ET_THREADS, 2) k_enc_rowqkv_tc(const RowQkvArg
         }
         mbar_wait(bar, it & 1);
         tc_fence_after();
-        const int c = valid ? t / a.R : 0, r = t - c * a.R;
-        const float qs = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale;   // axial_attention.py:81-82
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             uint32_t acc[32];

@@ -909,6 +909,7 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
     const float inv_scale = 1.0f / sqrtf((float)D * (float)C);   // model.py:118 (patch_num == C)
     for (int n0 = 0; n0 < N; n0 += step) {
         const int nc = (N - n0 < step) ? (N - n0) : step;
+        int tc_parts = 0;       // score partials per pair written by the tensor-core kernel of this launch
         if (glob && tc) {
             // blend + alpha partials in one tcgen05 kernel (fp32 x planes written on the way, partials per 64-site group - two when the
             // tile is split by site parity - indexed by physical slot) -> softmax -> fused score kernel
@@ -920,7 +921,7 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
                                                                         nb.pair_j, nb.pair_stride, n0, nc, nb.nAP, nb.RP, inv_scale, nb.alpha, 1, n_part);
             LAUNCH_CHECK();
             if (int e = launch_score_tc(m, nb.xf, TC_PAIRS, nb.nodes_h, nb.nodes_l, nb.alpha, nb.RP, PAIR_CHUNK, slot, nb.S, nb.pair_i,
-                                        nb.pair_stride, n0, nc, Rp, nb.S, C, B, mask, nb.score_part, nb.nSB, st)) return e;
+                                        nb.pair_stride, n0, nc, Rp, nb.S, C, B, mask, nb.score_part, nb.nSB, &tc_parts, st)) return e;
         } else if (glob) {
             const int node_tiles = (Rp + 63) / 64, pair_tiles = (nc + 63) / 64;
             prof_begin(KC_ALPHA, st);
@@ -944,7 +945,7 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
             LAUNCH_CHECK();
         }
         prof_begin(KC_MISC, st);
-        k_score_reduce<<<dim3((nc + 127) / 128, B), 128, 0, st>>>(nb.score_part, nb.nSB, (glob && tc) ? (C + 63) / 64 : nb.nSB, nc, scores, score_stride, n0);
+        k_score_reduce<<<dim3((nc + 127) / 128, B), 128, 0, st>>>(nb.score_part, nb.nSB, (glob && tc) ? tc_parts : nb.nSB, nc, scores, score_stride, n0);
         LAUNCH_CHECK();
     }
     return 0;

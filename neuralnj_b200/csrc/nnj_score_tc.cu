@@ -64,6 +64,7 @@ __device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiC
     for (int i = 0; i < e.my_sites; ++i) {
         const uint32_t par = i & 1;
         const int c = e.c_base + 2 * i + e.p;
+        const bool site_ok = !(a.mask && a.mask[(size_t)e.b * a.C + c]);      // loaded here, used after the GELU epilogue
         float4 x4[4 * NSUB];
         {
             // x tile of the site in shared memory (TMA, SWIZZLE_128B; 32-channel halves of [rows][128 B]): row prow, channels
@@ -135,7 +136,6 @@ __device__ __forceinline__ float score_epilogue(const ScoreTcArgs& a, const EpiC
             }
         }
         tc_fence_before();
-        const bool site_ok = !(a.mask && a.mask[(size_t)e.b * a.C + c]);
         if (site_ok) score += (acc.x + acc.y) + (col0 == 0 ? a.b2 : 0.f);
     }
     return row_ok ? score : 0.f;
@@ -332,7 +332,7 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
 //     the next [x_glob | g] while the 16 epilogue warps run the GELU / site-sum epilogue.
 // The alpha operand (A of UMMA 1) is rebuilt per work item from alpha[b] scattered to physical-slot order.
 constexpr int SI_THREADS = 608;            // 16 epilogue warps + issue warp + node-tile producer + x-tile producer
-constexpr int SI_SITES = 64;
+constexpr int SI_SITES = 128;               // sites per work item (the pipeline drains at every work-item boundary)
 constexpr int SI_A0 = 0;                   // staging of alpha by physical slot, fp32 [64 pairs][68] (the operand itself lives in tensor memory)
 constexpr int SI_A0_LD = 68;
 constexpr int SI_XCH = 9216;               // narrow mode (<= 32 pairs): x' word exchange between the two warps of a (half, column group), 16 KB behind the 32-row alpha staging
@@ -565,6 +565,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
             float score = 0.f;
             // w2 . GELU(s + b_s) (+ b2 once per row), masked site sum, for item `it` (global count) whose site of this thread is `site`
             auto ep2 = [&](uint32_t it, int site) {
+                const bool unmasked = site < n_sites && !(a.mask && a.mask[(size_t)b * a.C + c_base + site]);   // loaded before the wait
                 mbar_wait(s_done + (it & 1u), (it >> 1) & 1u);
                 tc_fence_after();
                 if (narrow && !(a.dbg & 4)) {
@@ -577,7 +578,6 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                         const float2 sb = fadd2(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), *reinterpret_cast<const float2*>(bsv + sub * 8 + e));
                         acc = ffma2(gelu_fast2(sb), *reinterpret_cast<const float2*>(w2v + sub * 8 + e), acc);
                     }
-                    const bool unmasked = site < n_sites && !(a.mask && a.mask[(size_t)b * a.C + c_base + site]);
                     if (unmasked) score += (acc.x + acc.y) + ((cg | sub) == 0 ? a.b2 : 0.f);
                 } else if (warp_rows && !(a.dbg & 4)) {
                     uint32_t sv[16];
@@ -589,7 +589,6 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                         const float2 sb = fadd2(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), *reinterpret_cast<const float2*>(bsv + e));
                         acc = ffma2(gelu_fast2(sb), *reinterpret_cast<const float2*>(w2v + e), acc);
                     }
-                    const bool unmasked = site < n_sites && !(a.mask && a.mask[(size_t)b * a.C + c_base + site]);
                     if (unmasked) score += (acc.x + acc.y) + (cg == 0 ? a.b2 : 0.f);
                 }
                 tc_fence_before();
@@ -768,7 +767,7 @@ static int make_tmap_xtile(CUtensorMap* map, const float* base, int pc, int nrow
 // <= 64 pairs per tree: the persistent site-parity kernel
 static int launch_score_inc(const Model* m, const float* xf, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
                             int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,
-                            int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, cudaStream_t st) {
+                            int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, int* n_part, cudaStream_t st) {
     static int n_sm = 0;
     if (!n_sm) {
         cudaError_t e = cudaFuncSetAttribute(k_score_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_SMEM_MAX);
@@ -801,6 +800,8 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
     a.alpha = alpha; a.RP = RP; a.alpha_pairs = alpha_pairs;
     a.slot_of = slot_of; a.slot_stride = slot_stride; a.pair_i = pair_i; a.pair_stride = pair_stride; a.n0 = n0; a.nc = nc;
     a.Rp = Rp; a.S = Rp; a.C = C; a.B = B; a.groups = (C + SI_SITES - 1) / SI_SITES;   // a.S: slots contracted by UMMA 1
+    *n_part = a.groups;
+    if (a.groups > nSG) return set_error(NNJ_ERR_INVALID, "score_inc: partial buffer too small");
     a.wsh = (const uint4*)m->nj_bf.wsh; a.wsl = (const uint4*)m->nj_bf.wsl;
     a.bg = m->nj.bg; a.bs = m->nj.bs; a.w2 = m->nj.w2; a.b2 = m->nj.b2;
     a.mask = mask; a.score_part = score_part; a.nSG = nSG;
@@ -825,7 +826,7 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
 
 int launch_score_tc(const Model* m, const float* xf, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
                     int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,
-                    int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, cudaStream_t st) {
+                    int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, int* n_part, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
@@ -838,8 +839,9 @@ int launch_score_tc(const Model* m, const float* xf, int pc, const void* nodes_h
         if (inc < 0) { const char* ev = getenv("NNJ_SCORE_INC"); inc = ev ? atoi(ev) : 1; }
         if (inc && nc <= 64)
             return launch_score_inc(m, xf, pc, nodes_h, nodes_l, alpha, RP, alpha_pairs, slot_of, slot_stride, pair_i, pair_stride, n0, nc, Rp, S, C, B,
-                                    mask, score_part, nSG, st);
+                                    mask, score_part, nSG, n_part, st);
     }
+    *n_part = (C + ST_SITES - 1) / ST_SITES;
     CUtensorMap mh, ml, mx;
     if (int e = make_tmap_xtile(&mx, xf, pc, nc, C, B)) return e;
     if (int e = make_tmap_nodes(&mh, nodes_h, S, B * C)) return e;

@@ -20,6 +20,8 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 3;
 constexpr int TC_PLANE_BYTES = TC_BM * TC_BK * 2;          // 16 KB: 128 rows x 128 B
 constexpr int TC_STAGE_BYTES = 4 * TC_PLANE_BYTES;         // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_LD = 36;                              // floats per row of an epilogue staging tile [32 rows][32 cols] (+4: conflict-free)
+constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_LD * 4;      // one tile per epilogue warp
 
 // grid (N tiles * nsplit, M tiles, Z).  C row-major with leading dimension ldc, batch stride sC (elements).
 // Split-K: split s = blockIdx.x % nsplit handles K chunks [s*cps, (s+1)*cps) and writes to C + s*split_stride.
@@ -48,6 +50,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     uint64_t* acc_full = empty + NSTG;      // [2]
     uint64_t* acc_free = acc_full + 2;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+    float* epi = reinterpret_cast<float*>(tiles + NSTG * STAGE + 256);     // [4 warps][32][TC_EPI_LD]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_chunks = (g.K + TC_BK - 1) / TC_BK;
@@ -98,10 +101,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = umma_idesc_bf16(TC_BM, BN) | (BMN ? (1u << 16) : 0u);
         int gc = 0, ti = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
             const int split = (t % nt) % g.nsplit;
+            // a ragged last N tile runs a narrower UMMA (N rounded up to 16): the tensor pipe time of an instruction is ~N/2 clk
+            const int n_left = g.N - ((t % nt) / g.nsplit) * BN;
+            const uint32_t idesc = umma_idesc_bf16(TC_BM, n_left >= BN ? BN : ((n_left + 15) & ~15)) | (BMN ? (1u << 16) : 0u);
             const int kc0 = split * g.chunks_per_split;
             const int nchunks = max(0, min(total_chunks - kc0, g.chunks_per_split));
             const int ab = ti & 1;
@@ -152,6 +157,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
             tc_fence_after();
             const int m = m0 + q * 32 + lane;
             float* crow = g.C + (size_t)z * g.sC + (size_t)m * g.ldc + (size_t)split * g.split_stride;
+            float* stg = epi + q * (32 * TC_EPI_LD);
+            const bool vec_ok = (g.ldc & 3) == 0 && (g.split_stride & 3) == 0 && (g.sC & 3) == 0;
 #pragma unroll 1
             for (int cb = 0; cb < BN / 32; ++cb) {
                 uint32_t v[32];
@@ -161,13 +168,24 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
                     for (int j = 0; j < 32; ++j) v[j] = 0u;
                 }
                 const int n = n0 + cb * 32;
-                if (m < g.M) {
-                    if (n + 31 < g.N && (g.ldc & 3) == 0 && (g.split_stride & 3) == 0) {
+                if (n + 31 < g.N && vec_ok) {
+                    // TMEM hands a thread one ROW (32 columns): stored directly, every instruction would touch 32 rows x 16 B.  The tile goes
+                    // through a padded shared-memory tile instead and leaves as 4 rows x 128 contiguous bytes per instruction.
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            st4(crow + n + j * 4, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-                    } else {
+                    for (int j = 0; j < 8; ++j)
+                        st4(stg + lane * TC_EPI_LD + j * 4, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                    __syncwarp();
+                    const int rr = lane >> 3, c4 = (lane & 7) * 4;
+                    float* cbase = g.C + (size_t)z * g.sC + (size_t)split * g.split_stride + (size_t)(m0 + q * 32) * g.ldc + n + c4;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + rr;
+                        if (m0 + q * 32 + row < g.M) st4(cbase + (size_t)row * g.ldc, ld4(stg + row * TC_EPI_LD + c4));
+                    }
+                    __syncwarp();
+                } else if (m < g.M) {
+                    {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (n + j < g.N) crow[n + j] = __uint_as_float(v[j]);
@@ -481,8 +499,8 @@ static int tc_sm_count() {
 int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                        size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st) {
     static bool attr = false;
-    constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256;
-    constexpr int SMEM256 = 2 * (6 * TC_PLANE_BYTES) + 1024 + 256;
+    constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
+    constexpr int SMEM256 = 2 * (6 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM256);
@@ -515,9 +533,9 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, int bn, int nsplit, int chunks_per_split, size_t split_stride,
                       cudaStream_t st) {
     static bool attr = false;
-    constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256;
-    constexpr int SMEM64 = TC_STAGES * (3 * TC_PLANE_BYTES) + 1024 + 256;
-    constexpr int SMEM256 = 2 * (6 * TC_PLANE_BYTES) + 1024 + 256;
+    constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
+    constexpr int SMEM64 = TC_STAGES * (3 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
+    constexpr int SMEM256 = 2 * (6 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64);
