@@ -33,8 +33,7 @@ struct TcGemmArgs {
 // BMN: B is given MN-major, [Z][K][N] with N contiguous (e.g. V of the row attention, [key site][taxon*8+d]); its tiles are loaded
 // as 64 x 64 boxes (64 N values = one 128-byte swizzle row per K index), the 64-column blocks of an N tile 8 KB apart.
 //
-// Persistent: grid = min(tiles, SMs); every role walks the same static tile list (t = blockIdx.x, += gridDim.x; N tiles fastest
-// so that neighbouring CTAs share the A rows in L2).  The TMA ring and its barriers run on across tiles, and the accumulator
+// Persistent: grid = min(tiles, SMs); every role walks the same static tile list (groups of N tiles dealt out round robin, see below).  The TMA ring and its barriers run on across tiles, and the accumulator
 // is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i drains while the tensor core works on tile i+1.
 template <int BN, bool BMN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -56,6 +55,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     const int total_chunks = (g.K + TC_BK - 1) / TC_BK;
     const int nt = ((g.N + BN - 1) / BN) * g.nsplit, mt = (g.M + TC_BM - 1) / TC_BM;
     const int n_tiles = g.Z * mt * nt;
+    // static schedule: the nt N tiles of one 128-row A block form a group that runs back to back on one SM (the A block is re-read
+    // from that SM's own L2 partition: with single tiles dealt out round robin, neighbouring CTAs on different dies each pulled
+    // their own copy of P from DRAM); groups are dealt out round robin, so neighbouring CTAs work on neighbouring row blocks of the
+    // same (tree, head) and share its B operand in L2.  (Contiguous tile ranges per CTA were tried: 148 different (tree, head)
+    // working sets at once do not fit L2 and both GEMMs ran 1.5-1.9x slower.)
+    // Measured (512 trees): P V (two N tiles, A = P streamed from DRAM) 64.7 -> 60.6 ms with groups; Q K^T (four N tiles, operands L2
+    // resident) 56.0 -> 60.9 ms, so only the MN-major instantiation groups.  Small problems: single tiles, so that every SM gets work.
+    const int gsz = (BMN && g.Z * mt >= (int)gridDim.x) ? nt : 1;
+    const int n_groups = n_tiles / gsz;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -73,7 +81,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     // addresses stay in uniform registers (a lane==0 branch makes ptxas emit a R2UR broadcast loop per MMA).
     if (warp == 0) {
         int gc = 0;     // chunks issued so far (ring position)
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) for (int t = grp * gsz; t < (grp + 1) * gsz; ++t) {
             const int xi = t % nt, r0 = t / nt, z = r0 / mt;
             const int split = xi % g.nsplit, n0 = (xi / g.nsplit) * BN, m0 = (r0 - z * mt) * TC_BM;
             const int kc0 = split * g.chunks_per_split;
@@ -102,7 +110,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
         }
     } else if (warp == 1) {
         int gc = 0, ti = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+        for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) for (int t = grp * gsz; t < (grp + 1) * gsz; ++t, ++ti) {
             const int split = (t % nt) % g.nsplit;
             // a ragged last N tile runs a narrower UMMA (N rounded up to 16): the tensor pipe time of an instruction is ~N/2 clk
             const int n_left = g.N - ((t % nt) / g.nsplit) * BN;
@@ -147,7 +155,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     } else {
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         int ti = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+        for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) for (int t = grp * gsz; t < (grp + 1) * gsz; ++t, ++ti) {
             const int xi = t % nt, r0 = t / nt, z = r0 / mt;
             const int split = xi % g.nsplit, n0 = (xi / g.nsplit) * BN, m0 = (r0 - z * mt) * TC_BM;
             const int kc0 = split * g.chunks_per_split;

@@ -19,4 +19,7 @@ cap alpha_step0 k_alpha_v3 0
 cap colblock k_enc_colblock 2
 cap ffn k_enc_ffn 2
 cap softmax k_softmax_rows 2
+cap rowqk k_tc_gemm 2
+cap rowpv k_tc_gemm 3
+cap merge k_merge 20
 ls -la gpurun_out | tail -30

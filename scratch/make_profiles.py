@@ -11,7 +11,7 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
-names = ["score_incr", "score_late", "score_step0", "alpha_incr", "alpha_late", "alpha_step0", "colblock", "rowqk", "rowpv", "ffn", "softmax"]
+names = ["score_incr", "score_late", "score_step0", "alpha_incr", "alpha_late", "alpha_step0", "colblock", "rowqk", "rowpv", "ffn", "softmax", "merge"]
 out, tr = [], {}
 def gb(v, u): return f(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
 for name in names:
@@ -35,7 +35,7 @@ for name in names:
     T = sum(f(x[si]) for x in data) or 1
     out.append("   warp-state samples: " + "  ".join(f"{h2[i][6:]}={100 * sum(f(x[i]) for x in data) / T:.1f}%" for i in st if sum(f(x[i]) for x in data) / T > 0.02))
 head = ("ncu --set full --import-source on --clock-control none, python scratch/prof_rollout.py 128 1 (one 128-alignment chunk, 50 x 1024, bf16x3); one launch per kernel\n"
-        "score_incr = k_score_inc launch #15 (NJ step 16, 33 pairs per tree); score_late = launch #36 (step 37, 12 pairs: narrow mode); alpha_incr = k_alpha_v3 launch #20 (step 16);\nalpha_late = launch #41 (step 37: 4-way site split); step0 = first launch, 256 pairs per tree\n")
+        "score_incr = k_score_inc launch #15 (NJ step 16, 33 pairs per tree); score_late = launch #36 (step 37, 12 pairs: narrow mode); alpha_incr = k_alpha_v3 launch #20 (step 16);\nalpha_late = launch #41 (step 37: 4-way site split); step0 = first launch, 256 pairs per tree; rowqk / rowpv = k_tc_gemm launches #2 / #3 (layer 1); merge = k_merge launch #20 (30 live nodes)\n")
 open("profiles/r01_ncu_full_summary_b128.txt", "w").write(head + "\n".join(out) + "\n")
 json.dump(tr, open("profiles/r01_traffic_b128.json", "w"), indent=1)
 # launch list

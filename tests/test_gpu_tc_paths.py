@@ -125,3 +125,35 @@ def test_large_alignment_200x4096(gpu_models):
         n = R - t
         assert bool(((0 <= mm[:, t, 0]) & (mm[:, t, 0] < mm[:, t, 1]) & (mm[:, t, 1] < n)).all())
     assert bool(torch.isfinite(s2).all())
+
+
+_TOGGLE_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/oracle")
+import nnj_oracle as O
+from neuralnj_b200 import PhyloATTN, inference_config
+torch.manual_seed(0)
+m = PhyloATTN(inference_config(), precision="bf16x3").cuda().eval()
+data = O.evolved_msa(2, 40, 256, seed=11)
+mask = torch.zeros(2, 256, dtype=torch.bool)
+merges, slp, trace = m.rollout_fused(data.cuda(), mask.cuda(), want_logits=True)
+torch.save({"merges": merges.cpu(), "trace": trace.cpu()}, sys.argv[2])
+"""
+
+
+def test_lane_quarter_modes_agree_with_the_two_way_split(tmp_path):
+    """<= 32 pairs: k_alpha_v3 splits the tile over four sites (NNJ_ALPHA_QUAD) and k_score_inc splits a pair's channels over
+    two warps (NNJ_SCORE_NARROW).  Both must reproduce the 2-way site-parity kernels they replace: same merges, logits within
+    the tolerance of the oracle comparison (the partial sums are grouped differently, nothing else changes).  The switches are
+    read once per process, hence the two subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tag, env in (("new", {}), ("old", {"NNJ_ALPHA_QUAD": "0", "NNJ_SCORE_NARROW": "0"})):
+        path = str(tmp_path / f"{tag}.pt")
+        subprocess.run([sys.executable, "-c", _TOGGLE_SCRIPT, root, path], check=True, env={**os.environ, **env}, timeout=300)
+        outs.append(torch.load(path))
+    assert torch.equal(outs[0]["merges"], outs[1]["merges"])
+    assert _rel(outs[0]["trace"], outs[1]["trace"]) < LOGIT_TOL
