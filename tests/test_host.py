@@ -138,3 +138,15 @@ def test_newick_helpers():
 def test_rollout_driver_refuses_training_mode():
     with pytest.raises(NotImplementedError):
         nnj.reinforce_rollout({}, None, None, None, eval=False)
+
+
+def test_library_path_override_fails_loudly(tmp_path):
+    """NNJ_LIB_PATH points the binding at another build of libnnj (A/B runs); a missing file raises, nothing falls back."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r)\n"
+            "from neuralnj_b200 import _lib\n"
+            "try:\n    _lib.lib()\nexcept _lib.NnjError as e:\n    print('NnjError'); sys.exit(0)\nsys.exit(1)\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NNJ_LIB_PATH=str(tmp_path / "absent.so"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "NnjError" in r.stdout, r.stderr
