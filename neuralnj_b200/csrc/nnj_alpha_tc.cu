@@ -3,9 +3,9 @@
 // For every listed pair n = (i, j) of a tree and every site c the reference forms (model.py:105-118)
 //     z = sigmoid(W_h (x_i - x_j) + b_h) = sigmoid(Y_i - Y_j + b_h),      x = z x_i + (1 - z) x_j
 //     alpha[n, r] = sum_{c,d} (W_q x + b_q)[c,d] K_r[c,d] = sum_{c,d} x[c,d] K'_r[c,d] + kappa_r        (K' = W_q^T K)
-// One CTA = one tree x 64 sites x up to 4 tiles of 128 pairs.  Per site a producer warp streams the site's node tile
+// One work item = one tree x 128 sites x up to 4 tiles of 128 pairs (persistent CTAs).  Per site a producer warp streams the site's node tile
 // (X, Y fp32 [slots x 64], K' bf16 hi/lo [slots x 64]) into a shared-memory ring by TMA (SWIZZLE_128B, so that
-// lanes reading different slots hit different banks); the ring is 3 deep; 16 blend warps form x for one pair row x 16 channels per thread,
+// lanes reading different slots hit different banks); the ring is 3..12 deep by the slot count; 16 blend warps form x for one pair row x 16 channels per thread,
 // write it (fp32, staged per warp and sent by TMA store) to the x planes the pair-score kernel reads later, and store its bf16 hi/lo split straight into TENSOR
 // MEMORY (tcgen05.st: row = TMEM lane, two bf16 per column) as the A operand; an issue warp runs
 //     acc[tile][pair, slot] += x[pair, site, :] . K'[slot, site, :]        (tcgen05.mma, A from TMEM, 3-product split)
@@ -15,7 +15,9 @@
 // lanes 0..63 hold the pairs at site 2k, lanes 64..127 the same pairs at site 2k+1, and two UMMA groups (K' of site 2k ->
 // accumulator 0, K' of site 2k+1 -> accumulator 1) leave the even-site sums in rows 0..63 of accumulator 0 and the
 // odd-site sums in rows 64..127 of accumulator 1 (the other halves are ignored).
-// The accumulators are written once per CTA as partials of this site group; k_alpha_softmax reduces them in fixed order.
+// With <= 32 pairs the split is 4-way: lane quarter q holds the pairs at site 4k+q, four UMMA groups, four accumulators.  A warp's
+// TMEM lane quarter and its SM sub-partition are both warp % 4, so this is what puts real rows on all four schedulers.
+// The accumulators are written once per work item as partials of this site group; k_alpha_softmax reduces them in fixed order.
 #include "nnj_internal.h"
 #include "nnj_tc.cuh"
 

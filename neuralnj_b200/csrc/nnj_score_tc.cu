@@ -321,7 +321,7 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
 
 // ------------------------------------------------------------------ incremental steps: <= 64 pairs per tree
 // Every NJ step after the first scores only the pairs of the new node (<= R-1 <= 63 rows), and the 48 of them dominate the loop.
-// k_score_inc is the pair-score kernel for that regime, persistent over work items (tree, 64-site group):
+// k_score_inc is the pair-score kernel for that regime, persistent over work items (tree, 128-site group):
 //   * the 128-row tile is split by site parity like k_alpha_v3: lanes 0..63 = the pairs at site 2k, lanes 64..127 = the same
 //     pairs at site 2k+1.  UMMA 1 runs once per site into its own accumulator ([x_glob | g] of site 2k in D1a rows 0..63,
 //     of site 2k+1 in D1b rows 64..127; the other halves are ignored); UMMA 2 (x' . W_s^T) runs ONCE for both sites, its A
@@ -331,6 +331,7 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
 //   * the issue warp queues UMMA 1 of the next site pair right behind UMMA 2 of the current one, so the tensor core works on
 //     the next [x_glob | g] while the 16 epilogue warps run the GELU / site-sum epilogue.
 // The alpha operand (A of UMMA 1) is rebuilt per work item from alpha[b] scattered to physical-slot order.
+// With <= 32 pairs (narrow mode, see the epilogue warps) lanes 32..63 / 96..127 repeat the pairs and share their channels.
 constexpr int SI_THREADS = 608;            // 16 epilogue warps + issue warp + node-tile producer + x-tile producer
 constexpr int SI_SITES = 128;               // sites per work item (the pipeline drains at every work-item boundary)
 constexpr int SI_A0 = 0;                   // staging of alpha by physical slot, fp32 [64 pairs][68] (the operand itself lives in tensor memory)
