@@ -1077,10 +1077,14 @@ int run_merge(Model* m, const float* state_in, int B, int Rp, int C, const int32
 // ---- fused rollout
 int nj_rollout_chunk(const Model* m, int B, int R, int C) {
     size_t per = nj_layout(nullptr, 1, R + 1, R, C, true, false, nj_use_tc(m, R + 1)).total + encoder_ws_bytes(m, 1, R, C);
-    size_t budget = (size_t)48 << 30;     // of 180 GB HBM3e
+    // defaults: 48 GB of the 180 GB HBM3e, at most 128 trees per chunk; NNJ_WS_GB / NNJ_CHUNK_MAX override them (tuning runs)
+    static int ws_gb = 0, ch_max = 0;
+    if (!ws_gb) { const char* e = getenv("NNJ_WS_GB"); ws_gb = e && atoi(e) > 0 ? atoi(e) : 48; }
+    if (!ch_max) { const char* e = getenv("NNJ_CHUNK_MAX"); ch_max = e && atoi(e) > 0 ? atoi(e) : 128; }
+    size_t budget = (size_t)ws_gb << 30;
     int ch = (int)(budget / per);
     if (ch < 1) ch = 1;
-    if (ch > 128) ch = 128;
+    if (ch > ch_max) ch = ch_max;
     if (ch > B) ch = B;
     const int n = (B + ch - 1) / ch;      // equal-sized chunks: no small tail launch
     return (B + n - 1) / n;
