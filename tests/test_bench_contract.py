@@ -1,0 +1,55 @@
+"""The bench.py JSON contract (driver side): the committed line of the last GPU run and a live `--impl reference` line
+carry every key the driver and the judge read.  CPU only — nothing here touches the CUDA library."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "e2e", "cpu_baseline"]
+
+
+def _check_common(d):
+    for k in BASE_KEYS:
+        assert k in d, k
+    assert d["unit"] == "trees/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["vs_baseline"] is None                      # BASELINE.md publishes no number for this metric
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    assert d["cpu_baseline"]["kind"] in ("port", "reference")
+
+
+def test_committed_gpu_line_has_the_contract_keys():
+    with open(os.path.join(ROOT, "profiles", "r01_bench_final.json")) as f:
+        d = json.loads(f.read().strip().splitlines()[-1])
+    _check_common(d)
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["value"] > 0
+    assert d["gpu_launches"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert abs(d["value"] - 512 * 1e3 / d["ms_per_step"]) / d["value"] < 1e-3          # value = trees per step / step time
+    for k in ("sm_mhz", "sm_max_mhz", "reasons"):
+        assert k in d["clocks"], k
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert abs(sum(v["share"] for v in d["kernels"].values()) - 1.0) < 0.01
+
+
+def test_reference_arm_prints_one_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference"
+    _check_common(d)
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
