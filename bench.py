@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """bench.py — trees/sec of Argmax inference on 50-taxa x 1024-site alignments (BASELINE.json metric, configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 512] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 512] [--scaling strong|weak] [--impl ours|reference]
+                    [--precision bf16x3|bf16|fp32] [--workload config2|config4|config1]
 
 One "step" = one pass of the hot path (encode + 49 learned-NJ steps) over a batch of synthetic MSAs
 (config 2: iid tokens over A,C,G,T,gap, seed 1234; weights torch.manual_seed(0) default init — the shipped
-checkpoint is a missing blob).  At N GPUs every rank processes its own `--batch` alignments (alignments are
-independent: no collective on the data path, "weak" scaling); value = all trees / max-over-ranks device time.
+checkpoint is a missing blob).  configs[1] reads "batch of 512 ... sharded by alignment over 1/2/4/8 B200", so the default
+is STRONG scaling: the 512 alignments of a step are cut into contiguous shards of 512/N per rank (alignments are independent:
+no collective on the data path); value = 512 x K / max-over-ranks device time.  `--scaling weak` gives every rank its own
+512 (the round-1 line); at N > 1 the default run also measures that and reports it under "weak".
 
 Printed keys beyond the base contract:
-  e2e          same metric through the C-ABI host-buffer entry point nnj_rollout_host (pinned host int8 MSA in,
-               merge lists out; H2D/D2H and workspace allocation inside the timed region)
-  roofline     the kernel class with the largest share of the step, timed live with CUDA events on the launching
-               stream (nnj_profile_*), algorithmic FLOPs / launch from BASELINE.md section 3
-  kernels      per-class milliseconds / launches / share of the profiled step
-  cpu_baseline the CPU oracle (port of the reference, oracle/nnj_oracle.py) timed on this box's host cores
-  --impl reference : the same oracle as the reference arm (the reference itself needs /root/reference, absent here)
+  e2e            same metric through the C-ABI host-buffer entry point nnj_rollout_host (pinned host int8 MSA in,
+                 merge lists out; H2D/D2H inside the timed region, staged per chunk on a copy stream)
+  roofline       the kernel class with the largest share of the step, timed live with CUDA events on the launching
+                 stream (nnj_profile_*), algorithmic FLOPs / launch from BASELINE.md section 3
+  roofline_step  the whole step: algorithmic TFLOP/s against the sustained bf16 peak, encoder and NJ loop separately, and the
+                 NJ loop's DRAM bytes per tree against SURVEY 8(d)'s 334 MB streaming figure
+  kernels        per-class milliseconds / launches / share of the profiled step
+  latency_b1_ms  one alignment, device-resident input -> merge list (median of 7)
+  gpu_eager_baseline  the reference formulation (the oracle restatement) in torch eager on this GPU at B = 1 / 8 / 32
+  parity_check   after the timed region: alignments of the bench batch replayed on the CPU oracle
+  cpu_baseline   the CPU oracle (port of the reference, oracle/nnj_oracle.py) timed on this box's host cores
+  --impl reference : the same oracle as the reference arm (the reference itself needs /root/reference, absent on the GPU box)
 """
 import argparse
 import ctypes as C
@@ -29,8 +37,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-R_TAXA, L_SITES, D, H = 50, 1024, 64, 8
-METRIC = "trees/sec, 50-taxa x 1024-site Argmax inference"
+D, H = 64, 8
+WORKLOADS = {
+    # name: (taxa, sites, default global batch, metric text)
+    "config2": (50, 1024, 512, "trees/sec, 50-taxa x 1024-site Argmax inference"),
+    "config4": (200, 4096, 4, "trees/sec, 200-taxa x 4096-site Argmax inference"),
+}
 UNIT = "trees/s"
 
 
@@ -63,6 +75,10 @@ def algorithmic_flops(R, Cc, layers=6):
         "node_derive": R * 3 * 2 * Cc * D * D,
     }
     return fl
+
+
+ENC_CLASSES = ("embed", "ln_qkv", "out_proj", "row_qk_gemm", "row_softmax", "row_pv_gemm", "col_attn", "ffn")
+NJ_CLASSES = ("node_derive", "alpha", "alpha_softmax", "pair_score", "pair_blend", "select", "merge", "misc")
 
 
 class ClockSampler:
@@ -102,19 +118,36 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_oracle_trees_per_sec(n_trees, seed=1234):
-    """Time the CPU oracle (port of the reference path) on `n_trees` config-2 alignments, one per call like the reference (B=1)."""
-    import torch
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import nnj_oracle as O
+    return O
+
+
+def cpu_oracle_run(data, mask, want_merges=None):
+    """Time the CPU oracle (port of the reference path) on the given alignments, one per call like the reference (B=1), and -
+    when `want_merges` is given - check the device's merge lists against it (identical, or a tie-ambiguous step: replay)."""
+    import torch
+    O = _oracle()
     sd = O.init_state_dict(0)
-    data = synthetic_msa(n_trees, R_TAXA, L_SITES, seed)
-    mask = torch.zeros(1, L_SITES, dtype=torch.bool)
+    n = data.shape[0]
+    identical, tie_ok, worst_gap = 0, 0, None
     t0 = time.perf_counter()
-    for b in range(n_trees):
-        O.rollout(sd, data[b:b + 1], mask)
+    refs = [O.rollout(sd, data[b:b + 1], mask[b:b + 1]) for b in range(n)]
     dt = time.perf_counter() - t0
-    return n_trees / dt, dt, torch.get_num_threads()
+    if want_merges is not None:
+        for b, ref in enumerate(refs):
+            got = want_merges[b:b + 1].long()
+            if torch.equal(got, ref["merges"]):
+                identical += 1
+                continue
+            rep = O.rollout(sd, data[b:b + 1], mask[b:b + 1], forced_merges=got)     # teacher-forced replay of OUR trajectory
+            slack = max(float(((lg.max(1).values - lg.gather(1, a.unsqueeze(1)).squeeze(1)) / lg.abs().max(1).values).max())
+                        for lg, a in zip(rep["logits"], rep["actions"]))
+            worst_gap = slack if worst_gap is None else max(worst_gap, slack)
+            tie_ok += int(slack < 1e-5)
+    return n / dt, dt, torch.get_num_threads(), {"trees": n, "identical_merges": identical, "tie_aware_ok": tie_ok,
+                                                  "worst_tie_slack": worst_gap, "tie_tolerance": 1e-5}
 
 
 def run_reference(args):
@@ -125,19 +158,21 @@ def run_reference(args):
         return
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
+    R, L, _, metric = WORKLOADS[args.workload]
     sample = 1
+    mask = torch.zeros(sample, L, dtype=torch.bool)
     for _ in range(args.warmup):
-        cpu_oracle_trees_per_sec(sample)
+        cpu_oracle_run(synthetic_msa(sample, R, L, 1234), mask)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        cpu_oracle_trees_per_sec(sample, seed=1234 + k)
+        cpu_oracle_run(synthetic_msa(sample, R, L, 1234 + k), mask)
     dt = time.perf_counter() - t0
     tps = args.steps * sample / dt
     cores = torch.get_num_threads()
     line = {
-        "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": f"configs[1]: synthetic MSAs {R_TAXA} taxa x {L_SITES} sites, Argmax; each step = {sample} alignment (bounded sample, B=1 per call as shipped)"},
+        "impl": "reference", "metric": metric, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"configs[1]: synthetic MSAs {R} taxa x {L} sites, Argmax; each step = {sample} alignment (bounded sample, B=1 per call as shipped)"},
         "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{args.steps} x {sample} alignment(s) of the config-2 generator"},
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -145,15 +180,46 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def gpu_eager_baseline(dev, R, L, budget_s=40.0):
+    """SURVEY 8(d) same-box GPU bar: the reference formulation (the oracle restatement, pure torch ops) run in torch eager
+    on this B200 at B = 1 / 8 / 32.  Step 0 is pair-chunked for B > 1 (the reference materialises ~3 GB per tree there)."""
+    import torch
+    O = _oracle()
+    sd = {k: v.to(dev) for k, v in O.init_state_dict(0).items()}
+    out = {}
+    t_start = time.perf_counter()
+    for B in (1, 8, 32):
+        if time.perf_counter() - t_start > budget_s:
+            break
+        data = synthetic_msa(B, R, L, 4321).to(dev)
+        mask = torch.zeros(B, L, dtype=torch.bool, device=dev)
+        try:
+            O.rollout(sd, data, mask, pair_chunk=0 if B == 1 else 128)      # warm (cuBLAS handles, allocator)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            O.rollout(sd, data, mask, pair_chunk=0 if B == 1 else 128)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out[f"B{B}"] = {"trees_per_s": round(B / dt, 3), "s_per_call": round(dt, 3)}
+        except Exception as e:   # noqa: BLE001  (an OOM at B = 32 must not take the bench line down)
+            out[f"B{B}"] = {"error": type(e).__name__}
+            torch.cuda.empty_cache()
+    out["note"] = "oracle/nnj_oracle.py on cuda (torch eager, fp32, TF32 off): the reference's formulation on this GPU, not the product path"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=512, help="alignments per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="GLOBAL alignments per step with --scaling strong, per GPU with weak (default: the workload's)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3"])
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip latency_b1 / gpu_eager_baseline / the weak-scaling second measurement")
     ap.add_argument("--cpu-trees", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -172,43 +238,58 @@ def main():
     import __graft_entry__ as graft
     graft.build()
     from neuralnj_b200 import PhyloATTN, inference_config, _lib
+    from neuralnj_b200.shard import shard_bounds
     L = _lib.lib()
+    R_TAXA, L_SITES, default_batch, METRIC = WORKLOADS[args.workload]
     torch.manual_seed(0)
     model = PhyloATTN(inference_config(), precision=args.precision).to(dev).eval()
-    B = args.batch
-    data_host = synthetic_msa(B, R_TAXA, L_SITES, 1234 + rank).pin_memory()
-    mask_host = torch.zeros(B, L_SITES, dtype=torch.bool).pin_memory()
-    data = data_host.to(dev)
-    mask = mask_host.to(dev)
+    G = args.batch or default_batch                     # global batch (strong) / per-GPU batch (weak)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        return model.rollout_fused(data, mask)
+    def make_inputs(scaling):
+        """This rank's alignments.  strong: rows [lo, hi) of ONE global batch (same seed on every rank); weak: its own batch."""
+        if scaling == "strong":
+            lo, hi = shard_bounds(G, rank, world)
+            host = synthetic_msa(G, R_TAXA, L_SITES, 1234)[lo:hi].contiguous().pin_memory()
+        else:
+            host = synthetic_msa(G, R_TAXA, L_SITES, 1234 + rank).pin_memory()
+        mask_h = torch.zeros(host.shape[0], L_SITES, dtype=torch.bool).pin_memory()
+        return host, mask_h
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    L.nnj_launch_count(1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        merges, slp, _ = step()
-    ev1.record()
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    launches = int(L.nnj_launch_count(0))
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
-    value = world * B * args.steps / (ms_total / 1e3)
+    def timed(scaling, steps, warmup, clocks_on):
+        data_host, mask_host = make_inputs(scaling)
+        data, mask = data_host.to(dev), mask_host.to(dev)
+        n_global = G if scaling == "strong" else G * world
+        for _ in range(warmup):
+            model.rollout_fused(data, mask)
+        barrier()
+        sampler = ClockSampler(local) if (rank == 0 and clocks_on) else None
+        if sampler:
+            sampler.start()
+        L.nnj_launch_count(1)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            merges, slp, _ = model.rollout_fused(data, mask)
+        ev1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        launches = int(L.nnj_launch_count(0))
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms)
+        return {"value": n_global * steps / (ms_total / 1e3), "ms_total": ms_total, "launches": launches, "clocks": clocks, "merges": merges,
+                "data_host": data_host, "mask_host": mask_host, "data": data, "mask": mask, "n_global": n_global}
+
+    main_run = timed(args.scaling, args.steps, args.warmup, True)
+    value, ms_total, launches, clocks, merges = (main_run[k] for k in ("value", "ms_total", "launches", "clocks", "merges"))
+    data_host, mask_host, data, mask = (main_run[k] for k in ("data_host", "mask_host", "data", "mask"))
+    B_local = data_host.shape[0]
 
     # ---- end to end through the host-buffer C-ABI entry point
     model.rollout_host(data_host, mask_host)       # warm
@@ -221,13 +302,13 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * e2e_steps / float(e2e_s)
+    e2e_val = main_run["n_global"] * e2e_steps / float(e2e_s)
     assert torch.equal(mh, merges.cpu()), "host entry point and device path disagree"
 
     # ---- per-kernel-class timing (one extra step with CUDA events around every launch)
     n_cls = L.nnj_profile_classes()
     L.nnj_profile_enable(1)
-    step()
+    model.rollout_fused(data, mask)
     cls_ms = (C.c_double * n_cls)()
     cls_n = (C.c_int64 * n_cls)()
     _lib.check(L.nnj_profile_read(n_cls, cls_ms, cls_n))
@@ -235,6 +316,7 @@ def main():
     names = [L.nnj_profile_name(i).decode() for i in range(n_cls)]
     tot_ms = sum(cls_ms)
     fl = algorithmic_flops(R_TAXA, L_SITES)
+    B = B_local
     kernels = {n: {"ms": round(cls_ms[i], 3), "launches": int(cls_n[i]), "share": round(cls_ms[i] / tot_ms, 4)} for i, n in enumerate(names) if cls_n[i]}
     top = max((n for n in kernels if n in fl), key=lambda n: kernels[n]["ms"])
     peaks = {}
@@ -244,6 +326,7 @@ def main():
     except OSError:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     top_flops_per_launch = fl[top] * B / kernels[top]["launches"]
     top_ms_per_launch = kernels[top]["ms"] / kernels[top]["launches"]
@@ -255,70 +338,104 @@ def main():
     for n in kernels:
         if n in fl:
             kernels[n]["tflops"] = round(fl[n] * B / (kernels[n]["ms"] * 1e-3) / 1e12, 3)
-    # DRAM traffic per launch.  The NJ kernels stream only the n live node slots of a step, so their bytes change from step to
-    # step: the mean over a rollout comes from the algorithmic byte count (node tiles of the live slots + x planes), which the
-    # committed `ncu --set full` captures reproduce within 1 % at the captured launches (profiles/r01_traffic_b128.json; its
-    # "model" ratios are printed below).  Step-0 pair-score launches (two pair tiles re-read the node tile) use the ncu figure.
+    # DRAM traffic.  The NJ kernels stream only the n live node slots of a step, so their bytes change from step to step: the
+    # mean over a rollout comes from the algorithmic byte count (node tiles of the live slots + x planes), which the committed
+    # `ncu --set full` captures reproduce within 1 % at the captured launches (profiles/r01_traffic_b128.json).
     roofline_hbm = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic_b128.json")) as f:
-            tr = json.load(f)
-        chunks = max(1, kernels["node_derive"]["launches"])
-        trees = B / chunks                                   # trees per launch
+    nj_bytes_per_tree = None
+    if args.workload == "config2":
         site_bytes = 256 * L_SITES                           # one fp32 [sites x 64] row set: 256 KB at 1024 sites
-        step0_pairs = [256] * (R_TAXA * (R_TAXA - 1) // 2 // 256) + [R_TAXA * (R_TAXA - 1) // 2 % 256]
-
-        def alpha_bytes(n, pairs):       # X, Y fp32 + K' bf16 hi/lo of n slots, x planes of the pairs
-            return trees * (3 * n + pairs) * site_bytes
-
-        def score_inc_bytes(n, pairs):   # [X | W_g X] bf16 hi/lo of n slots, x tiles of the pairs
-            return trees * (2 * n + pairs) * site_bytes
-        alpha_tot = sum(alpha_bytes(R_TAXA, p) for p in step0_pairs) + sum(alpha_bytes(n, n) for n in range(R_TAXA - 1, 2, -1))
-        alpha_n = len(step0_pairs) + R_TAXA - 3
-        score_tot = sum(tr["score_step0"]["dram_bytes"] * trees / 128.0 * (p / 256.0 * 0.6 + 0.4) for p in step0_pairs) + \
-            sum(score_inc_bytes(n, n) for n in range(R_TAXA - 1, 2, -1))
-        score_n = len(step0_pairs) + R_TAXA - 3 + 1
-        model = {"alpha_incr_model_over_ncu": round(alpha_bytes(34, 34) * 128.0 / trees / tr["alpha_incr"]["dram_bytes"], 3),
-                 "score_incr_model_over_ncu": round(score_inc_bytes(34, 34) * 128.0 / trees / tr["score_incr"]["dram_bytes"], 3)}
-        means = {"alpha": alpha_tot / alpha_n, "pair_score": score_tot / score_n}
-        if top in means:
-            roofline["traffic"] = round(means[top])
-            roofline["traffic_source"] = "mean over the launches of a rollout: algorithmic bytes of the live node slots + x planes (= ncu dram__bytes at the captured launches, profiles/r01_traffic_b128.json), ncu figure for the step-0 launches"
+        P0 = R_TAXA * (R_TAXA - 1) // 2
+        step0_pairs = [256] * (P0 // 256) + ([P0 % 256] if P0 % 256 else [])
+        alpha_b = [(3 * R_TAXA + p) * site_bytes for p in step0_pairs] + [(3 * n + n) * site_bytes for n in range(R_TAXA - 1, 2, -1)]
+        score_b = [(2 * R_TAXA * (2 if p > 128 else 1) + p) * site_bytes for p in step0_pairs] + [(2 * n + n) * site_bytes for n in range(R_TAXA - 1, 1, -1)]
+        merge_b = [(n + 4 + 12) * site_bytes + n * site_bytes for n in range(R_TAXA, 2, -1)]     # k_merge (all nodes + pair + new node's planes) + k_alpha1 (K of all nodes)
+        derive_b = 8 * R_TAXA * site_bytes
+        nj_bytes_per_tree = sum(alpha_b) + sum(score_b) + sum(merge_b) + derive_b
+        if top in ("alpha", "pair_score"):
+            per = alpha_b if top == "alpha" else score_b
+            roofline["traffic"] = round(sum(per) / len(per) * B / max(1, kernels["node_derive"]["launches"]))
+            roofline["traffic_source"] = "mean over the launches of a rollout: algorithmic bytes of the live node slots + x planes (= ncu dram__bytes at the captured launches, profiles/r01_traffic_b128.json)"
         if "alpha" in kernels:
-            hbm_peak = peaks.get("hbm_gbs", 6554.2)
-            a_ms = kernels["alpha"]["ms"] / kernels["alpha"]["launches"]
-            a_bytes = means["alpha"] * alpha_n * chunks / kernels["alpha"]["launches"]
+            a_ms = kernels["alpha"]["ms"]
+            a_bytes = sum(alpha_b) * B
             roofline_hbm = {"bound": "hbm", "kernel": "alpha", "achieved": round(a_bytes / (a_ms * 1e-3) / 1e9, 1), "peak": hbm_peak,
-                            "unit": "GB/s", "frac": round(a_bytes / (a_ms * 1e-3) / 1e9 / hbm_peak, 4), "traffic": round(a_bytes),
-                            "ms_per_launch": round(a_ms, 4), "model_check": model,
-                            "note": "k_alpha_v3: mean bytes per launch = live node slots (X, Y, K') once + x planes; the late steps (few live nodes) are latency-bound, which pulls the mean below the 6.1-6.3 TB/s of the early launches"}
-    except (OSError, KeyError, ValueError, ZeroDivisionError):
-        pass
+                            "unit": "GB/s", "frac": round(a_bytes / (a_ms * 1e-3) / 1e9 / hbm_peak, 4), "traffic": round(a_bytes / kernels["alpha"]["launches"]),
+                            "ms_per_launch": round(a_ms / kernels["alpha"]["launches"], 4),
+                            "note": "k_alpha_v3 over a whole rollout: live node slots (X, Y, K') once + x planes per launch; the late steps (few live nodes) are latency-bound, which pulls the mean below the 6.1-6.3 TB/s of the early launches"}
+    enc_ms = sum(kernels[n]["ms"] for n in ENC_CLASSES if n in kernels)
+    nj_ms = sum(kernels[n]["ms"] for n in NJ_CLASSES if n in kernels)
+    enc_fl = sum(fl[n] for n in ENC_CLASSES if n in fl)
+    nj_fl = sum(fl[n] for n in NJ_CLASSES if n in fl)
+    step_ms = ms_total / args.steps
+    roofline_step = {
+        "algorithmic_gflop_per_tree": round((enc_fl + nj_fl) / 1e9, 1),
+        "step_tflops": round((enc_fl + nj_fl) * B / (step_ms * 1e-3) / 1e12, 2), "step_frac_of_tensor_peak": round((enc_fl + nj_fl) * B / (step_ms * 1e-3) / 1e12 / peak_tf, 4),
+        "encoder": {"ms": round(enc_ms, 2), "tflops": round(enc_fl * B / (enc_ms * 1e-3) / 1e12, 2), "frac_of_tensor_peak": round(enc_fl * B / (enc_ms * 1e-3) / 1e12 / peak_tf, 4)},
+        "nj_loop": {"ms": round(nj_ms, 2), "tflops": round(nj_fl * B / (nj_ms * 1e-3) / 1e12, 2), "frac_of_tensor_peak": round(nj_fl * B / (nj_ms * 1e-3) / 1e12 / peak_tf, 4)},
+        "precision_note": "bf16x3 executes 3 MMAs per algorithmic product: 100 % tensor-pipe utilisation reads as 0.333 here" if args.precision == "bf16x3" else None,
+    }
+    if nj_bytes_per_tree:
+        stream = sum(n * L_SITES * D * 4 for n in range(2, R_TAXA + 1))        # state re-read once per step
+        roofline_step["nj_loop"].update({"dram_bytes_per_tree": nj_bytes_per_tree, "streaming_bytes_per_tree": stream,
+                                         "traffic_ratio": round(nj_bytes_per_tree / stream, 2),
+                                         "hbm_gbs": round(nj_bytes_per_tree * B / (nj_ms * 1e-3) / 1e9, 1),
+                                         "frac_of_hbm_peak": round(nj_bytes_per_tree * B / (nj_ms * 1e-3) / 1e9 / hbm_peak, 4)})
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        tps, secs, cores = cpu_oracle_trees_per_sec(args.cpu_trees)
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        d1, m1 = data[:1].contiguous(), mask[:1].contiguous()
+        for _ in range(3):
+            model.rollout_fused(d1, m1)
+        ts = []
+        for _ in range(7):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            model.rollout_fused(d1, m1)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        extras["latency_b1_ms"] = round(sorted(ts)[len(ts) // 2], 3)
+        if world == 1:
+            extras["gpu_eager_baseline"] = gpu_eager_baseline(dev, R_TAXA, L_SITES, budget_s=40.0 if args.workload == "config2" else 0.0)
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_extras:
+        w = timed("weak", max(1, min(args.steps, 3)), 1, False)
+        weak = {"value": round(w["value"], 3), "unit": UNIT, "scaling": "weak", "per_gpu_batch": G, "steps": max(1, min(args.steps, 3)),
+                "ms_per_step": round(w["ms_total"] / max(1, min(args.steps, 3)), 3)}
+
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "config2":
+        n = min(args.cpu_trees, B_local)
+        tps, secs, cores, parity = cpu_oracle_run(data_host[:n], mask_host[:n], merges[:n].cpu())
         cpu_baseline = {"value": round(tps, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{args.cpu_trees} alignments of the same generator, B=1 per call, {secs:.1f} s"}
+                        "sample": f"the first {n} alignments of the timed batch, B=1 per call, {secs:.1f} s"}
 
     if rank == 0:
+        shard = f"{G} alignments per step cut into {world} contiguous shard(s) of {B_local}" if args.scaling == "strong" else f"{G} alignments per GPU per step"
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16x3 (split-bf16 tcgen05, fp32 accumulate) + f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: {B} synthetic MSAs per GPU per step, {R_TAXA} taxa x {L_SITES} sites, Argmax, sharded by alignment",
-                       "global_batch": B * world, "parallelism": f"alignment-sharded x{world}, no collectives",
+            "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 tcgen05, fp32 accumulate) + f32", "bf16": "bf16 (tcgen05, fp32 accumulate) + f32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": f"configs[{1 if args.workload == 'config2' else 3}]: synthetic MSAs, {R_TAXA} taxa x {L_SITES} sites, Argmax, sharded by alignment: {shard}",
+                       "global_batch": main_run["n_global"], "parallelism": f"alignment-sharded x{world}, no collectives",
                        "weights": "torch.manual_seed(0) default init (checkpoint blob absent)", "precision": args.precision,
-                       "l2": "inputs_larger_than_l2 (105 MB int8 MSA + 6.7 GB fp32 node state per step)"},
+                       "l2": f"inputs_larger_than_l2 ({data_host.numel() / 1e6:.0f} MB int8 MSA + {B_local * R_TAXA * L_SITES * 256 / 1e9:.1f} GB fp32 node state per rank per step)"},
             "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": int(data_host.numel() + mask_host.numel()),
-                    "d2h_bytes_per_step": int(mh.numel() * 4), "api": "nnj_rollout_host (C ABI, pinned host buffers)", "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(mh.numel() * 4), "api": "nnj_rollout_host (C ABI, pinned host buffers, per-chunk staging on a copy stream)", "steps": e2e_steps},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
             "roofline_hbm": roofline_hbm,
+            "roofline_step": roofline_step,
             "kernels": kernels,
             "cpu_baseline": cpu_baseline,
+            "parity_check": parity,
         }
+        if weak:
+            line["weak"] = weak
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -29,27 +29,60 @@ class nnj_config(C.Structure):
                 ("vocab_size", C.c_int32), ("patch_size", C.c_int32), ("precision", C.c_int32)]
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
+OBJ_DIR = os.path.join(_HERE, "_build")
+
+
+def _headers():
     src_dir = os.path.join(_HERE, "csrc")
-    deps = [os.path.join(src_dir, f) for f in os.listdir(src_dir)] + [os.path.join(_HERE, "..", "include", "nnj.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".h", ".cuh"))] + [os.path.join(_HERE, "..", "include", "nnj.h")]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into neuralnj_b200/libnnj.so (in-tree, travels with the repo)."""
-    if not force and not _stale():
-        return LIB_PATH
+def _mtime(path: str) -> float:
+    return os.path.getmtime(path) if os.path.exists(path) else -1.0
+
+
+def build(force: bool = False, verbose: bool = False, jobs: int = 0) -> str:
+    """Compile csrc/*.cu for sm_100a into neuralnj_b200/libnnj.so (in-tree, travels with the repo).
+
+    Every source becomes an object under neuralnj_b200/_build/ (compiled in parallel, rebuilt when the source or any header is
+    newer - or always with force=True / NNJ_FORCE_BUILD=1), then the objects are linked.  nvcc cross-compiles without a GPU."""
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("NNJ_EXTRA_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
-          [os.path.join(_HERE, "csrc", s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise NnjError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        sys.stderr.write(r.stderr)
+    extra = os.environ.get("NNJ_EXTRA_NVCC_FLAGS", "").split()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    flags_tag = os.path.join(OBJ_DIR, "flags.txt")
+    flags_now = " ".join(NVCC_FLAGS + extra)
+    if _mtime(flags_tag) < 0 or open(flags_tag).read() != flags_now:
+        force = True
+    hdr_t = max(_mtime(h) for h in _headers())
+    todo, objs = [], []
+    for src in SOURCES:
+        sp, op = os.path.join(_HERE, "csrc", src), os.path.join(OBJ_DIR, src[:-3] + ".o")
+        objs.append(op)
+        if force or _mtime(op) < max(_mtime(sp), hdr_t):
+            todo.append((sp, op))
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared", "-cudart", "static")]
+
+    def cc(job):
+        sp, op = job
+        cmd = [nvcc] + compile_flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", op]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return sp, r
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=jobs or min(len(todo), os.cpu_count() or 4)) as ex:
+            for sp, r in ex.map(cc, todo):
+                if r.returncode != 0:
+                    raise NnjError(f"nvcc failed on {sp}:\n" + r.stdout + r.stderr)
+                if verbose:
+                    sys.stderr.write(r.stderr)
+    if todo or _mtime(LIB_PATH) < max(_mtime(o) for o in objs):
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB_PATH] + objs,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise NnjError("nvcc link failed:\n" + r.stdout + r.stderr)
+        with open(flags_tag, "w") as f:
+            f.write(flags_now)
     return LIB_PATH
 
 

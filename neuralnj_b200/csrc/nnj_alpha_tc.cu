@@ -387,15 +387,13 @@ static int make_tmap_kprime(CUtensorMap* map, const void* base, int S, int n_liv
 int launch_alpha_tc(const Model* m, const float* X, const float* Y, size_t tree_stride, const int32_t* slot_of, int slot_stride, const int32_t* pair_i,
                     const int32_t* pair_j, int pair_stride, int n0, int nc, int S, int n_live, int C, int B, const void* kp_h, const void* kp_l, float* xf,
                     int pc, float* alpha_part, int alpha_pairs, int nSG, int RP, int* n_part, cudaStream_t st) {
-    static int n_sm = 0;
-    if (!n_sm) {
+    static DevOnce once;      // per device, not per process
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_alpha_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, AV_SMEM_MAX);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess || n_sm <= 0) { n_sm = 0; return set_cuda_error(e, __FILE__, __LINE__); }
+        once.done();
     }
+    const int n_sm = sm_count();
     if (S > 64) return set_error(NNJ_ERR_INVALID, "alpha_tc: at most 63 taxa on the tensor-core path");
     if (nc > AV_MAXT * 128 || nc > pc) return set_error(NNJ_ERR_INVALID, "alpha_tc: at most 512 pairs per launch");
     const int groups = (C + AV_SITES - 1) / AV_SITES;

@@ -22,6 +22,23 @@ int set_cuda_error(cudaError_t e, const char* file, int line) {
     return NNJ_ERR_CUDA;
 }
 
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
+int sm_count() {
+    static std::atomic<int> cache[64];
+    const int dev = current_device() & 63;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 // ---- optional per-kernel-class timing with CUDA events on the launching stream ----
 struct ProfRec { int cls; cudaEvent_t a, b; };
 static thread_local bool g_prof_on = false;
@@ -145,10 +162,12 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
             snprintf(msg, sizeof(msg), "model_create: tensor %d has %lld elements, expected %lld", i, (long long)numels[i], (long long)expect[i]);
             return set_error(NNJ_ERR_INVALID, msg);
         }
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);              // the caller's current device (PyTorch's) is restored on return
+    if (guard.err != cudaSuccess) return set_cuda_error(guard.err, __FILE__, __LINE__);
     nnj_model* m = new (std::nothrow) nnj_model();
     if (!m) return set_error(NNJ_ERR_NOMEM, "model_create: out of host memory");
     m->cfg = *cfg; m->device = device; m->num_layers = Lyr; m->blob = nullptr; m->blob_bf = nullptr; m->blob_enc = nullptr; m->host_ws = nullptr; m->host_ws_bytes = 0;
+    m->host_compute = nullptr; m->host_copy = nullptr;
 
     Packer pk;
     struct AttnOff { size_t ln_g, ln_b, qt, kt, vt, ot, qb, kb, vb, ob, qkvb; };
@@ -280,10 +299,14 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
 
 void nnj_model_destroy(nnj_model* m) {
     if (!m) return;
+    DeviceGuard guard(m->device);
     if (m->blob) cudaFree(m->blob);
     if (m->blob_bf) cudaFree(m->blob_bf);
     if (m->blob_enc) cudaFree(m->blob_enc);
     if (m->host_ws) cudaFree(m->host_ws);
+    for (cudaEvent_t e : m->host_events) cudaEventDestroy(e);
+    if (m->host_compute) cudaStreamDestroy(m->host_compute);
+    if (m->host_copy) cudaStreamDestroy(m->host_copy);
     delete m;
 }
 
@@ -299,46 +322,57 @@ int64_t nnj_workspace_bytes(const nnj_model* m, int what, int B, int R, int L) {
 
 #define CHECK_ARGS(cond, msg) \
     do { if (!(cond)) return set_error(NNJ_ERR_INVALID, msg); } while (0)
+// every compute entry point runs on the model's device whatever the caller's current device is
+#define ON_MODEL_DEVICE(m)                                                              \
+    DeviceGuard guard_((m)->device);                                                    \
+    if (guard_.err != cudaSuccess) return set_cuda_error(guard_.err, __FILE__, __LINE__)
 
 int nnj_encode(nnj_model* m, const int8_t* data, const uint8_t* mask, int B, int R, int L, float* out, void* ws, int64_t ws_bytes,
                void* stream) {
     CHECK_ARGS(m && data && out && ws && B >= 1 && R >= 2 && L >= 1, "encode: bad arguments");
+    ON_MODEL_DEVICE(m);
     return run_encoder(m, data, mask, B, R, L, out, (size_t)R * L * D, ws, (size_t)ws_bytes, (cudaStream_t)stream);
 }
 
 int nnj_pair_scores_full(nnj_model* m, const float* state, const uint8_t* mask, int B, int Rp, int C, float* logits, void* ws,
                          int64_t ws_bytes, void* stream) {
     CHECK_ARGS(m && state && logits && ws && B >= 1, "pair_scores_full: bad arguments");
+    ON_MODEL_DEVICE(m);
     return run_pair_scores(m, state, mask, B, Rp, C, nullptr, nullptr, 0, true, logits, ws, (size_t)ws_bytes, (cudaStream_t)stream);
 }
 
 int nnj_pair_scores_list(nnj_model* m, const float* state, const uint8_t* mask, int B, int Rp, int C, const int32_t* pi,
                          const int32_t* pj, int N, float* scores, void* ws, int64_t ws_bytes, void* stream) {
     CHECK_ARGS(m && state && scores && ws && pi && pj && B >= 1 && N >= 1, "pair_scores_list: bad arguments");
+    ON_MODEL_DEVICE(m);
     return run_pair_scores(m, state, mask, B, Rp, C, pi, pj, N, false, scores, ws, (size_t)ws_bytes, (cudaStream_t)stream);
 }
 
 int nnj_pair_scores_incr(nnj_model* m, const float* state, const uint8_t* mask, int B, int Rp, int C, const int32_t* prev_ij,
                          const float* logits_prev, float* logits_out, void* ws, int64_t ws_bytes, void* stream) {
     CHECK_ARGS(m && state && prev_ij && logits_prev && logits_out && ws && B >= 1, "pair_scores_incr: bad arguments");
+    ON_MODEL_DEVICE(m);
     return run_pair_scores_incr(m, state, mask, B, Rp, C, prev_ij, logits_prev, logits_out, ws, (size_t)ws_bytes, (cudaStream_t)stream);
 }
 
 int nnj_aggregate(nnj_model* m, const float* state, int B, int Rp, int C, const int32_t* ij, float* out, void* ws, int64_t ws_bytes,
                   void* stream) {
     CHECK_ARGS(m && state && ij && out && ws && B >= 1, "aggregate: bad arguments");
+    ON_MODEL_DEVICE(m);
     return run_aggregate(m, state, B, Rp, C, ij, out, (size_t)C * D, ws, (size_t)ws_bytes, (cudaStream_t)stream);
 }
 
 int nnj_merge(nnj_model* m, const float* state_in, int B, int Rp, int C, const int32_t* ij, float* state_out, void* ws,
               int64_t ws_bytes, void* stream) {
     CHECK_ARGS(m && state_in && ij && state_out && ws && B >= 1 && Rp >= 3, "merge: bad arguments (need R' >= 3)");
+    ON_MODEL_DEVICE(m);
     return run_merge(m, state_in, B, Rp, C, ij, state_out, ws, (size_t)ws_bytes, (cudaStream_t)stream);
 }
 
 int nnj_rollout(nnj_model* m, const int8_t* data, const uint8_t* mask, int B, int R, int L, int select_mode, const float* gumbel,
                 int32_t* merges, float* logits_trace, float* selected_logp, void* ws, int64_t ws_bytes, void* stream) {
     CHECK_ARGS(m && data && merges && ws && B >= 1 && R >= 2 && L >= 1, "rollout: bad arguments");
+    ON_MODEL_DEVICE(m);
     return run_rollout(m, data, nullptr, mask, B, R, L, select_mode, gumbel, merges, logits_trace, selected_logp, ws, (size_t)ws_bytes,
                        (cudaStream_t)stream);
 }
@@ -347,6 +381,7 @@ int nnj_rollout_from_state(nnj_model* m, const float* state, const uint8_t* mask
                            const float* gumbel, int32_t* merges, float* logits_trace, float* selected_logp, void* ws,
                            int64_t ws_bytes, void* stream) {
     CHECK_ARGS(m && state && merges && ws && B >= 1 && R >= 2 && C >= 1, "rollout_from_state: bad arguments");
+    ON_MODEL_DEVICE(m);
     return run_rollout(m, nullptr, state, mask, B, R, C, select_mode, gumbel, merges, logits_trace, selected_logp, ws, (size_t)ws_bytes,
                        (cudaStream_t)stream);
 }
@@ -364,40 +399,67 @@ int nnj_tc_selftest(const float* A, const float* B, float* Dm, int N, void* stre
 int nnj_rollout_host(nnj_model* m, const int8_t* data_h, const uint8_t* mask_h, int B, int R, int L, int select_mode,
                      const float* gumbel_h, int32_t* merges_h, float* selected_logp_h) {
     CHECK_ARGS(m && data_h && merges_h && B >= 1 && R >= 2 && L >= 1, "rollout_host: bad arguments");
-    CUDA_TRY(cudaSetDevice(m->device));
-    const size_t ws_bytes = nj_rollout_ws_bytes(m, B, R, L);
-    const size_t n_data = (size_t)B * R * L * 4, n_mask = (size_t)B * L, n_mg = (size_t)B * (R - 1) * 2;
-    const size_t n_gum = gumbel_h ? (size_t)B * (R - 1) * (R * (R - 1) / 2) : 0;
-    const size_t io_bytes = ((n_data + 255) & ~(size_t)255) + ((n_mask + 255) & ~(size_t)255) + ((n_mg * 4 + 255) & ~(size_t)255) +
-                            ((n_mg * 2 + 255) & ~(size_t)255) + n_gum * 4 + 256;
+    ON_MODEL_DEVICE(m);
+    std::lock_guard<std::mutex> lock(m->host_lock);          // the workspace and the streams below belong to the model
+    // The batch is processed in the library's rollout chunks.  Chunk i+1 is staged host -> device on a copy stream while chunk i
+    // runs on a compute stream (both non-blocking: the caller's streams, PyTorch's included, are not serialised against).
+    const int chunk = nj_rollout_chunk(m, B, R, L);
+    const int n_chunks = (B + chunk - 1) / chunk;
+    const size_t ws_bytes = nj_rollout_ws_bytes(m, chunk, R, L);
+    const size_t P0 = (size_t)R * (R - 1) / 2;
+    const size_t t_data = (size_t)R * L * 4, t_mask = (size_t)L, t_mg = (size_t)(R - 1) * 2, t_gum = gumbel_h ? (size_t)(R - 1) * P0 : 0;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t io_bytes = up(B * t_data) + up(B * t_mask) + up(B * t_mg * 4) + up(B * t_mg * 2) + up(B * t_gum * 4) + 256;
     // workspace + staging buffers live in one grow-only allocation owned by the model (no cudaMalloc on the steady-state path)
-    const size_t need = ((ws_bytes + 255) & ~(size_t)255) + io_bytes;
+    const size_t need = up(ws_bytes) + io_bytes;
     if (m->host_ws_bytes < need) {
-        if (m->host_ws) { cudaFree(m->host_ws); m->host_ws = nullptr; m->host_ws_bytes = 0; }
+        if (m->host_ws) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(m->host_ws); m->host_ws = nullptr; m->host_ws_bytes = 0; }
         CUDA_TRY(cudaMalloc(&m->host_ws, need));
         m->host_ws_bytes = need;
     }
+    if (!m->host_compute) CUDA_TRY(cudaStreamCreateWithFlags(&m->host_compute, cudaStreamNonBlocking));
+    if (!m->host_copy) CUDA_TRY(cudaStreamCreateWithFlags(&m->host_copy, cudaStreamNonBlocking));
+    while ((int)m->host_events.size() < n_chunks) {
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        m->host_events.push_back(ev);
+    }
     char* ws = reinterpret_cast<char*>(m->host_ws);
-    char* io = ws + ((ws_bytes + 255) & ~(size_t)255);
-    cudaError_t e = cudaSuccess;
+    char* io = ws + up(ws_bytes);
     int8_t* d_data = (int8_t*)io;
-    uint8_t* d_mask = (uint8_t*)(io + ((n_data + 255) & ~(size_t)255));
-    int32_t* d_mg = (int32_t*)((char*)d_mask + ((n_mask + 255) & ~(size_t)255));
-    float* d_slp = (float*)((char*)d_mg + ((n_mg * 4 + 255) & ~(size_t)255));
-    float* d_gum = gumbel_h ? (float*)((char*)d_slp + ((n_mg * 2 + 255) & ~(size_t)255)) : nullptr;
-    cudaStream_t st = 0;
+    uint8_t* d_mask = (uint8_t*)(io + up(B * t_data));
+    int32_t* d_mg = (int32_t*)((char*)d_mask + up(B * t_mask));
+    float* d_slp = (float*)((char*)d_mg + up(B * t_mg * 4));
+    float* d_gum = gumbel_h ? (float*)((char*)d_slp + up(B * t_mg * 2)) : nullptr;
+    cudaStream_t cs = m->host_compute, xs = m->host_copy;
+    cudaError_t e = cudaSuccess;
     int rc = NNJ_OK;
     do {
-        if ((e = cudaMemcpyAsync(d_data, data_h, n_data, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
-        if (mask_h) { if ((e = cudaMemcpyAsync(d_mask, mask_h, n_mask, cudaMemcpyHostToDevice, st)) != cudaSuccess) break; }
-        if (gumbel_h) { if ((e = cudaMemcpyAsync(d_gum, gumbel_h, n_gum * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) break; }
-        rc = run_rollout(m, d_data, nullptr, mask_h ? d_mask : nullptr, B, R, L, select_mode, d_gum, d_mg, nullptr,
-                         selected_logp_h ? d_slp : nullptr, ws, ws_bytes, st);
-        if (rc != NNJ_OK) break;
-        if ((e = cudaMemcpyAsync(merges_h, d_mg, n_mg * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
-        if (selected_logp_h) { if ((e = cudaMemcpyAsync(selected_logp_h, d_slp, n_mg * 2, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break; }
-        e = cudaStreamSynchronize(st);
+        for (int c = 0; c < n_chunks && e == cudaSuccess; ++c) {      // all H2D copies are queued up front, one event per chunk
+            const size_t b0 = (size_t)c * chunk, nb = (size_t)((B - (int)b0 < chunk) ? (B - (int)b0) : chunk);
+            if ((e = cudaMemcpyAsync(d_data + b0 * t_data, data_h + b0 * t_data, nb * t_data, cudaMemcpyHostToDevice, xs)) != cudaSuccess) break;
+            if (mask_h && (e = cudaMemcpyAsync(d_mask + b0 * t_mask, mask_h + b0 * t_mask, nb * t_mask, cudaMemcpyHostToDevice, xs)) != cudaSuccess) break;
+            if (gumbel_h && (e = cudaMemcpyAsync(d_gum + b0 * t_gum, gumbel_h + b0 * t_gum, nb * t_gum * 4, cudaMemcpyHostToDevice, xs)) != cudaSuccess) break;
+            e = cudaEventRecord(m->host_events[c], xs);
+        }
+        if (e != cudaSuccess) break;
+        for (int c = 0; c < n_chunks; ++c) {
+            const size_t b0 = (size_t)c * chunk;
+            const int nb = (B - (int)b0 < chunk) ? (B - (int)b0) : chunk;
+            if ((e = cudaStreamWaitEvent(cs, m->host_events[c], 0)) != cudaSuccess) break;
+            rc = run_rollout(m, d_data + b0 * t_data, nullptr, mask_h ? d_mask + b0 * t_mask : nullptr, nb, R, L, select_mode,
+                             d_gum ? d_gum + b0 * t_gum : nullptr, d_mg + b0 * t_mg, nullptr, selected_logp_h ? d_slp + b0 * (R - 1) : nullptr,
+                             ws, ws_bytes, cs);
+            if (rc != NNJ_OK) break;
+            // results of this chunk go home while the next chunk computes
+            if ((e = cudaMemcpyAsync(merges_h + b0 * t_mg, d_mg + b0 * t_mg, (size_t)nb * t_mg * 4, cudaMemcpyDeviceToHost, cs)) != cudaSuccess) break;
+            if (selected_logp_h && (e = cudaMemcpyAsync(selected_logp_h + b0 * (R - 1), d_slp + b0 * (R - 1), (size_t)nb * (R - 1) * 4,
+                                                        cudaMemcpyDeviceToHost, cs)) != cudaSuccess) break;
+        }
+        if (rc != NNJ_OK || e != cudaSuccess) break;
+        e = cudaStreamSynchronize(cs);
     } while (0);
+    if (rc != NNJ_OK || e != cudaSuccess) { cudaStreamSynchronize(xs); cudaStreamSynchronize(cs); }
     if (rc != NNJ_OK) return rc;
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     return NNJ_OK;

@@ -305,28 +305,31 @@ __global__ void __launch_bounds__(NTHREADS) k_gemm(const float* __restrict__ A, 
     const int lrow = tid >> 1, lk = (tid & 1) * 4;          // K-contiguous operands: 128 rows x 8 k
     const int bk = tid >> 5, bn = (tid & 31) * 4;           // N-contiguous B: 8 k x 128 n
     float4 ra, rb;
+    // 16-byte loads need rows that start on a 16-byte boundary: a site count that is not a multiple of 4 (the logits S have
+    // row pitch C) falls back to scalar loads
+    const bool va = (lda & 3) == 0 && (sA & 3) == 0, vb = (ldb & 3) == 0 && (sB & 3) == 0;
     auto gload = [&](int k0) {
         ra = make_float4(0.f, 0.f, 0.f, 0.f);
         rb = ra;
         int m = m0 + lrow, kk = k0 + lk;
         if (m < M) {
             const float* p = A + (size_t)m * lda + kk;
-            if (kk + 3 < K) ra = ld4(p);
-            else { if (kk < K) ra.x = p[0]; if (kk + 1 < K) ra.y = p[1]; if (kk + 2 < K) ra.z = p[2]; }
+            if (kk + 3 < K && va) ra = ld4(p);
+            else { if (kk < K) ra.x = p[0]; if (kk + 1 < K) ra.y = p[1]; if (kk + 2 < K) ra.z = p[2]; if (kk + 3 < K) ra.w = p[3]; }
         }
         if (BT) {
             int n = n0 + lrow;
             if (n < N) {
                 const float* p = Bm + (size_t)n * ldb + kk;
-                if (kk + 3 < K) rb = ld4(p);
-                else { if (kk < K) rb.x = p[0]; if (kk + 1 < K) rb.y = p[1]; if (kk + 2 < K) rb.z = p[2]; }
+                if (kk + 3 < K && vb) rb = ld4(p);
+                else { if (kk < K) rb.x = p[0]; if (kk + 1 < K) rb.y = p[1]; if (kk + 2 < K) rb.z = p[2]; if (kk + 3 < K) rb.w = p[3]; }
             }
         } else {
             int k = k0 + bk, n = n0 + bn;
             if (k < K) {
                 const float* p = Bm + (size_t)k * ldb + n;
-                if (n + 3 < N) rb = ld4(p);
-                else { if (n < N) rb.x = p[0]; if (n + 1 < N) rb.y = p[1]; if (n + 2 < N) rb.z = p[2]; }
+                if (n + 3 < N && vb) rb = ld4(p);
+                else { if (n < N) rb.x = p[0]; if (n + 1 < N) rb.y = p[1]; if (n + 2 < N) rb.z = p[2]; if (n + 3 < N) rb.w = p[3]; }
             }
         }
     };
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(NTHREADS) k_gemm(const float* __restrict__ A, 
         for (int jh = 0; jh < 2; ++jh) {
             int n = n0 + jh * 64 + tx * 4;
             float* p = Cm + (size_t)m * ldc + n;
-            if (n + 3 < N && (ldc & 3) == 0) st4(p, make_float4(acc[i][jh * 4], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]));
+            if (n + 3 < N && (ldc & 3) == 0 && (sC & 3) == 0) st4(p, make_float4(acc[i][jh * 4], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]));
             else for (int j = 0; j < 4; ++j) if (n + j < N) p[j] = acc[i][jh * 4 + j];
         }
     }
@@ -655,8 +658,8 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
     const size_t smem_qkv = (TILE_ROWS * LDA + 4096) * sizeof(float);
     const size_t smem_ffn = (2 * TILE_ROWS * LDA + 2 * 4096) * sizeof(float);
     const size_t smem_col = (size_t)2 * R * D * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DevOnce attr_once;      // per device, not per process
+    if (attr_once.need()) {
         cudaFuncSetAttribute(k_ffn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ffn);
         cudaFuncSetAttribute(k_ln_qkv<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qkv);
         cudaFuncSetAttribute(k_ln_qkv<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qkv);
@@ -664,7 +667,7 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
         cudaFuncSetAttribute(k_out_proj<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qkv);
         cudaFuncSetAttribute(k_out_proj<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qkv);
         cudaFuncSetAttribute(k_col_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
+        attr_once.done();
     }
     if (!(mk & 2) && smem_col > 200 * 1024) return set_error(NNJ_ERR_INVALID, "encode: too many taxa for the column-attention kernel (max 400)");
     if (R == 1) return set_error(NNJ_ERR_INVALID, "encode: R == 1 is not supported");

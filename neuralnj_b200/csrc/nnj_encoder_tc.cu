@@ -635,25 +635,14 @@ __global__ void __launch_bounds__(256) k_sm_to_nm(const float* __restrict__ xs, 
 }
 
 // ------------------------------------------------------------------ launchers
-static int g_sms = 0;
-static int sm_count() {
-    if (!g_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sms <= 0) g_sms = 148;
-    }
-    return g_sms;
-}
-
 static int enc_tc_attrs() {
-    static bool done = false;
-    if (done) return 0;
+    static DevOnce once;      // per device, not per process
+    if (!once.need()) return 0;
     cudaError_t e = cudaFuncSetAttribute(k_enc_rowqkv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_ffn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM);
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-    done = true;
+    once.done();
     return 0;
 }
 

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -48,6 +50,11 @@ struct Model {
     std::vector<EncTcW> enc_tc;  // per layer
     void* blob_enc;              // device allocation behind enc_tc
     void* host_ws; size_t host_ws_bytes;   // grow-only device workspace of nnj_rollout_host
+    // nnj_rollout_host: its own non-blocking streams (H2D staging of chunk i+1 overlaps the rollout of chunk i) and a lock,
+    // because the workspace above is owned by the model (one host call at a time per model; use one model per thread otherwise)
+    cudaStream_t host_compute, host_copy;
+    std::vector<cudaEvent_t> host_events;
+    std::mutex host_lock;
 };
 
 // kernel classes for the optional per-class CUDA-event profiler (nnj_profile_*)
@@ -58,6 +65,26 @@ void prof_end(cudaStream_t st);
 
 int set_error(int code, const char* msg);
 int set_cuda_error(cudaError_t e, const char* file, int line);
+
+// ---- per-device state.  cudaFuncSetAttribute and the SM count belong to a DEVICE, not to the process: a second model on another
+// GPU of the same process must raise the shared-memory limits there too.  `DevOnce` is a bit mask of initialised devices (the
+// initialisers are idempotent, so two threads racing on the same device both succeed).
+int current_device();
+int sm_count();                                   // multiprocessors of the current device (cached per device)
+struct DevOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool need() const { return !((mask.load(std::memory_order_acquire) >> (current_device() & 63)) & 1ull); }
+    void done() { mask.fetch_or(1ull << (current_device() & 63), std::memory_order_release); }
+};
+// RAII: make the model's device current for the duration of an entry point, restore the caller's device afterwards
+struct DeviceGuard {
+    int prev = -1; bool switched = false; cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = (err == cudaSuccess); }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 // encoder (nnj_encoder.cu)
 size_t encoder_ws_bytes(const Model* m, int B, int R, int C);

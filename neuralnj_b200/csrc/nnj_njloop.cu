@@ -834,7 +834,10 @@ struct NjBuffers {
 // carve the NJ workspace; X_in_ws: the node pool X lives in the workspace too (rollout)
 constexpr int TC_PAIRS = 256;   // pairs per launch on the tensor-core pair-score path
 
-static bool nj_use_tc(const Model* m, int S) { return m->cfg.precision == NNJ_PREC_BF16X3 && S <= 64; }
+// The tcgen05 NJ kernels (k_alpha_v3, k_score_tc, k_score_inc) take at most 64 physical slots and - like the tensor-core encoder
+// (use_tc in nnj_encoder.cu) - need C % 8 == 0: their TMA boxes and the two-sites-per-item ring assume 16-byte rows and an even
+// site count.  Every other shape runs the fp32 CUDA-core kernels of this file, whatever the precision mode.
+static bool nj_use_tc(const Model* m, int S, int C) { return m->cfg.precision != NNJ_PREC_FP32 && S <= 64 && (C % 8) == 0; }
 
 static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws, bool need_newx, bool tc) {
     NjBuffers nb{};
@@ -880,8 +883,8 @@ static size_t smem_merge(int Rp) { return (2 * TILE_ROWS * LDA + 4096 + 128 + 2 
 static const size_t smem_derive = (2 * TILE_ROWS * LDA + 4096 + 128) * sizeof(float);
 
 static int set_attrs() {
-    static bool done = false;
-    if (done) return 0;
+    static DevOnce once;      // per device, not per process
+    if (!once.need()) return 0;
     const int big = 220 * 1024;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
@@ -889,7 +892,7 @@ static int set_attrs() {
     if ((e = cudaFuncSetAttribute(k_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     if ((e = cudaFuncSetAttribute(k_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     if ((e = cudaFuncSetAttribute(k_node_derive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_derive)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-    done = true;
+    once.done();
     return 0;
 }
 
@@ -992,7 +995,7 @@ static int derive_all(const Model* m, const float* X, const NjBuffers& nb, int B
 
 size_t nj_scores_ws_bytes(const Model* m, int B, int Rp, int C, int N) {
     (void)N;
-    return nj_layout(nullptr, B, Rp, Rp, C, false, true, nj_use_tc(m, Rp)).total;
+    return nj_layout(nullptr, B, Rp, Rp, C, false, true, nj_use_tc(m, Rp, C)).total;
 }
 
 static Pool make_pool(const float* X, const NjBuffers& nb, int S, int C) {
@@ -1006,7 +1009,7 @@ int run_pair_scores(Model* m, const float* state, const uint8_t* mask, int B, in
                     bool full, float* scores, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (int e = check_dims(Rp, C)) return e;
     if (int e = set_attrs()) return e;
-    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp));
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp, C));
     if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "pair scores: workspace too small");
     if (full) N = Rp * (Rp - 1) / 2;
     if (N > nb.pair_stride) return set_error(NNJ_ERR_INVALID, "pair scores: more pairs than R(R-1)/2");
@@ -1031,7 +1034,7 @@ int run_pair_scores_incr(Model* m, const float* state, const uint8_t* mask, int 
                          const float* logits_prev, float* logits_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (int e = check_dims(Rp, C)) return e;
     if (int e = set_attrs()) return e;
-    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp));
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp, C));
     if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "pair scores: workspace too small");
     prof_begin(KC_MISC, st);
     k_fill_slots<<<B, 128, 0, st>>>(nb.slot[0], nb.S, Rp, nullptr);
@@ -1054,7 +1057,7 @@ int run_aggregate(Model* m, const float* state, int B, int Rp, int C, const int3
                   size_t ws_bytes, cudaStream_t st) {
     if (int e = check_dims(Rp, C)) return e;
     if (int e = set_attrs()) return e;
-    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp));
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp, C));
     if (ws_bytes < nb.total) return set_error(NNJ_ERR_WORKSPACE, "aggregate: workspace too small");
     prof_begin(KC_MISC, st);
     k_fill_slots<<<B, 128, 0, st>>>(nb.slot[0], nb.S, Rp, nullptr);
@@ -1066,7 +1069,7 @@ int run_aggregate(Model* m, const float* state, int B, int Rp, int C, const int3
 
 int run_merge(Model* m, const float* state_in, int B, int Rp, int C, const int32_t* ij, float* state_out, void* ws, size_t ws_bytes,
               cudaStream_t st) {
-    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp));
+    NjBuffers nb = nj_layout(ws_align(ws), B, Rp, Rp, C, false, true, nj_use_tc(m, Rp, C));
     if (int e = run_aggregate(m, state_in, B, Rp, C, ij, nb.newx, (size_t)C * D, ws, ws_bytes, st)) return e;
     prof_begin(KC_MISC, st);
     k_reindex_copy<<<dim3(8, Rp - 1, B), 256, 0, st>>>(state_in, nb.newx, state_out, Rp, (size_t)C * D, ij);
@@ -1076,7 +1079,7 @@ int run_merge(Model* m, const float* state_in, int B, int Rp, int C, const int32
 
 // ---- fused rollout
 int nj_rollout_chunk(const Model* m, int B, int R, int C) {
-    size_t per = nj_layout(nullptr, 1, R + 1, R, C, true, false, nj_use_tc(m, R + 1)).total + encoder_ws_bytes(m, 1, R, C);
+    size_t per = nj_layout(nullptr, 1, R + 1, R, C, true, false, nj_use_tc(m, R + 1, C)).total + encoder_ws_bytes(m, 1, R, C);
     // defaults: 48 GB of the 180 GB HBM3e, at most 128 trees per chunk; NNJ_WS_GB / NNJ_CHUNK_MAX override them (tuning runs)
     static int ws_gb = 0, ch_max = 0;
     if (!ws_gb) { const char* e = getenv("NNJ_WS_GB"); ws_gb = e && atoi(e) > 0 ? atoi(e) : 48; }
@@ -1092,7 +1095,7 @@ int nj_rollout_chunk(const Model* m, int B, int R, int C) {
 
 size_t nj_rollout_ws_bytes(const Model* m, int B, int R, int C) {
     int ch = nj_rollout_chunk(m, B, R, C);
-    return nj_layout(nullptr, ch, R + 1, R, C, true, false, nj_use_tc(m, R + 1)).total + encoder_ws_bytes(m, ch, R, C) + 512;
+    return nj_layout(nullptr, ch, R + 1, R, C, true, false, nj_use_tc(m, R + 1, C)).total + encoder_ws_bytes(m, ch, R, C) + 512;
 }
 
 int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t* mask, int B, int R, int L, int select_mode,
@@ -1108,7 +1111,7 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
     const int chunk = nj_rollout_chunk(m, B, R, C);
     const int S = R + 1;
     char* base = ws_align(ws);
-    NjBuffers nb = nj_layout(base, chunk, S, R, C, true, false, nj_use_tc(m, S));
+    NjBuffers nb = nj_layout(base, chunk, S, R, C, true, false, nj_use_tc(m, S, C));
     void* enc_ws = base + nb.total;
     const size_t enc_bytes = encoder_ws_bytes(m, chunk, R, C);
     const size_t tree_stride = (size_t)S * C * D;
@@ -1154,10 +1157,9 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
             if (t == 0) {
                 if (int e = score_pairs(m, pool, nb, slot, n, C, P0, mk, nbt, nb.logits[0], P0, st)) return e;
             } else {
-                // the last step has a single candidate pair: its log-probability is 0 whatever its score (any finite value left in new_scores
-                // does), so the score is computed only when the caller records the logits
-                if (n > 2 || ltr || R <= 3)      // R = 3: no earlier incremental step has filled new_scores
-                    if (int e = score_pairs(m, pool, nb, slot, n, C, n, mk, nbt, nb.new_scores, nb.pair_stride, st)) return e;
+                // (the last step has a single candidate pair; it is scored like any other so that logits_cur / the trace never hold a
+                // stale value - one small fp32 launch per chunk)
+                if (int e = score_pairs(m, pool, nb, slot, n, C, n, mk, nbt, nb.new_scores, nb.pair_stride, st)) return e;
                 cur ^= 1;
             }
             prof_begin(KC_SELECT, st);

@@ -344,17 +344,25 @@ constexpr int SI_MISC_BYTES = 768 + 2048 + 512;   // biases | score partials [4]
 constexpr int SI_SMEM_MAX = 232448;
 constexpr uint32_t SI_TM_D1 = 0, SI_TM_S = 256, SI_TM_A1 = 320, SI_TM_S1 = 384, SI_TM_A0 = 448;   // TMEM: D1a 128 | D1b 128 | s[0] 64 | x' hi/lo 64 | s[1] 64 | alpha hi/lo 64
 
-// timeline trace of CTA 0 (NNJ_SCORE_TRACE=<pair count>): one clock64 stamp per (tag, item), no atomics on the traced path
+// Timing experiments (clock64 timeline of CTA 0, partial-math modes that give WRONG scores) exist only in builds made with
+// -DNNJ_DEBUG_TOOLS; the default library reads none of NNJ_SCORE_TRACE / NNJ_SCORE_DBG / NNJ_SCORE_PF.
+#ifdef NNJ_DEBUG_TOOLS
 #define SI_TRACE(tag, item) do { if (a.trace && blockIdx.x == 0 && lane == 0 && (item) < 600) a.trace[(tag) * 600 + (item)] = clock64(); } while (0)
+#define SI_DBG(a) ((a).dbg)
+#else
+#define SI_TRACE(tag, item) do { } while (0)
+#define SI_DBG(a) 0
+#endif
 
 struct ScoreIncArgs {
     const float* alpha; int RP; int alpha_pairs;
     const int32_t* slot_of; int slot_stride;
     const int32_t* pair_i; int pair_stride; int n0; int nc;
     int Rp, S, C, B, groups;
-    int pf;                                  // L2 prefetch distance in sites (0: off)
+#ifdef NNJ_DEBUG_TOOLS
     long long* trace;                        // NNJ_SCORE_TRACE: clock64 stamps of CTA 0 (tag, item, clock) triples, else null
-    int dbg;                                 // timing experiments only (NNJ_SCORE_DBG): 1 = one UMMA-1 product of three, 2 = no gate math, 4 = no GELU math
+    int dbg;                                 // timing experiments only (NNJ_SCORE_DBG): 2 = no gate math, 4 = no GELU math
+#endif
     int narrow;                              // nc <= 32: lanes 32..63 of a half repeat the pairs; the two warps of a (half, column group) split its 16 channels
     int node_rows, x_rows, nst;              // ring geometry: node blocks [node_rows][128 B] x 4, x halves [x_rows][128 B] x 2
     const uint4* wsh; const uint4* wsl;
@@ -569,7 +577,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                 const bool unmasked = site < n_sites && !(a.mask && a.mask[(size_t)b * a.C + c_base + site]);   // loaded before the wait
                 mbar_wait(s_done + (it & 1u), (it >> 1) & 1u);
                 tc_fence_after();
-                if (narrow && !(a.dbg & 4)) {
+                if (narrow && !(SI_DBG(a) & 4)) {
                     uint32_t sv[8];
                     tmem_ld8_nw(lane_base + ((it & 1u) ? SI_TM_S1 : SI_TM_S) + cg * 16 + sub * 8, sv);
                     tmem_ld_wait();
@@ -580,7 +588,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                         acc = ffma2(gelu_fast2(sb), *reinterpret_cast<const float2*>(w2v + sub * 8 + e), acc);
                     }
                     if (unmasked) score += (acc.x + acc.y) + ((cg | sub) == 0 ? a.b2 : 0.f);
-                } else if (warp_rows && !(a.dbg & 4)) {
+                } else if (warp_rows && !(SI_DBG(a) & 4)) {
                     uint32_t sv[16];
                     tmem_ld16_nw(lane_base + ((it & 1u) ? SI_TM_S1 : SI_TM_S) + cg * 16, sv);
                     tmem_ld_wait();
@@ -630,7 +638,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                 if (gi >= 1) mbar_wait(s_done + ((gi - 1) & 1u), ((gi - 1) >> 1) & 1u);   // UMMA 2 of the previous item has read the x' operand
                 if (warp == 0 || warp == 2) SI_TRACE(12 + 5 * warp, (int)gi);
                 tc_fence_after();
-                if (!warp_rows || (a.dbg & 2)) {          // no listed pair in this warp's 32 rows: x' = 0 (keeps UMMA 2's operand finite), nothing to score
+                if (!warp_rows || (SI_DBG(a) & 2)) {          // no listed pair in this warp's 32 rows: x' = 0 (keeps UMMA 2's operand finite), nothing to score
                     uint32_t z[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) z[e] = 0u;
@@ -769,22 +777,21 @@ static int make_tmap_xtile(CUtensorMap* map, const float* base, int pc, int nrow
 static int launch_score_inc(const Model* m, const float* xf, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
                             int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,
                             int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, int* n_part, cudaStream_t st) {
-    static int n_sm = 0;
-    if (!n_sm) {
+    static DevOnce once;      // per device, not per process
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_score_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_SMEM_MAX);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess || n_sm <= 0) { n_sm = 0; return set_cuda_error(e, __FILE__, __LINE__); }
+        once.done();
     }
+    const int n_sm = sm_count();
     ScoreIncArgs a;
+#ifdef NNJ_DEBUG_TOOLS
     a.trace = nullptr;
     static long long* trace_buf = nullptr; static int trace_state = -1;
     if (trace_state < 0) { const char* ev = getenv("NNJ_SCORE_TRACE"); trace_state = ev ? atoi(ev) : 0; }
     if (trace_state > 0 && nc == trace_state) { if (!trace_buf) cudaMalloc(&trace_buf, 32 * 600 * 8); cudaMemsetAsync(trace_buf, 0, 32 * 600 * 8, st); a.trace = trace_buf; }
     { static int dbg = -1; if (dbg < 0) { const char* ev = getenv("NNJ_SCORE_DBG"); dbg = ev ? atoi(ev) : 0; } a.dbg = dbg; }
-    { static int pf = -1; if (pf < 0) { const char* ev = getenv("NNJ_SCORE_PF"); pf = ev ? atoi(ev) : 0; } a.pf = pf; }
+#endif
     // the live nodes occupy physical slots [0, Rp) (k_select keeps them compact): only those rows are streamed / contracted
     { static int nw = -1; if (nw < 0) { const char* ev = getenv("NNJ_SCORE_NARROW"); nw = ev ? atoi(ev) : 1; } a.narrow = (nw && nc <= 32) ? 1 : 0; }
     a.node_rows = (Rp + 7) & ~7; a.x_rows = (nc + 7) & ~7;
@@ -793,7 +800,7 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
     if (a.nst > SI_MAXST) a.nst = SI_MAXST;
     a.nst &= ~1;                      // even: the two half-pipelines own the even / odd ring stages (see the kernel)
     if (a.nst < 2) return set_error(NNJ_ERR_INVALID, "score_inc: ring does not fit");
-    if ((C % SI_SITES) & 1) return set_error(NNJ_ERR_INVALID, "score_inc: odd site count");   // unreachable: the tensor-core path needs C % 8 == 0
+    if (C & 7) return set_error(NNJ_ERR_INVALID, "score_inc: the tensor-core NJ kernels need a site count that is a multiple of 8 (nj_use_tc routes other shapes to the fp32 kernels)");
     CUtensorMap mh, ml, mx;
     if (int e = make_tmap_xtile(&mx, xf + (size_t)0, pc, nc, C, B, a.x_rows)) return e;
     if (int e = make_tmap_nodes(&mh, nodes_h, S, B * C, a.node_rows, Rp)) return e;
@@ -812,6 +819,7 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
     k_score_inc<<<n_work < n_sm ? n_work : n_sm, SI_THREADS, smem, st>>>(mh, ml, mx, a);
     ++g_launches;
     prof_end(st);
+#ifdef NNJ_DEBUG_TOOLS
     if (a.trace) {
         cudaStreamSynchronize(st);
         std::vector<long long> h(32 * 600);
@@ -820,6 +828,7 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
         if (f) { for (int t = 0; t < 32; ++t) for (int i = 0; i < 600; ++i) if (h[t * 600 + i]) fprintf(f, "%d %d %lld\n", t, i, h[t * 600 + i]); fclose(f); }
         trace_state = 0;
     }
+#endif
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     return 0;
@@ -828,11 +837,11 @@ static int launch_score_inc(const Model* m, const float* xf, int pc, const void*
 int launch_score_tc(const Model* m, const float* xf, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
                     int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,
                     int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, int* n_part, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static DevOnce once;      // per device, not per process
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-        attr = true;
+        once.done();
     }
     if (S > 64) return set_error(NNJ_ERR_INVALID, "score_tc: at most 63 taxa on the tensor-core pair-score path");
     {

@@ -493,27 +493,19 @@ static int make_tmap_mn_major(CUtensorMap* map, const void* base, int N, int K, 
     return 0;
 }
 
-static int tc_sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
+static int tc_sm_count() { return sm_count(); }    // of the current device (cached per device, nnj_api.cu)
 
 // C[z] = (Ah+Al)[z] * (Bh+Bl)[z] with B MN-major: B planes [Z][K][N] (N contiguous, pitch ldb).  128 x 128 tiles.
 int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                        size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st) {
-    static bool attr = false;
+    static DevOnce once;      // per device, not per process
     constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
     constexpr int SMEM256 = 2 * (6 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
-    if (!attr) {
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM256);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-        attr = true;
+        once.done();
     }
     CUtensorMap mAh, mAl, mBh, mBl;
     if (int e = make_tmap_k_major(&mAh, Ah, K, M, Z, lda, sA, TC_BM)) return e;
@@ -540,16 +532,16 @@ int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, 
 int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, int bn, int nsplit, int chunks_per_split, size_t split_stride,
                       cudaStream_t st) {
-    static bool attr = false;
+    static DevOnce once;      // per device, not per process
     constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
     constexpr int SMEM64 = TC_STAGES * (3 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
     constexpr int SMEM256 = 2 * (6 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
-    if (!attr) {
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM256);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-        attr = true;
+        once.done();
     }
     CUtensorMap mAh, mAl, mBh, mBl;
     if (int e = make_tmap_k_major(&mAh, Ah, K, M, Z, lda, sA, TC_BM)) return e;

@@ -24,7 +24,11 @@ import torch.nn as nn
 from . import _lib
 from ._lib import NnjError, check, nnj_config
 
-PRECISIONS = {"fp32": 0, "bf16x3": 1}
+# fp32: CUDA-core arithmetic everywhere.  bf16x3: dense contractions on tcgen05 as split-bf16 (3 products, ~16 operand mantissa bits):
+# the mode that keeps Argmax topologies identical to the fp32 reference and the default.  bf16: the same kernels with ONE product
+# (plain bf16 operands, fp32 accumulate - the literal "bf16 operands" of the north star): scores within 1e-2 relative, topologies may differ.
+PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+DEFAULT_PRECISION = "bf16x3"
 
 
 class _Attn(nn.Module):
@@ -74,9 +78,11 @@ def _stream():
 
 
 class PhyloATTN(nn.Module):
-    def __init__(self, cfgs, precision: str = "fp32"):
+    def __init__(self, cfgs, precision: Optional[str] = None):
         super().__init__()
         mc = cfgs.model
+        if precision is None:      # cfgs.model.precision (an extension key, absent from the reference YAMLs) or the library default
+            precision = mc.get("precision", DEFAULT_PRECISION) if hasattr(mc, "get") else DEFAULT_PRECISION
         self.vocab_size = mc.vocab_size
         self.patch_size = mc.patch_size
         self.patch_num = mc.fixed_length // self.patch_size
@@ -140,7 +146,8 @@ class PhyloATTN(nn.Module):
         ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in host])
         numels = (C.c_int64 * n)(*[t.numel() for t in host])
         h = C.c_void_p()
-        check(L.nnj_model_create(C.byref(h), C.byref(cfg), ptrs, numels, n, dev.index or 0), "nnj_model_create")
+        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        check(L.nnj_model_create(C.byref(h), C.byref(cfg), ptrs, numels, n, dev_index), "nnj_model_create")
         self._handle, self._handle_key = h, key
         return h
 

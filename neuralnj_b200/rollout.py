@@ -132,8 +132,11 @@ def Agmax_one_instance(cfgs, MSA_file, policy_network, env, c_best_tree_file=Non
     return out
 
 
-def _load_policy(cfgs, device) -> PhyloATTN:
-    net = PhyloATTN(cfgs).to(device)
+PRECISION = None                        # --precision of the CLI; None = cfgs.model.precision or the library default (bf16x3)
+
+
+def _load_policy(cfgs, device, precision=None) -> PhyloATTN:
+    net = PhyloATTN(cfgs, precision=precision or PRECISION).to(device)
     if cfgs.reload_checkpoint_path and os.path.exists(cfgs.reload_checkpoint_path):
         ckpt = torch.load(cfgs.reload_checkpoint_path, map_location="cpu")
         net.load_state_dict(ckpt["model_state_dict"])
@@ -150,11 +153,11 @@ def _cfg(c):
     return c
 
 
-def Argmax_inference(test_file_path, write_dir, write_file_name=None, branch_optimize=False, cfgs=None, device=None):
+def Argmax_inference(test_file_path, write_dir, write_file_name=None, branch_optimize=False, cfgs=None, device=None, precision=None):
     c = _cfg(cfgs)
     device = device or torch.device("cuda")
     env = PhyInferEnv(c, device)
-    policy = _load_policy(c, device)
+    policy = _load_policy(c, device, precision)
     os.makedirs(write_dir, exist_ok=True)
     written = []
     for file in sorted(f for f in os.listdir(test_file_path) if f.endswith(".phy")):
@@ -213,11 +216,11 @@ def RL_Search(cfgs, MSA_file, policy_network, env, c_best_tree_file=None, raw_tr
                 time_when_best_score_max=t_best, relative_rf_distance=rel_rf, step_cur=step_cur, distinct_topologies=len(seen))
 
 
-def Search_inference(test_file_path, write_dir, write_file_name=None, cfgs=None, device=None, scorer=None, stop_step=None):
+def Search_inference(test_file_path, write_dir, write_file_name=None, cfgs=None, device=None, scorer=None, stop_step=None, precision=None):
     c = _cfg(cfgs)
     device = device or torch.device("cuda")
     env = PhyInferEnv(c, device)
-    policy = _load_policy(c, device)
+    policy = _load_policy(c, device, precision)
     os.makedirs(write_dir, exist_ok=True)
     written = []
     for file in sorted(f for f in os.listdir(test_file_path) if f.endswith(".phy")):
@@ -233,14 +236,17 @@ def Search_inference(test_file_path, write_dir, write_file_name=None, cfgs=None,
 def main(argv=None):
     """CLI with the reference's flags (finetune_rl_search.py:583-621)."""
     import argparse
-    global cfgs, STOP_STEP
+    global cfgs, STOP_STEP, PRECISION
     ap = argparse.ArgumentParser(description="NeuralNJ inference (B200 path)")
     ap.add_argument("--config_path", type=str, default="")
     ap.add_argument("--infer_opt", type=str, default="Argmax", help='"Argmax" (NeuralNJ) or "Search" (NeuralNJ-MC)')
     ap.add_argument("--stop_step", type=int, default=100)
     ap.add_argument("--evolution_model", type=str, default="GTR+I+G")
     ap.add_argument("--branch_optimize", action="store_true")
+    ap.add_argument("--precision", type=str, default=None, choices=["fp32", "bf16x3", "bf16"],
+                    help="arithmetic of the CUDA path (not a reference flag); default bf16x3: tcgen05 split-bf16, topologies identical to fp32")
     args = ap.parse_args(argv)
+    PRECISION = args.precision
     cfgs = empty_config()
     if args.config_path:
         cfgs.merge_from_file(args.config_path)

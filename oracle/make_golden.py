@@ -1,6 +1,8 @@
 """Generate tests/golden/ by executing the UNMODIFIED reference (build container only).
 
     python oracle/make_golden.py            # writes tests/golden/*.npz + tests/golden/msa/*.phy
+    python oracle/make_golden.py wide       # round 2: 16 files of data_gen/data/test/len1024/taxa50 + 4 of len1024/taxa100
+                                            #          as "lite" records under tests/golden/wide/ (see main_wide)
 
 The reference (/root/reference, read-only, absent on the GPU box) is imported
 with the stub packages under oracle/ref_stubs/ standing in for its missing
@@ -210,5 +212,80 @@ def main():
     print("cache index map: closed form == reference for n<=12")
 
 
+def main_wide():
+    """Breadth set: every 8th file of data_gen/data/test/len1024/taxa50 (16 files) and every 32nd of
+    len1024/taxa100 (4 files), run through the unmodified reference.  To keep the fixtures small a "lite" record holds what
+    topology parity needs - merge list, Newick, selected_log_ps, the step-0 logits, and per step the maximum |logit| and the
+    top-1 / top-2 gap - while the input travels as the .phy file itself (read back through neuralnj_b200.load_pi_instance)."""
+    torch.set_num_threads(8)
+    import utils as ref_utils
+    import finetune_rl_search as ref_main
+    from environment import PhyInferEnv
+    from model import PhyloATTN
+    from phydata import load_pi_instance
+
+    torch.autograd.set_detect_anomaly(False)
+    cfgs = ref_utils.empty_config()
+    cfgs.merge_from_file(os.path.join(REF, "config/finetune_reinforce_search_example.yaml"))
+    ref_main.cfgs = cfgs
+    ref_main.device = torch.device("cpu")
+    torch.manual_seed(0)
+    model = PhyloATTN(cfgs).eval()
+    sd = O.init_state_dict(0)
+    for k, v in model.state_dict().items():
+        assert torch.equal(sd[k], v), k
+    out_dir = os.path.join(GOLD, "wide")
+    os.makedirs(out_dir, exist_ok=True)
+    sets = [("w50", "data_gen/data/test/len1024/taxa50", 8), ("w100", "data_gen/data/test/len1024/taxa100", 32)]
+    index = []
+    for tag, d, stride in sets:
+        files = sorted(f for f in os.listdir(os.path.join(REF, d)) if f.endswith(".phy"))[::stride]
+        for k, fn in enumerate(files):
+            name = f"{tag}_{k:02d}"
+            src = os.path.join(REF, d, fn)
+            shutil.copyfile(src, os.path.join(out_dir, name + ".phy"))
+            batch = load_pi_instance(src)
+            env = PhyInferEnv(cfgs, torch.device("cpu"))
+            rec = {"logits": [], "merges": []}
+            orig_dec, orig_step = model.decode_zxr, env.step
+
+            def dec(*a, **kw):
+                o = orig_dec(*a, **kw)
+                rec["logits"].append(o["logits"].detach().clone())
+                return o
+
+            def step(actions, *a, **kw):
+                n = env.states[0].num_trees
+                rec["merges"].append([list(map(int, env.tree_pairs_dict[n][int(x)])) for x in actions])
+                return orig_step(actions, *a, **kw)
+
+            model.decode_zxr, env.step = dec, step
+            try:
+                t = time.time()
+                sel, _, _, _ = ref_main.reinforce_rollout(batch, model, env, cfgs, eval=True, argmax=True, branch_optimize=False)
+                dt = time.time() - t
+            finally:
+                del model.decode_zxr
+            newick = env.states[0].subtrees[0].utree_op_str
+            lmax, gap = [], []
+            for lg in rec["logits"]:
+                lmax.append(float(lg.abs().max()))
+                gap.append(float(lg.topk(2, dim=1).values.diff(dim=1).abs().max()) if lg.shape[1] > 1 else float("inf"))
+            np.savez_compressed(os.path.join(out_dir, name + ".npz"),
+                                source=np.array(os.path.join(d, fn)),
+                                merges=np.array(rec["merges"], dtype=np.int32).transpose(1, 0, 2),
+                                newick=np.array([newick]), selected_log_ps=sel.numpy().astype(np.float32),
+                                logits0=rec["logits"][0].numpy().astype(np.float32),
+                                step_max_abs_logit=np.array(lmax, dtype=np.float32), step_top2_gap=np.array(gap, dtype=np.float32))
+            rel_gap = min(g / m for g, m in zip(gap, lmax) if np.isfinite(g))
+            print(f"[{name}] {fn}: reference rollout {dt:.1f}s, min relative top-2 gap {rel_gap:.2e}", flush=True)
+            index.append(name)
+    with open(os.path.join(out_dir, "INDEX.txt"), "w") as f:
+        f.write("\n".join(index) + "\n")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "wide":
+        main_wide()
+    else:
+        main()

@@ -273,7 +273,7 @@ def pair_scores(sd: State, nodes: torch.Tensor, valid: torch.Tensor, i_idx: torc
     B, N = i_idx.shape
     step = pair_chunk if pair_chunk > 0 else N
     out = []
-    ar = torch.arange(B).unsqueeze(1)
+    ar = torch.arange(B, device=nodes.device).unsqueeze(1)
     for s in range(0, N, step):
         ii, jj = i_idx[:, s:s + step], j_idx[:, s:s + step]
         x = aggregate(sd, nodes, nodes[ar, ii], nodes[ar, jj], ii, jj, patch_num)
@@ -419,37 +419,38 @@ def rollout(sd: State, data: torch.Tensor, seq_mask: torch.Tensor, num_heads: in
         C = math.ceil(L / patch)
         X = encode(sd, data, seq_mask, num_heads, patch, chunked) if state is None else state
         state0 = X
+        dev = X.device                        # CPU for the oracle proper; "cuda" turns this restatement into the eager-GPU bar of bench.py
         valid = (~seq_mask[:, None, ::patch]).to(X.dtype)
         merges = torch.zeros(B, R - 1, 2, dtype=torch.int64)
         logits_all, logp_all, sel, acts = [], [], [], []
         prev_ij = None
         logits_prev = None
-        ar = torch.arange(B)
+        ar = torch.arange(B, device=dev)
         for t in range(R - 1):
             n = X.size(1)
             if logits_prev is None:
-                ii, jj = torch.triu_indices(n, n, offset=1)
+                ii, jj = torch.triu_indices(n, n, offset=1, device=dev)
                 logits = pair_scores(sd, X, valid, ii.unsqueeze(0).expand(B, -1),
                                      jj.unsqueeze(0).expand(B, -1), C, pair_chunk)
             else:
-                r_all = torch.arange(n).unsqueeze(0).expand(B, n)
+                r_all = torch.arange(n, device=dev).unsqueeze(0).expand(B, n)
                 a_i = prev_ij[:, :1].expand(B, n)
                 lo, hi = torch.minimum(a_i, r_all), torch.maximum(a_i, r_all)
                 new = pair_scores(sd, X, valid, lo, hi, C)  # includes the unused self pair (model.py:186-197)
                 idx = torch.tensor([score_indices_to_prev(int(a), int(b), n) for a, b in prev_ij.tolist()],
-                                   dtype=torch.int64)
+                                   dtype=torch.int64, device=dev)
                 logits = torch.gather(torch.cat([logits_prev, new], -1), 1, idx)
             logp = torch.log_softmax(logits, -1)
             if forced_merges is not None:
                 fm = forced_merges[:, t]
-                a = torch.tensor([pair_index(int(i), int(j), n) for i, j in fm.tolist()])
+                a = torch.tensor([pair_index(int(i), int(j), n) for i, j in fm.tolist()], device=dev)
             elif gumbel is None:
                 a = torch.argmax(logits, -1)
             else:
                 a = torch.argmax(logits + gumbel[:, t, :logits.size(1)].to(logits.dtype), -1)
             pl = pair_list(n)
-            ij = torch.tensor([pl[k] for k in a.tolist()], dtype=torch.int64)
-            merges[:, t] = ij
+            ij = torch.tensor([pl[k] for k in a.tolist()], dtype=torch.int64, device=dev)
+            merges[:, t] = ij.cpu()
             logits_all.append(logits)
             acts.append(a)
             if n == 2:
@@ -470,7 +471,7 @@ def rollout(sd: State, data: torch.Tensor, seq_mask: torch.Tensor, num_heads: in
             logits_prev = logits
         return {
             "merges": merges, "logits": logits_all, "actions": acts, "log_ps": logp_all,
-            "selected_log_ps": torch.cat(sel, 1) if sel else torch.zeros(B, 0),
+            "selected_log_ps": torch.cat(sel, 1) if sel else torch.zeros(B, 0, device=dev),
             "state0": state0,
         }
 
