@@ -68,16 +68,33 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
     return d;
 }
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
-// sigmoid_fast / gelu_fast on two values: the same operations in the same order as the scalar forms
-__device__ __forceinline__ float2 sigmoid_fast2(float2 x) {
-    const float2 t = fmul2(splat2(-1.4426950408889634f), x);
-    const float2 d = fadd2(splat2(1.0f), make_float2(ex2_approx(t.x), ex2_approx(t.y)));
+// sigmoid_fast / gelu_fast on two values.  The score / blend epilogues are bound by the MUFU pipe (16 results per clock and SM: a
+// warp instruction holds a quadrant's unit for 8 clocks, four MUFU per pair-site-channel), so the two reciprocals of a value pair
+// share ONE MUFU: r = rcp(a b), 1/a = b r, 1/b = a r (two extra FMA-pipe multiplies).  Both results carry the 2^-22 of rcp.approx plus
+// one rounding - the same grade as the scalar forms, not bit-identical to them.  NNJ_RCP_PAIR=0 restores one rcp per value.
+#ifndef NNJ_RCP_PAIR
+#define NNJ_RCP_PAIR 1
+#endif
+__device__ __forceinline__ float2 rcp_pair(float2 d) {
+#if NNJ_RCP_PAIR
+    const float r = rcp_approx(d.x * d.y);
+    return fmul2(make_float2(d.y, d.x), splat2(r));
+#else
     return make_float2(rcp_approx(d.x), rcp_approx(d.y));
+#endif
+}
+__device__ __forceinline__ float2 sigmoid_fast2(float2 x) {
+    float2 t = fmul2(splat2(-1.4426950408889634f), x);
+#if NNJ_RCP_PAIR
+    t.x = fminf(t.x, 60.0f); t.y = fminf(t.y, 60.0f);      // (1 + 2^60)^2 stays finite; sigmoid < 2^-60 reads as 2^-60
+#endif
+    const float2 d = fadd2(splat2(1.0f), make_float2(ex2_approx(t.x), ex2_approx(t.y)));
+    return rcp_pair(d);
 }
 __device__ __forceinline__ float2 gelu_fast2(float2 x) {
     const float2 z = make_float2(fabsf(x.x), fabsf(x.y));
     const float2 d = ffma2(splat2(2.760034502e-01f), z, splat2(1.0f));
-    const float2 u = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+    const float2 u = rcp_pair(d);
     float2 p = splat2(-1.134462506e-01f);
     p = ffma2(p, u, splat2(4.407724440e-01f));
     p = ffma2(p, u, splat2(-3.137964904e-01f));

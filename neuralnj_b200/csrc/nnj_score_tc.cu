@@ -342,7 +342,11 @@ constexpr int SI_RING = 49152;
 constexpr int SI_MAXST = 6;
 constexpr int SI_MISC_BYTES = 768 + 2048 + 512;   // biases | score partials [4][128] | barriers (4 x 6 + 7), tmem slot
 constexpr int SI_SMEM_MAX = 232448;
-constexpr uint32_t SI_TM_D1 = 0, SI_TM_S = 256, SI_TM_A1 = 320, SI_TM_S1 = 384, SI_TM_A0 = 448;   // TMEM: D1a 128 | D1b 128 | s[0] 64 | x' hi/lo 64 | s[1] 64 | alpha hi/lo 64
+constexpr uint32_t SI_TM_D1 = 0, SI_TM_S = 256, SI_TM_A1 = 320, SI_TM_A0 = 448;   // TMEM: D1a 128 | D1b 128 | s 64 | x'[0] hi/lo 64 | x'[1] hi/lo 64 | alpha hi/lo 64
+// The x' operand of UMMA 2 is double-buffered by item parity and s is single: the gate epilogue of item k+1 then never waits for UMMA 2 of
+// item k (with one x' buffer it did, and the ~2700 clk from "gate done" over "both halves ready -> UMMA 2 issued -> retired" to the next
+// gate exceeded the ~1500 clk GELU epilogue that was meant to fill it: 1250 idle clk of a 4170 clk item period, profiles/r01_score_inc_experiments.txt).
+// UMMA 2 of item k now waits for the GELU epilogue of item k-1 to have drained s (s_free) and runs while the warps work on gate k+1.
 
 // Timing experiments (clock64 timeline of CTA 0, partial-math modes that give WRONG scores) exist only in builds made with
 // -DNNJ_DEBUG_TOOLS; the default library reads none of NNJ_SCORE_TRACE / NNJ_SCORE_DBG / NNJ_SCORE_PF.
@@ -389,7 +393,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
     // the node tiles (freed by UMMA 1) and the x tiles (freed by the gate epilogue) run as two rings with their own barriers, so a
     // node stage is refilled as soon as its UMMA 1 has retired, one item earlier than the x tile of the same site
     uint64_t *full = bars, *stage_free = bars + SI_MAXST, *x_full = bars + 2 * SI_MAXST, *x_free = bars + 3 * SI_MAXST,
-             *a0_ready = bars + 4 * SI_MAXST, *d1_done = a0_ready + 1, *a1_ready = d1_done + 2, *s_done = a1_ready + 2;   // d1_done[2] a1_ready[2] s_done[2]
+             *a0_ready = bars + 4 * SI_MAXST, *d1_done = a0_ready + 1, *a1_ready = d1_done + 2, *s_done = a1_ready + 2, *s_free = s_done + 1;   // d1_done[2] a1_ready[2] s_done s_free
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_done + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -398,7 +402,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(full + i, 1); mbar_init(stage_free + i, 1); mbar_init(x_full + i, 1); mbar_init(x_free + i, 8); }
         mbar_init(a0_ready, 16); mbar_init(d1_done, 1); mbar_init(d1_done + 1, 1); mbar_init(a1_ready, 8); mbar_init(a1_ready + 1, 8);
-        mbar_init(s_done, 1); mbar_init(s_done + 1, 1);
+        mbar_init(s_done, 1); mbar_init(s_free, 16);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) tmem_alloc(tmem_slot, 512);
@@ -463,7 +467,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
             mbar_wait(a0_ready, wi & 1u);
             // The two sites of an item are two half-pipelines: while the 8 epilogue warps of one half run the gate epilogue on their
             // accumulator (D1a / D1b), the tensor core refills the other one.  Issue order: U1a(0) U1b(0), then per item k:
-            //   [half A done with D1a(k)] U1a(k+1)   [half B done with D1b(k)] U2(k) U1b(k+1)
+            //   [half A done with D1a(k)] U1a(k+1)   [half B done with D1b(k)] U1b(k+1)   [GELU epilogue of item k-1 done] U2(k)
             // (sites stay in ring order A(k) B(k) A(k+1) ...).  [x_glob | g] = alpha . [X | W_g X]: alpha from TENSOR MEMORY (a 128 x 128
             // x 16 UMMA costs ~75 clk with A in TMEM against ~107 clk from shared memory), B MN-major from the node ring.
             auto issue_u1 = [&](int h) {
@@ -498,10 +502,12 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                 SI_TRACE(4, (int)gi);
                 if (2 * (k + 1) < n_sites) issue_u1(0);
                 mbar_wait(a1_ready + 1, gi & 1u);       // half B likewise (it arrives with zeros when the item has no second site)
+                if (2 * (k + 1) + 1 < n_sites) issue_u1(1);     // both D1 accumulators are refilled before UMMA 2 waits for the GELU epilogue
+                if (gi >= 1) mbar_wait(s_free, (gi - 1) & 1u);   // all 16 epilogue warps have read s of the previous item
                 SI_TRACE(5, (int)gi);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t ta = tmem_base + SI_TM_A1, ts = tmem_base + ((gi & 1u) ? SI_TM_S1 : SI_TM_S);
+                    const uint32_t ta = tmem_base + SI_TM_A1 + (gi & 1u) * 64, ts = tmem_base + SI_TM_S;
                     const uint32_t wh = umma_desc_lo(wsh), wl = umma_desc_lo(wsl);
                     umma_ts<false>(ts, ta + 32, wh, id_s);          // s = x' . W_s^T for both sites at once; small terms first
                     umma_ts<true>(ts, ta, wl, id_s);
@@ -512,12 +518,10 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                         umma_ts<true>(ts, ta + kk * 8, wl + kk * 2, id_s);
                         umma_ts<true>(ts, ta + kk * 8, wh + kk * 2, id_s);
                     }
-                    umma_commit(s_done + (gi & 1u));
+                    umma_commit(s_done);
                 }
                 __syncwarp();
                 SI_TRACE(6, (int)gi);
-                if (2 * (k + 1) + 1 < n_sites) issue_u1(1);
-                SI_TRACE(7, (int)gi);
             }
         }
     } else {
@@ -575,11 +579,11 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
             // w2 . GELU(s + b_s) (+ b2 once per row), masked site sum, for item `it` (global count) whose site of this thread is `site`
             auto ep2 = [&](uint32_t it, int site) {
                 const bool unmasked = site < n_sites && !(a.mask && a.mask[(size_t)b * a.C + c_base + site]);   // loaded before the wait
-                mbar_wait(s_done + (it & 1u), (it >> 1) & 1u);
+                mbar_wait(s_done, it & 1u);
                 tc_fence_after();
                 if (narrow && !(SI_DBG(a) & 4)) {
                     uint32_t sv[8];
-                    tmem_ld8_nw(lane_base + ((it & 1u) ? SI_TM_S1 : SI_TM_S) + cg * 16 + sub * 8, sv);
+                    tmem_ld8_nw(lane_base + SI_TM_S + cg * 16 + sub * 8, sv);
                     tmem_ld_wait();
                     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
@@ -590,7 +594,7 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                     if (unmasked) score += (acc.x + acc.y) + ((cg | sub) == 0 ? a.b2 : 0.f);
                 } else if (warp_rows && !(SI_DBG(a) & 4)) {
                     uint32_t sv[16];
-                    tmem_ld16_nw(lane_base + ((it & 1u) ? SI_TM_S1 : SI_TM_S) + cg * 16, sv);
+                    tmem_ld16_nw(lane_base + SI_TM_S + cg * 16, sv);
                     tmem_ld_wait();
                     float2 acc = make_float2(0.f, 0.f);          // packed fp32x2 math: channel pairs (e, e+1) share every FMA-pipe instruction
 #pragma unroll
@@ -601,6 +605,8 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                     if (unmasked) score += (acc.x + acc.y) + (cg == 0 ? a.b2 : 0.f);
                 }
                 tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_free);      // s may be overwritten by UMMA 2 of the next item
                 if (warp == 0 || warp == 2) SI_TRACE(14 + 5 * warp, (int)it);
             };
             for (int k = 0; k < n_items; ++k, ++gi) {
@@ -635,16 +641,17 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                 if (warp == 0 || warp == 2) SI_TRACE(10 + 5 * warp, (int)gi);
                 if (site_ok) { mbar_wait(d1_done + h, c_d1 & 1u); ++c_d1; }      // this half's [x_glob | g]
                 if (warp == 0 || warp == 2) SI_TRACE(11 + 5 * warp, (int)gi);
-                if (gi >= 1) mbar_wait(s_done + ((gi - 1) & 1u), ((gi - 1) >> 1) & 1u);   // UMMA 2 of the previous item has read the x' operand
+                // x'[gi & 1] was last read by UMMA 2 of item gi-2, whose completion this warp saw in that item's GELU epilogue
                 if (warp == 0 || warp == 2) SI_TRACE(12 + 5 * warp, (int)gi);
                 tc_fence_after();
+                const uint32_t t_xp = lane_base + SI_TM_A1 + (gi & 1u) * 64;
                 if (!warp_rows || (SI_DBG(a) & 2)) {          // no listed pair in this warp's 32 rows: x' = 0 (keeps UMMA 2's operand finite), nothing to score
                     uint32_t z[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) z[e] = 0u;
-                    if (gi < 2 || k == 0) {
-                        tmem_st8(lane_base + SI_TM_A1 + cg * 8, z);
-                        tmem_st8(lane_base + SI_TM_A1 + 32 + cg * 8, z);
+                    if (gi < 2 || k < 2) {
+                        tmem_st8(t_xp + cg * 8, z);
+                        tmem_st8(t_xp + 32 + cg * 8, z);
                         tmem_st_wait();
                     }
                 } else if (narrow && site_ok) {
@@ -671,10 +678,10 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
                     xch[(sub * 2 + 1) * 32 + lane] = ol;
                     asm volatile("bar.sync %0, 64;" ::"r"(xch_bar) : "memory");
                     const uint4 ph_ = xch[((sub ^ 1) * 2) * 32 + lane], pl_ = xch[((sub ^ 1) * 2 + 1) * 32 + lane];
-                    tmem_st4(lane_base + SI_TM_A1 + cg * 8 + sub * 4, oh.x, oh.y, oh.z, oh.w);
-                    tmem_st4(lane_base + SI_TM_A1 + cg * 8 + (sub ^ 1) * 4, ph_.x, ph_.y, ph_.z, ph_.w);
-                    tmem_st4(lane_base + SI_TM_A1 + 32 + cg * 8 + sub * 4, ol.x, ol.y, ol.z, ol.w);
-                    tmem_st4(lane_base + SI_TM_A1 + 32 + cg * 8 + (sub ^ 1) * 4, pl_.x, pl_.y, pl_.z, pl_.w);
+                    tmem_st4(t_xp + cg * 8 + sub * 4, oh.x, oh.y, oh.z, oh.w);
+                    tmem_st4(t_xp + cg * 8 + (sub ^ 1) * 4, ph_.x, ph_.y, ph_.z, ph_.w);
+                    tmem_st4(t_xp + 32 + cg * 8 + sub * 4, ol.x, ol.y, ol.z, ol.w);
+                    tmem_st4(t_xp + 32 + cg * 8 + (sub ^ 1) * 4, pl_.x, pl_.y, pl_.z, pl_.w);
                     tmem_st_wait();
                 } else {
                     uint32_t g[16], xg[16];
@@ -694,8 +701,8 @@ k_score_inc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ C
 #pragma unroll
                         for (int e = 0; e < 8; ++e) { hh[e] = 0u; ll[e] = 0u; }
                     }
-                    tmem_st8(lane_base + SI_TM_A1 + cg * 8, hh);
-                    tmem_st8(lane_base + SI_TM_A1 + 32 + cg * 8, ll);
+                    tmem_st8(t_xp + cg * 8, hh);
+                    tmem_st8(t_xp + 32 + cg * 8, ll);
                     tmem_st_wait();
                 }
                 tc_fence_before();

@@ -32,16 +32,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Blocking wait.  try_wait itself suspends the warp for a hardware-chosen time slice before it reports failure, so the loop below
+// turns over slowly; the time-out check reads the clock only once per 64 turns (a clock64 per turn showed up as 3 % of all
+// executed instructions - CS2R - in the score kernel, issue slots taken from the warps that had work).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    long long t0 = 0;
+    uint32_t turns = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 40000000000LL) {   // ~20 s at 1.9 GHz (instrumented profiler passes run 100x slower): protocol error, fail loudly instead of hanging
+        if ((++turns & 63u) == 0u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 40000000000LL) {   // ~20 s at 1.9 GHz (instrumented profiler passes run 100x slower): protocol error, fail loudly instead of hanging
 #ifdef NNJ_MBAR_DEBUG
-            printf("mbar timeout: block (%d,%d,%d) thread %d bar smem+%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x,
-                   smem_u32(bar), parity);
+                printf("mbar timeout: block (%d,%d,%d) thread %d bar smem+%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x,
+                       smem_u32(bar), parity);
 #endif
-            __trap();
+                __trap();
+            }
         }
     }
 }
