@@ -330,6 +330,54 @@ __global__ void __launch_bounds__(NTHREADS) k_alpha_softmax(const float* __restr
     for (int r = lane; r < Rp; r += 32) out[r] *= inv;
 }
 
+// The same for up to 256 nodes with many partials (large-slot path: <= 64 K splits of the alpha GEMM, indexed by physical slot): one CTA
+// per (tree, pair), thread r = node r, so the partial rows are read coalesced and the dependent-load chain of a lane is the number of
+// partials, not partials x nodes / 32.  Fixed summation order: deterministic.
+__global__ void __launch_bounds__(NTHREADS) k_alpha_softmax_wide(const float* __restrict__ alpha_part, const float* __restrict__ kap,
+                                                                 const int32_t* __restrict__ slot_of, int slot_stride, int S, int nCT, int Rp,
+                                                                 const int32_t* __restrict__ pair_i, const int32_t* __restrict__ pair_j,
+                                                                 int pair_stride, int n0, int nc, int nSB, int RP, float inv_scale,
+                                                                 float* __restrict__ alpha, int n_part) {
+    __shared__ float s_red[NTHREADS / 32];
+    const int n = blockIdx.x, b = blockIdx.y, r = threadIdx.x, warp = r >> 5, lane = r & 31;
+    const int li = pair_i[(size_t)b * pair_stride + n0 + n], lj = pair_j[(size_t)b * pair_stride + n0 + n];
+    float* out = alpha + ((size_t)b * PAIR_CHUNK + n) * RP;
+    if (li < 0) {
+        if (r < Rp) out[r] = 0.f;
+        return;
+    }
+    float v = -INFINITY;
+    if (r < Rp) {
+        const int col = slot_of[(size_t)b * slot_stride + r];
+        const float* ap = alpha_part + ((size_t)b * PAIR_CHUNK + n) * nSB * RP + col;
+        float s = 0.f;
+        for (int k = 0; k < n_part; ++k) s += ap[(size_t)k * RP];
+        const float* kp = kap + ((size_t)b * S + col) * nCT;
+        float kk = 0.f;
+        for (int k = 0; k < nCT; ++k) kk += kp[k];
+        v = (r == li || r == lj) ? -INFINITY : (s + kk) * inv_scale;
+    }
+    float m = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    m = s_red[0];
+#pragma unroll
+    for (int w = 1; w < NTHREADS / 32; ++w) m = fmaxf(m, s_red[w]);
+    __syncthreads();
+    const float e = r < Rp ? expf(v - m) : 0.f;
+    float l = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane == 0) s_red[warp] = l;
+    __syncthreads();
+    l = 0.f;
+#pragma unroll
+    for (int w = 0; w < NTHREADS / 32; ++w) l += s_red[w];
+    if (r < Rp) out[r] = e * (1.0f / l);
+}
+
 // ------------------------------------------------------------------ pair scores
 // grid (nSG, ceil(nc/32), B).  CTA tile = 32 pairs x 4 sites per iteration, 8 iterations (32 sites).
 // rows of the [128][64] tile: row = site_local*32 + pair_local.
@@ -823,10 +871,13 @@ struct NjBuffers {
     float *Y, *K, *kap, *alpha_part, *alpha, *score_part, *new_scores, *logits[2], *newx;
     int32_t *slot[2], *free_slot, *new_slot, *pair_i, *pair_j;
     float* X;         // pool X when owned by the workspace (rollout), else null
-    float* xf;                // tensor-core path: x planes of the current pair chunk [B][TC_PAIRS][C][64] fp32
+    float* xf;                // tensor-core path: x planes of the current pair chunk [B][pc][C][64] fp32
+    void *xh, *xl;            // large-slot tensor-core path: the same rows as K-major bf16 hi / lo planes (A operand of the alpha-logit GEMM)
     void *nodes_h, *nodes_l;  // tensor-core path: site-major node planes [B][C][S][128] bf16 = [X | W_g X]
     void *kp_h, *kp_l;        // tensor-core path: K' planes [B][S][C][64] bf16 (B operand of the alpha GEMM)
-    bool tc;
+    bool tc;                  // tcgen05 NJ kernels: 1 = fused kernels (<= 64 slots), 2 handled via `big`
+    bool big;                 // 65 .. 256 slots: blend -> split-K alpha GEMM -> k_score_big
+    int pc;                   // pairs per launch on the tensor-core path (capacity of the x planes)
     int S, nCT, nSB, nAP, RP, pair_stride, P0;   // nSB: 32-site groups (fp32 kernels); nAP: alpha partials allocated per pair (stride)
     size_t total;
 };
@@ -837,12 +888,14 @@ constexpr int TC_PAIRS = 256;   // pairs per launch on the tensor-core pair-scor
 // The tcgen05 NJ kernels (k_alpha_v3, k_score_tc, k_score_inc) take at most 64 physical slots and - like the tensor-core encoder
 // (use_tc in nnj_encoder.cu) - need C % 8 == 0: their TMA boxes and the two-sites-per-item ring assume 16-byte rows and an even
 // site count.  Every other shape runs the fp32 CUDA-core kernels of this file, whatever the precision mode.
-static bool nj_use_tc(const Model* m, int S, int C) { return m->cfg.precision != NNJ_PREC_FP32 && S <= 64 && (C % 8) == 0; }
+static bool nj_use_tc(const Model* m, int S, int C) { return m->cfg.precision != NNJ_PREC_FP32 && S <= 256 && (C % 8) == 0; }
+constexpr int BIG_PAIRS = 512;  // pairs per launch of the large-slot path (4 pair tiles share one pass over the K' planes in the alpha GEMM)
 
 static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws, bool need_newx, bool tc) {
     NjBuffers nb{};
     nb.S = S; nb.nCT = (C + TILE_ROWS - 1) / TILE_ROWS; nb.nSB = (C + SB_SITES - 1) / SB_SITES;
-    const int tc_parts = tc ? 4 * ((C + 63) / 64) : 0;                       // tensor-core alpha: up to four partials per 64-site group
+    const bool big = tc && S > 64;
+    const int tc_parts = tc ? (big ? 64 : 4 * ((C + 63) / 64)) : 0;          // tensor-core alpha: up to four partials per 64-site group; large-slot path: <= 64 K splits
     nb.nAP = nb.nSB > tc_parts ? nb.nSB : tc_parts;
     nb.RP = (S + 3) & ~3;     // >= S: tensor-core alpha partials are indexed by physical slot
     nb.P0 = R * (R - 1) / 2;
@@ -867,10 +920,11 @@ static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws,
     nb.new_slot = (int32_t*)take((size_t)B * sizeof(int32_t));
     nb.pair_i = (int32_t*)take((size_t)B * nb.pair_stride * sizeof(int32_t));
     nb.pair_j = (int32_t*)take((size_t)B * nb.pair_stride * sizeof(int32_t));
-    nb.tc = tc;
+    nb.tc = tc; nb.big = big; nb.pc = big ? BIG_PAIRS : TC_PAIRS;
     if (tc) {
-        const size_t xp = (size_t)B * TC_PAIRS * C * D * 4, np = (size_t)B * C * S * D * 2;
+        const size_t xp = (size_t)B * nb.pc * C * D * 4, np = (size_t)B * C * S * D * 2;
         nb.xf = (float*)take(xp); nb.nodes_h = take(2 * np); nb.nodes_l = take(2 * np); nb.kp_h = take(np); nb.kp_l = take(np);
+        if (big) { nb.xh = take(xp / 2); nb.xl = take(xp / 2); }
     }
     nb.total = off + 256;
     return nb;
@@ -908,12 +962,33 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
                        const uint8_t* mask, int B, float* scores, int score_stride, cudaStream_t st) {
     const bool glob = Rp > 2;     // model.py:111
     const bool tc = nb.tc && glob;
-    const int step = tc ? TC_PAIRS : PAIR_CHUNK;
+    const int step = tc ? nb.pc : PAIR_CHUNK;
     const float inv_scale = 1.0f / sqrtf((float)D * (float)C);   // model.py:118 (patch_num == C)
     for (int n0 = 0; n0 < N; n0 += step) {
         const int nc = (N - n0 < step) ? (N - n0) : step;
         int tc_parts = 0;       // score partials per pair written by the tensor-core kernel of this launch
-        if (glob && tc) {
+        if (glob && tc && nb.big) {
+            // 65 .. 256 slots: pair blend -> x planes (fp32 + bf16 hi / lo), alpha logits as a split-K tcgen05 GEMM
+            // [pairs x C*64] . [slots x C*64]^T over the K' planes (one 64-element K chunk = one site; partials per split, indexed by
+            // physical slot), softmax, then the K-blocked fused score kernel
+            if (int e = launch_blend_planes(m, pool.X, pool.Y, pool.tree_stride, C, B, slot, nb.S, nb.pair_i, nb.pair_j, nb.pair_stride, n0, nc, nb.xf,
+                                            nb.xh, nb.xl, nb.pc, st)) return e;
+            const int bn = Rp <= 64 ? 64 : (Rp <= 128 ? 128 : 256);
+            // K splits: a function of the site count only (NOT of the batch or the pair count), so that a tree's logits do not depend on
+            // what else is in the batch: >= 32 sites per split, <= 64 partials per pair
+            const int cps = (C + 63) / 64 > 32 ? (C + 63) / 64 : 32;
+            const int nsplit = (C + cps - 1) / cps;
+            if (nsplit > nb.nAP) return set_error(NNJ_ERR_INVALID, "large-slot alpha: partial buffer too small");
+            const size_t K = (size_t)C * D;
+            if (int e = launch_tc_gemm_ex(KC_ALPHA, nb.xh, nb.xl, nb.kp_h, nb.kp_l, nb.alpha_part, B, nc, Rp, (int)K, K, (size_t)nb.pc * K, K, (size_t)nb.S * K,
+                                          nb.nAP * nb.RP, (size_t)PAIR_CHUNK * nb.nAP * nb.RP, bn, nsplit, cps, (size_t)nb.RP, st)) return e;
+            prof_begin(KC_ALPHA_SOFTMAX, st);
+            k_alpha_softmax_wide<<<dim3(nc, B), NTHREADS, 0, st>>>(nb.alpha_part, pool.kap, slot, nb.S, nb.S, nb.nCT, Rp, nb.pair_i,
+                                                                   nb.pair_j, nb.pair_stride, n0, nc, nb.nAP, nb.RP, inv_scale, nb.alpha, nsplit);
+            LAUNCH_CHECK();
+            if (int e = launch_score_big(m, nb.xf, nb.pc, nb.nodes_h, nb.nodes_l, nb.alpha, nb.RP, PAIR_CHUNK, slot, nb.S, nb.pair_i, nb.pair_stride, n0, nc,
+                                         Rp, nb.S, C, B, mask, nb.score_part, nb.nSB, &tc_parts, st)) return e;
+        } else if (glob && tc) {
             // blend + alpha partials in one tcgen05 kernel (fp32 x planes written on the way, partials per 64-site group - two when the
             // tile is split by site parity - indexed by physical slot) -> softmax -> fused score kernel
             int n_part = 0;
