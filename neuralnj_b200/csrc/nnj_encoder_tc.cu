@@ -337,9 +337,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
 }
 
 // ------------------------------------------------------------------ K2: row out_proj + residual, LN2, column attention block
-// 512 threads: warp w owns TMEM lane quarter w & 3 (row = 32*(w&3) + lane) and column quarter cq = w >> 2 (16 columns = heads
-// 2cq, 2cq+1), i.e. four threads per token row.  A tile holds s = 128 / rb whole sites, each in a block of rb = 32 / 64 / 128 rows
-// (the power of two >= R), so the 32 rows of a warp belong to one site and every key / value read is a single broadcast.
+// 512 threads.  In the projection stages warp w owns TMEM lane quarter w & 3 (row = 32*(w&3) + lane) and column quarter cq = w >> 2
+// (16 columns = heads 2cq, 2cq+1), i.e. four threads per token row.  A tile holds s = 128 / rb whole sites, each in a block of
+// rb = 32 / 64 / 128 rows (the power of two >= R).  In the attention stage a warp owns one (site, head) UNIT and a lane RPL = rb / 32
+// query rows of it (lane, lane + 32, ...): every K / V row of the unit is fetched once per warp (a broadcast LDS.128) and serves all
+// RPL rows of every lane.  Round 1 mapped (row, two heads) to a thread: 8 LDS.128 per key and THREAD, and the kernel sat on the
+// shared-memory pipe (l1tex 73 %, 15 k of the 27 k clocks of a tile in this loop); q goes through shared memory now as well.
 struct ColBlkArgs {
     float* x; size_t x_tree_stride;             // site-major, updated in place
     int R, C, B, rb_shift, groups_per_tree;     // rb = 1 << rb_shift rows per site block, s = 128 >> rb_shift sites per tile
@@ -350,10 +353,9 @@ struct ColBlkArgs {
 };
 
 constexpr int K2_THREADS = 512;
-constexpr int CB_CH = 5;                       // keys per online-softmax chunk of the column attention
 constexpr int K2_W = 81920;
-constexpr int CB_LDK = 68;                     // fp32 row pitch of the K / V tiles: lanes = consecutive rows store 16 B each without bank conflicts
-constexpr int K2_SMEM = 1024 + K2_W + 32768 + 2 * 128 * CB_LDK * 4 + (64 + 192 + 64 + 128) * 4 + 4096 + 64;
+constexpr int CB_LDK = 68;                     // fp32 row pitch of the q / K / V tiles: lanes = consecutive rows move 16 B each without bank conflicts
+constexpr int K2_SMEM = 1024 + K2_W + 32768 + 3 * 128 * CB_LDK * 4 + (64 + 192 + 64 + 128) * 4 + 4096 + 64;
 
 __device__ __forceinline__ float dot8(const float2 (&q)[4], float4 k0, float4 k1) {
     float2 acc = fmul2(q[0], make_float2(k0.x, k0.y));
@@ -397,6 +399,174 @@ __device__ __forceinline__ void a_store16(uint8_t* a_hi, uint8_t* a_lo, int row,
     a_store8(a_hi, a_lo, row, cq * 2 + 1, &v[8]);
 }
 
+#ifdef NNJ_COL_TRACE
+// stage timeline of CTA 0 (thread 0), first 32 work items: debug builds only (scratch/col_trace.py)
+__device__ long long g_col_trace[32 * 16];
+#define COL_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && trace_it < 32) g_col_trace[trace_it * 16 + (i)] = clock64(); } while (0)
+#else
+#define COL_STAMP(i) do { } while (0)
+#endif
+
+// Attention of RPL query rows (one head) over the R keys of their site: chunked online softmax (logits carry log2 e, probabilities
+// are exp2; the running maximum moves - and the accumulators are rescaled - once per CH keys, not per key).
+template <int RPL, int CH>
+__device__ __forceinline__ void col_attend(const float* __restrict__ qb, const float* __restrict__ kb, const float* __restrict__ vb, int R, int lane,
+                                           float (&o)[RPL][8]) {
+    float2 q[RPL][4], acc[RPL][4];
+    float m[RPL], l[RPL];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+        const float4 q0 = ld4(qb + (lane + 32 * k) * CB_LDK), q1 = ld4(qb + (lane + 32 * k) * CB_LDK + 4);
+        q[k][0] = make_float2(q0.x, q0.y); q[k][1] = make_float2(q0.z, q0.w); q[k][2] = make_float2(q1.x, q1.y); q[k][3] = make_float2(q1.z, q1.w);
+        m[k] = -INFINITY; l[k] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[k][e] = make_float2(0.f, 0.f);
+    }
+    int j0 = 0;
+    for (; j0 + CH <= R; j0 += CH) {
+        float s[RPL][CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const float4 k0 = ld4(kb + (j0 + u) * CB_LDK), k1 = ld4(kb + (j0 + u) * CB_LDK + 4);
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) s[k][u] = dot8(q[k], k0, k1);
+        }
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            float n = m[k];
+#pragma unroll
+            for (int u = 0; u < CH; ++u) n = fmaxf(n, s[k][u]);
+            const float f = ex2_approx(m[k] - n);          // 0 on the first chunk (m = -inf), 1 when the maximum stays
+            l[k] *= f; m[k] = n;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[k][e] = fmul2(acc[k][e], splat2(f));
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const float4 v0 = ld4(vb + (j0 + u) * CB_LDK), v1 = ld4(vb + (j0 + u) * CB_LDK + 4);
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                const float p = ex2_approx(s[k][u] - m[k]);
+                l[k] += p;
+                acc[k][0] = ffma2(splat2(p), make_float2(v0.x, v0.y), acc[k][0]); acc[k][1] = ffma2(splat2(p), make_float2(v0.z, v0.w), acc[k][1]);
+                acc[k][2] = ffma2(splat2(p), make_float2(v1.x, v1.y), acc[k][2]); acc[k][3] = ffma2(splat2(p), make_float2(v1.z, v1.w), acc[k][3]);
+            }
+        }
+    }
+#pragma unroll 1
+    for (; j0 < R; ++j0) {                                   // the R % CH last keys, one at a time
+        const float4 k0 = ld4(kb + j0 * CB_LDK), k1 = ld4(kb + j0 * CB_LDK + 4);
+        const float4 v0 = ld4(vb + j0 * CB_LDK), v1 = ld4(vb + j0 * CB_LDK + 4);
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            const float s = dot8(q[k], k0, k1);
+            const float n = fmaxf(m[k], s);
+            const float f = ex2_approx(m[k] - n), p = ex2_approx(s - n);
+            m[k] = n;
+            l[k] = fmaf(l[k], f, p);
+            acc[k][0] = ffma2(splat2(p), make_float2(v0.x, v0.y), fmul2(acc[k][0], splat2(f))); acc[k][1] = ffma2(splat2(p), make_float2(v0.z, v0.w), fmul2(acc[k][1], splat2(f)));
+            acc[k][2] = ffma2(splat2(p), make_float2(v1.x, v1.y), fmul2(acc[k][2], splat2(f))); acc[k][3] = ffma2(splat2(p), make_float2(v1.z, v1.w), fmul2(acc[k][3], splat2(f)));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+        const float inv = 1.0f / l[k];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { o[k][2 * e] = acc[k][e].x * inv; o[k][2 * e + 1] = acc[k][e].y * inv; }
+    }
+}
+
+// ---- tensor-path attention (R <= 64).  q | k | v of the tile sit in shared memory as bf16 hi / lo planes [128 rows][64] (128 B per row,
+// the 16-byte chunk of head h stored at h ^ (row & 7): the A-operand swizzle, conflict-free for the fragment loads below).
+constexpr int K2_PLANE = 128 * 128;
+// D[16 x 8] += A[16 x 16] . B[16 x 8] on register fragments (bf16 operands, fp32 accumulate).  Lane (g = lane >> 2, t = lane & 3):
+// a0 = A[g][2t, 2t+1], a1 = A[g+8][2t, 2t+1], a2 = A[g][8+2t, 9+2t], a3 = A[g+8][8+2t, 9+2t]; b0 = B[2t, 2t+1][g], b1 = B[8+2t, 9+2t][g];
+// d0 d1 = D[g][2t, 2t+1], d2 d3 = D[g+8][2t, 2t+1].  Measured on B200 (scratch/hmma_bench.cu): one m16n8k16 and one m16n8k8 both hold a
+// sub-partition's legacy tensor pipe for 8 clocks (20 clocks latency), so the K = 16 form is used throughout.
+__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// four 8 x 8 b16 matrices (rows of 16 B, lane l supplies the address of row l & 7 of matrix l >> 3), transposed on the way in:
+// lane (g, t) receives M[2t, 2t+1][g] of every matrix = a B fragment half for a row-major [k][n] operand
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// One (site, head, 16-query-row block): S = Q K^T [16 x 8 NT], softmax over the R keys in registers (the C fragments of two key blocks
+// ARE the A fragment of the next m16n8k16), O = P V, normalised and written as bf16 hi / lo into the A operand of the column
+// out-projection.  The 3-product bf16 split costs two instructions per 8 keys in Q K^T - the head dimension is 8, so the K = 16 of one
+// instruction holds [q_hi | q_lo] . [k_hi | k_hi], a second one [q_hi | 0] . [k_lo | 0] - and three per 16 keys in P V.
+// NT = ceil(R / 8) key blocks is a template constant: no predication inside.
+template <int NT>
+__device__ __forceinline__ void col_attend_mma(const uint8_t* __restrict__ pl, uint8_t* __restrict__ a_hi, uint8_t* __restrict__ a_lo, int row_base, int mt, int h, int R,
+                                               int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = row_base + mt * 16 + g;                                  // rows r0 and r0 + 8; row & 7 = g for both
+    const uint32_t sw = (uint32_t)(((h ^ g) << 4) + t * 4);
+    const uint8_t* qp = pl + r0 * 128 + sw;
+    const uint32_t qh0 = *reinterpret_cast<const uint32_t*>(qp), qh1 = *reinterpret_cast<const uint32_t*>(qp + 1024);
+    const uint32_t ql0 = *reinterpret_cast<const uint32_t*>(qp + K2_PLANE), ql1 = *reinterpret_cast<const uint32_t*>(qp + K2_PLANE + 1024);
+    const uint8_t* kp = pl + 2 * K2_PLANE + (row_base + g) * 128 + sw;      // key rows 8 n + g
+    float sc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const uint32_t kh = *reinterpret_cast<const uint32_t*>(kp + n * 1024), kl = *reinterpret_cast<const uint32_t*>(kp + K2_PLANE + n * 1024);
+        sc[n][0] = 0.f; sc[n][1] = 0.f; sc[n][2] = 0.f; sc[n][3] = 0.f;
+        mma_m16n8k16(sc[n], qh0, qh1, 0u, 0u, kl, 0u);        // q_hi . k_lo (small term first)
+        mma_m16n8k16(sc[n], qh0, qh1, ql0, ql1, kh, kh);      // q_hi . k_hi + q_lo . k_hi
+    }
+    {   // keys >= R do not exist (only the last key block can hold them)
+        const int j = (NT - 1) * 8 + 2 * t;
+        if (j >= R) { sc[NT - 1][0] = -INFINITY; sc[NT - 1][2] = -INFINITY; }
+        if (j + 1 >= R) { sc[NT - 1][1] = -INFINITY; sc[NT - 1][3] = -INFINITY; }
+    }
+    float m_a = fmaxf(sc[0][0], sc[0][1]), m_b = fmaxf(sc[0][2], sc[0][3]);
+#pragma unroll
+    for (int n = 1; n < NT; ++n) { m_a = fmaxf(m_a, fmaxf(sc[n][0], sc[n][1])); m_b = fmaxf(m_b, fmaxf(sc[n][2], sc[n][3])); }
+    m_a = fmaxf(m_a, __shfl_xor_sync(0xffffffffu, m_a, 1)); m_a = fmaxf(m_a, __shfl_xor_sync(0xffffffffu, m_a, 2));
+    m_b = fmaxf(m_b, __shfl_xor_sync(0xffffffffu, m_b, 1)); m_b = fmaxf(m_b, __shfl_xor_sync(0xffffffffu, m_b, 2));
+    float2 l_a = make_float2(0.f, 0.f), l_b = make_float2(0.f, 0.f);
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};      // two accumulators: alternate 16-key steps
+    // lane l supplies row l & 7 of matrix l >> 3: matrices 0, 1 = v_hi of two consecutive key blocks, 2, 3 = v_lo of the same
+    const uint32_t vaddr = smem_u32(pl) + (uint32_t)((4 + ((lane >> 4) & 1)) * K2_PLANE + (row_base + ((lane >> 3) & 1) * 8 + (lane & 7)) * 128 + ((h ^ (lane & 7)) << 4));
+#pragma unroll
+    for (int n2 = 0; n2 < (NT + 1) / 2; ++n2) {
+        uint32_t vf[4];      // v_hi(2 n2), v_hi(2 n2 + 1), v_lo(2 n2), v_lo(2 n2 + 1)
+        ldsm_x4_t(vf, vaddr + n2 * 2048);
+        uint32_t ph[4], pw[4];                                  // P hi / lo as the A fragment: [row g | row g+8] of block 2 n2, then of block 2 n2 + 1
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int n = 2 * n2 + e;
+            if (n < NT) {
+                const float2 da = fsub2(make_float2(sc[n][0], sc[n][1]), splat2(m_a)), db = fsub2(make_float2(sc[n][2], sc[n][3]), splat2(m_b));
+                const float2 pa = make_float2(ex2_approx(da.x), ex2_approx(da.y)), pb = make_float2(ex2_approx(db.x), ex2_approx(db.y));
+                l_a = fadd2(l_a, pa); l_b = fadd2(l_b, pb);
+                split2(pa.x, pa.y, ph[2 * e], pw[2 * e]);
+                split2(pb.x, pb.y, ph[2 * e + 1], pw[2 * e + 1]);
+            } else {                                            // NT odd: the second block of the last step does not exist
+                ph[2 * e] = 0u; ph[2 * e + 1] = 0u; pw[2 * e] = 0u; pw[2 * e + 1] = 0u;
+            }
+        }
+        float (&o)[4] = (n2 & 1) ? o1 : o0;
+        mma_m16n8k16(o, pw[0], pw[1], pw[2], pw[3], vf[0], vf[1]);      // P_lo . V_hi
+        mma_m16n8k16(o, ph[0], ph[1], ph[2], ph[3], vf[2], vf[3]);      // P_hi . V_lo
+        mma_m16n8k16(o, ph[0], ph[1], ph[2], ph[3], vf[0], vf[1]);      // P_hi . V_hi
+    }
+    float s_a = l_a.x + l_a.y, s_b = l_b.x + l_b.y;
+    s_a += __shfl_xor_sync(0xffffffffu, s_a, 1); s_a += __shfl_xor_sync(0xffffffffu, s_a, 2);
+    s_b += __shfl_xor_sync(0xffffffffu, s_b, 1); s_b += __shfl_xor_sync(0xffffffffu, s_b, 2);
+    const float i_a = 1.0f / s_a, i_b = 1.0f / s_b;
+    uint32_t oh, ol;
+    split2((o0[0] + o1[0]) * i_a, (o0[1] + o1[1]) * i_a, oh, ol);
+    *reinterpret_cast<uint32_t*>(a_hi + r0 * 128 + sw) = oh;
+    *reinterpret_cast<uint32_t*>(a_lo + r0 * 128 + sw) = ol;
+    split2((o0[2] + o1[2]) * i_b, (o0[3] + o1[3]) * i_b, oh, ol);
+    *reinterpret_cast<uint32_t*>(a_hi + (r0 + 8) * 128 + sw) = oh;
+    *reinterpret_cast<uint32_t*>(a_lo + (r0 + 8) * 128 + sw) = ol;
+}
+
+// NT = 0: CUDA-core attention (col_attend, 64 < R <= 128); NT > 0: tensor-path attention with NT = ceil(R / 8) key blocks (R <= 64)
+template <int RPL, int NT>
 __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_align1024(smem_raw);
@@ -405,7 +575,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
     uint8_t* w_co = sm + 65536;                // column out_proj
     uint8_t* a_hi = sm + K2_W;
     uint8_t* a_lo = a_hi + 16384;
-    float* ks = reinterpret_cast<float*>(a_lo + 16384);   // [128][CB_LDK]
+    float* qsm = reinterpret_cast<float*>(a_lo + 16384);   // NT = 0: [128][CB_LDK] fp32 q (scaled), then K, then V
+    uint8_t* pl = a_lo + 16384;                            // NT > 0: planes q_hi | q_lo | k_hi | k_lo | v_hi | v_lo (same region)
+    float* ks = qsm + 128 * CB_LDK;
     float* vs = ks + 128 * CB_LDK;
     float* s_rob = vs + 128 * CB_LDK;
     float* s_qkvb = s_rob + 64;
@@ -432,35 +604,57 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t id64 = umma_idesc_bf16(128, 64), id192 = umma_idesc_bf16(128, 192);
     const int R = a.R, KD = a.R * DH;
-    const int rb = 1 << a.rb_shift, s_tile = 128 >> a.rb_shift;
-    const int si = row >> a.rb_shift, r = row & (rb - 1);
+    constexpr int rb_shift = RPL == 1 ? 5 : (RPL == 2 ? 6 : 7);
+    constexpr int rb = 1 << rb_shift, s_tile = 128 >> rb_shift;
+    const int si = row >> rb_shift, r = row & (rb - 1);
     const int n_work = a.B * a.groups_per_tree;
+    // this thread's piece of work item w: 16 values of the row-attention context (heads 2cq, 2cq+1), 16 of x, the padded-site flag.
+    // Item w + grid is fetched while the tensor core runs stage 4 of item w, so the DRAM latency is off the serial chain.
+    auto load_tile = [&](int w, float (&vv)[16], float (&xx)[16], float& qsc) {
+        const int b = w / a.groups_per_tree, grp = w - b * a.groups_per_tree;
+        const int c = grp * s_tile + si;
+        const bool valid = w < n_work && r < R && c < a.C;
+        // all keys of a padded site get the same logit (-10000, axial_attention.py:220-224): softmax is uniform, i.e. q = 0
+        qsc = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale_log2e;
+        if (valid) {
+            const float* xq = a.x + (size_t)b * a.x_tree_stride + ((size_t)c * R + r) * D + cq * 16;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const float* cp = a.ctx + (((size_t)b * H + cq * 2 + hh) * a.C + c) * KD + (size_t)r * DH;
+                const float4 f0 = ld4(cp), f1 = ld4(cp + 4);
+                vv[hh * 8] = f0.x; vv[hh * 8 + 1] = f0.y; vv[hh * 8 + 2] = f0.z; vv[hh * 8 + 3] = f0.w;
+                vv[hh * 8 + 4] = f1.x; vv[hh * 8 + 5] = f1.y; vv[hh * 8 + 6] = f1.z; vv[hh * 8 + 7] = f1.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float4 f = ld4(xq + k * 4); xx[4 * k] = f.x; xx[4 * k + 1] = f.y; xx[4 * k + 2] = f.z; xx[4 * k + 3] = f.w; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { vv[k] = 0.f; xx[k] = 0.f; }
+        }
+    };
+    float xn[16], vn[16], qsn = 0.f;
+    load_tile(blockIdx.x, vn, xn, qsn);
     uint32_t ph = 0;   // completions of `bar` so far
+#ifdef NNJ_COL_TRACE
+    int trace_it = -1;
+#endif
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+#ifdef NNJ_COL_TRACE
+        ++trace_it;
+#endif
+        COL_STAMP(0);
         const int b = w / a.groups_per_tree, grp = w - b * a.groups_per_tree;
         const int c = grp * s_tile + si;
         const bool valid = r < R && c < a.C;
         float* xp = a.x + (size_t)b * a.x_tree_stride + ((size_t)c * R + r) * D + cq * 16;
         float xr[16], v[16];
-        // all keys of a padded site get the same logit (-10000, axial_attention.py:220-224): softmax is uniform, i.e. q = 0
-        const float qs = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale_log2e;   // loaded with the tile, used in stage 2
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { xr[k] = xn[k]; v[k] = vn[k]; }
+        const float qs = qsn;
         // ---- stage 1: x += ctx_row . W_o^T + b_o
-        if (valid) {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const float* cp = a.ctx + (((size_t)b * H + cq * 2 + hh) * a.C + c) * KD + (size_t)r * DH;
-                const float4 f0 = ld4(cp), f1 = ld4(cp + 4);
-                v[hh * 8] = f0.x; v[hh * 8 + 1] = f0.y; v[hh * 8 + 2] = f0.z; v[hh * 8 + 3] = f0.w;
-                v[hh * 8 + 4] = f1.x; v[hh * 8 + 5] = f1.y; v[hh * 8 + 6] = f1.z; v[hh * 8 + 7] = f1.w;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { const float4 f = ld4(xp + k * 4); xr[4 * k] = f.x; xr[4 * k + 1] = f.y; xr[4 * k + 2] = f.z; xr[4 * k + 3] = f.w; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) { v[k] = 0.f; xr[k] = 0.f; }
-        }
         a_store16(a_hi, a_lo, row, cq, v);
         ET_PUBLISH_A();
+        COL_STAMP(1);
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
@@ -471,6 +665,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         }
         mbar_wait(bar, ph & 1); ++ph;
         tc_fence_after();
+        COL_STAMP(2);
         {
             uint32_t acc[16];
             tmem_ld16_nw(t_o + lane_off + cq * 16, acc);
@@ -485,6 +680,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         ln_quarter(v, part, row, cq, s_g, s_b);
         a_store16(a_hi, a_lo, row, cq, v);
         ET_PUBLISH_A();
+        COL_STAMP(3);
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
@@ -495,101 +691,56 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         }
         mbar_wait(bar, ph & 1); ++ph;
         tc_fence_after();
-        float2 q0[4], q1[4];   // heads 2cq, 2cq+1 (scaled by dh^-0.5 log2 e)
-        {
-            uint32_t aq[16], ak[16], av[16];
-            tmem_ld16_nw(t_qkv + lane_off + cq * 16, aq);
-            tmem_ld16_nw(t_qkv + lane_off + 64 + cq * 16, ak);
-            tmem_ld16_nw(t_qkv + lane_off + 128 + cq * 16, av);
-            tmem_ld_wait();
+        COL_STAMP(4);
+        {   // q (scaled by dh^-0.5 log2 e, 0 on a padded site) | k | v + bias -> fp32 tiles (NT = 0) or bf16 hi / lo planes (NT > 0)
+            uint32_t acc[16];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                q0[k] = make_float2((__uint_as_float(aq[2 * k]) + s_qkvb[cq * 16 + 2 * k]) * qs, (__uint_as_float(aq[2 * k + 1]) + s_qkvb[cq * 16 + 2 * k + 1]) * qs);
-                q1[k] = make_float2((__uint_as_float(aq[8 + 2 * k]) + s_qkvb[cq * 16 + 8 + 2 * k]) * qs, (__uint_as_float(aq[8 + 2 * k + 1]) + s_qkvb[cq * 16 + 8 + 2 * k + 1]) * qs);
-            }
+            for (int p = 0; p < 3; ++p) {
+                tmem_ld16_nw(t_qkv + lane_off + p * 64 + cq * 16, acc);
+                tmem_ld_wait();
+                const float sc = p == 0 ? qs : 1.0f;
+                if constexpr (NT > 0) {
+                    float f[16];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                st4(ks + row * CB_LDK + cq * 16 + k * 4, make_float4(__uint_as_float(ak[4 * k]) + s_qkvb[64 + cq * 16 + 4 * k], __uint_as_float(ak[4 * k + 1]) + s_qkvb[64 + cq * 16 + 4 * k + 1],
-                                                                 __uint_as_float(ak[4 * k + 2]) + s_qkvb[64 + cq * 16 + 4 * k + 2], __uint_as_float(ak[4 * k + 3]) + s_qkvb[64 + cq * 16 + 4 * k + 3]));
-                st4(vs + row * CB_LDK + cq * 16 + k * 4, make_float4(__uint_as_float(av[4 * k]) + s_qkvb[128 + cq * 16 + 4 * k], __uint_as_float(av[4 * k + 1]) + s_qkvb[128 + cq * 16 + 4 * k + 1],
-                                                                 __uint_as_float(av[4 * k + 2]) + s_qkvb[128 + cq * 16 + 4 * k + 2], __uint_as_float(av[4 * k + 3]) + s_qkvb[128 + cq * 16 + 4 * k + 3]));
+                    for (int k = 0; k < 16; ++k) f[k] = (__uint_as_float(acc[k]) + s_qkvb[p * 64 + cq * 16 + k]) * sc;
+                    a_store8(pl + (2 * p) * K2_PLANE, pl + (2 * p + 1) * K2_PLANE, row, cq * 2, &f[0]);
+                    a_store8(pl + (2 * p) * K2_PLANE, pl + (2 * p + 1) * K2_PLANE, row, cq * 2 + 1, &f[8]);
+                } else {
+                    float* dst = qsm + p * 128 * CB_LDK + row * CB_LDK + cq * 16;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        st4(dst + k * 4, make_float4((__uint_as_float(acc[4 * k]) + s_qkvb[p * 64 + cq * 16 + 4 * k]) * sc, (__uint_as_float(acc[4 * k + 1]) + s_qkvb[p * 64 + cq * 16 + 4 * k + 1]) * sc,
+                                                     (__uint_as_float(acc[4 * k + 2]) + s_qkvb[p * 64 + cq * 16 + 4 * k + 2]) * sc, (__uint_as_float(acc[4 * k + 3]) + s_qkvb[p * 64 + cq * 16 + 4 * k + 3]) * sc));
+                }
             }
         }
         tc_fence_before();
         __syncthreads();
-        // ---- stage 3: attention of token (site si, taxon r) over the R taxa of its site; chunked online softmax
-        //      (logits carry log2 e, probabilities are exp2)
-        if (valid) {
-            const float* kb = ks + (si << a.rb_shift) * CB_LDK + cq * 16;
-            const float* vb = vs + (si << a.rb_shift) * CB_LDK + cq * 16;
-            // keys in chunks of CB_CH: the running maximum moves (and the accumulators are rescaled) once per chunk, not per key
-            float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-            float2 o0[4], o1[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { o0[k] = make_float2(0.f, 0.f); o1[k] = make_float2(0.f, 0.f); }
-            int j0 = 0;
-            for (; j0 + CB_CH <= R; j0 += CB_CH) {
-                const float* kc = kb + j0 * CB_LDK;
-                const float* vc = vb + j0 * CB_LDK;
-                float s0[CB_CH], s1[CB_CH];
-#pragma unroll
-                for (int u = 0; u < CB_CH; ++u) {
-                    s0[u] = dot8(q0, ld4(kc + u * CB_LDK), ld4(kc + u * CB_LDK + 4));
-                    s1[u] = dot8(q1, ld4(kc + u * CB_LDK + 8), ld4(kc + u * CB_LDK + 12));
-                }
-                float n0 = m0, n1 = m1;
-#pragma unroll
-                for (int u = 0; u < CB_CH; ++u) { n0 = fmaxf(n0, s0[u]); n1 = fmaxf(n1, s1[u]); }
-                {
-                    const float f0 = ex2_approx(m0 - n0), f1 = ex2_approx(m1 - n1);   // 0 on the first chunk (m = -inf), 1 when the maximum stays
-                    const float2 ff0 = make_float2(f0, f0), ff1 = make_float2(f1, f1);
-                    l0 *= f0; l1 *= f1; m0 = n0; m1 = n1;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { o0[k] = fmul2(o0[k], ff0); o1[k] = fmul2(o1[k], ff1); }
-                }
-#pragma unroll
-                for (int u = 0; u < CB_CH; ++u) {
-                    const float* vj = vc + u * CB_LDK;
-                    const float4 v0 = ld4(vj), v1 = ld4(vj + 4), v2 = ld4(vj + 8), v3 = ld4(vj + 12);
-                    const float p0 = ex2_approx(s0[u] - m0), p1 = ex2_approx(s1[u] - m1);
-                    const float2 pp0 = make_float2(p0, p0), pp1 = make_float2(p1, p1);
-                    l0 += p0; l1 += p1;
-                    o0[0] = ffma2(pp0, make_float2(v0.x, v0.y), o0[0]); o0[1] = ffma2(pp0, make_float2(v0.z, v0.w), o0[1]);
-                    o0[2] = ffma2(pp0, make_float2(v1.x, v1.y), o0[2]); o0[3] = ffma2(pp0, make_float2(v1.z, v1.w), o0[3]);
-                    o1[0] = ffma2(pp1, make_float2(v2.x, v2.y), o1[0]); o1[1] = ffma2(pp1, make_float2(v2.z, v2.w), o1[1]);
-                    o1[2] = ffma2(pp1, make_float2(v3.x, v3.y), o1[2]); o1[3] = ffma2(pp1, make_float2(v3.z, v3.w), o1[3]);
-                }
-            }
-#pragma unroll 1
-            for (; j0 < R; ++j0) {                               // the R % CB_CH last keys, one at a time
-                const float* kj = kb + j0 * CB_LDK;
-                const float* vj = vb + j0 * CB_LDK;
-                const float s0 = dot8(q0, ld4(kj), ld4(kj + 4)), s1 = dot8(q1, ld4(kj + 8), ld4(kj + 12));
-                const float4 v0 = ld4(vj), v1 = ld4(vj + 4), v2 = ld4(vj + 8), v3 = ld4(vj + 12);
-                const float n0 = fmaxf(m0, s0), n1 = fmaxf(m1, s1);
-                const float f0 = ex2_approx(m0 - n0), f1 = ex2_approx(m1 - n1);
-                const float p0 = ex2_approx(s0 - n0), p1 = ex2_approx(s1 - n1);
-                const float2 ff0 = make_float2(f0, f0), ff1 = make_float2(f1, f1), pp0 = make_float2(p0, p0), pp1 = make_float2(p1, p1);
-                m0 = n0; m1 = n1;
-                l0 = fmaf(l0, f0, p0); l1 = fmaf(l1, f1, p1);
-                o0[0] = ffma2(pp0, make_float2(v0.x, v0.y), fmul2(o0[0], ff0)); o0[1] = ffma2(pp0, make_float2(v0.z, v0.w), fmul2(o0[1], ff0));
-                o0[2] = ffma2(pp0, make_float2(v1.x, v1.y), fmul2(o0[2], ff0)); o0[3] = ffma2(pp0, make_float2(v1.z, v1.w), fmul2(o0[3], ff0));
-                o1[0] = ffma2(pp1, make_float2(v2.x, v2.y), fmul2(o1[0], ff1)); o1[1] = ffma2(pp1, make_float2(v2.z, v2.w), fmul2(o1[1], ff1));
-                o1[2] = ffma2(pp1, make_float2(v3.x, v3.y), fmul2(o1[2], ff1)); o1[3] = ffma2(pp1, make_float2(v3.z, v3.w), fmul2(o1[3], ff1));
-            }
-            const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                v[2 * k] = o0[k].x * i0; v[2 * k + 1] = o0[k].y * i0;
-                v[8 + 2 * k] = o1[k].x * i1; v[8 + 2 * k + 1] = o1[k].y * i1;
+        COL_STAMP(5);
+        // ---- stage 3.  Rows >= R of a site block hold finite padding (LN of zeros); their results are never stored.
+        if constexpr (NT > 0) {
+            // warp = (site, head, 16-row block) items
+            constexpr int MT = (NT + 1) / 2;
+            for (int item = warp; item < s_tile * H * MT; item += K2_THREADS / 32) {
+                const int mt = item % MT, uh = item / MT;
+                col_attend_mma<NT>(pl, a_hi, a_lo, (uh >> 3) << rb_shift, mt, uh & 7, R, lane);
             }
         } else {
+            // warp = (site, head) unit, lane = RPL query rows
+            for (int unit = warp; unit < s_tile * H; unit += K2_THREADS / 32) {
+                const int s_i = unit >> 3, h = unit & 7;
+                const int base = (s_i << rb_shift) * CB_LDK + h * 8;
+                float o[RPL][8];
+                col_attend<RPL, RPL == 4 ? 2 : 5>(qsm + base, ks + base, vs + base, R, lane, o);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = 0.f;
+                for (int k = 0; k < RPL; ++k) a_store8(a_hi, a_lo, (s_i << rb_shift) + lane + 32 * k, h, o[k]);
+            }
         }
+        COL_STAMP(6);
+        load_tile(w + gridDim.x, vn, xn, qsn);      // next work item's rows: in flight during stage 4
         // ---- stage 4: x += ctx_col . W_o^T + b_o
-        a_store16(a_hi, a_lo, row, cq, v);
         ET_PUBLISH_A();
+        COL_STAMP(7);
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
@@ -600,6 +751,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         }
         mbar_wait(bar, ph & 1); ++ph;
         tc_fence_after();
+        COL_STAMP(8);
         {
             uint32_t acc[16];
             tmem_ld16_nw(t_o + lane_off + cq * 16, acc);
@@ -614,10 +766,14 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
             }
         }
         tc_fence_before();
+        COL_STAMP(9);
     }
     __syncthreads();
     if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
+#ifdef NNJ_COL_TRACE
+extern "C" int nnj_col_trace_read(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_col_trace, sizeof(long long) * 32 * 16); }
+#endif
 
 // ------------------------------------------------------------------ site-major -> node-major (the NJ pool / public layout [B,R,C,64])
 __global__ void __launch_bounds__(256) k_sm_to_nm(const float* __restrict__ xs, size_t xs_tree_stride, float* __restrict__ out, size_t out_tree_stride,
@@ -639,7 +795,15 @@ static int enc_tc_attrs() {
     static DevOnce once;      // per device, not per process
     if (!once.need()) return 0;
     cudaError_t e = cudaFuncSetAttribute(k_enc_rowqkv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc<2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc<2, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_colblock_tc<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_enc_ffn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM);
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     once.done();
@@ -687,7 +851,17 @@ int launch_enc_colblock_tc(const Model* m, int layer, float* xs, size_t xs_tree_
     const int work = B * a.groups_per_tree;
     const int grid = work < sm_count() ? work : sm_count();
     prof_begin(KC_COL_ATTN, st);
-    k_enc_colblock_tc<<<grid, K2_THREADS, K2_SMEM, st>>>(a);
+    switch (R <= 64 ? (R + 7) / 8 : 0) {     // key blocks of the tensor-path attention (R <= 64); CUDA-core attention above
+        case 1: k_enc_colblock_tc<1, 1><<<grid, K2_THREADS, K2_SMEM, st>>>(a); break;
+        case 2: k_enc_colblock_tc<1, 2><<<grid, K2_THREADS, K2_SMEM, st>>>(a); break;
+        case 3: k_enc_colblock_tc<1, 3><<<grid, K2_THREADS, K2_SMEM, st>>>(a); break;
+        case 4: k_enc_colblock_tc<1, 4><<<grid, K2_THREADS, K2_SMEM, st>>>(a); break;
+        case 5: k_enc_colblock_tc<2, 5><<<grid, K2_THREADS, K2_SMEM, st>>>(a); break;
+        case 6: k_enc_colblock_tc<2, 6><<<grid, K2_THREADS, K2_SMEM, st>>>(a); break;
+        case 7: k_enc_colblock_tc<2, 7><<<grid, K2_THREADS, K2_SMEM, st>>>(a); break;
+        case 8: k_enc_colblock_tc<2, 8><<<grid, K2_THREADS, K2_SMEM, st>>>(a); break;
+        default: k_enc_colblock_tc<4, 0><<<grid, K2_THREADS, K2_SMEM, st>>>(a); break;
+    }
     ETC_DONE();
     return 0;
 }

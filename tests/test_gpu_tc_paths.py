@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 # taxa -> step-0 pairs: 12 -> 66 (one full tile), 17 -> 136 (128 + 8: second score tile duplicated), 24 -> 276 (second
 # alpha launch of 20 pairs: parity split at step 0), 33 -> 528 (two launches + 16), 63 -> 1953 (largest tensor-core size)
-@pytest.mark.parametrize("R,L", [(12, 128), (17, 192), (24, 128), (33, 64), (63, 72)])
+@pytest.mark.parametrize("R,L", [(12, 128), (17, 192), (24, 128), (33, 64), (63, 72), (64, 64), (49, 136)])
 def test_tile_shapes_match_oracle(R, L, sd0, gpu_models):
     import nnj_oracle as O
     data = O.evolved_msa(2, R, L, seed=100 + R)
@@ -155,5 +155,21 @@ def test_lane_quarter_modes_agree_with_the_two_way_split(tmp_path):
         path = str(tmp_path / f"{tag}.pt")
         subprocess.run([sys.executable, "-c", _TOGGLE_SCRIPT, root, path], check=True, env={**os.environ, **env}, timeout=300)
         outs.append(torch.load(path))
-    assert torch.equal(outs[0]["merges"], outs[1]["merges"])
-    assert _rel(outs[0]["trace"], outs[1]["trace"]) < LOGIT_TOL
+    # Same merges - or, where the two groupings of the partial sums break a numerical tie differently, both choices within the logit
+    # tolerance of each other in BOTH runs (the trajectories part there, so only the steps up to that one are compared).
+    m0, m1, t0, t1 = outs[0]["merges"].long(), outs[1]["merges"].long(), outs[0]["trace"], outs[1]["trace"]
+    R = m0.shape[1] + 1
+    for b in range(m0.shape[0]):
+        diff = (m0[b] != m1[b]).any(dim=1).nonzero()
+        t_end = int(diff[0]) if len(diff) else R - 1
+        off = 0
+        for t in range(min(t_end + 1, R - 1)):
+            n = R - t
+            P = n * (n - 1) // 2
+            a0, a1 = t0[b, off:off + P], t1[b, off:off + P]
+            scale = float(a0.abs().max())
+            assert float((a0 - a1).abs().max()) / scale < LOGIT_TOL
+            if t == t_end:
+                idx = [i * n - i * (i + 1) // 2 + (j - i - 1) for i, j in (m0[b, t].tolist(), m1[b, t].tolist())]
+                assert abs(float(a0[idx[0]] - a0[idx[1]])) / scale < LOGIT_TOL and abs(float(a1[idx[0]] - a1[idx[1]])) / scale < LOGIT_TOL
+            off += P
