@@ -27,8 +27,11 @@ __device__ __forceinline__ void tok_rc(int t, int R, int C, int& r, int& c) {
     if (CMAJOR) { c = t / R; r = t - c * R; } else { r = t / C; c = t - r * C; }
 }
 
-// element offset of token (taxon r, site c) in the residual stream: node-major [R][C][64] or site-major [C][R][64] (xsm)
-__device__ __forceinline__ size_t x_off(int r, int c, int R, int C, int xsm) { return (xsm ? (size_t)c * R + r : (size_t)r * C + c) * D; }
+// element offset of the 16-byte column chunk c4 of token (taxon r, site c) in the residual stream: node-major [R][C][64], or (xsm)
+// the site-major tile-planar stream of the tensor-core encoder (xs_off in nnj_internal.h)
+__device__ __forceinline__ size_t x_off(int r, int c, int R, int C, int xsm, int c4) {
+    return xsm ? xs_off((size_t)c * R + r, c4) : ((size_t)r * C + c) * D + c4 * 4;
+}
 
 template <bool CMAJOR>
 __device__ __forceinline__ void load_x_tile(float* __restrict__ xs, const float* __restrict__ xb, int tile, int R, int C, int xsm = 0) {
@@ -36,13 +39,13 @@ __device__ __forceinline__ void load_x_tile(float* __restrict__ xs, const float*
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         int idx = it * NTHREADS + threadIdx.x;
-        int row = idx >> 4, c4 = idx & 15;
+        int row = xsm ? (idx & 127) : (idx >> 4), c4 = xsm ? (idx >> 7) : (idx & 15);   // lanes follow the contiguous direction of the stream
         int t = tile * TILE_ROWS + row;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t < T) {
             int r, c;
             tok_rc<CMAJOR>(t, R, C, r, c);
-            v = ld4(xb + x_off(r, c, R, C, xsm) + c4 * 4);
+            v = ld4(xb + x_off(r, c, R, C, xsm, c4));
         }
         st4(xs + row * LDA + c4 * 4, v);
     }
@@ -77,8 +80,16 @@ __global__ void __launch_bounds__(NTHREADS) k_embed(const int8_t* __restrict__ d
     for (int it = 0; it < 64; ++it) {
         int idx = it * NTHREADS + tid;
         int t = t0 + (idx >> 4), c4 = idx & 15;
-        if (t >= T) break;
-        char4 v = *reinterpret_cast<const char4*>(db + (size_t)t * 4);
+        int r, c;
+        if (xsm) {      // tile-planar site-major stream: lanes follow its tokens (site * R + taxon), one column chunk per pass
+            t = t0 + (idx & 1023); c4 = idx >> 10;
+            if (t >= T) continue;
+            c = t / R; r = t - c * R;
+        } else {
+            if (t >= T) break;
+            r = t / L; c = t - r * L;
+        }
+        char4 v = *reinterpret_cast<const char4*>(db + ((size_t)r * L + c) * 4);
         float4 o;
         if (((v.x | v.y | v.z | v.w) & ~1) == 0) {
             int p = v.x | (v.y << 1) | (v.z << 2) | (v.w << 3);
@@ -94,8 +105,7 @@ __global__ void __launch_bounds__(NTHREADS) k_embed(const int8_t* __restrict__ d
             }
             o = make_float4(acc[0], acc[1], acc[2], acc[3]);
         }
-        const int r = t / L, c = t - r * L;
-        st4(xb + x_off(r, c, R, L, xsm) + c4 * 4, o);
+        st4(xb + x_off(r, c, R, L, xsm, c4), o);
     }
 }
 
@@ -187,7 +197,7 @@ __global__ void __launch_bounds__(NTHREADS) k_out_proj(float* __restrict__ x, si
         if (t < T) {
             int r, c;
             tok_rc<ROW>(t, R, C, r, c);
-            float* p = xb + x_off(r, c, R, C, xsm) + tx * 4;
+            float* p = xb + x_off(r, c, R, C, xsm, tx);
             float4 o = ld4(p);
             o.x += acc[i][0]; o.y += acc[i][1]; o.z += acc[i][2]; o.w += acc[i][3];
             st4(p, o);
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__(NTHREADS) k_out_proj(float* __restrict__ x, si
 }
 
 // ------------------------------------------------------------------ feed-forward
-__global__ void __launch_bounds__(NTHREADS) k_ffn(float* __restrict__ x, size_t x_tree_stride, int R, int C, FfnW w) {
+__global__ void __launch_bounds__(NTHREADS) k_ffn(float* __restrict__ x, size_t x_tree_stride, int R, int C, FfnW w, int xsm) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
     float* hs = xs + TILE_ROWS * LDA;
@@ -206,7 +216,8 @@ __global__ void __launch_bounds__(NTHREADS) k_ffn(float* __restrict__ x, size_t 
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int T = R * C;
     float* xb = x + (size_t)b * x_tree_stride;
-    load_x_tile<false>(xs, xb, tile, R, C);
+    if (xsm) load_x_tile<true>(xs, xb, tile, R, C, 1);   // per-token work: any token order will do, take the stream's own
+    else load_x_tile<false>(xs, xb, tile, R, C);
     __syncthreads();
     tile_layernorm(xs, w.ln_g, w.ln_b);
     float out[8][4];
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(NTHREADS) k_ffn(float* __restrict__ x, size_t 
     for (int i = 0; i < 8; ++i) {
         int t = tile * TILE_ROWS + ty * 8 + i;
         if (t < T) {
-            float* p = xb + (size_t)t * D + tx * 4;
+            float* p = xb + (xsm ? xs_off((size_t)t, tx) : (size_t)t * D + tx * 4);
             float4 o = ld4(p);
             o.x += out[i][0]; o.y += out[i][1]; o.z += out[i][2]; o.w += out[i][3];
             st4(p, o);
@@ -610,7 +621,7 @@ static size_t enc_tree_floats(const Model* m, int R, int C) {
     size_t act = (size_t)R * C * D;
     size_t s = (size_t)H * C * C;         // row-attention logits; also holds the column-attention context
     size_t p = use_tc(m, C) ? s : 0;      // probabilities as bf16 hi/lo planes (tensor-core path)
-    size_t xs = enc_tc_mask(m, R, C) ? act : 0;   // site-major residual stream
+    size_t xs = enc_tc_mask(m, R, C) ? xs_tree_floats(R * C) : 0;   // site-major residual stream (tile-planar, whole 128-token tiles)
     return 3 * act + (s > act ? s : act) + p + xs; // q (row ctx), k, v, S [, P] [, xs]
 }
 
@@ -652,7 +663,7 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
     const int xsm = mk ? 1 : 0;
     const size_t s_floats = (size_t)H * C * C > act ? (size_t)H * C * C : act;
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(S + s_floats * chunk);   // [2 planes][chunk*H][C][C] (tensor-core path only)
-    float* xs_ws = S + s_floats * chunk + (tc ? (size_t)H * C * C * chunk : 0);  // site-major residual stream [chunk][C][R][64]
+    float* xs_ws = S + s_floats * chunk + (tc ? (size_t)H * C * C * chunk : 0);  // site-major residual stream [chunk][tiles of 128 tokens t = c R + r][16 chunks][128][4]
     const int T = R * C;
     const int tiles = (T + TILE_ROWS - 1) / TILE_ROWS;
     const size_t smem_qkv = (TILE_ROWS * LDA + 4096) * sizeof(float);
@@ -677,7 +688,7 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
         const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
         float* xout = x + (size_t)b0 * x_tree_stride;
         float* xb = xsm ? xs_ws : xout;                       // the residual stream the layers work on
-        const size_t xstr = xsm ? act : x_tree_stride;
+        const size_t xstr = xsm ? xs_tree_floats(R * C) : x_tree_stride;
         const int8_t* db = data + (size_t)b0 * R * L * 4;
         const uint8_t* mb = mask ? mask + (size_t)b0 * C : nullptr;
         prof_begin(KC_EMBED, st);
@@ -752,7 +763,7 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
                 if (int e = launch_enc_ffn_tc(m, l, xb, xstr, nb, R, C, st)) return e;
             } else {
                 prof_begin(KC_FFN, st);
-                k_ffn<<<dim3(tiles, nb), NTHREADS, smem_ffn, st>>>(xb, xstr, R, C, lw.ffn);
+                k_ffn<<<dim3(tiles, nb), NTHREADS, smem_ffn, st>>>(xb, xstr, R, C, lw.ffn, xsm);
                 LAUNCH_CHECK();
             }
         }

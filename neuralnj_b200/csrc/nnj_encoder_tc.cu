@@ -1,8 +1,8 @@
 // nnj_encoder_tc.cu — the MSA encoder's per-token work on tcgen05 (precision bf16x3).
 //
-// The residual stream is kept SITE-MAJOR inside the encoder, xs [B][C][R][64] fp32, so that a tile of 128 consecutive tokens
-// (site c, taxon r -> t = c*R + r) is one contiguous 32 KB block and the head-major row-attention planes [B,H,C,R*8] are
-// written in 16-byte pieces that are contiguous across the lanes of a warp.  Between two tied row attentions everything is
+// The residual stream is kept SITE-MAJOR inside the encoder (token t = c*R + r for site c, taxon r) in the tile-planar layout of
+// xs_off (nnj_internal.h): a tile of 128 consecutive tokens is one contiguous 32 KB block, every 16-byte column chunk a plane of
+// its own, and the head-major row-attention planes [B,H,C,R*8] are written in 16-byte pieces that are contiguous across the lanes.  Between two tied row attentions everything is
 // per token or per site, so one layer is three fused kernels (msa_modules.py:62-125):
 //   k_enc_rowqkv_tc   LN1 + q|k|v projection of the tied row attention (axial_attention.py:75-82) -> bf16 hi/lo planes
 //   k_enc_colblock_tc row out_proj + residual (:116), LN2 + column q|k|v (:211-214), per-site attention over taxa (:216-234),
@@ -114,9 +114,9 @@ __global__ void __launch_bounds__(ET_THREADS, 2) k_enc_rowqkv_tc(const RowQkvArg
         const float qs = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale;   // axial_attention.py:81-82 (loaded with the tile, used after the UMMA)
         float v[32];
         if (valid) {
-            const float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + hf * 32;
+            const float* xp = a.x + (size_t)b * a.x_tree_stride + xs_off((size_t)t, hf * 8);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const float4 f = ld4(xp + k * 4); v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w; }
+            for (int k = 0; k < 8; ++k) { const float4 f = ld4(xp + k * 512); v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w; }
         } else {
 #pragma unroll
             for (int k = 0; k < 32; ++k) v[k] = 0.f;
@@ -217,9 +217,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
         const int b = w / a.tiles_per_tree, tile = w - b * a.tiles_per_tree;
         const int t = tile * 128 + row;
         if (w < n_work && t < a.T) {
-            const float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + cq * 16;
+            const float* xp = a.x + (size_t)b * a.x_tree_stride + xs_off((size_t)t, cq * 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = ld4(xp + k * 4);
+            for (int k = 0; k < 4; ++k) dst[k] = ld4(xp + k * 512);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
         const int b = w / a.tiles_per_tree, tile = w - b * a.tiles_per_tree;
         const int t = tile * 128 + row;
         const bool valid = t < a.T;
-        float* xp = a.x + (size_t)b * a.x_tree_stride + (size_t)t * D + cq * 16;
+        float* xp = a.x + (size_t)b * a.x_tree_stride + xs_off((size_t)t, cq * 4);
         float xr[16], v[16];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { xr[4 * k] = xnext[k].x; xr[4 * k + 1] = xnext[k].y; xr[4 * k + 2] = xnext[k].z; xr[4 * k + 3] = xnext[k].w; }
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
             if (valid) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    st4(xp + k * 4, make_float4(xr[4 * k] + __uint_as_float(acc[4 * k]) + s_b2[cq * 16 + 4 * k],
+                    st4(xp + k * 512, make_float4(xr[4 * k] + __uint_as_float(acc[4 * k]) + s_b2[cq * 16 + 4 * k],
                                                 xr[4 * k + 1] + __uint_as_float(acc[4 * k + 1]) + s_b2[cq * 16 + 4 * k + 1],
                                                 xr[4 * k + 2] + __uint_as_float(acc[4 * k + 2]) + s_b2[cq * 16 + 4 * k + 2],
                                                 xr[4 * k + 3] + __uint_as_float(acc[4 * k + 3]) + s_b2[cq * 16 + 4 * k + 3]));
@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         // all keys of a padded site get the same logit (-10000, axial_attention.py:220-224): softmax is uniform, i.e. q = 0
         qsc = (valid && a.mask && a.mask[(size_t)b * a.C + c]) ? 0.f : a.q_scale_log2e;
         if (valid) {
-            const float* xq = a.x + (size_t)b * a.x_tree_stride + ((size_t)c * R + r) * D + cq * 16;
+            const float* xq = a.x + (size_t)b * a.x_tree_stride + xs_off((size_t)c * R + r, cq * 4);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const float* cp = a.ctx + (((size_t)b * H + cq * 2 + hh) * a.C + c) * KD + (size_t)r * DH;
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
                 vv[hh * 8 + 4] = f1.x; vv[hh * 8 + 5] = f1.y; vv[hh * 8 + 6] = f1.z; vv[hh * 8 + 7] = f1.w;
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { const float4 f = ld4(xq + k * 4); xx[4 * k] = f.x; xx[4 * k + 1] = f.y; xx[4 * k + 2] = f.z; xx[4 * k + 3] = f.w; }
+            for (int k = 0; k < 4; ++k) { const float4 f = ld4(xq + k * 512); xx[4 * k] = f.x; xx[4 * k + 1] = f.y; xx[4 * k + 2] = f.z; xx[4 * k + 3] = f.w; }
         } else {
 #pragma unroll
             for (int k = 0; k < 16; ++k) { vv[k] = 0.f; xx[k] = 0.f; }
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         const int b = w / a.groups_per_tree, grp = w - b * a.groups_per_tree;
         const int c = grp * s_tile + si;
         const bool valid = r < R && c < a.C;
-        float* xp = a.x + (size_t)b * a.x_tree_stride + ((size_t)c * R + r) * D + cq * 16;
+        float* xp = a.x + (size_t)b * a.x_tree_stride + xs_off((size_t)c * R + r, cq * 4);
         float xr[16], v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) { xr[k] = xn[k]; v[k] = vn[k]; }
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
             if (valid) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    st4(xp + k * 4, make_float4(xr[4 * k] + __uint_as_float(acc[4 * k]) + s_cob[cq * 16 + 4 * k],
+                    st4(xp + k * 512, make_float4(xr[4 * k] + __uint_as_float(acc[4 * k]) + s_cob[cq * 16 + 4 * k],
                                                 xr[4 * k + 1] + __uint_as_float(acc[4 * k + 1]) + s_cob[cq * 16 + 4 * k + 1],
                                                 xr[4 * k + 2] + __uint_as_float(acc[4 * k + 2]) + s_cob[cq * 16 + 4 * k + 2],
                                                 xr[4 * k + 3] + __uint_as_float(acc[4 * k + 3]) + s_cob[cq * 16 + 4 * k + 3]));
@@ -780,13 +780,13 @@ __global__ void __launch_bounds__(256) k_sm_to_nm(const float* __restrict__ xs, 
                                                   int R, int C) {
     const int b = blockIdx.y;
     const size_t n4 = (size_t)R * C * 16;
-    const float4* src = reinterpret_cast<const float4*>(xs + (size_t)b * xs_tree_stride);
+    const float* src = xs + (size_t)b * xs_tree_stride;
     float* dst = out + (size_t)b * out_tree_stride;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const size_t tok = i >> 4;
         const int c4 = (int)(i & 15);
         const int c = (int)(tok / R), r = (int)(tok - (size_t)c * R);
-        st4(dst + ((size_t)r * C + c) * D + c4 * 4, src[i]);
+        st4(dst + ((size_t)r * C + c) * D + c4 * 4, ld4(src + xs_off(tok, c4)));
     }
 }
 

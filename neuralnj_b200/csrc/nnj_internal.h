@@ -13,6 +13,14 @@
 
 namespace nnj {
 
+// Site-major residual stream of the tensor-core encoder ("xs"): tokens t = site * R + taxon in tiles of 128; inside a tile the 64
+// channels are split into 16-byte column chunks and every chunk is a plane of its own, [tile][chunk 0..15][token 0..127][4 floats].
+// The encoder kernels own TMEM lane = token row and a few column chunks per thread, so a warp instruction that moves one chunk of
+// 32 consecutive rows touches 512 contiguous bytes (4 lines); with a row-major [token][64] stream the same instruction touched
+// 32 lines of 256-byte rows, 16 bytes each, and the loads / stores of a tile queued on the L1 tag stage.
+__host__ __device__ __forceinline__ size_t xs_off(size_t t, int chunk) { return (t >> 7) * 8192 + (size_t)chunk * 512 + (t & 127) * 4; }
+__host__ __device__ __forceinline__ size_t xs_tree_floats(size_t tokens) { return ((tokens + 127) >> 7) * 8192; }
+
 // "t" suffix: transposed to [in k][out col] so a CTA can copy it straight into shared memory.
 struct EmbedW { const float *w1, *b1, *w2t, *b2; };                 // model.py:39-43
 struct AttnW { const float *ln_g, *ln_b, *qt, *kt, *vt, *ot, *qb, *kb, *vb, *ob; };
