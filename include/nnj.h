@@ -138,6 +138,28 @@ int nnj_rollout_from_state(nnj_model* m, const float* state_dev, const uint8_t* 
 int nnj_rollout_host(nnj_model* m, const int8_t* data_host, const uint8_t* seq_mask_host, int B, int R, int L,
                      int select_mode, const float* gumbel_host, int32_t* merges_host, float* selected_logp_host);
 
+/* ---- Tree likelihood: what Search / branch_optimize=True use to score a topology.
+ * Replaces the reference's native binding raxmlpy.compute_llh / raxmlpy.optimize_brlen
+ * (RAxMLpy/raxmlpy/core.py:6-12 -> RAxMLpy/cpp/raxmlpy.cpp:1790-1805, 1854-1872; call sites environment.py:365-379, 625-670).
+ * Model GTR+I+G4 (raxmlpy's model string "GTR+I+G"); one CTA per tree, fp64.
+ *   tips_dev      uint8 [B,R,L]   4-bit state masks per taxon and alignment pattern (bit a = state a possible; gap / N = 15)
+ *   weights_dev   double [B,L]    pattern multiplicities (1 for uncompressed columns)
+ *   children_host int32 [B,R-1,2] topology in join order: leaves 0..R-1, inner node R+k = (children[k][0], children[k][1]),
+ *                                 the last join is the root (the NJ merge list replayed, neuralnj_b200/likelihood.py)
+ *   brlen_host    double [B,2R-2] length of the branch above node v; the two root branches are one branch of the unrooted tree
+ *   model_host    double [B,48]   eigenvalues 4 | eigenvectors U 16 | U^-1 16 | base frequencies 4 | class rates 4 | p_inv | pad 3
+ * nnj_llh_eval returns log L per tree; nnj_llh_optimize_brlen maximises it over the branch lengths (Newton-Raphson per branch,
+ * depth-first sweeps until a sweep gains less than eps or max_passes), updates brlen_host (root branch split evenly) and returns
+ * log L before / after.  Both synchronise `stream` (their results are host values). */
+int64_t nnj_llh_workspace_bytes(int B, int R, int L);
+int nnj_llh_eval(const uint8_t* tips_dev, const double* weights_dev, const int32_t* children_host, const double* brlen_host,
+                 const double* model_host, int B, int R, int L, double* llh_host, void* ws_dev, int64_t ws_bytes, void* stream);
+int nnj_llh_optimize_brlen(const uint8_t* tips_dev, const double* weights_dev, const int32_t* children_host, double* brlen_host,
+                           const double* model_host, int B, int R, int L, int max_passes, double eps,
+                           double* llh_before_host, double* llh_after_host, void* ws_dev, int64_t ws_bytes, void* stream);
+/* Mean rates of the ncat equal-probability classes of Gamma(alpha, alpha) (Yang 1994): rates_host double [ncat]. */
+int nnj_gamma_rates(double alpha, int ncat, double* rates_host);
+
 /* Building block of the tensor-core path (precision NNJ_PREC_BF16X3), exposed for unit tests and reuse:
  * C[z] = A[z] * B[z]^T with fp32 A [Z,M,K], B [Z,N,K], C [Z,M,N]; operands are split into bf16 hi/lo planes and
  * multiplied on tcgen05 as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM.  K must be a multiple of 8;

@@ -12,7 +12,8 @@ from .phydata import load_pi_instance               # noqa: F401
 from .rollout import (Agmax_one_instance, Argmax_inference, RL_Search, Search_inference,   # noqa: F401
                       reinforce_rollout)
 from .treeutil import rf_distance, treestr_to_tuples   # noqa: F401
+from .likelihood import compute_llh, optimize_brlen          # noqa: F401
 
 __all__ = ["PhyloATTN", "PhyInferEnv", "PhyloTree", "reinforce_rollout", "Agmax_one_instance", "Argmax_inference",
            "RL_Search", "Search_inference", "load_pi_instance", "empty_config", "inference_config", "CfgNode",
-           "rf_distance", "treestr_to_tuples", "format_rtree", "build", "lib", "NnjError"]
+           "rf_distance", "treestr_to_tuples", "format_rtree", "build", "lib", "NnjError", "optimize_brlen", "compute_llh"]

@@ -68,7 +68,7 @@ void prof_end(cudaStream_t st) {
 }
 
 static const char* kclass_names[KC_COUNT] = {"embed", "ln_qkv", "row_qk_gemm", "row_softmax", "row_pv_gemm", "out_proj", "col_attn",
-                                             "ffn", "node_derive", "alpha", "alpha_softmax", "pair_score", "select", "merge", "misc", "pair_blend"};
+                                             "ffn", "node_derive", "alpha", "alpha_softmax", "pair_score", "select", "merge", "misc", "pair_blend", "tree_llh"};
 
 #define CUDA_TRY(x)                                                        \
     do {                                                                   \
@@ -389,6 +389,32 @@ int nnj_rollout_from_state(nnj_model* m, const float* state, const uint8_t* mask
 int nnj_gemm_split_bf16(const float* A, const float* B, float* Cm, int Z, int M, int N, int K, void* ws, int64_t ws_bytes, void* stream) {
     CHECK_ARGS(A && B && Cm && ws && Z >= 1 && M >= 1 && N >= 1 && K >= 8, "gemm_split_bf16: bad arguments");
     return run_gemm_split_bf16(A, B, Cm, Z, M, N, K, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
+int64_t nnj_llh_workspace_bytes(int B, int R, int L) { return (B >= 1 && R >= 3 && L >= 1) ? (int64_t)llh_ws_bytes(B, R, L) : -1; }
+
+int nnj_llh_eval(const uint8_t* tips, const double* weights, const int32_t* children_h, const double* brlen_h, const double* model_h, int B, int R, int L,
+                 double* llh_h, void* ws, int64_t ws_bytes, void* stream) {
+    CHECK_ARGS(tips && weights && children_h && brlen_h && model_h && llh_h && ws && B >= 1 && R >= 3 && R <= 4096 && L >= 1, "llh_eval: bad arguments");
+    std::vector<double> both((size_t)B * 2);
+    int rc = run_llh(tips, weights, children_h, const_cast<double*>(brlen_h), model_h, B, R, L, 0, 0, 0.0, both.data(), ws, (size_t)ws_bytes, (cudaStream_t)stream);
+    if (rc == 0) for (int b = 0; b < B; ++b) llh_h[b] = both[2 * b + 1];
+    return rc;
+}
+
+int nnj_llh_optimize_brlen(const uint8_t* tips, const double* weights, const int32_t* children_h, double* brlen_h, const double* model_h, int B, int R, int L,
+                           int max_passes, double eps, double* llh_before_h, double* llh_after_h, void* ws, int64_t ws_bytes, void* stream) {
+    CHECK_ARGS(tips && weights && children_h && brlen_h && model_h && llh_after_h && ws && B >= 1 && R >= 3 && R <= 4096 && L >= 1 && max_passes >= 1,
+               "llh_optimize_brlen: bad arguments");
+    std::vector<double> both((size_t)B * 2);
+    int rc = run_llh(tips, weights, children_h, brlen_h, model_h, B, R, L, 1, max_passes, eps, both.data(), ws, (size_t)ws_bytes, (cudaStream_t)stream);
+    if (rc == 0) for (int b = 0; b < B; ++b) { if (llh_before_h) llh_before_h[b] = both[2 * b]; llh_after_h[b] = both[2 * b + 1]; }
+    return rc;
+}
+
+int nnj_gamma_rates(double alpha, int ncat, double* rates_h) {
+    CHECK_ARGS(rates_h, "gamma_rates: bad arguments");
+    return gamma_rates(alpha, ncat, rates_h);
 }
 
 int nnj_tc_selftest(const float* A, const float* B, float* Dm, int N, void* stream) {

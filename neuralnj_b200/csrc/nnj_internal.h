@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <atomic>
 #include <mutex>
+#include <vector>
 #include <string>
 #include <vector>
 
@@ -67,7 +68,7 @@ struct Model {
 
 // kernel classes for the optional per-class CUDA-event profiler (nnj_profile_*)
 enum KClass { KC_EMBED = 0, KC_LN_QKV, KC_ROW_QK, KC_ROW_SOFTMAX, KC_ROW_PV, KC_OUT_PROJ, KC_COL_ATTN, KC_FFN, KC_DERIVE,
-              KC_ALPHA, KC_ALPHA_SOFTMAX, KC_SCORE, KC_SELECT, KC_MERGE, KC_MISC, KC_BLEND, KC_COUNT };
+              KC_ALPHA, KC_ALPHA_SOFTMAX, KC_SCORE, KC_SELECT, KC_MERGE, KC_MISC, KC_BLEND, KC_LLH, KC_COUNT };
 void prof_begin(int cls, cudaStream_t st);   // no-op unless profiling is enabled
 void prof_end(cudaStream_t st);
 
@@ -145,5 +146,11 @@ int launch_enc_ffn_tc(const Model* m, int layer, float* xs, size_t xs_tree_strid
 int launch_sm_to_nm(const float* xs, size_t xs_tree_stride, float* out, size_t out_tree_stride, int B, int R, int C, cudaStream_t st);
 int run_tc_unit(const float* A, const float* B, float* Dm, int bn, cudaStream_t st);
 int run_gemm_split_bf16(const float* A, const float* B, float* Cm, int Z, int M, int N, int K, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// tree likelihood / branch-length optimisation (nnj_llh.cu)
+size_t llh_ws_bytes(int B, int R, int L);
+int run_llh(const uint8_t* tips, const double* weights, const int32_t* children_h, double* brlen_h, const double* model_h, int B, int R, int L,
+            int optimise, int max_passes, double eps, double* llh_h, void* ws, size_t ws_bytes, cudaStream_t st);
+int gamma_rates(double alpha, int ncat, double* out);
 
 }  // namespace nnj

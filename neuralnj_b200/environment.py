@@ -9,9 +9,9 @@ What callers of the inference path rely on is kept: `init_states`, `step`, `eval
 environment.py:760-835) runs in one CUDA call (`agent.merge_state`).  `replay_merges` rebuilds the
 same host state from a device-produced merge list (fused rollout).
 
-Out of scope: label-tree supervision (training) and RAxML-NG branch-length /
-likelihood optimisation (`branch_optimize=True` raises; the native raxmlpy binding is not part of
-the hot path and cannot be built offline).
+`branch_optimize=True` (`optimize_branch_length_sequential`, environment.py:648-671: RAxML-NG through the native raxmlpy
+binding) scores the finished trees with the GPU likelihood of `neuralnj_b200.likelihood` (GTR+I+G4, csrc/nnj_llh.cu): all
+trees of the batch in one call.  Out of scope: label-tree supervision (training).
 """
 from __future__ import annotations
 
@@ -24,6 +24,7 @@ from .treeutil import treestr_to_tuples
 
 PLACEHOLDER_BRANCH = 0.12345      # environment.py:284
 UNSCORED = -111111                # environment.py:686
+EVOLUTION_MODEL = "GTR+I+G"       # environment.py:44
 
 CHARACTERS_MAPS = {
     "DNA": dict(A=[1., 0., 0., 0.], C=[0., 1., 0., 0.], G=[0., 0., 1., 0.], T=[0., 0., 0., 1.], N=[1., 1., 1., 1.]),
@@ -200,16 +201,58 @@ class PhyInferEnv:
         tree.utree_op_str = rtree_str
         tree.log_score = UNSCORED
 
+    def _finish_scored(self, trees: List[PhyloTree]) -> None:
+        """`optimize_branch_length_sequential` (environment.py:648-671) for the whole batch at once: branch lengths and the
+        GTR+I+G model parameters are optimised on the GPU (likelihood.TreeLikelihood), the optimised lengths go back onto the
+        rooted trees and `log_score` is the maximised log-likelihood."""
+        from . import likelihood as LH
+        R = len(self.batch_seqs[0])
+        masks_all = LH.onehot_to_masks(self.init_state_tensor) if self.init_state_tensor is not None else None
+        pats, wts, children = [], [], []
+        for b, tree in enumerate(trees):
+            masks = masks_all[b] if masks_all is not None else LH.sequences_to_masks(self.batch_seqs[b])
+            p, w = LH.compress_patterns(masks)
+            pats.append(p); wts.append(w)
+            ch = []
+
+            def visit(t):
+                if t.is_leaf:
+                    return t.seq_indices[0]
+                a, c = visit(t.left_tree_data["tree"]), visit(t.right_tree_data["tree"])
+                ch.append((a, c))
+                return R + len(ch) - 1
+            visit(tree)
+            children.append(ch)
+        Lp = max(p.shape[1] for p in pats)
+        P = np.full((len(trees), R, Lp), 15, dtype=np.uint8)     # padding patterns: fully undetermined, weight 0
+        W = np.zeros((len(trees), Lp))
+        for b, (p, w) in enumerate(zip(pats, wts)):
+            P[b, :, :p.shape[1]] = p
+            W[b, :len(w)] = w
+        children = np.asarray(children, dtype=np.int32)
+        eng = LH.TreeLikelihood(P, W, device=self.device)
+        freqs = np.stack([LH.empirical_freqs(masks_all[b] if masks_all is not None else LH.sequences_to_masks(self.batch_seqs[b])) for b in range(len(trees))])
+        model = LH.SubstModel(EVOLUTION_MODEL, freqs, len(trees))
+        t, _, ll = eng.optimize_all(children, np.full((len(trees), 2 * R - 2), LH.BRLEN_DEFAULT), model)
+        for b, tree in enumerate(trees):
+            keys = self.seq_keys[b]
+            tree.rtree_op_tuple = LH.tuples_with_lengths(children[b], t[b], keys, unrooted=False)
+            tree.utree_op_tuple = LH.tuples_with_lengths(children[b], t[b], keys, unrooted=True)
+            tree.utree_op_str = LH.tuples_to_newick(tree.utree_op_tuple)
+            assign_branch_length_rtree(tree, tree.rtree_op_tuple)
+            tree.log_score = float(ll[b])
+
     def _advance_host(self, ij: Sequence[Tuple[int, int]], edge_actions, branch_optimize: bool) -> bool:
         done = False
         new_states = []
+        joined = [self._join(b, i, j, edge_actions[b] if edge_actions is not None else (None, None)) for b, (i, j) in enumerate(ij)]
+        if joined and joined[0][1] and branch_optimize:
+            self._finish_scored([t for t, _ in joined])
         for b, (i, j) in enumerate(ij):
-            tree, last = self._join(b, i, j, edge_actions[b] if edge_actions is not None else (None, None))
+            tree, last = joined[b]
             if last:
-                if branch_optimize:
-                    raise RuntimeError("branch_optimize=True needs the reference's native raxmlpy binding (RAxML-NG), "
-                                       "which is outside the hot path and not available; run with branch_optimize=False")
-                self._finish_unscored(b, tree)
+                if not branch_optimize:
+                    self._finish_unscored(b, tree)
                 ut = tree.to_unrooted_tree()
                 ut.rtree_op_tuple, ut.utree_op_tuple, ut.utree_op_str = tree.rtree_op_tuple, tree.utree_op_tuple, tree.utree_op_str
                 ns = PhylogeneticTreeState([ut])
@@ -254,11 +297,12 @@ class PhyInferEnv:
             rows.append(xb)
         return torch.stack(rows)
 
-    def replay_merges(self, merges) -> None:
-        """Apply a device-produced merge list [B,R-1,2] to the host trees (fused rollout epilogue)."""
+    def replay_merges(self, merges, branch_optimize: bool = False) -> None:
+        """Apply a device-produced merge list [B,R-1,2] to the host trees (fused rollout epilogue); with `branch_optimize`
+        the finished trees are scored like `step(..., branch_optimize=True)` does."""
         merges = np.asarray(merges.cpu() if torch.is_tensor(merges) else merges)
         for t in range(merges.shape[1]):
-            self._advance_host([(int(a), int(b)) for a, b in merges[:, t]], None, False)
+            self._advance_host([(int(a), int(b)) for a, b in merges[:, t]], None, branch_optimize and t == merges.shape[1] - 1)
         self.state_tensor = None
 
     def dump_end_trees(self):

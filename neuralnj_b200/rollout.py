@@ -64,13 +64,13 @@ def reinforce_rollout(batch, agent, env, cfgs, replay_buffer=None, eval=False, a
     agent.eval()
     B, R = batch_array.shape[:2]
 
-    if fused and hasattr(agent, "rollout_fused") and not branch_optimize:
+    if fused and hasattr(agent, "rollout_fused"):
         with torch.no_grad():
             gumbel = None if argmax else sample_gumbel((B, R - 1, R * (R - 1) // 2), device, generator)
             merges, slp, trace = agent.rollout_fused(batch_array, batch_seq_mask, gumbel=gumbel, want_logits=True)
             log_ps = [torch.log_softmax(trace[:, a:b] / EXPLORE_TEMPERTURE(t), dim=-1) for t, (a, b) in enumerate(_step_slices(R))][:-1]
             selected_log_ps = slp[:, :R - 2]
-        env.replay_merges(merges)
+        env.replay_merges(merges, branch_optimize=branch_optimize)
     else:
         selected, log_ps = [], []
         actions_ij_prev = logits_prev = None
@@ -173,11 +173,15 @@ def RL_Search(cfgs, MSA_file, policy_network, env, c_best_tree_file=None, raw_tr
               generator: Optional[torch.Generator] = None):
     """NeuralNJ-MC: sampled rollouts, keep the best-scoring tree (finetune_rl_search.py:338-427).
 
-    One encoder pass is shared by every sampled rollout (the reference re-encodes the same MSA each
-    time, :112).  `scorer(newick, seq_keys, seqs) -> float` stands in for the RAxML-NG likelihood
-    (`optimize_brlen`, environment.py:365-379), which is not part of this path; without a scorer the
-    policy's own trajectory log-probability ranks the candidates.
+    One encoder pass is shared by every sampled rollout (the reference re-encodes the same MSA each time, :112), the
+    rollouts are sampled on the device (Gumbel-max), identical topologies are scored once, and the score is what the
+    reference uses: the log-likelihood under GTR+I+G after branch-length / model optimisation (`optimize_brlen`,
+    environment.py:365-379) - here on the GPU (`neuralnj_b200.likelihood.score_topologies`), all new topologies of an
+    episode in one call.  `scorer` overrides it: a callable `scorer(newick, seq_keys, seqs) -> float`, or "logp" to rank by
+    the policy's own trajectory log-probability (no likelihood at all).
     """
+    from . import likelihood as LH
+    from .environment import EVOLUTION_MODEL
     stop = STOP_STEP if stop_step is None else stop_step
     device = _device_of(policy_network)
     batch = _expand(load_pi_instance(MSA_file), cfgs.env.batch_size)
@@ -189,6 +193,8 @@ def RL_Search(cfgs, MSA_file, policy_network, env, c_best_tree_file=None, raw_tr
     start = time.time()
     best_tree, best_score, t_best = None, -np.inf, None
     seen = {}
+    masks = LH.onehot_to_masks(batch["data"][0]) if scorer is None else None
+    keys = batch["seq_keys"][0]
     with torch.no_grad():
         state = policy_network.encode_zxr(data[:1], mask[:1]).expand(B, -1, -1, -1).contiguous()
         step_cur = 0
@@ -199,15 +205,26 @@ def RL_Search(cfgs, MSA_file, policy_network, env, c_best_tree_file=None, raw_tr
                 env.init_states(batch["seqs"], batch["seq_keys"], data)
                 env.replay_merges(merges)
                 traj_logp = slp[:, :R - 2].sum(1).tolist()
+                fresh = {}
                 for b, st in enumerate(env.states):
-                    tree = st.subtrees[0]
-                    if tree.topo_repr in seen:
-                        score = seen[tree.topo_repr]
-                    else:
-                        score = scorer(tree.utree_op_str, batch["seq_keys"][b], batch["seqs"][b]) if scorer else traj_logp[b]
-                        seen[tree.topo_repr] = score
+                    tr = st.subtrees[0].topo_repr
+                    if tr not in seen and tr not in fresh:
+                        fresh[tr] = b
+                if fresh and scorer is None:
+                    mg = merges.cpu().numpy()
+                    ch = np.stack([LH.children_from_merges(mg[b], R) for b in fresh.values()])
+                    ll, brl = LH.score_topologies(masks, ch, keys, model=EVOLUTION_MODEL, opt_model=True, device=device)
+                    for k, tr in enumerate(fresh):
+                        seen[tr] = (float(ll[k]), LH.tuples_to_newick(LH.tuples_with_lengths(ch[k], brl[k], keys, unrooted=True)))
+                else:
+                    for tr, b in fresh.items():
+                        tree = env.states[b].subtrees[0]
+                        sc = traj_logp[b] if scorer == "logp" else scorer(tree.utree_op_str, batch["seq_keys"][b], batch["seqs"][b])
+                        seen[tr] = (float(sc), tree.utree_op_str)
+                for st in env.states:
+                    score, newick = seen[st.subtrees[0].topo_repr]
                     if best_tree is None or score > best_score:
-                        best_tree, best_score, t_best = tree.utree_op_str, score, time.time() - start
+                        best_tree, best_score, t_best = newick, score, time.time() - start
                 step_cur = 1 + episode + (epoch - 1) * cfgs.num_episodes
             if step_cur >= stop:
                 break
