@@ -397,12 +397,23 @@ int gamma_rates(double alpha, int ncat, double* out) {
     std::vector<double> cdf(ncat + 1, 0.0);
     cdf[ncat] = 1.0;
     for (int i = 1; i < ncat; ++i) {
-        // quantile x of Gamma(alpha, 1) at i / ncat by bisection on P(alpha, x) (monotone; 200 halvings of a bracket that contains it)
-        const double target = (double)i / ncat;
+        // quantile x of Gamma(alpha, 1) at i / ncat: Newton on P(alpha, x) (monotone, density known) kept inside a bracket, a bisection
+        // step whenever Newton leaves it
+        const double target = (double)i / ncat, gln = lgamma(alpha);
         double lo = 0.0, hi = alpha + 1.0;
         while (gammp(alpha, hi) < target) hi *= 2.0;
-        for (int it = 0; it < 200; ++it) { const double mid = 0.5 * (lo + hi); if (gammp(alpha, mid) < target) lo = mid; else hi = mid; }
-        cdf[i] = gammp(alpha + 1.0, 0.5 * (lo + hi));
+        double x = 0.5 * (lo + hi);
+        for (int it = 0; it < 200; ++it) {
+            const double f = gammp(alpha, x) - target;
+            if (f < 0.0) lo = x; else hi = x;
+            const double pdf = exp((alpha - 1.0) * log(x) - x - gln);
+            double xn = pdf > 0.0 ? x - f / pdf : 0.5 * (lo + hi);
+            if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+            const bool done = fabs(xn - x) <= 1e-15 * x || hi - lo <= 1e-300;
+            x = xn;
+            if (done) break;
+        }
+        cdf[i] = gammp(alpha + 1.0, x);
     }
     for (int i = 0; i < ncat; ++i) out[i] = ncat * (cdf[i + 1] - cdf[i]);
     return 0;

@@ -89,6 +89,7 @@ class SubstModel:
         self.freqs = np.tile(np.asarray(freqs, dtype=np.float64) if self.gtr else np.full(4, 0.25), (B, 1)) if np.ndim(freqs) == 1 else np.asarray(freqs, dtype=np.float64)
         self.alpha = np.ones(B)
         self.pinv = np.zeros(B)
+        self._gamma_cache = {}
 
     def free_params(self) -> List[Tuple[str, int]]:
         p = [("rate", i) for i in range(5)] if self.gtr else []
@@ -116,7 +117,9 @@ class SubstModel:
         if self.gamma:
             L = _lib.lib()
             buf = (C.c_double * 4)()
-            cache = {}
+            cache = self._gamma_cache
+            if len(cache) > 4096:
+                cache.clear()
             for b in range(B):
                 a = float(self.alpha[b])
                 if a not in cache:

@@ -37,3 +37,24 @@ def sharded_rollout(model, data: torch.Tensor, mask: torch.Tensor) -> torch.Tens
     lo, hi = shard_bounds(data.shape[0], rank, world)
     merges, _, _ = model.rollout_fused(data[lo:hi], mask[lo:hi])
     return gather_merges(merges, data.shape[0], rank, world)
+
+
+def sharded_search(search_fn, seed: int = 0) -> dict:
+    """Search mode (NeuralNJ-MC) over the ranks of the default process group - BASELINE config 3, "batched on 8 x B200".
+    Every rank runs `search_fn(rank_seed)`: its own sampled rollouts of the SAME alignment (shared encoder pass, on-device
+    Gumbel-max, likelihood scoring on its GPU; e.g. `lambda s: RL_Search(cfgs, path, model, env, generator=make_gen(s))`) with a
+    rank-specific seed, so the ranks explore different trajectories.  Only (score, Newick string) pairs are exchanged; the
+    best-scoring tree over all ranks is returned on every rank (ties go to the lowest rank: deterministic)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    res = dict(search_fn(seed + rank))
+    if world == 1:
+        res["best_rank"] = 0
+        return res
+    mine = (float(res["the_best_score"]), res["the_best_tree"], int(res.get("distinct_topologies", 0)))
+    every = [None] * world
+    dist.all_gather_object(every, mine)
+    best = max(range(world), key=lambda r: (every[r][0], -r))
+    res.update(the_best_score=every[best][0], the_best_tree=every[best][1], best_rank=best,
+               distinct_topologies_per_rank=[e[2] for e in every])
+    return res

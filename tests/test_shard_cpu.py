@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from neuralnj_b200.shard import gather_merges, shard_bounds
+from neuralnj_b200.shard import gather_merges, shard_bounds, sharded_search
 
 
 def _worker(rank, world, port, total, out):
@@ -18,6 +18,9 @@ def _worker(rank, world, port, total, out):
     full = gather_merges(local, total, rank, world)
     t = torch.tensor([float(rank + 1)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # Search mode: rank r "finds" a tree with score -10 + r from its own seed; every rank must end up with rank 1's tree
+    res = sharded_search(lambda seed: dict(the_best_score=-10.0 + (seed - 40), the_best_tree=f"(tree_of_seed_{seed});", distinct_topologies=seed), seed=40)
+    assert res["the_best_tree"] == "(tree_of_seed_41);" and res["best_rank"] == 1 and res["distinct_topologies_per_rank"] == [40, 41]
     if rank == 0:
         out.put((full[:, 0, 0].tolist(), float(t)))
     dist.barrier()
@@ -48,3 +51,8 @@ def test_shard_bounds_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_sharded_search_single_process():
+    res = sharded_search(lambda seed: dict(the_best_score=-3.5, the_best_tree="(a,b,c);", distinct_topologies=2), seed=9)
+    assert res["the_best_tree"] == "(a,b,c);" and res["best_rank"] == 0
