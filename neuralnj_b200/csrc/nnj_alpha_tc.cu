@@ -387,6 +387,14 @@ static int make_tmap_kprime(CUtensorMap* map, const void* base, int S, int n_liv
 int launch_alpha_tc(const Model* m, const float* X, const float* Y, size_t tree_stride, const int32_t* slot_of, int slot_stride, const int32_t* pair_i,
                     const int32_t* pair_j, int pair_stride, int n0, int nc, int S, int n_live, int C, int B, const void* kp_h, const void* kp_l, float* xf,
                     int pc, float* alpha_part, int alpha_pairs, int nSG, int RP, int* n_part, cudaStream_t st) {
+    {   // late steps (<= 16 pairs over <= 16 live nodes): the register-fragment kernel, whose cost follows the number of live pairs (nnj_alpha_small.cu)
+        static int small_on = -1;
+        if (small_on < 0) { const char* ev = getenv("NNJ_ALPHA_SMALL"); small_on = ev ? atoi(ev) : 1; }
+        const int lim = small_on > 1 ? 32 : 16;          // NNJ_ALPHA_SMALL=2: the 32-row variant as well (slower than k_alpha_v3's 4-way split below 25 pairs)
+        if (small_on && nc <= lim && n_live <= lim && !(C & 7))
+            return launch_alpha_small(m, X, Y, tree_stride, slot_of, slot_stride, pair_i, pair_j, pair_stride, n0, nc, S, n_live, C, B, kp_h, kp_l, xf, pc,
+                                      alpha_part, alpha_pairs, nSG, RP, n_part, st);
+    }
     static DevOnce once;      // per device, not per process
     if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_alpha_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, AV_SMEM_MAX);

@@ -784,6 +784,13 @@ static int make_tmap_xtile(CUtensorMap* map, const float* base, int pc, int nrow
 static int launch_score_inc(const Model* m, const float* xf, int pc, const void* nodes_h, const void* nodes_l, const float* alpha, int RP,
                             int alpha_pairs, const int32_t* slot_of, int slot_stride, const int32_t* pair_i, int pair_stride, int n0, int nc, int Rp,
                             int S, int C, int B, const uint8_t* mask, float* score_part, int nSG, int* n_part, cudaStream_t st) {
+    {   // late steps (<= 16 pairs over <= 16 live nodes; NNJ_SCORE_SMALL=2: <= 32, slower than the narrow mode below): the register-fragment kernel, whose cost follows the number of live pairs (nnj_score_small.cu)
+        static int small_on = -1;
+        if (small_on < 0) { const char* ev = getenv("NNJ_SCORE_SMALL"); small_on = ev ? atoi(ev) : 1; }
+        if (small_on && nc <= (small_on > 1 ? 32 : 16) && Rp <= (small_on > 1 ? 32 : 16) && !(C & 7))
+            return launch_score_small(m, xf, pc, nodes_h, nodes_l, alpha, RP, alpha_pairs, slot_of, slot_stride, pair_i, pair_stride, n0, nc, Rp, S, C, B, mask,
+                                      score_part, nSG, n_part, st);
+    }
     static DevOnce once;      // per device, not per process
     if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(k_score_inc, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_SMEM_MAX);

@@ -1,0 +1,19 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT
+o=gpurun_out/r2sp; mkdir -p $o
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tc_paths.py -m gpu -x -q -k "not 200x4096" > $o/pytest.log 2>&1; echo "pytest rc=$?" >> $o/pytest.log
+tail -4 $o/pytest.log
+for w8 in 0 1; do
+NNJ_SCORE_SMALL_W8=$w8 ncu --metrics gpu__time_duration.sum --clock-control none --csv -k regex:k_score --log-file $o/launches_$w8.csv python scratch/prof_rollout.py 128 1 > $o/ncu_launch.log 2>&1
+python - <<PY
+import csv
+rows=[r for r in csv.reader(open("gpurun_out/r2sp/launches_$w8.csv")) if len(r)>5]
+hdr=rows[0]; ki=hdr.index("Kernel Name"); vi=hdr.index("Metric Value")
+for name in ("k_score_small","k_score_inc"):
+    t=[float(r[vi].replace(",",""))/1e3 for r in rows[1:] if name in r[ki]]
+    print("w8=$w8", name, len(t), round(sum(t)), [round(x) for x in t])
+PY
+done
+for v in 1 0; do
+  NNJ_SCORE_SMALL=$v timeout 300 python scratch/r2_explore.py 128 50 1024 bf16x3 3 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('small=$v', d['trees_per_s'], d['classes']['pair_score'])"
+done
