@@ -2,7 +2,7 @@
 """bench.py — trees/sec of Argmax inference on 50-taxa x 1024-site alignments (BASELINE.json metric, configs[1]).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 512] [--scaling strong|weak] [--impl ours|reference]
-                    [--precision bf16x3|bf16|fp32] [--workload config2|config4|config1]
+                    [--precision bf16x3|fp32] [--workload config2|config4|config1]
 
 One "step" = one pass of the hot path (encode + 49 learned-NJ steps) over a batch of synthetic MSAs
 (config 2: iid tokens over A,C,G,T,gap, seed 1234; weights torch.manual_seed(0) default init — the shipped
@@ -217,7 +217,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip latency_b1 / gpu_eager_baseline / the weak-scaling second measurement")
     ap.add_argument("--cpu-trees", type=int, default=2)
@@ -416,7 +416,7 @@ def main():
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 tcgen05, fp32 accumulate) + f32", "bf16": "bf16 (tcgen05, fp32 accumulate) + f32"}[args.precision],
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 tcgen05, fp32 accumulate) + f32"}[args.precision],
             "data": "synthetic",
             "config": {"workload": f"configs[{1 if args.workload == 'config2' else 3}]: synthetic MSAs, {R_TAXA} taxa x {L_SITES} sites, Argmax, sharded by alignment: {shard}",
                        "global_batch": main_run["n_global"], "parallelism": f"alignment-sharded x{world}, no collectives",
