@@ -11,7 +11,7 @@ for ch in 2 4 8 16 32 64 128; do
   NNJ_CHUNK_MAX=$ch timeout 300 python scratch/r2_explore.py 128 50 1024 bf16x3 2 >> $o/chunk_sweep.jsonl 2>> $o/chunk_sweep.err
 done
 NNJ_LIB_PATH=$GRAFT_REPO_ROOT/scratch/libnnj_trace.so timeout 300 python scratch/col_trace.py 32 50 1024 > $o/col_trace.txt 2>&1
-./scratch/hmma_bench > $o/hmma_bench.txt 2>&1
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 scratch/hmma_bench.cu -o scratch/hmma_bench && ./scratch/hmma_bench > $o/hmma_bench.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $o/launches.csv python scratch/prof_rollout.py 128 1 > $o/ncu_launch.log 2>&1
 cap() {  # name regex skip
   ncu --set full --import-source on --clock-control none -k regex:$2 -s $3 -c 1 -o $o/$1 -f python scratch/prof_rollout.py 128 1 > $o/ncu_$1.log 2>&1
