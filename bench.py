@@ -340,7 +340,7 @@ def main():
             kernels[n]["tflops"] = round(fl[n] * B / (kernels[n]["ms"] * 1e-3) / 1e12, 3)
     # DRAM traffic.  The NJ kernels stream only the n live node slots of a step, so their bytes change from step to step: the
     # mean over a rollout comes from the algorithmic byte count (node tiles of the live slots + x planes), which the committed
-    # `ncu --set full` captures reproduce within 1 % at the captured launches (profiles/r01_traffic_b128.json).
+    # `ncu --set full` captures reproduce within 1 % at the captured launches (profiles/r02_traffic_b128.json).
     roofline_hbm = None
     nj_bytes_per_tree = None
     if args.workload == "config2":
@@ -355,7 +355,7 @@ def main():
         if top in ("alpha", "pair_score"):
             per = alpha_b if top == "alpha" else score_b
             roofline["traffic"] = round(sum(per) / len(per) * B / max(1, kernels["node_derive"]["launches"]))
-            roofline["traffic_source"] = "mean over the launches of a rollout: algorithmic bytes of the live node slots + x planes (= ncu dram__bytes at the captured launches, profiles/r01_traffic_b128.json)"
+            roofline["traffic_source"] = "mean over the launches of a rollout: algorithmic bytes of the live node slots + x planes (= ncu dram__bytes at the captured launches, profiles/r02_traffic_b128.json)"
         if "alpha" in kernels:
             a_ms = kernels["alpha"]["ms"]
             a_bytes = sum(alpha_b) * B

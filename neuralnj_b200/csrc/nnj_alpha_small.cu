@@ -86,21 +86,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_alpha_small(const AlphaSmallA
 #pragma unroll
         for (int j = 0; j < 2 * T; ++j) { acc[m][j][0] = 0.f; acc[m][j][1] = 0.f; acc[m][j][2] = 0.f; acc[m][j][3] = 0.f; }
 
+    const int ld_slot0 = lane >> 4, ld_ch = lane & 15;
+    const size_t ld_stride_x = (size_t)2 * a.C * 64, ld_stride_k = (size_t)4 * a.C * 64;
     for (int site = warp; site < n_sites; site += WARPS) {
         const int c = c_base + site;
-        for (int i = lane; i < a.Rp * 16; i += 32) {    // X, Y rows of the live slots at this site
-            const int slot = i >> 4, ch = i & 15;
-            const uint32_t off = slot * 256 + ((ch ^ (slot & 7)) << 4);
-            const size_t src = tb + ((size_t)slot * a.C + c) * 64 + ch * 4;
-            as_cp16(mybuf_u + off, a.X + src);
-            as_cp16(mybuf_u + XB + off, a.Y + src);
-        }
-        for (int i = lane; i < a.Rp * 8; i += 32) {     // K' rows (hi, lo)
-            const int slot = i >> 3, ch = i & 7;
-            const uint32_t off = slot * 128 + ((ch ^ (slot & 7)) << 4);
-            const size_t src = (((size_t)b * a.S + slot) * a.C + c) * 64 + ch * 8;
-            as_cp16(mybuf_u + 2 * XB + off, a.kph + src);
-            as_cp16(mybuf_u + 2 * XB + KB + off, a.kpl + src);
+        {   // X, Y rows of the live slots at this site: lane = (slot parity, 16-byte chunk), two slots per pass; pointers advance by constant strides
+            const float* px = a.X + tb + ((size_t)ld_slot0 * a.C + c) * 64 + ld_ch * 4;
+            const float* py = a.Y + tb + ((size_t)ld_slot0 * a.C + c) * 64 + ld_ch * 4;
+            for (int slot = ld_slot0; slot < a.Rp; slot += 2, px += ld_stride_x, py += ld_stride_x) {
+                const uint32_t off = mybuf_u + slot * 256 + ((ld_ch ^ (slot & 7)) << 4);
+                as_cp16(off, px);
+                as_cp16(off + XB, py);
+            }
+            // K' rows (hi, lo): lane = (slot mod 4, chunk), four slots per pass
+            const __nv_bfloat16* ph = a.kph + (((size_t)b * a.S + (lane >> 3)) * a.C + c) * 64 + (lane & 7) * 8;
+            const __nv_bfloat16* pl = a.kpl + (((size_t)b * a.S + (lane >> 3)) * a.C + c) * 64 + (lane & 7) * 8;
+            for (int slot = lane >> 3; slot < a.Rp; slot += 4, ph += ld_stride_k, pl += ld_stride_k) {
+                const uint32_t off = mybuf_u + 2 * XB + slot * 128 + (((lane & 7) ^ (slot & 7)) << 4);
+                as_cp16(off, ph);
+                as_cp16(off + KB, pl);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -52,7 +52,8 @@ __device__ __forceinline__ void ss_cp16(uint32_t dst, const void* src) {
 // sub-partition: 770 clocks per site and SM) and loses to k_score_inc's narrow mode (860 vs 770 us per launch) - it is kept for
 // reference but not dispatched; T = 1 with 8 warps ran at 43 % of the legacy tensor pipe (two warps per sub-partition cannot
 // cover the 20-clock dependent instruction chains and the gate math between the two GEMMs), hence 16 warps.
-template <int T, int SS_WARPS, int NBUF>
+// HALF (T = 1 only): at most 8 listed pairs - rows 8..15 of the tile are padding and their gate / GELU math is compiled out.
+template <int T, int SS_WARPS, int NBUF, bool HALF>
 __global__ void __launch_bounds__(SS_WARPS * 32, 1) k_score_small(const ScoreSmallArgs a) {
     constexpr int ROWS = 16 * T;
     constexpr int NODE_B = ROWS * 256;                  // one node plane of a site: [slot][128 ch] bf16, 16-byte chunk c stored at c ^ (slot & 7)
@@ -113,15 +114,20 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) k_score_small(const ScoreSma
         const uint32_t dst = mybuf_u + buf * BUF;
         const uint8_t* nh = reinterpret_cast<const uint8_t*>(a.nodes_h + ((size_t)b * a.C + c) * node_site_stride);
         const uint8_t* nl = reinterpret_cast<const uint8_t*>(a.nodes_l + ((size_t)b * a.C + c) * node_site_stride);
-        for (int i = lane; i < a.Rp * 16; i += 32) {    // 16-byte chunks of the live node rows (contiguous in both planes)
-            const int slot = i >> 4, ch = i & 15;
-            const uint32_t off = slot * 256 + ((ch ^ (slot & 7)) << 4);
-            ss_cp16(dst + off, nh + (size_t)i * 16);
-            ss_cp16(dst + NODE_B + off, nl + (size_t)i * 16);
-        }
-        for (int i = lane; i < a.nc * 16; i += 32) {    // x rows of the listed pairs at this site
-            const int row = i >> 4, ch = i & 15;
-            ss_cp16(dst + 2 * NODE_B + row * 256 + ((ch ^ (row & 7)) << 4), a.xf + (((size_t)b * a.pc + row) * a.C + c) * 64 + ch * 4);
+        {   // live node rows (contiguous in both planes): lane = (slot parity, 16-byte chunk), two slots per pass
+            const int ch = lane & 15;
+            const uint8_t* ph = nh + lane * 16;
+            const uint8_t* pl = nl + lane * 16;
+            for (int slot = lane >> 4; slot < a.Rp; slot += 2, ph += 512, pl += 512) {
+                const uint32_t off = dst + slot * 256 + ((ch ^ (slot & 7)) << 4);
+                ss_cp16(off, ph);
+                ss_cp16(off + NODE_B, pl);
+            }
+            // x rows of the listed pairs at this site (one 256-byte row per pair, C rows apart)
+            const float* px = a.xf + (((size_t)b * a.pc + (lane >> 4)) * a.C + c) * 64 + ch * 4;
+            const size_t xstride = (size_t)2 * a.C * 64;
+            for (int row = lane >> 4; row < a.nc; row += 2, px += xstride)
+                ss_cp16(dst + 2 * NODE_B + row * 256 + ((ch ^ (row & 7)) << 4), px);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) k_score_small(const ScoreSma
 #pragma unroll
                     for (int hrow = 0; hrow < 2; ++hrow) {
                         const int row = 16 * m + g + 8 * hrow;
-                        if (16 * m + 8 * hrow >= a.nc) { xh[m][2 * e + hrow] = 0u; xl[m][2 * e + hrow] = 0u; continue; }   // a whole 8-row block past the listed pairs (warp-uniform)
+                        if (HALF && hrow == 1) { xh[m][2 * e + hrow] = 0u; xl[m][2 * e + hrow] = 0u; continue; }
                         const float2 x2 = *reinterpret_cast<const float2*>(xt + row * 256 + (((ch >> 2) ^ (row & 7)) << 4) + (ch & 3) * 4);
                         const float2 w = sigmoid_fast2(fadd2(make_float2(gg[m][2 * hrow], gg[m][2 * hrow + 1]), bgv));
                         const float2 pp = ffma2(w, fsub2(make_float2(xg[m][2 * hrow], xg[m][2 * hrow + 1]), x2), x2);       // (1-w) x + w x_glob
@@ -212,8 +218,8 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) k_score_small(const ScoreSma
 #pragma unroll
                 for (int f = 0; f < 8; ++f) {
                     const float2 bsv = *reinterpret_cast<const float2*>(s_bias + 64 + 8 * f + 2 * t), w2v = *reinterpret_cast<const float2*>(s_bias + 128 + 8 * f + 2 * t);
-                    if (16 * m < a.nc) acc0 = ffma2(gelu_fast2(fadd2(make_float2(sacc[m][f][0], sacc[m][f][1]), bsv)), w2v, acc0);
-                    if (16 * m + 8 < a.nc) acc1 = ffma2(gelu_fast2(fadd2(make_float2(sacc[m][f][2], sacc[m][f][3]), bsv)), w2v, acc1);
+                    acc0 = ffma2(gelu_fast2(fadd2(make_float2(sacc[m][f][0], sacc[m][f][1]), bsv)), w2v, acc0);
+                    if (!HALF) acc1 = ffma2(gelu_fast2(fadd2(make_float2(sacc[m][f][2], sacc[m][f][3]), bsv)), w2v, acc1);
                 }
                 part[m][0] += acc0.x + acc0.y;
                 part[m][1] += acc1.x + acc1.y;
@@ -241,16 +247,16 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 1) k_score_small(const ScoreSma
     }
 }
 
-template <int T, int W, int NB>
+template <int T, int W, int NB, bool HALF = false>
 static int launch_small_t(const ScoreSmallArgs& a, int groups, int B, cudaStream_t st) {
     constexpr size_t smem = 1024 + 2 * 64 * SS_WPITCH + (32 * 33 + 192) * 4 + 1024 + (size_t)W * NB * (3 * 16 * T * 256);
     static DevOnce once;      // per device, not per process
     if (once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(k_score_small<T, W, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_score_small<T, W, NB, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
         once.done();
     }
-    k_score_small<T, W, NB><<<dim3(groups, B), W * 32, smem, st>>>(a);
+    k_score_small<T, W, NB, HALF><<<dim3(groups, B), W * 32, smem, st>>>(a);
     return 0;
 }
 
@@ -272,7 +278,8 @@ int launch_score_small(const Model* m, const float* xf, int pc, const void* node
     static int w8 = -1;
     if (w8 < 0) { const char* ev = getenv("NNJ_SCORE_SMALL_W8"); w8 = ev ? atoi(ev) : 0; }      // A/B: the 8-warp double-buffered variant
     prof_begin(KC_SCORE, st);
-    int rc = T == 1 ? (w8 ? launch_small_t<1, 8, 2>(a, groups, B, st) : launch_small_t<1, 16, 1>(a, groups, B, st)) : launch_small_t<2, 8, 1>(a, groups, B, st);
+    int rc = T == 1 ? (w8 ? launch_small_t<1, 8, 2>(a, groups, B, st) : (nc <= 8 ? launch_small_t<1, 16, 1, true>(a, groups, B, st) : launch_small_t<1, 16, 1>(a, groups, B, st)))
+                    : launch_small_t<2, 8, 1>(a, groups, B, st);
     ++g_launches;
     prof_end(st);
     if (rc) return rc;
