@@ -147,16 +147,23 @@ int nnj_rollout_host(nnj_model* m, const int8_t* data_host, const uint8_t* seq_m
  *   children_host int32 [B,R-1,2] topology in join order: leaves 0..R-1, inner node R+k = (children[k][0], children[k][1]),
  *                                 the last join is the root (the NJ merge list replayed, neuralnj_b200/likelihood.py)
  *   brlen_host    double [B,2R-2] length of the branch above node v; the two root branches are one branch of the unrooted tree
- *   model_host    double [B,48]   eigenvalues 4 | eigenvectors U 16 | U^-1 16 | base frequencies 4 | class rates 4 | p_inv | pad 3
+ *   model_host    double [B,64]   eigenvalues 4 | eigenvectors U 16 | U^-1 16 | base frequencies 4 | class rates 4 | p_inv | alpha |
+ *                                 flags (1: GTR rates free, 2: +G, 4: +I) | pad | GTR rates AC AG AT CG CT GT | pad 10
  * nnj_llh_eval returns log L per tree; nnj_llh_optimize_brlen maximises it over the branch lengths (Newton-Raphson per branch,
  * depth-first sweeps until a sweep gains less than eps or max_passes), updates brlen_host (root branch split evenly) and returns
- * log L before / after.  Both synchronise `stream` (their results are host values). */
+ * log L before / after.  nnj_llh_optimize_all also searches the free model parameters named by `flags` inside the kernel (golden
+ * section per parameter, eigen-system and class rates rebuilt on the device; rounds of parameters + branch sweeps until a round
+ * gains < lh_eps - the loop shape of raxmlpy.cpp:1721-1746 with lh_epsilon = lh_eps) and returns the optimised model in model_host.
+ * All three synchronise `stream` (their results are host values). */
 int64_t nnj_llh_workspace_bytes(int B, int R, int L);
 int nnj_llh_eval(const uint8_t* tips_dev, const double* weights_dev, const int32_t* children_host, const double* brlen_host,
                  const double* model_host, int B, int R, int L, double* llh_host, void* ws_dev, int64_t ws_bytes, void* stream);
 int nnj_llh_optimize_brlen(const uint8_t* tips_dev, const double* weights_dev, const int32_t* children_host, double* brlen_host,
                            const double* model_host, int B, int R, int L, int max_passes, double eps,
                            double* llh_before_host, double* llh_after_host, void* ws_dev, int64_t ws_bytes, void* stream);
+int nnj_llh_optimize_all(const uint8_t* tips_dev, const double* weights_dev, const int32_t* children_host, double* brlen_host,
+                         double* model_host, int B, int R, int L, int max_passes, double eps, double lh_eps, int max_rounds,
+                         double* llh_before_host, double* llh_after_host, void* ws_dev, int64_t ws_bytes, void* stream);
 /* Mean rates of the ncat equal-probability classes of Gamma(alpha, alpha) (Yang 1994): rates_host double [ncat]. */
 int nnj_gamma_rates(double alpha, int ncat, double* rates_host);
 

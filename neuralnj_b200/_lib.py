@@ -18,7 +18,7 @@ EXPORTS = ["nnj_last_error", "nnj_abi_version", "nnj_model_create", "nnj_model_d
            "nnj_encode", "nnj_pair_scores_full", "nnj_pair_scores_list", "nnj_pair_scores_incr", "nnj_aggregate",
            "nnj_merge", "nnj_rollout", "nnj_rollout_from_state", "nnj_rollout_host", "nnj_launch_count",
            "nnj_profile_enable", "nnj_profile_classes", "nnj_profile_name", "nnj_profile_read", "nnj_gemm_split_bf16", "nnj_tc_selftest",
-           "nnj_llh_workspace_bytes", "nnj_llh_eval", "nnj_llh_optimize_brlen", "nnj_gamma_rates"]
+           "nnj_llh_workspace_bytes", "nnj_llh_eval", "nnj_llh_optimize_brlen", "nnj_llh_optimize_all", "nnj_gamma_rates"]
 
 
 class NnjError(RuntimeError):
@@ -128,6 +128,8 @@ def lib() -> C.CDLL:
     L.nnj_llh_eval.restype = i32
     L.nnj_llh_optimize_brlen.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_double, vp, vp, vp, i64, vp]
     L.nnj_llh_optimize_brlen.restype = i32
+    L.nnj_llh_optimize_all.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_double, C.c_double, i32, vp, vp, vp, i64, vp]
+    L.nnj_llh_optimize_all.restype = i32
     L.nnj_gamma_rates.argtypes = [C.c_double, i32, dp]
     L.nnj_gamma_rates.restype = i32
     L.nnj_launch_count.argtypes = [i32]

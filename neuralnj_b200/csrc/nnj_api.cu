@@ -397,7 +397,8 @@ int nnj_llh_eval(const uint8_t* tips, const double* weights, const int32_t* chil
                  double* llh_h, void* ws, int64_t ws_bytes, void* stream) {
     CHECK_ARGS(tips && weights && children_h && brlen_h && model_h && llh_h && ws && B >= 1 && R >= 3 && R <= 4096 && L >= 1, "llh_eval: bad arguments");
     std::vector<double> both((size_t)B * 2);
-    int rc = run_llh(tips, weights, children_h, const_cast<double*>(brlen_h), model_h, B, R, L, 0, 0, 0.0, both.data(), ws, (size_t)ws_bytes, (cudaStream_t)stream);
+    int rc = run_llh(tips, weights, children_h, const_cast<double*>(brlen_h), const_cast<double*>(model_h), B, R, L, 0, 0, 0.0, 0.0, 0, 0, both.data(), ws,
+                     (size_t)ws_bytes, (cudaStream_t)stream);
     if (rc == 0) for (int b = 0; b < B; ++b) llh_h[b] = both[2 * b + 1];
     return rc;
 }
@@ -407,7 +408,20 @@ int nnj_llh_optimize_brlen(const uint8_t* tips, const double* weights, const int
     CHECK_ARGS(tips && weights && children_h && brlen_h && model_h && llh_after_h && ws && B >= 1 && R >= 3 && R <= 4096 && L >= 1 && max_passes >= 1,
                "llh_optimize_brlen: bad arguments");
     std::vector<double> both((size_t)B * 2);
-    int rc = run_llh(tips, weights, children_h, brlen_h, model_h, B, R, L, 1, max_passes, eps, both.data(), ws, (size_t)ws_bytes, (cudaStream_t)stream);
+    int rc = run_llh(tips, weights, children_h, brlen_h, const_cast<double*>(model_h), B, R, L, 1, max_passes, eps, 0.0, 0, 0, both.data(), ws, (size_t)ws_bytes,
+                     (cudaStream_t)stream);
+    if (rc == 0) for (int b = 0; b < B; ++b) { if (llh_before_h) llh_before_h[b] = both[2 * b]; llh_after_h[b] = both[2 * b + 1]; }
+    return rc;
+}
+
+int nnj_llh_optimize_all(const uint8_t* tips, const double* weights, const int32_t* children_h, double* brlen_h, double* model_h, int B, int R, int L,
+                         int max_passes, double eps, double lh_eps, int max_rounds, double* llh_before_h, double* llh_after_h, void* ws, int64_t ws_bytes,
+                         void* stream) {
+    CHECK_ARGS(tips && weights && children_h && brlen_h && model_h && llh_after_h && ws && B >= 1 && R >= 3 && R <= 4096 && L >= 1 && max_passes >= 1 && max_rounds >= 1,
+               "llh_optimize_all: bad arguments");
+    std::vector<double> both((size_t)B * 2);
+    int rc = run_llh(tips, weights, children_h, brlen_h, model_h, B, R, L, 2, max_passes, eps, lh_eps, max_rounds, 24, both.data(), ws, (size_t)ws_bytes,
+                     (cudaStream_t)stream);
     if (rc == 0) for (int b = 0; b < B; ++b) { if (llh_before_h) llh_before_h[b] = both[2 * b]; llh_after_h[b] = both[2 * b + 1]; }
     return rc;
 }

@@ -155,8 +155,9 @@ int run_gemm_split_bf16(const float* A, const float* B, float* Cm, int Z, int M,
 
 // tree likelihood / branch-length optimisation (nnj_llh.cu)
 size_t llh_ws_bytes(int B, int R, int L);
-int run_llh(const uint8_t* tips, const double* weights, const int32_t* children_h, double* brlen_h, const double* model_h, int B, int R, int L,
-            int optimise, int max_passes, double eps, double* llh_h, void* ws, size_t ws_bytes, cudaStream_t st);
+int run_llh(const uint8_t* tips, const double* weights, const int32_t* children_h, double* brlen_h, double* model_h, int B, int R, int L,
+            int optimise, int max_passes, double eps, double lh_eps, int max_rounds, int golden_iters, double* llh_h, void* ws, size_t ws_bytes,
+            cudaStream_t st);
 int gamma_rates(double alpha, int ncat, double* out);
 
 }  // namespace nnj

@@ -18,7 +18,8 @@
 namespace nnj {
 
 constexpr int LLH_THREADS = 512;
-constexpr int LLH_MODEL = 48;      // lam 4 | U 16 | Uinv 16 | freqs 4 | class rates 4 | pinv | pad 3   (oracle Model.packed)
+constexpr int LLH_MODEL = 64;      // lam 4 | U 16 | Uinv 16 | freqs 4 | class rates 4 | p_inv | alpha | flags (1 GTR rates free, 2 +G, 4 +I) | pad | 6 GTR rates | pad 10
+constexpr double RATE_LO = 1e-3, RATE_HI = 1e3, ALPHA_LO = 0.02, ALPHA_HI = 100.0, PINV_HI = 0.99, GOLD = 0.3819660112501051;   // as in oracle/llh_oracle.py
 constexpr double BRLEN_MIN = 1e-6, BRLEN_MAX = 100.0;
 enum { OP_OPT = 0, OP_UP = 1, OP_DOWN = 2, OP_SWAPROOT = 3 };
 
@@ -31,8 +32,10 @@ struct LlhArgs {
     const double* model;        // [B][LLH_MODEL]
     double *D, *U, *S, *inv;    // workspace: [B][R-1][L][16], [B][2R-2][L][16], [B][L][16], [B][L]
     double* llh;                // [B][2]: before, after
-    int B, R, L, n_ops, max_passes, optimise;
+    int B, R, L, n_ops, max_passes, optimise;     // optimise: 0 evaluate, 1 branch lengths, 2 branch lengths + model parameters
     double eps;
+    double lh_eps; int max_rounds, golden_iters;  // optimise = 2: rounds of (free parameters one at a time, branch sweeps) until a round gains < lh_eps
+    double* model_out;                            // [B][LLH_MODEL] optimised model (optimise = 2)
 };
 
 __device__ __forceinline__ double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -104,6 +107,97 @@ __device__ __forceinline__ void block_sum2(double& v0, double& v1, double* red) 
     __syncthreads();
 }
 
+// ---- model parameters on the device (optimise = 2): one thread rebuilds the eigen-system and the class rates of its tree
+// regularised lower incomplete gamma P(a, x): series / continued fraction (Lentz), as gammp below on the host
+__device__ double gammp_dev(double a, double x) {
+    if (x <= 0.0) return 0.0;
+    const double gln = lgamma(a);
+    if (x < a + 1.0) {
+        double ap = a, sum = 1.0 / a, del = sum;
+        for (int n = 0; n < 2000; ++n) { ap += 1.0; del *= x / ap; sum += del; if (fabs(del) < fabs(sum) * 1e-17) break; }
+        return sum * exp(-x + a * log(x) - gln);
+    }
+    double b = x + 1.0 - a, c = 1e300, d = 1.0 / b, h = d;
+    for (int i = 1; i < 2000; ++i) {
+        const double an = -i * (i - a);
+        b += 2.0;
+        d = an * d + b; if (fabs(d) < 1e-300) d = 1e-300;
+        c = b + an / c; if (fabs(c) < 1e-300) c = 1e-300;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-17) break;
+    }
+    return 1.0 - exp(-x + a * log(x) - gln) * h;
+}
+// class i (0..3) boundary quantile of Gamma(alpha, 1) at (i + 1) / 4, then P(alpha + 1, .) - what gamma_rates() does on the host
+__device__ double gamma_cdf1_dev(double alpha, int i) {
+    const double target = (double)(i + 1) * 0.25, gln = lgamma(alpha);
+    double lo = 0.0, hi = alpha + 1.0;
+    while (gammp_dev(alpha, hi) < target) hi *= 2.0;
+    double x = 0.5 * (lo + hi);
+    for (int it = 0; it < 200; ++it) {
+        const double f = gammp_dev(alpha, x) - target;
+        if (f < 0.0) lo = x; else hi = x;
+        const double pdf = exp((alpha - 1.0) * log(x) - x - gln);
+        double xn = pdf > 0.0 ? x - f / pdf : 0.5 * (lo + hi);
+        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+        const bool done = fabs(xn - x) <= 1e-15 * x || hi - lo <= 1e-300;
+        x = xn;
+        if (done) break;
+    }
+    return gammp_dev(alpha + 1.0, x);
+}
+// mdl: raw parameters (rates [48..53], freqs [36..39], alpha [45]) -> eigenvalues [0..3], U [4..19], U^-1 [20..35], class rates [40..43].
+// Threads 0 (eigen-system: cyclic Jacobi on the symmetrised rate matrix) and 1..3 (class boundaries) work, then a barrier.
+__device__ void rebuild_model(double* mdl, double* scratch /* 4 doubles */, bool eigen, bool gamma) {
+    const int tid = threadIdx.x;
+    if (tid == 0 && eigen) {
+        const double* pi = mdl + 36;
+        double r[4][4] = {{0, mdl[48], mdl[49], mdl[50]}, {mdl[48], 0, mdl[51], mdl[52]}, {mdl[49], mdl[51], 0, mdl[53]}, {mdl[50], mdl[52], mdl[53], 0}};
+        double Q[4][4], S[4][4], V[4][4];
+        double norm = 0.0;
+        for (int a = 0; a < 4; ++a) {
+            double d = 0.0;
+            for (int c = 0; c < 4; ++c) { Q[a][c] = r[a][c] * pi[c]; if (c != a) d += Q[a][c]; }
+            Q[a][a] = -d;
+            norm += pi[a] * d;
+        }
+        for (int a = 0; a < 4; ++a)
+            for (int c = 0; c < 4; ++c) { S[a][c] = sqrt(pi[a]) * Q[a][c] / (norm * sqrt(pi[c])); V[a][c] = a == c ? 1.0 : 0.0; }
+        for (int a = 0; a < 4; ++a)
+            for (int c = a + 1; c < 4; ++c) { const double m = 0.5 * (S[a][c] + S[c][a]); S[a][c] = m; S[c][a] = m; }
+        double diag2 = 0.0;
+        for (int p = 0; p < 4; ++p) diag2 += S[p][p] * S[p][p];
+        for (int sweep = 0; sweep < 16; ++sweep) {           // quadratic convergence: 5-6 sweeps reach the rounding level of a 4 x 4 matrix
+            double off = 0.0;
+            for (int p = 0; p < 4; ++p) for (int q = p + 1; q < 4; ++q) off += S[p][q] * S[p][q];
+            if (off < 1e-31 * diag2) break;
+            for (int p = 0; p < 4; ++p)
+                for (int q = p + 1; q < 4; ++q) {
+                    if (fabs(S[p][q]) < 1e-300) continue;
+                    const double theta = (S[q][q] - S[p][p]) / (2.0 * S[p][q]);
+                    const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double cs = 1.0 / sqrt(tt * tt + 1.0), sn = tt * cs;
+                    for (int k = 0; k < 4; ++k) { const double skp = S[k][p], skq = S[k][q]; S[k][p] = cs * skp - sn * skq; S[k][q] = sn * skp + cs * skq; }
+                    for (int k = 0; k < 4; ++k) { const double spk = S[p][k], sqk = S[q][k]; S[p][k] = cs * spk - sn * sqk; S[q][k] = sn * spk + cs * sqk; }
+                    for (int k = 0; k < 4; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = cs * vkp - sn * vkq; V[k][q] = sn * vkp + cs * vkq; }
+                }
+        }
+        for (int j = 0; j < 4; ++j) mdl[j] = S[j][j];
+        for (int a = 0; a < 4; ++a)
+            for (int j = 0; j < 4; ++j) { mdl[4 + a * 4 + j] = V[a][j] / sqrt(pi[a]); mdl[20 + j * 4 + a] = V[a][j] * sqrt(pi[a]); }
+    }
+    if (gamma && tid >= 1 && tid <= 3) scratch[tid] = gamma_cdf1_dev(mdl[45], tid - 1);
+    __syncthreads();
+    if (gamma && tid == 0) {
+        scratch[0] = 0.0;
+        const double c4 = 1.0;
+        mdl[40] = 4.0 * (scratch[1] - 0.0); mdl[41] = 4.0 * (scratch[2] - scratch[1]); mdl[42] = 4.0 * (scratch[3] - scratch[2]); mdl[43] = 4.0 * (c4 - scratch[3]);
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(LLH_THREADS) k_llh(const LlhArgs a) {
     extern __shared__ double sm_d[];
     double* mdl = sm_d;                 // [48]
@@ -128,12 +222,12 @@ __global__ void __launch_bounds__(LLH_THREADS) k_llh(const LlhArgs a) {
     if (a.optimise)
         for (int v = tid; v < 2 * R - 2; v += LLH_THREADS) t[v] = clampd(t[v], BRLEN_MIN, BRLEN_MAX);
     __syncthreads();
-    const double pinv = mdl[44], wk = (1.0 - pinv) * 0.25;
+    double pinv = mdl[44], wk = (1.0 - pinv) * 0.25;            // re-read after every change of the model (optimise = 2)
     // invariant-site term: pi_x where every tip of the pattern is compatible with exactly one state x
     for (int s = tid; s < L; s += LLH_THREADS) {
         int m = 15;
         for (int v = 0; v < R; ++v) m &= tips[(size_t)v * L + s];
-        invt[s] = (m != 0 && (m & (m - 1)) == 0) ? pinv * mdl[36 + (31 - __clz(m))] : 0.0;
+        invt[s] = (m != 0 && (m & (m - 1)) == 0) ? mdl[36 + (31 - __clz(m))] : 0.0;      // times p_inv where it is used
     }
     // ---- subtree vectors, children before parents (join order); the virtual root itself is never needed
     auto combine = [&](int x, int y, double* dst_base /* [L][16] */, const double* xsrc_U /* non-null: take U[x] instead of D[x] */) {
@@ -150,7 +244,8 @@ __global__ void __launch_bounds__(LLH_THREADS) k_llh(const LlhArgs a) {
         }
         __syncthreads();      // Pm is rewritten by the next operation
     };
-    for (int k = 0; k < R - 2; ++k) combine(ch[2 * k], ch[2 * k + 1], Dt + (size_t)k * L * 16, nullptr);
+    auto down_pass = [&]() { for (int k = 0; k < R - 2; ++k) combine(ch[2 * k], ch[2 * k + 1], Dt + (size_t)k * L * 16, nullptr); };
+    down_pass();
     auto root_loglik = [&]() {
         pmat2(Pm, mdl, t[c1], 0.0);
         double acc = 0.0, dummy = 0.0;
@@ -164,15 +259,16 @@ __global__ void __launch_bounds__(LLH_THREADS) k_llh(const LlhArgs a) {
             for (int k = 0; k < 4; ++k)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) l = fma(mdl[36 + c] * p1[k * 4 + c], v2[k * 4 + c], l);
-            acc += wts[s] * log(wk * l + invt[s]);
+            acc += wts[s] * log(wk * l + pinv * invt[s]);
         }
         block_sum2(acc, dummy, red);
         return acc;
     };
     double ll = root_loglik();
     const double ll0 = ll;
-    if (a.optimise) {
-        const int32_t* ops = a.ops + (size_t)b * a.n_ops * 4;
+    const int32_t* ops = a.ops + (size_t)b * a.n_ops * 4;
+    // branch-length sweeps from the current subtree vectors (which must match t[] and the model) until a sweep gains < eps
+    auto sweeps = [&]() {
         for (int pass = 0; pass < a.max_passes; ++pass) {
             // U[c1] = D[c2]
             for (int s = tid; s < L; s += LLH_THREADS) {
@@ -229,7 +325,7 @@ __global__ void __launch_bounds__(LLH_THREADS) k_llh(const LlhArgs a) {
                                 const double se = sv[i] * ek[i];
                                 l0 += se; l1 = fma(se, ek[16 + i], l1); l2 = fma(se, ek[32 + i], l2);
                             }
-                            const double L0 = wk * l0 + invt[s], g = wk * l1 / L0;
+                            const double L0 = wk * l0 + pinv * invt[s], g = wk * l1 / L0;
                             f1 = fma(wts[s], g, f1);
                             f2 = fma(wts[s], wk * l2 / L0 - g * g, f2);
                         }
@@ -249,6 +345,41 @@ __global__ void __launch_bounds__(LLH_THREADS) k_llh(const LlhArgs a) {
             const double gain = nl - ll;
             ll = nl;
             if (gain < a.eps) break;
+        }
+    };
+    if (a.optimise) {
+        sweeps();
+        if (a.optimise == 2) {
+            // ---- model parameters: rounds of (every free parameter by golden section, all else fixed; branch sweeps) until a round
+            //      gains < lh_eps - the loop of oracle/llh_oracle.py optimize_all, one tree per CTA, no host round trips
+            const int flags = (int)mdl[46];
+            auto objective = [&](int prm, double x) {            // set parameter prm to x (log scale for rates / alpha), rebuild, evaluate
+                if (tid == 0) {
+                    if (prm < 5) mdl[48 + prm] = exp(x); else if (prm == 5) mdl[45] = exp(x); else mdl[44] = x;
+                }
+                __syncthreads();
+                rebuild_model(mdl, ek, prm < 5, prm == 5);
+                pinv = mdl[44]; wk = (1.0 - pinv) * 0.25;
+                down_pass();
+                return root_loglik();
+            };
+            for (int round = 0; round < a.max_rounds; ++round) {
+                const double start = ll;
+                for (int prm = 0; prm < 7; ++prm) {
+                    if (prm < 5 ? !(flags & 1) : (prm == 5 ? !(flags & 2) : !(flags & 4))) continue;
+                    double lo = prm < 5 ? log(RATE_LO) : (prm == 5 ? log(ALPHA_LO) : 0.0), hi = prm < 5 ? log(RATE_HI) : (prm == 5 ? log(ALPHA_HI) : PINV_HI);
+                    double x1 = lo + GOLD * (hi - lo), x2 = hi - GOLD * (hi - lo);
+                    double f1 = objective(prm, x1), f2 = objective(prm, x2);
+                    for (int it = 0; it < a.golden_iters; ++it) {
+                        if (f1 < f2) { lo = x1; x1 = x2; f1 = f2; x2 = hi - GOLD * (hi - lo); f2 = objective(prm, x2); }
+                        else { hi = x2; x2 = x1; f2 = f1; x1 = lo + GOLD * (hi - lo); f1 = objective(prm, x1); }
+                    }
+                    ll = objective(prm, f1 > f2 ? x1 : x2);
+                }
+                sweeps();
+                if (ll - start < a.lh_eps) break;
+            }
+            if (tid < LLH_MODEL) a.model_out[(size_t)b * LLH_MODEL + tid] = mdl[tid];
         }
         __syncthreads();
         if (tid == 0) { const double h = 0.5 * t[c1]; t[c1] = h; t[c2] = h; }     // the rooted form splits the root branch evenly
@@ -321,8 +452,9 @@ static int check_tree(const int32_t* ch, int R) {
     return 0;
 }
 
-int run_llh(const uint8_t* tips, const double* weights, const int32_t* children_h, double* brlen_h, const double* model_h, int B, int R, int L,
-            int optimise, int max_passes, double eps, double* llh_h, void* ws, size_t ws_bytes, cudaStream_t st) {
+int run_llh(const uint8_t* tips, const double* weights, const int32_t* children_h, double* brlen_h, double* model_h, int B, int R, int L,
+            int optimise, int max_passes, double eps, double lh_eps, int max_rounds, int golden_iters, double* llh_h, void* ws, size_t ws_bytes,
+            cudaStream_t st) {
     std::vector<int32_t> ops_all;
     int n_ops = 0;
     for (int b = 0; b < B; ++b) {
@@ -356,6 +488,7 @@ int run_llh(const uint8_t* tips, const double* weights, const int32_t* children_
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     a.children = d_ch; a.ops = d_ops; a.brlen = d_br; a.model = d_md; a.llh = d_ll;
     a.B = B; a.R = R; a.L = L; a.n_ops = n_ops; a.max_passes = max_passes; a.optimise = optimise; a.eps = eps;
+    a.lh_eps = lh_eps; a.max_rounds = max_rounds; a.golden_iters = golden_iters; a.model_out = d_md;
     const size_t smem = (LLH_MODEL + 128 + 66 + 48 + 2 * (size_t)R) * sizeof(double);
     prof_begin(KC_LLH, st);
     k_llh<<<B, LLH_THREADS, smem, st>>>(a);
@@ -364,6 +497,7 @@ int run_llh(const uint8_t* tips, const double* weights, const int32_t* children_
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(llh_h, d_ll, (size_t)B * 2 * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && optimise) e = cudaMemcpyAsync(brlen_h, d_br, (size_t)B * (2 * R - 2) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && optimise == 2) e = cudaMemcpyAsync(model_h, d_md, (size_t)B * LLH_MODEL * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);       // the small results are host values: the call returns them
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     return 0;

@@ -15,7 +15,8 @@ Model: GTR (or JC) + optional invariant sites (+I) + optional discrete gamma, 4 
 frequencies.  RAxML-NG itself is not available (the reference git-clones it at install time): parity with its numbers is
 UNPINNED; tests pin this implementation against an independent CPU restatement and brute-force enumeration
 (oracle/llh_oracle.py).  The optimiser is this repo's own (coordinate golden-section over 5 rates, alpha, p_inv between
-branch-length sweeps, stopping when a round gains < 1 log-unit like `optimize_model(treeinfo, 1.0)`, raxmlpy.cpp:1721-1746).
+branch-length sweeps, stopping when a round gains < 1 log-unit like `optimize_model(treeinfo, 1.0)`, raxmlpy.cpp:1721-1746) and
+runs inside the kernel, one tree per CTA.
 """
 from __future__ import annotations
 
@@ -100,7 +101,7 @@ class SubstModel:
         return p
 
     def pack(self) -> np.ndarray:
-        """[B, 48] doubles for the kernels: eigenvalues 4 | U 16 | U^-1 16 | freqs 4 | class rates 4 | p_inv | pad 3."""
+        """[B, 64] doubles for the kernels: eigenvalues 4 | U 16 | U^-1 16 | freqs 4 | class rates 4 | p_inv | alpha | flags | pad | 6 rates | pad 10."""
         B, pi = self.B, self.freqs
         r = np.zeros((B, 4, 4))
         for k, (a, b) in enumerate(itertools.combinations(range(4), 2)):
@@ -126,7 +127,13 @@ class SubstModel:
                     _lib.check(L.nnj_gamma_rates(a, 4, buf), "nnj_gamma_rates")
                     cache[a] = np.array(buf[:])
                 cat[b] = cache[a]
-        return np.ascontiguousarray(np.concatenate([lam, U.reshape(B, 16), Ui.reshape(B, 16), pi, cat, self.pinv[:, None], np.zeros((B, 3))], axis=1))
+        flags = np.full((B, 1), float((1 if self.gtr else 0) | (2 if self.gamma else 0) | (4 if self.inv else 0)))
+        return np.ascontiguousarray(np.concatenate([lam, U.reshape(B, 16), Ui.reshape(B, 16), pi, cat, self.pinv[:, None], self.alpha[:, None], flags,
+                                                    np.zeros((B, 1)), self.rates, np.zeros((B, 10))], axis=1))
+
+    def unpack(self, packed: np.ndarray) -> None:
+        """Take the parameters the kernel optimised (nnj_llh_optimize_all) back into this object."""
+        self.pinv, self.alpha, self.rates = packed[:, 44].copy(), packed[:, 45].copy(), packed[:, 48:54].copy()
 
 
 # ------------------------------------------------------------------ trees
@@ -288,47 +295,28 @@ class TreeLikelihood:
         """-> (brlen_opt [B, 2R-2], llh_before [B], llh_after [B])"""
         return self._call(children, brlen, model, True, max_passes, eps)
 
-    def optimize_all(self, children, brlen, model: SubstModel, lh_eps=1.0, max_rounds=10, golden_iters=24):
-        """Branch lengths, then rounds of (free model parameters one at a time, branch lengths) until a round gains < lh_eps
-        on every tree.  Every objective evaluation is one kernel launch over all B trees."""
-        t, ll0, ll = self.optimize_branches(children, brlen, model)
-        B = model.B
-
-        def setter(kind, i):
-            if kind == "rate":
-                return (np.log(RATE_LO), np.log(RATE_HI), lambda x: model.rates.__setitem__((slice(None), i), np.exp(x)))
-            if kind == "alpha":
-                return (np.log(ALPHA_LO), np.log(ALPHA_HI), lambda x: setattr(model, "alpha", np.exp(x)))
-            return (0.0, PINV_HI, lambda x: setattr(model, "pinv", np.asarray(x, dtype=np.float64).copy()))
-
-        active = np.ones(B, dtype=bool)
-        for _ in range(max_rounds):
-            start = ll.copy()
-            for kind, i in model.free_params():
-                lo, hi, put = setter(kind, i)
-
-                def f(x):
-                    put(x)
-                    return self.loglik(children, t, model)
-                a, b = np.full(B, lo), np.full(B, hi)
-                x1, x2 = a + _GOLD * (b - a), b - _GOLD * (b - a)
-                f1, f2 = f(x1), f(x2)
-                for _it in range(golden_iters):
-                    left = f1 >= f2                                  # keep [a, x2] where the left probe is better
-                    b = np.where(left, x2, b)
-                    a = np.where(left, a, x1)
-                    nx1 = np.where(left, a + _GOLD * (b - a), x2)
-                    nx2 = np.where(left, x1, b - _GOLD * (b - a))
-                    probe = np.where(left, nx1, nx2)
-                    fp = f(probe)
-                    f1, f2 = np.where(left, fp, f2), np.where(left, f1, fp)
-                    x1, x2 = nx1, nx2
-                put(np.where(f1 > f2, x1, x2))
-            t, _, ll = self.optimize_branches(children, t, model)
-            active = (ll - start) >= lh_eps
-            if not active.any():
-                break
-        return t, ll0, ll
+    def optimize_all(self, children, brlen, model: SubstModel, lh_eps=1.0, max_rounds=10, max_passes=32, eps=1e-3):
+        """Branch lengths, then rounds of (every free model parameter by golden section, branch lengths) until a round gains
+        < lh_eps - per tree, entirely inside the kernel (nnj_llh_optimize_all: eigen-system and class rates are rebuilt on the
+        device, no host round trips).  Updates `model` in place.  -> (brlen_opt, llh_before, llh_after)"""
+        children = np.ascontiguousarray(children, dtype=np.int32)
+        B = children.shape[0]
+        brlen = np.ascontiguousarray(brlen, dtype=np.float64).copy()
+        if children.shape != (B, self.R - 1, 2) or brlen.shape != (B, 2 * self.R - 2) or model.B != B:
+            raise ValueError("children must be [B, R-1, 2], brlen [B, 2R-2], one model row per tree")
+        tips, w = self._staged(B)
+        ws = self._workspace(B)
+        packed = model.pack()
+        before, after = np.zeros(B), np.zeros(B)
+        vp = C.c_void_p
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().nnj_llh_optimize_all(vp(tips.data_ptr()), vp(w.data_ptr()), children.ctypes.data_as(vp), brlen.ctypes.data_as(vp),
+                                                 packed.ctypes.data_as(vp), B, self.R, self.L, int(max_passes), float(eps), float(lh_eps), int(max_rounds),
+                                                 before.ctypes.data_as(vp), after.ctypes.data_as(vp), vp(ws.data_ptr()), ws.numel(), vp(stream))
+        _lib.check(rc, "nnj_llh_optimize_all")
+        model.unpack(packed)
+        return brlen, before, after
 
 
 # ------------------------------------------------------------------ raxmlpy-compatible entry points

@@ -143,15 +143,16 @@ torch.save({"merges": merges.cpu(), "trace": trace.cpu()}, sys.argv[2])
 
 def test_lane_quarter_modes_agree_with_the_two_way_split(tmp_path):
     """<= 32 pairs: k_alpha_v3 splits the tile over four sites (NNJ_ALPHA_QUAD) and k_score_inc splits a pair's channels over
-    two warps (NNJ_SCORE_NARROW).  Both must reproduce the 2-way site-parity kernels they replace: same merges, logits within
-    the tolerance of the oracle comparison (the partial sums are grouped differently, nothing else changes).  The switches are
-    read once per process, hence the two subprocesses."""
+    two warps (NNJ_SCORE_NARROW); <= 16 pairs: the register-fragment kernels k_alpha_small / k_score_small take over
+    (NNJ_ALPHA_SMALL, NNJ_SCORE_SMALL).  All must reproduce the 2-way site-parity tcgen05 kernels they replace: same merges, logits
+    within the tolerance of the oracle comparison (the partial sums are grouped differently, nothing else changes).  The switches
+    are read once per process, hence the two subprocesses."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for tag, env in (("new", {}), ("old", {"NNJ_ALPHA_QUAD": "0", "NNJ_SCORE_NARROW": "0"})):
+    for tag, env in (("new", {}), ("old", {"NNJ_ALPHA_QUAD": "0", "NNJ_SCORE_NARROW": "0", "NNJ_SCORE_SMALL": "0", "NNJ_ALPHA_SMALL": "0"})):
         path = str(tmp_path / f"{tag}.pt")
         subprocess.run([sys.executable, "-c", _TOGGLE_SCRIPT, root, path], check=True, env={**os.environ, **env}, timeout=300)
         outs.append(torch.load(path))

@@ -145,7 +145,7 @@ def test_masks_and_frequencies():
     sm = LH.SubstModel("GTR+I+G", f, 2)
     packed = sm.pack()
     ref = O.Model(freqs=f, alpha=1.0, pinv=0.0).packed()
-    assert packed.shape == (2, 48)
+    assert packed.shape == (2, 64) and packed[0, 46] == 7.0 and np.allclose(packed[0, 48:54], 1.0)
     # eigenvectors are defined up to sign / order within degenerate eigenvalues: compare what they generate
     lam, U, Ui = packed[0, :4], packed[0, 4:20].reshape(4, 4), packed[0, 20:36].reshape(4, 4)
     P = U @ np.diag(np.exp(lam * 0.3)) @ Ui
