@@ -1232,9 +1232,13 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
             if (t == 0) {
                 if (int e = score_pairs(m, pool, nb, slot, n, C, P0, mk, nbt, nb.logits[0], P0, st)) return e;
             } else {
-                // (the last step has a single candidate pair; it is scored like any other so that logits_cur / the trace never hold a
-                // stale value - one small fp32 launch per chunk)
-                if (int e = score_pairs(m, pool, nb, slot, n, C, n, mk, nbt, nb.new_scores, nb.pair_stride, st)) return e;
+                // The last step has a single candidate pair: its score cannot change the merge, and log_softmax of one logit is 0.  It is
+                // evaluated only when the caller records the logits (one fp32 launch, 1.4 ms per 128 trees); otherwise the score buffer is
+                // set to a defined 0 so that logits_cur never holds a stale value.
+                if (n == 2 && !ltr) {
+                    cudaError_t e0 = cudaMemsetAsync(nb.new_scores, 0, (size_t)nbt * nb.pair_stride * sizeof(float), st);
+                    if (e0 != cudaSuccess) return set_cuda_error(e0, __FILE__, __LINE__);
+                } else if (int e = score_pairs(m, pool, nb, slot, n, C, n, mk, nbt, nb.new_scores, nb.pair_stride, st)) return e;
                 cur ^= 1;
             }
             prof_begin(KC_SELECT, st);

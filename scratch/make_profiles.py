@@ -58,7 +58,12 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append(f"{k[:34]:34s} {a[0]:8d} {a[1] / 1e6:10.3f} {100 * a[1] / tot:6.2f}% {a[1] / a[0] / 1e3:10.1f}")
 lines.append(f"{'total':34s} {sum(a[0] for a in agg.values()):8d} {tot / 1e6:10.3f}")
 byc = collections.defaultdict(float)
-for k, a in agg.items(): byc[cls.get(k, "misc")] += a[1]
+def klass(k):
+    if k in cls: return cls[k]
+    for pre, c in (("k_score_small", "pair_score"), ("k_alpha_small", "alpha"), ("k_enc_colblock_tc", "col_attn"), ("k_score_big", "pair_score"), ("k_pair_blend", "pair_blend")):
+        if k.startswith(pre): return c
+    return "misc"
+for k, a in agg.items(): byc[klass(k)] += a[1]
 b = json.loads(open(f"{src}/bench.json").read().strip().splitlines()[-1])
 lines += ["", f"share by bench.py class (ncu)  vs  live CUDA events (bench line of the same run, profiles/{rnd}_bench_final.json)"]
 for c, v in sorted(byc.items(), key=lambda kv: -kv[1]):
