@@ -20,6 +20,7 @@ Printed keys beyond the base contract:
                  NJ loop's DRAM bytes per tree against SURVEY 8(d)'s 334 MB streaming figure
   kernels        per-class milliseconds / launches / share of the profiled step
   latency_b1_ms  one alignment, device-resident input -> merge list (median of 7)
+  tree_llh       the Search-mode scorer: 32 topologies of the batch scored with the GPU likelihood (branch lengths / + model search)
   gpu_eager_baseline  the reference formulation (the oracle restatement) in torch eager on this GPU at B = 1 / 8 / 32
   parity_check   after the timed region: alignments of the bench batch replayed on the CPU oracle
   cpu_baseline   the CPU oracle (port of the reference, oracle/nnj_oracle.py) timed on this box's host cores
@@ -178,6 +179,27 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def llh_scoring_rate(merges, onehot, R):
+    """Search-mode scorer on the side: the first 32 topologies of the timed batch scored on ONE alignment with the GPU
+    likelihood (GTR+I+G4, csrc/nnj_llh.cu) - branch lengths only, and with the in-kernel model-parameter search."""
+    import numpy as np
+    import torch
+    from neuralnj_b200 import likelihood as LH
+    masks = LH.onehot_to_masks(onehot)
+    ch = np.stack([LH.children_from_merges(m, R) for m in merges])
+    labels = [f"t{i}" for i in range(R)]
+    LH.score_topologies(masks, ch[:2], labels, opt_model=False)
+    out = {"topologies": int(ch.shape[0]), "model": "GTR+I+G4, empirical frequencies, fp64"}
+    for key, full in (("branch_lengths_only", False), ("with_model_search", True)):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        ll, _ = LH.score_topologies(masks, ch, labels, opt_model=full)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        out[key] = {"s": round(dt, 3), "trees_per_s": round(ch.shape[0] / dt, 1), "best_llh": round(float(ll.max()), 3)}
+    return out
 
 
 def gpu_eager_baseline(dev, R, L, budget_s=40.0):
@@ -398,6 +420,8 @@ def main():
         extras["latency_b1_ms"] = round(sorted(ts)[len(ts) // 2], 3)
         if world == 1:
             extras["gpu_eager_baseline"] = gpu_eager_baseline(dev, R_TAXA, L_SITES, budget_s=40.0 if args.workload == "config2" else 0.0)
+        if world == 1 and args.workload == "config2":
+            extras["tree_llh"] = llh_scoring_rate(merges[:32].cpu().numpy(), data_host[0], R_TAXA)
     weak = None
     if world > 1 and args.scaling == "strong" and not args.no_extras:
         w = timed("weak", max(1, min(args.steps, 3)), 1, False)
