@@ -235,7 +235,7 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
         for (int w = 0; w < 2; ++w)
             for (int i = 0; i < 4096; ++i) {
                 __nv_bfloat16 h = __float2bfloat16_rn(src[w][i]);
-                __nv_bfloat16 l = __float2bfloat16_rn(src[w][i] - __bfloat162float(h));
+                __nv_bfloat16 l = NNJ_LO_BF16(__float2bfloat16_rn(src[w][i] - __bfloat162float(h)));
                 planes[(2 * w) * 4096 + i] = __bfloat16_as_ushort(h);
                 planes[(2 * w + 1) * 4096 + i] = __bfloat16_as_ushort(l);
             }
@@ -254,7 +254,7 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
             for (int n = 0; n < n_rows; ++n)
                 for (int k = 0; k < 64; ++k) {
                     const float v = W[(size_t)n * ldw + k0 + k];
-                    const __nv_bfloat16 h = __float2bfloat16_rn(v), l = __float2bfloat16_rn(v - __bfloat162float(h));
+                    const __nv_bfloat16 h = __float2bfloat16_rn(v), l = NNJ_LO_BF16(__float2bfloat16_rn(v - __bfloat162float(h)));
                     const int rn = row0 + n;
                     const size_t off = (size_t)rn * 64 + (size_t)(((k >> 3) ^ (rn & 7)) << 3) + (k & 7);
                     dst_h[off] = __bfloat16_as_ushort(h);

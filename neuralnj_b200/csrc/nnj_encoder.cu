@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(NTHREADS) k_softmax_rows(float* __restrict__ S
 // ------------------------------------------------------------------ tensor-core row attention (precision bf16x3)
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    lo = NNJ_LO_BF16(__float2bfloat16_rn(v - __bfloat162float(hi)));
 }
 
 // LN + q/k/v projections of the tied row attention, written as bf16 hi/lo planes for the tcgen05 GEMMs:

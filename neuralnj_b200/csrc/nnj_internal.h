@@ -12,6 +12,16 @@
 #include "../../include/nnj.h"
 #include "nnj_common.cuh"
 
+// Experiment builds only (-DNNJ_ONE_PRODUCT, scratch/one_product_report.py): every low part of the bf16 split is forced to zero, i.e. the
+// kernels compute with plain bf16 operands - the NUMERICS of a one-product mode, not its speed.  Never set in the product build.
+#ifdef NNJ_ONE_PRODUCT
+#define NNJ_LO_BF16(x) __float2bfloat16_rn(0.0f)
+#define NNJ_LO_WORD(x) 0u
+#else
+#define NNJ_LO_BF16(x) (x)
+#define NNJ_LO_WORD(x) (x)
+#endif
+
 namespace nnj {
 
 // Site-major residual stream of the tensor-core encoder ("xs"): tokens t = site * R + taxon in tiles of 128; inside a tile the 64

@@ -186,7 +186,7 @@ k_score_tc(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CU
             const int row = idx / a.Rp, r = idx - row * a.Rp;
             const float v = a.alpha[((size_t)b * a.alpha_pairs + pt * 128 + row) * a.RP + r];
             const int slot = so[r];
-            const __nv_bfloat16 h = __float2bfloat16_rn(v), l = __float2bfloat16_rn(v - __bfloat162float(h));
+            const __nv_bfloat16 h = __float2bfloat16_rn(v), l = NNJ_LO_BF16(__float2bfloat16_rn(v - __bfloat162float(h)));
             const int off = row * 128 + (((slot >> 3) ^ (row & 7)) << 4) + (slot & 7) * 2;
             *reinterpret_cast<__nv_bfloat16*>(sm + ST_A0 + off) = h;
             *reinterpret_cast<__nv_bfloat16*>(sm + ST_A0 + 16384 + off) = l;

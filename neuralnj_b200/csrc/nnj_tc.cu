@@ -218,7 +218,7 @@ __global__ void k_split_bf16(const float* __restrict__ x, __nv_bfloat16* __restr
         float v = x[i];
         __nv_bfloat16 h = __float2bfloat16_rn(v);
         hi[i] = h;
-        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+        lo[i] = NNJ_LO_BF16(__float2bfloat16_rn(v - __bfloat162float(h)));
     }
 }
 
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_unit(const float* __restrict__ A,
         const float* ar = A + (size_t)tid * 64;
         for (int j = 0; j < 8; ++j) {
             __align__(16) __nv_bfloat16 h[8], l[8];
-            for (int e = 0; e < 8; ++e) { float v = ar[j * 8 + e]; h[e] = __float2bfloat16_rn(v); l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e])); }
+            for (int e = 0; e < 8; ++e) { float v = ar[j * 8 + e]; h[e] = __float2bfloat16_rn(v); l[e] = NNJ_LO_BF16(__float2bfloat16_rn(v - __bfloat162float(h[e]))); }
             const int off = tid * 128 + ((j ^ (tid & 7)) << 4);
             *reinterpret_cast<uint4*>(a_hi + off) = *reinterpret_cast<uint4*>(h);
             *reinterpret_cast<uint4*>(a_lo + off) = *reinterpret_cast<uint4*>(l);
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_unit(const float* __restrict__ A,
             const float* br = Bm + (size_t)tid * BN;
             for (int j = 0; j < BN / 8; ++j) {
                 __align__(16) __nv_bfloat16 h[8], l[8];
-                for (int e = 0; e < 8; ++e) { float v = br[j * 8 + e]; h[e] = __float2bfloat16_rn(v); l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e])); }
+                for (int e = 0; e < 8; ++e) { float v = br[j * 8 + e]; h[e] = __float2bfloat16_rn(v); l[e] = NNJ_LO_BF16(__float2bfloat16_rn(v - __bfloat162float(h[e]))); }
                 const int off = (j >> 3) * 8192 + tid * 128 + (((j & 7) ^ (tid & 7)) << 4);
                 *reinterpret_cast<uint4*>(b_hi + off) = *reinterpret_cast<uint4*>(h);
                 *reinterpret_cast<uint4*>(b_lo + off) = *reinterpret_cast<uint4*>(l);

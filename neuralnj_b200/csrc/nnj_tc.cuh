@@ -7,6 +7,10 @@
 #include <cstdio>
 #endif
 
+#ifndef NNJ_LO_WORD
+#define NNJ_LO_WORD(x) (x)     // see nnj_internal.h (experiment builds zero the low parts)
+#endif
+
 namespace nnj {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -188,7 +192,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     hi = pack_bf16x2(a, b);
     const float2 r = fsub2(make_float2(a, b), make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)));   // one FADD2
-    lo = pack_bf16x2(r.x, r.y);
+    lo = NNJ_LO_WORD(pack_bf16x2(r.x, r.y));
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }          // element 0 of a bf16x2 word
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }  // element 1
