@@ -51,7 +51,8 @@ __device__ __forceinline__ void ss_cp16(uint32_t dst, const void* src) {
 // Measured (128 trees, profiles/r02_score_small.txt): T = 2 is bound by its 384 tensor instructions per site (8 clocks each and
 // sub-partition: 770 clocks per site and SM) and loses to k_score_inc's narrow mode (860 vs 770 us per launch) - it is kept for
 // reference but not dispatched; T = 1 with 8 warps ran at 43 % of the legacy tensor pipe (two warps per sub-partition cannot
-// cover the 20-clock dependent instruction chains and the gate math between the two GEMMs), hence 16 warps.
+// cover the 20-clock dependent instruction chains and the gate math between the two GEMMs; an 8-warp double-buffered
+// variant measured 355 vs 340 us), hence 16 warps with one buffer each.
 // HALF (T = 1 only): at most 8 listed pairs - rows 8..15 of the tile are padding and their gate / GELU math is compiled out.
 template <int T, int SS_WARPS, int NBUF, bool HALF>
 __global__ void __launch_bounds__(SS_WARPS * 32, 1) k_score_small(const ScoreSmallArgs a) {
@@ -275,11 +276,9 @@ int launch_score_small(const Model* m, const float* xf, int pc, const void* node
     const int groups = (C + SS_SITES - 1) / SS_SITES;
     *n_part = groups;
     if (groups > nSG) return set_error(NNJ_ERR_INVALID, "score_small: partial buffer too small");
-    static int w8 = -1;
-    if (w8 < 0) { const char* ev = getenv("NNJ_SCORE_SMALL_W8"); w8 = ev ? atoi(ev) : 0; }      // A/B: the 8-warp double-buffered variant
     prof_begin(KC_SCORE, st);
-    int rc = T == 1 ? (w8 ? launch_small_t<1, 8, 2>(a, groups, B, st) : (nc <= 8 ? launch_small_t<1, 16, 1, true>(a, groups, B, st) : launch_small_t<1, 16, 1>(a, groups, B, st)))
-                    : launch_small_t<2, 8, 1>(a, groups, B, st);
+    const int rc = T == 1 ? (nc <= 8 ? launch_small_t<1, 16, 1, true>(a, groups, B, st) : launch_small_t<1, 16, 1>(a, groups, B, st))
+                          : launch_small_t<2, 8, 1>(a, groups, B, st);
     ++g_launches;
     prof_end(st);
     if (rc) return rc;

@@ -12,7 +12,7 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.max"]
-names = ["score_incr", "score_late", "score_step0", "alpha_incr", "alpha_late", "alpha_step0", "colblock", "rowqkv", "rowqk", "rowpv", "ffn", "softmax", "merge"]
+names = ["score_incr", "score_late", "score_small", "score_step0", "alpha_incr", "alpha_late", "alpha_small", "alpha_step0", "colblock", "rowqkv", "rowqk", "rowpv", "ffn", "softmax", "merge"]
 out, tr = [], {}
 def gb(v, u): return f(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
 for name in names:
@@ -35,8 +35,10 @@ for name in names:
     data = [x for x in rs[2:] if len(x) == len(h2)]
     T = sum(f(x[si]) for x in data) or 1
     out.append("   warp-state samples: " + "  ".join(f"{h2[i][6:]}={100 * sum(f(x[i]) for x in data) / T:.1f}%" for i in st if sum(f(x[i]) for x in data) / T > 0.02))
-head = ("round 2 (" + rnd + "): " + "ncu --set full --import-source on --clock-control none, python scratch/prof_rollout.py 128 1 (one 128-alignment chunk, 50 x 1024, bf16x3); one launch per kernel\n"
-        "score_incr = k_score_inc launch #15 (NJ step 16, 33 pairs per tree); score_late = launch #36 (step 37, 12 pairs: narrow mode); alpha_incr = k_alpha_v3 launch #20 (step 16);\nalpha_late = launch #41 (step 37: 4-way site split); step0 = first launch, 256 pairs per tree; rowqk / rowpv = k_tc_gemm launches #2 / #3 (layer 1); merge = k_merge launch #20 (30 live nodes)\n")
+head = ("round 2 (" + rnd + "): ncu --set full --import-source on --clock-control none, python scratch/prof_rollout.py 128 1 (one 128-alignment chunk, 50 x 1024, bf16x3); one launch per kernel\n"
+        "score_incr = k_score_inc launch #15 (NJ step 16, 33 pairs per tree); score_late = k_score_inc launch #30 (19 pairs: narrow mode); score_small = k_score_small launch #4 (12 pairs);\n"
+        "alpha_incr = k_alpha_v3 launch #20 (step 16); alpha_late = k_alpha_v3 launch #36 (4-way site split, ~18 pairs); alpha_small = k_alpha_small launch #4; step0 = first launch, 256 pairs per tree;\n"
+        "rowqk / rowpv = k_tc_gemm launches #2 / #3 (layer 1); merge = k_merge launch #20 (30 live nodes)\n")
 open(f"profiles/{rnd}_ncu_full_summary_b128.txt", "w").write(head + "\n".join(out) + "\n")
 json.dump(tr, open(f"profiles/{rnd}_traffic_b128.json", "w"), indent=1)
 # launch list

@@ -20,10 +20,12 @@ cap() {  # name regex skip
   rm -f $o/$1.ncu-rep
 }
 cap score_incr k_score_inc 15
-cap score_late k_score_inc 36
+cap score_late k_score_inc 30
+cap score_small k_score_small 4
 cap score_step0 k_score_tc 0
 cap alpha_incr k_alpha_v3 20
-cap alpha_late k_alpha_v3 41
+cap alpha_late k_alpha_v3 36
+cap alpha_small k_alpha_small 4
 cap colblock k_enc_colblock 2
 cap ffn k_enc_ffn 2
 cap rowqkv k_enc_rowqkv 2
