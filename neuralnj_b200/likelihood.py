@@ -264,7 +264,8 @@ class TreeLikelihood:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def _call(self, children, brlen, model: SubstModel, optimise: bool, max_passes=32, eps=1e-3):
+    def _call(self, mode: str, children, brlen, model: SubstModel, max_passes=32, eps=1e-3, lh_eps=1.0, max_rounds=10):
+        """One C-ABI call over all B trees: mode "eval" (nnj_llh_eval), "brlen" (nnj_llh_optimize_brlen) or "all" (nnj_llh_optimize_all)."""
         children = np.ascontiguousarray(children, dtype=np.int32)
         B = children.shape[0]
         brlen = np.ascontiguousarray(brlen, dtype=np.float64).copy()
@@ -277,46 +278,33 @@ class TreeLikelihood:
         after, before = np.zeros(B), np.zeros(B)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         vp = C.c_void_p
+        dev = (vp(tips.data_ptr()), vp(w.data_ptr()), children.ctypes.data_as(vp), brlen.ctypes.data_as(vp), packed.ctypes.data_as(vp), B, self.R, self.L)
+        tail = (vp(ws.data_ptr()), ws.numel(), vp(stream))
         with torch.cuda.device(self.device):
-            if optimise:
-                rc = L.nnj_llh_optimize_brlen(vp(tips.data_ptr()), vp(w.data_ptr()), children.ctypes.data_as(vp), brlen.ctypes.data_as(vp),
-                                              packed.ctypes.data_as(vp), B, self.R, self.L, int(max_passes), float(eps),
-                                              before.ctypes.data_as(vp), after.ctypes.data_as(vp), vp(ws.data_ptr()), ws.numel(), vp(stream))
+            if mode == "eval":
+                rc = L.nnj_llh_eval(*dev, after.ctypes.data_as(vp), *tail)
+            elif mode == "brlen":
+                rc = L.nnj_llh_optimize_brlen(*dev, int(max_passes), float(eps), before.ctypes.data_as(vp), after.ctypes.data_as(vp), *tail)
             else:
-                rc = L.nnj_llh_eval(vp(tips.data_ptr()), vp(w.data_ptr()), children.ctypes.data_as(vp), brlen.ctypes.data_as(vp),
-                                    packed.ctypes.data_as(vp), B, self.R, self.L, after.ctypes.data_as(vp), vp(ws.data_ptr()), ws.numel(), vp(stream))
-        _lib.check(rc, "nnj_llh")
+                rc = L.nnj_llh_optimize_all(*dev, int(max_passes), float(eps), float(lh_eps), int(max_rounds), before.ctypes.data_as(vp),
+                                            after.ctypes.data_as(vp), *tail)
+        _lib.check(rc, "nnj_llh_" + mode)
+        if mode == "all":
+            model.unpack(packed)
         return brlen, before, after
 
     def loglik(self, children, brlen, model: SubstModel) -> np.ndarray:
-        return self._call(children, brlen, model, False)[2]
+        return self._call("eval", children, brlen, model)[2]
 
     def optimize_branches(self, children, brlen, model: SubstModel, max_passes=32, eps=1e-3):
         """-> (brlen_opt [B, 2R-2], llh_before [B], llh_after [B])"""
-        return self._call(children, brlen, model, True, max_passes, eps)
+        return self._call("brlen", children, brlen, model, max_passes, eps)
 
     def optimize_all(self, children, brlen, model: SubstModel, lh_eps=1.0, max_rounds=10, max_passes=32, eps=1e-3):
         """Branch lengths, then rounds of (every free model parameter by golden section, branch lengths) until a round gains
         < lh_eps - per tree, entirely inside the kernel (nnj_llh_optimize_all: eigen-system and class rates are rebuilt on the
         device, no host round trips).  Updates `model` in place.  -> (brlen_opt, llh_before, llh_after)"""
-        children = np.ascontiguousarray(children, dtype=np.int32)
-        B = children.shape[0]
-        brlen = np.ascontiguousarray(brlen, dtype=np.float64).copy()
-        if children.shape != (B, self.R - 1, 2) or brlen.shape != (B, 2 * self.R - 2) or model.B != B:
-            raise ValueError("children must be [B, R-1, 2], brlen [B, 2R-2], one model row per tree")
-        tips, w = self._staged(B)
-        ws = self._workspace(B)
-        packed = model.pack()
-        before, after = np.zeros(B), np.zeros(B)
-        vp = C.c_void_p
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        with torch.cuda.device(self.device):
-            rc = _lib.lib().nnj_llh_optimize_all(vp(tips.data_ptr()), vp(w.data_ptr()), children.ctypes.data_as(vp), brlen.ctypes.data_as(vp),
-                                                 packed.ctypes.data_as(vp), B, self.R, self.L, int(max_passes), float(eps), float(lh_eps), int(max_rounds),
-                                                 before.ctypes.data_as(vp), after.ctypes.data_as(vp), vp(ws.data_ptr()), ws.numel(), vp(stream))
-        _lib.check(rc, "nnj_llh_optimize_all")
-        model.unpack(packed)
-        return brlen, before, after
+        return self._call("all", children, brlen, model, max_passes, eps, lh_eps, max_rounds)
 
 
 # ------------------------------------------------------------------ raxmlpy-compatible entry points
@@ -344,42 +332,41 @@ def optimize_brlen(tree_str, msa, is_root=False, iters=32, model="JC", opt_model
 
 def compute_llh(tree_str, msa, is_root=False, model="JC", opt_model=True, device=None):
     """raxmlpy.compute_llh (core.py:10-12): log L of the tree as given; with opt_model the model parameters (not the branch
-    lengths) are optimised first (raxmlpy.cpp:1783-1787)."""
+    lengths) are optimised first (raxmlpy.cpp:1783-1787): coordinate golden section from the host, one evaluation per launch."""
     labels, eng, ch, bl, sm = _prepare(tree_str, msa, model)
+    best = float(eng.loglik(ch, bl, sm)[0])
     if not opt_model:
-        return float(eng.loglik(ch, bl, sm)[0])
-    best = eng.loglik(ch, bl, sm)
-    for _ in range(10):
-        start = best.copy()
-        # model parameters only: reuse the coordinate search with the branch sweeps switched off
-        for kind, i in sm.free_params():
-            lo, hi = (np.log(RATE_LO), np.log(RATE_HI)) if kind == "rate" else ((np.log(ALPHA_LO), np.log(ALPHA_HI)) if kind == "alpha" else (0.0, PINV_HI))
+        return best
+    bounds = {"rate": (np.log(RATE_LO), np.log(RATE_HI)), "alpha": (np.log(ALPHA_LO), np.log(ALPHA_HI)), "pinv": (0.0, PINV_HI)}
 
-            def put(x, kind=kind, i=i):
-                if kind == "rate":
-                    sm.rates[:, i] = np.exp(x)
-                elif kind == "alpha":
-                    sm.alpha = np.exp(np.atleast_1d(x))
-                else:
-                    sm.pinv = np.atleast_1d(np.asarray(x, dtype=np.float64))
-            a, b = lo, hi
+    def objective(kind, i, x):
+        if kind == "rate":
+            sm.rates[:, i] = np.exp(x)
+        elif kind == "alpha":
+            sm.alpha = np.exp(np.atleast_1d(x))
+        else:
+            sm.pinv = np.atleast_1d(np.asarray(x, dtype=np.float64))
+        return float(eng.loglik(ch, bl, sm)[0])
+
+    for _ in range(10):
+        start = best
+        for kind, i in sm.free_params():
+            a, b = bounds[kind]
             x1, x2 = a + _GOLD * (b - a), b - _GOLD * (b - a)
-            put(x1); f1 = float(eng.loglik(ch, bl, sm)[0])
-            put(x2); f2 = float(eng.loglik(ch, bl, sm)[0])
+            f1, f2 = objective(kind, i, x1), objective(kind, i, x2)
             for _it in range(24):
                 if f1 >= f2:
                     b, x2, f2 = x2, x1, f1
                     x1 = a + _GOLD * (b - a)
-                    put(x1); f1 = float(eng.loglik(ch, bl, sm)[0])
+                    f1 = objective(kind, i, x1)
                 else:
                     a, x1, f1 = x1, x2, f2
                     x2 = b - _GOLD * (b - a)
-                    put(x2); f2 = float(eng.loglik(ch, bl, sm)[0])
-            put(x1 if f1 > f2 else x2)
-        best = eng.loglik(ch, bl, sm)
-        if float(best[0] - start[0]) < 1.0:
+                    f2 = objective(kind, i, x2)
+            best = objective(kind, i, x1 if f1 > f2 else x2)
+        if best - start < 1.0:
             break
-    return float(best[0])
+    return best
 
 
 def score_topologies(masks: np.ndarray, children: np.ndarray, labels: Sequence[str], model="GTR+I+G", opt_model=True, device=None):

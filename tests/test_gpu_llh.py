@@ -109,7 +109,11 @@ def test_raxmlpy_style_entry_points():
     rooted = LH.tuples_to_newick(LH.tuples_with_lengths(ch, bl, labels, unrooted=False))
     jc = LH.compute_llh(rooted, msa, is_root=True, model="JC", opt_model=False)
     assert abs(jc - O.loglik(ch, bl, tips, np.ones(L), O.Model(gamma=False))) < 1e-5          # Newick carries 8 decimals
+    fixed = LH.compute_llh(rooted, msa, is_root=True, model="GTR+I+G", opt_model=False)
+    tuned = LH.compute_llh(rooted, msa, is_root=True, model="GTR+I+G", opt_model=True)          # model parameters only, branch lengths as given
+    assert tuned > fixed
     newick, before, after = LH.optimize_brlen(rooted, msa, is_root=True, iters=3, model="GTR+I+G", opt_model=True)
+    assert after >= tuned - 1.0 and abs(before - fixed) < 1e-6 * abs(fixed)
     assert after > before and rf_distance(newick, rooted) == 0 and newick.count(":") == 2 * R - 3 + 0 * R
     assert all(lbl in newick for lbl in labels)
     # a wrong topology scores worse than the generating one after optimisation
