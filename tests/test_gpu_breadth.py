@@ -83,7 +83,10 @@ def _check_against_oracle(tag, prec, data, mask, sd0, model, parity_report, pair
     entry["max_logit_rel_err"] = _max_trace_err(trace, ref["logits"])
     assert entry["max_logit_rel_err"] < LOGIT_TOL_BY_PREC[prec]
     R = data.shape[1]
-    assert float((slp.cpu()[:, :R - 2] - ref["selected_log_ps"]).abs().max()) < 1e-3
+    # log_softmax(logits)[action] moves by at most twice the absolute logit error, which is the relative tolerance times the logit scale
+    # (200 x 4096: |logit| reaches the hundreds, a fixed 1e-3 would be tighter than the logit tolerance itself)
+    scale = max(float(lg.abs().max()) for lg in ref["logits"])
+    assert float((slp.cpu()[:, :R - 2] - ref["selected_log_ps"]).abs().max()) < max(1e-3, 2 * LOGIT_TOL_BY_PREC[prec] * scale)
 
 
 # (taxa, sites, padded sites): 12 x 2048 -> rows longer than 1024 sites (k_softmax_rows_split) with a padded tail;
