@@ -421,7 +421,10 @@ def main():
         if world == 1:
             extras["gpu_eager_baseline"] = gpu_eager_baseline(dev, R_TAXA, L_SITES, budget_s=40.0 if args.workload == "config2" else 0.0)
         if world == 1 and args.workload == "config2":
-            extras["tree_llh"] = llh_scoring_rate(merges[:32].cpu().numpy(), data_host[0], R_TAXA)
+            try:        # a side measurement: it must never take the headline line down with it
+                extras["tree_llh"] = llh_scoring_rate(merges[:32].cpu().numpy(), data_host[0], R_TAXA)
+            except Exception as exc:   # noqa: BLE001
+                extras["tree_llh"] = {"error": f"{type(exc).__name__}: {exc}"}
     weak = None
     if world > 1 and args.scaling == "strong" and not args.no_extras:
         w = timed("weak", max(1, min(args.steps, 3)), 1, False)
