@@ -52,7 +52,10 @@ typedef enum nnj_precision {
 
 typedef enum nnj_select_mode {
     NNJ_SELECT_ARGMAX = 0,    /* torch.argmax(logits)            finetune_rl_search.py:145 */
-    NNJ_SELECT_GUMBEL = 1     /* argmax(logits + gumbel noise) == Categorical(logits).sample()  :147 */
+    NNJ_SELECT_GUMBEL = 1,    /* argmax(logits + gumbel noise) == Categorical(logits).sample()  :147 */
+    NNJ_SELECT_FORCED = 2     /* teacher forcing, train.py:116-119 (supervise_rollout): the merge-list buffer holds the actions (i < j in the
+                               * current node list) ON ENTRY; an entry that is not such a pair falls back to the argmax, and the buffer holds the
+                               * actions actually taken on return */
 } nnj_select_mode;
 
 typedef struct nnj_model nnj_model;   /* opaque: device copy of the state_dict tensors */
@@ -166,6 +169,19 @@ int nnj_llh_optimize_all(const uint8_t* tips_dev, const double* weights_dev, con
                          double* llh_before_host, double* llh_after_host, void* ws_dev, int64_t ws_bytes, void* stream);
 /* Mean rates of the ncat equal-probability classes of Gamma(alpha, alpha) (Yang 1994): rates_host double [ncat]. */
 int nnj_gamma_rates(double alpha, int ncat, double* rates_host);
+
+/* ---- Pre-training loss, forward (train.py:448-545, BALANCED_ELU_LOSS) over the logits trace of a teacher-forced rollout
+ * (nnj_rollout with NNJ_SELECT_FORCED and a logits_trace buffer).  The backward pass is not part of this library.
+ *   logits_trace_dev fp32  [B, trace_len]  step t at offset sum_{s<t} P_s, P_s = (R-s)(R-s-1)/2, trace_len = sum over all R-1 steps
+ *   in_set_dev       uint8 [B, trace_len]  same layout: 1 = the pair is in the step's action set (train.py:30-39), 0 = complement
+ *   margin 0.5 (train.py:478); ratio = max(1 - 3/80 * epoch / 2, 1/4) * cfgs.ratio_factor (train.py:495): per step the K = min(W, max(int(W*ratio), 8))
+ *   largest complement scores enter the loss, W = the batch's widest complement of that step.
+ *   out_dev          fp32  [R]  out[0] = loss (mean over the R-2 steps with more than one candidate), out[1] = precision (fraction of
+ *                               (set, top-K complement) pairs ranked correctly), out[2+t] = loss of step t.
+ * R <= 256; an action set holds at most R pairs (a tree has at most n/2 cherries) - a larger one yields NaN. */
+int64_t nnj_rank_loss_workspace_bytes(int B, int R);
+int nnj_rank_loss(const float* logits_trace_dev, const uint8_t* in_set_dev, int B, int R, float margin, double ratio,
+                  float* out_dev, void* ws_dev, int64_t ws_bytes, void* stream);
 
 /* Building block of the tensor-core path (precision NNJ_PREC_BF16X3), exposed for unit tests and reuse:
  * C[z] = A[z] * B[z]^T with fp32 A [Z,M,K], B [Z,N,K], C [Z,M,N]; operands are split into bf16 hi/lo planes and

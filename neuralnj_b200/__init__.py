@@ -13,7 +13,9 @@ from .rollout import (Agmax_one_instance, Argmax_inference, RL_Search, Search_in
                       reinforce_rollout)
 from .treeutil import rf_distance, treestr_to_tuples   # noqa: F401
 from .likelihood import compute_llh, optimize_brlen          # noqa: F401
+from .supervise import balanced_elu_loss, supervise_rollout   # noqa: F401
 
 __all__ = ["PhyloATTN", "PhyInferEnv", "PhyloTree", "reinforce_rollout", "Agmax_one_instance", "Argmax_inference",
            "RL_Search", "Search_inference", "load_pi_instance", "empty_config", "inference_config", "CfgNode",
-           "rf_distance", "treestr_to_tuples", "format_rtree", "build", "lib", "NnjError", "optimize_brlen", "compute_llh"]
+           "rf_distance", "treestr_to_tuples", "format_rtree", "build", "lib", "NnjError", "optimize_brlen", "compute_llh",
+           "supervise_rollout", "balanced_elu_loss"]

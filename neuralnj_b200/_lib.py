@@ -10,7 +10,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnnj.so")
-SOURCES = ["nnj_api.cu", "nnj_encoder.cu", "nnj_encoder_tc.cu", "nnj_njloop.cu", "nnj_tc.cu", "nnj_score_tc.cu", "nnj_alpha_tc.cu", "nnj_score_big.cu", "nnj_llh.cu", "nnj_score_small.cu", "nnj_alpha_small.cu"]
+SOURCES = ["nnj_api.cu", "nnj_encoder.cu", "nnj_encoder_tc.cu", "nnj_njloop.cu", "nnj_tc.cu", "nnj_score_tc.cu", "nnj_alpha_tc.cu", "nnj_score_big.cu", "nnj_llh.cu", "nnj_score_small.cu", "nnj_alpha_small.cu", "nnj_rankloss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
@@ -18,7 +18,8 @@ EXPORTS = ["nnj_last_error", "nnj_abi_version", "nnj_model_create", "nnj_model_d
            "nnj_encode", "nnj_pair_scores_full", "nnj_pair_scores_list", "nnj_pair_scores_incr", "nnj_aggregate",
            "nnj_merge", "nnj_rollout", "nnj_rollout_from_state", "nnj_rollout_host", "nnj_launch_count",
            "nnj_profile_enable", "nnj_profile_classes", "nnj_profile_name", "nnj_profile_read", "nnj_gemm_split_bf16", "nnj_tc_selftest",
-           "nnj_llh_workspace_bytes", "nnj_llh_eval", "nnj_llh_optimize_brlen", "nnj_llh_optimize_all", "nnj_gamma_rates"]
+           "nnj_llh_workspace_bytes", "nnj_llh_eval", "nnj_llh_optimize_brlen", "nnj_llh_optimize_all", "nnj_gamma_rates",
+           "nnj_rank_loss_workspace_bytes", "nnj_rank_loss"]
 
 
 class NnjError(RuntimeError):
@@ -132,6 +133,10 @@ def lib() -> C.CDLL:
     L.nnj_llh_optimize_all.restype = i32
     L.nnj_gamma_rates.argtypes = [C.c_double, i32, dp]
     L.nnj_gamma_rates.restype = i32
+    L.nnj_rank_loss_workspace_bytes.argtypes = [i32, i32]
+    L.nnj_rank_loss_workspace_bytes.restype = i64
+    L.nnj_rank_loss.argtypes = [vp, vp, i32, i32, C.c_float, C.c_double, vp, vp, i64, vp]
+    L.nnj_rank_loss.restype = i32
     L.nnj_launch_count.argtypes = [i32]
     L.nnj_launch_count.restype = i64
     L.nnj_profile_enable.argtypes = [i32]

@@ -431,6 +431,14 @@ int nnj_gamma_rates(double alpha, int ncat, double* rates_h) {
     return gamma_rates(alpha, ncat, rates_h);
 }
 
+int64_t nnj_rank_loss_workspace_bytes(int B, int R) { return (B >= 1 && R >= 3 && R <= 256) ? (int64_t)rank_loss_ws_bytes(B, R) : -1; }
+
+int nnj_rank_loss(const float* logits_trace, const uint8_t* in_set, int B, int R, float margin, double ratio, float* out, void* ws, int64_t ws_bytes,
+                  void* stream) {
+    CHECK_ARGS(logits_trace && in_set && out && ws && B >= 1, "rank_loss: bad arguments");
+    return run_rank_loss(logits_trace, in_set, B, R, margin, ratio, out, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
 int nnj_tc_selftest(const float* A, const float* B, float* Dm, int N, void* stream) {
     CHECK_ARGS(A && B && Dm, "tc_selftest: bad arguments");
     return run_tc_unit(A, B, Dm, N, (cudaStream_t)stream);
@@ -480,6 +488,8 @@ int nnj_rollout_host(nnj_model* m, const int8_t* data_h, const uint8_t* mask_h, 
             if ((e = cudaMemcpyAsync(d_data + b0 * t_data, data_h + b0 * t_data, nb * t_data, cudaMemcpyHostToDevice, xs)) != cudaSuccess) break;
             if (mask_h && (e = cudaMemcpyAsync(d_mask + b0 * t_mask, mask_h + b0 * t_mask, nb * t_mask, cudaMemcpyHostToDevice, xs)) != cudaSuccess) break;
             if (gumbel_h && (e = cudaMemcpyAsync(d_gum + b0 * t_gum, gumbel_h + b0 * t_gum, nb * t_gum * 4, cudaMemcpyHostToDevice, xs)) != cudaSuccess) break;
+            if (select_mode == NNJ_SELECT_FORCED &&      // teacher forcing: the merge lists are inputs as well
+                (e = cudaMemcpyAsync(d_mg + b0 * t_mg, merges_h + b0 * t_mg, nb * t_mg * 4, cudaMemcpyHostToDevice, xs)) != cudaSuccess) break;
             e = cudaEventRecord(m->host_events[c], xs);
         }
         if (e != cudaSuccess) break;

@@ -170,4 +170,9 @@ int run_llh(const uint8_t* tips, const double* weights, const int32_t* children_
             cudaStream_t st);
 int gamma_rates(double alpha, int ncat, double* out);
 
+// pre-training loss over a teacher-forced rollout's logits trace (nnj_rankloss.cu)
+size_t rank_loss_ws_bytes(int B, int R);
+int run_rank_loss(const float* logits_trace, const uint8_t* in_set, int B, int R, float margin, double ratio, float* out, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
+
 }  // namespace nnj

@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(NTHREADS) k_select(int t, int n, int R, const 
                                                      size_t trace_stride, size_t trace_off, const int32_t* __restrict__ slot_cur,
                                                      int32_t* __restrict__ slot_next, int slot_stride, int32_t* __restrict__ free_slot,
                                                      int32_t* __restrict__ new_slot, int32_t* __restrict__ pair_i,
-                                                     int32_t* __restrict__ pair_j, int pair_stride) {
+                                                     int32_t* __restrict__ pair_j, int pair_stride, int forced) {
     __shared__ float s_val[NTHREADS];
     __shared__ int s_idx[NTHREADS];
     __shared__ float s_red[NTHREADS];
@@ -806,7 +806,11 @@ __global__ void __launch_bounds__(NTHREADS) k_select(int t, int n, int R, const 
         }
         __syncthreads();
     }
-    const int act = s_idx[0];
+    int act = s_idx[0];
+    if (forced) {     // teacher forcing (train.py:116-119): merges[b][t] holds the action on entry; anything that is not a pair i < j < n falls back to the argmax
+        const int fi = merges[((size_t)b * (R - 1) + t) * 2], fj = merges[((size_t)b * (R - 1) + t) * 2 + 1];
+        if (fi >= 0 && fi < fj && fj < n) act = pair_index(fi, fj, n);
+    }
     const float gmax = s_red[0];
     __syncthreads();
     float se = 0.f;
@@ -1181,7 +1185,8 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
     if (int e = check_dims(R, C)) return e;
     if (int e = set_attrs()) return e;
     if (select_mode == NNJ_SELECT_GUMBEL && !gumbel) return set_error(NNJ_ERR_INVALID, "rollout: gumbel noise required for NNJ_SELECT_GUMBEL");
-    if (select_mode == NNJ_SELECT_ARGMAX) gumbel = nullptr;
+    if (select_mode != NNJ_SELECT_GUMBEL) gumbel = nullptr;
+    if (select_mode < NNJ_SELECT_ARGMAX || select_mode > NNJ_SELECT_FORCED) return set_error(NNJ_ERR_INVALID, "rollout: unknown select mode");
     if (ws_bytes < nj_rollout_ws_bytes(m, B, R, C)) return set_error(NNJ_ERR_WORKSPACE, "rollout: workspace too small");
     const int chunk = nj_rollout_chunk(m, B, R, C);
     const int S = R + 1;
@@ -1244,7 +1249,7 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
             prof_begin(KC_SELECT, st);
             k_select<<<nbt, NTHREADS, 0, st>>>(t, n, R, nb.logits[cur ^ 1], nb.new_scores, nb.pair_stride, nb.logits[cur], P0, gmb, mg, slp, ltr,
                                                trace_stride, trace_off, slot, nb.slot[(t + 1) & 1], S, nb.free_slot, nb.new_slot, nb.pair_i,
-                                               nb.pair_j, nb.pair_stride);
+                                               nb.pair_j, nb.pair_stride, select_mode == NNJ_SELECT_FORCED);
             LAUNCH_CHECK();
             trace_off += (size_t)n * (n - 1) / 2;
             if (n == 2) break;

@@ -243,13 +243,14 @@ class PhyloATTN(nn.Module):
         return out
 
     def rollout_fused(self, batch_input=None, batch_seq_mask=None, gumbel: Optional[torch.Tensor] = None,
-                      state: Optional[torch.Tensor] = None, want_logits: bool = False
-                      ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+                      state: Optional[torch.Tensor] = None, want_logits: bool = False,
+                      forced: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
         """Encode + all R-1 NJ steps on the device (finetune_rl_search.py:107-175 without host round trips).
 
         Returns (merges int32 [B,R-1,2], selected_logp fp32 [B,R-1], logits trace [B, sum_t P_t] or None).
         `gumbel` fp32 [B,R-1,R(R-1)/2] switches selection to argmax(logits + gumbel) (sampling);
-        `state` supplies a pre-computed encoder output shared by several rollouts (Search mode).
+        `state` supplies a pre-computed encoder output shared by several rollouts (Search mode);
+        `forced` int32 [B,R-1,2] replays the given actions instead of selecting (teacher forcing, train.py:116-119).
         """
         dev = self._device()
         L = _lib.lib()
@@ -263,12 +264,18 @@ class PhyloATTN(nn.Module):
             B, R, Ls, _ = data.shape
             self.patch_num = math.ceil(Ls / self.patch_size)
         merges = torch.empty(B, R - 1, 2, dtype=torch.int32, device=dev)
+        if forced is not None:
+            if gumbel is not None:
+                raise NnjError("rollout_fused: `forced` and `gumbel` exclude each other")
+            if tuple(forced.shape) != (B, R - 1, 2):
+                raise NnjError("rollout_fused: forced must be [B, R-1, 2]")
+            merges.copy_(forced)                 # NNJ_SELECT_FORCED reads the actions from the merge-list buffer
         slp = torch.empty(B, R - 1, dtype=torch.float32, device=dev)
         trace = None
         if want_logits:
             tot = sum(n * (n - 1) // 2 for n in range(2, R + 1))
             trace = torch.empty(B, tot, dtype=torch.float32, device=dev)
-        mode = 0
+        mode = 2 if forced is not None else 0
         if gumbel is not None:
             gumbel = gumbel.to(device=dev, dtype=torch.float32).contiguous()
             if tuple(gumbel.shape) != (B, R - 1, R * (R - 1) // 2):

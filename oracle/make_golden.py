@@ -284,8 +284,108 @@ def main_wide():
         f.write("\n".join(index) + "\n")
 
 
+def main_supervise():
+    """Row f3, forward half: teacher-forced rollouts and the pre-training loss, executed by the unmodified reference.
+
+    For each case: the label tree next to the alignment is read by the reference's own `phydata.load_tree_file` (on the Bio.Phylo
+    stand-in of oracle/ref_stubs), a bottom-up trajectory and its per-step action sets come from `sample_trajectory_set_bottom_top`
+    (phydata.py:779-834) under a recorded `random.seed`, `train.supervise_rollout(eval=True, pretrained=True)` (train.py:43-161)
+    supplies the per-step logits, and the loss is computed by EXECUTING the reference's own statements (train.py, from
+    "Policy_loss = 0" to "policy_loss = Policy_loss/len(logitss)", read from the source file at generation time - nothing of it is
+    stored in this repository) for two epochs of the K-ratio schedule.  Records go to tests/golden/supervise/."""
+    import random
+    import textwrap
+    torch.set_num_threads(8)
+    import utils as ref_utils
+    import phydata as ref_phy
+    import train as ref_train
+    from environment import PhyInferEnv
+    from model import PhyloATTN
+    import torch.nn.functional as F
+
+    torch.autograd.set_detect_anomaly(False)
+    cfgs = ref_utils.empty_config()
+    cfgs.merge_from_file(os.path.join(REF, "config/pretrain_mix.yaml"))
+    ref_train.device = torch.device("cpu")
+    torch.manual_seed(0)
+    model = PhyloATTN(cfgs).eval()
+    sd = O.init_state_dict(0)
+    for k, v in model.state_dict().items():
+        assert torch.equal(sd[k], v), k
+
+    src_lines = open(os.path.join(REF, "train.py")).read().split("\n")
+    lo = next(i for i, l in enumerate(src_lines) if l.strip() == "Policy_loss = 0")
+    hi = next(i for i, l in enumerate(src_lines) if l.strip() == "policy_loss = Policy_loss/len(logitss)")
+    loss_src = textwrap.dedent("\n".join(src_lines[lo:hi + 1]))
+
+    def reference_loss(ret, epoch):
+        logitss, _, set_masks, sets, comp_masks, comps, _ = ret
+        ns = dict(torch=torch, F=F, os=os, cfgs=cfgs, epoch=epoch, BALANCED_ELU_LOSS=cfgs.loss.BALANCED_ELU_LOSS,
+                  ELU_LOSS=cfgs.loss.ELU_LOSS, logitss=[l.clone() for l in logitss], actions_set_masks=set_masks, actions_sets=sets,
+                  actions_set_complement_masks=comp_masks, actions_sets_complement=comps)
+        exec(loss_src, ns)
+        return float(ns["policy_loss"]), float(ns["precision"])
+
+    out_dir = os.path.join(GOLD, "supervise")
+    os.makedirs(out_dir, exist_ok=True)
+    t20 = "data_gen/data/test/len256/taxa20/"
+    cases = [
+        ("sup_20x256_b2", [t20 + "G_l_256_n_20_0_0.01_10", t20 + "G_l_256_n_20_0_0.01_103"], 5),
+        ("sup_50x256", [_pick("data_gen/data/test/len256/taxa50", 3)[:-4]], 6),
+        ("sup_50x1024", ["examples/len1024taxa50/G_l_1024_n_50_0_0.03_73"], 7),
+    ]
+    for name, stems, seed in cases:
+        items = []
+        random.seed(seed)
+        for stem in stems:
+            b = ref_phy.load_pi_instance(os.path.join(REF, stem + ".phy"))
+            tree = ref_phy.load_tree_file(os.path.join(REF, stem + ".tre"), None, pos=5)
+            acts, sets = ref_phy.sample_trajectory_set_bottom_top(tree, pos=5)
+            items.append((b, tree, acts, sets, open(os.path.join(REF, stem + ".tre")).read().strip()))
+        batch = {
+            "data": torch.cat([it[0]["data"] for it in items]),
+            "seq_weights": torch.cat([it[0]["seq_weights"] for it in items]),
+            "seqs": [it[0]["seqs"][0] for it in items],
+            "seq_keys": [it[0]["seq_keys"][0] for it in items],
+            "trees": [it[1] for it in items],
+            "actions": torch.from_numpy(np.array([[it[2]] for it in items], dtype=np.int32)),
+            "actions_set": [[it[3]] for it in items],
+        }
+        env = PhyInferEnv(cfgs, torch.device("cpu"))
+        t = time.time()
+        ret = ref_train.supervise_rollout(batch, model, env, eval=True, pretrained=True)
+        dt = time.time() - t
+        logitss, sets_list, _, _, _, _, sel = ret
+        losses = {ep: reference_loss(ret, ep) for ep in (0, 30)}
+        B, R = batch["data"].shape[:2]
+        flat_sets = []          # per tree and step: pair indices of the action set, -1 padded
+        width = max(len(s) for st in sets_list for s in st)
+        set_idx = -np.ones((B, len(sets_list), width), dtype=np.int32)
+        for st, step_sets in enumerate(sets_list):
+            for bb, s in enumerate(step_sets):
+                set_idx[bb, st, :len(s)] = s
+        lg = [l.numpy() for l in logitss]
+        offs = np.cumsum([0] + [l.shape[1] for l in lg]).astype(np.int64)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"),
+                            data=batch["data"].numpy().astype(np.int8), seq_mask=(batch["seq_weights"] == 0).numpy(),
+                            seq_keys=np.array(batch["seq_keys"]), label_newick=np.array([it[4] for it in items]),
+                            random_seed=np.array([seed]), actions=batch["actions"][:, 0].numpy().astype(np.int32),
+                            action_set_pair_index=set_idx, logits=np.concatenate(lg, 1).astype(np.float32), logit_offsets=offs,
+                            selected_log_ps=sel.numpy().astype(np.float32),
+                            loss_epochs=np.array(sorted(losses)), loss=np.array([losses[e][0] for e in sorted(losses)]),
+                            precision=np.array([losses[e][1] for e in sorted(losses)]),
+                            ratio_factor=np.array([cfgs.ratio_factor]), margin=np.array([0.5]))
+        # the oracle along the same forced trajectory
+        r = O.rollout(sd, batch["data"], batch["seq_weights"] == 0, forced_merges=batch["actions"][:, 0].long())
+        dl = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(r["logits"], logitss))
+        print(f"[{name}] reference supervise_rollout {dt:.1f}s, steps {len(logitss)}, loss {losses}, oracle max rel dlogit {dl:.2e}", flush=True)
+        assert dl < 1e-5
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "wide":
         main_wide()
+    elif len(sys.argv) > 1 and sys.argv[1] == "supervise":
+        main_supervise()
     else:
         main()

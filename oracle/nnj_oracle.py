@@ -29,6 +29,8 @@ Reference citations (relative to /root/reference):
 from __future__ import annotations
 
 import math
+
+import numpy as np
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -481,6 +483,38 @@ def rollout(sd: State, data: torch.Tensor, seq_mask: torch.Tensor, num_heads: in
 # --------------------------------------------------------------------------
 _ONEHOT = {"A": (1, 0, 0, 0), "C": (0, 1, 0, 0), "G": (0, 0, 1, 0), "T": (0, 0, 0, 1),
            "-": (1, 1, 1, 1), "N": (1, 1, 1, 1), "*": (0, 0, 0, 0)}  # phydata.py:38-46
+
+
+def ranking_loss(logits_steps: Sequence[np.ndarray], set_index: np.ndarray, epoch: int = 0, ratio_factor: float = 0.5,
+                 margin: float = 0.5) -> Tuple[float, float, List[float]]:
+    """Balanced-ELU margin ranking loss of the pre-training step, restated (train.py:448-545, BALANCED_ELU_LOSS branch).
+
+    `logits_steps[t]` [B, P_t] are the logits of the steps supervise_rollout records (all but the last, train.py:131-136);
+    `set_index` int [B, T, width] holds each step's action set as pair indices, -1 padded (train.py:30-39).
+    Per step: the complement of the action set is padded to the batch's widest one, its K = min(W, max(int(W * ratio), 8))
+    largest scores are kept (padding masked out again), and elu(-(s - margin - u)) is averaged over all (set, kept) pairs of the
+    batch; the loss is the mean over steps, `precision` the share of pairs with s > u over all steps.  float64 throughout.
+    Returns (loss, precision, per-step losses)."""
+    ratio = max(1 - 3 / (4 * 20) * epoch / 2, 1 / 4) * ratio_factor
+    step_losses, right, pairs_total = [], 0.0, 0.0
+    for t, lg in enumerate(logits_steps):
+        lg = np.asarray(lg, dtype=np.float64)
+        B, P = lg.shape
+        members = [np.array([p for p in set_index[b, t] if p >= 0], dtype=np.int64) for b in range(B)]
+        others = [np.setdiff1d(np.arange(P), m) for m in members]
+        W = max(len(o) for o in others)
+        K = min(W, max(int(W * ratio), 8))
+        total, pairs = 0.0, 0.0
+        for b in range(B):
+            s = lg[b, members[b]]
+            u = np.sort(lg[b, others[b]])[::-1][:K]
+            x = -(s[:, None] - margin - u[None, :])
+            total += float(np.where(x > 0, x, np.expm1(np.minimum(x, 0))).sum())
+            pairs += s.size * u.size
+            right += float((s[:, None] > u[None, :]).sum())
+        step_losses.append(total / pairs)
+        pairs_total += pairs
+    return float(np.mean(step_losses)), right / pairs_total, step_losses
 
 
 def load_phy(path: str):
