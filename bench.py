@@ -202,6 +202,38 @@ def llh_scoring_rate(merges, onehot, R):
     return out
 
 
+def supervised_eval_rate(model, data, mask, merges, R):
+    """Training step, forward half on the side: the first 128 alignments of the timed batch replayed along their own
+    merge lists with teacher forcing (NNJ_SELECT_FORCED, logits trace kept) and ranked by the balanced-ELU loss kernel
+    (nnj_rank_loss, action set of a step = the action taken).  Device time, CUDA events."""
+    import torch
+    from neuralnj_b200.supervise import SupervisedRollout, balanced_elu_loss, trace_offsets
+    n = min(128, data.shape[0])
+    d, m, f = data[:n].contiguous(), mask[:n].contiguous(), merges[:n].contiguous()
+    offs = torch.tensor(trace_offsets(R)[:-1], device=d.device)
+    nn = R - torch.arange(R - 1, device=d.device)
+    i, j = f[..., 0].long(), f[..., 1].long()
+    pidx = i * nn - i * (i + 1) // 2 + (j - i - 1) + offs                      # position of every taken action in the logits trace
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    out = {}
+    for it in range(2):                                                        # the second pass is the timed one
+        ev[0].record()
+        mg, slp, trace = model.rollout_fused(d, m, want_logits=True, forced=f)
+        ev[1].record()
+        flags = torch.zeros(trace.shape, dtype=torch.uint8, device=d.device)
+        flags.scatter_(1, pidx, 1)
+        roll = SupervisedRollout(([], [], [], [], [], [], slp))
+        roll.trace, roll.in_set, roll.taxa = trace, flags, R
+        loss = balanced_elu_loss(roll, epoch=0, ratio_factor=0.5)
+        ev[2].record()
+        torch.cuda.synchronize()
+        assert torch.equal(mg, f)
+        out = {"alignments": n, "forced_rollout_ms": round(ev[0].elapsed_time(ev[1]), 2), "loss_ms": round(ev[1].elapsed_time(ev[2]), 3),
+               "trees_per_s": round(n / (ev[0].elapsed_time(ev[2]) * 1e-3), 1), "loss": round(loss["loss"], 5), "precision": round(loss["precision"], 5),
+               "note": "forward only: supervise_rollout(eval=True) + BALANCED_ELU_LOSS (train.py:43-161, 448-545); no backward pass in this library"}
+    return out
+
+
 def gpu_eager_baseline(dev, R, L, budget_s=40.0):
     """SURVEY 8(d) same-box GPU bar: the reference formulation (the oracle restatement, pure torch ops) run in torch eager
     on this B200 at B = 1 / 8 / 32.  Step 0 is pair-chunked for B > 1 (the reference materialises ~3 GB per tree there)."""
@@ -425,6 +457,10 @@ def main():
                 extras["tree_llh"] = llh_scoring_rate(merges[:32].cpu().numpy(), data_host[0], R_TAXA)
             except Exception as exc:   # noqa: BLE001
                 extras["tree_llh"] = {"error": f"{type(exc).__name__}: {exc}"}
+            try:
+                extras["supervised_eval"] = supervised_eval_rate(model, data, mask, merges, R_TAXA)
+            except Exception as exc:   # noqa: BLE001
+                extras["supervised_eval"] = {"error": f"{type(exc).__name__}: {exc}"}
     weak = None
     if world > 1 and args.scaling == "strong" and not args.no_extras:
         w = timed("weak", max(1, min(args.steps, 3)), 1, False)
