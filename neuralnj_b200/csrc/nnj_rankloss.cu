@@ -30,9 +30,9 @@ __host__ __device__ inline size_t trace_offset(int R, int t) {     // sum_{s<t} 
     return o;
 }
 
-// set_count[b][t] = |S|
+// set_count[b][t] = |S|;  widest[t] = max_b (P - |S|): the width the reference pads every tree's complement to (utils.py:198-209)
 __global__ void __launch_bounds__(RL_THREADS) k_rank_count(const uint8_t* __restrict__ in_set, size_t trace_stride, int R, int T,
-                                                           int32_t* __restrict__ set_count) {
+                                                           int32_t* __restrict__ set_count, int32_t* __restrict__ widest) {
     __shared__ int s_cnt[RL_THREADS];
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int n = R - t, P = n * (n - 1) / 2;
@@ -45,38 +45,29 @@ __global__ void __launch_bounds__(RL_THREADS) k_rank_count(const uint8_t* __rest
         if (tid < o) s_cnt[tid] += s_cnt[tid + o];
         __syncthreads();
     }
-    if (tid == 0) set_count[(size_t)b * T + t] = s_cnt[0];
+    if (tid == 0) {
+        set_count[(size_t)b * T + t] = s_cnt[0];
+        atomicMax(&widest[t], P - s_cnt[0]);          // a maximum: independent of the order of arrival
+    }
 }
 
 // part[b][t] = { sum of elu terms, number of (s, u) pairs, number of pairs with s > u }
 __global__ void __launch_bounds__(RL_THREADS) k_rank_loss(const float* __restrict__ logits, const uint8_t* __restrict__ in_set, size_t trace_stride,
-                                                          int B, int R, int T, float margin, double ratio, const int32_t* __restrict__ set_count,
-                                                          double* __restrict__ part, int u_cap) {
+                                                          int R, int T, float margin, double ratio, const int32_t* __restrict__ set_count,
+                                                          const int32_t* __restrict__ widest, double* __restrict__ part, int u_cap) {
     extern __shared__ float sm[];
     float* u = sm;                    // [u_cap] complement scores, sorted descending
     float* sv = sm + u_cap;           // [R] action-set scores in pair order
     __shared__ int s_scan[RL_THREADS + 1];
     __shared__ double s_acc[RL_THREADS];
     __shared__ double s_prec[RL_THREADS];
-    __shared__ int s_W;
     const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int n = R - t, P = n * (n - 1) / 2;
     const size_t off = (size_t)b * trace_stride + trace_offset(R, t);
     const float* lg = logits + off;
     const uint8_t* f = in_set + off;
 
-    // W: the widest complement of this step over the batch (the reference pads every tree's complement to it, utils.py:198-209)
-    int w = 0;
-    for (int bb = tid; bb < B; bb += RL_THREADS) w = max(w, P - set_count[(size_t)bb * T + t]);
-    s_scan[tid] = w;
-    __syncthreads();
-    for (int o = RL_THREADS / 2; o > 0; o >>= 1) {
-        if (tid < o) s_scan[tid] = max(s_scan[tid], s_scan[tid + o]);
-        __syncthreads();
-    }
-    if (tid == 0) s_W = s_scan[0];
-    __syncthreads();
-    const int W = s_W;
+    const int W = widest[t];
     const int K = min(W, max((int)((double)W * ratio), 8));
     const int ns = set_count[(size_t)b * T + t];
     const int U = P - ns;
@@ -170,18 +161,24 @@ inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 size_t rank_loss_ws_bytes(int B, int R) {
     const size_t T = (size_t)R - 2;
-    return up256((size_t)B * T * sizeof(int32_t)) + up256((size_t)B * T * 3 * sizeof(double)) + 256;
+    return up256((size_t)B * T * sizeof(int32_t)) + up256((size_t)B * T * 3 * sizeof(double)) + up256(T * sizeof(int32_t)) + 256;
 }
 
 int run_rank_loss(const float* logits_trace, const uint8_t* in_set, int B, int R, float margin, double ratio, float* out, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
     if (R < 3 || R > 256) return set_error(NNJ_ERR_INVALID, "rank_loss: 3 <= taxa <= 256");
+    if (B < 1 || B > 65535) return set_error(NNJ_ERR_INVALID, "rank_loss: 1 <= trees <= 65535 per call");
     if (!(ratio > 0.0) || !(ratio <= 1.0)) return set_error(NNJ_ERR_INVALID, "rank_loss: ratio must be in (0, 1]");
     if (ws_bytes < rank_loss_ws_bytes(B, R)) return set_error(NNJ_ERR_WORKSPACE, "rank_loss: workspace too small (nnj_rank_loss_workspace_bytes)");
     const int T = R - 2;
     char* base = reinterpret_cast<char*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     int32_t* set_count = reinterpret_cast<int32_t*>(base);
     double* part = reinterpret_cast<double*>(base + up256((size_t)B * T * sizeof(int32_t)));
+    int32_t* widest = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(part) + up256((size_t)B * T * 3 * sizeof(double)));
+    {
+        cudaError_t e = cudaMemsetAsync(widest, 0, (size_t)T * sizeof(int32_t), st);
+        if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    }
     const size_t trace_stride = trace_offset(R, R - 1);
     int u_cap = 1;
     while (u_cap < R * (R - 1) / 2) u_cap <<= 1;
@@ -192,10 +189,10 @@ int run_rank_loss(const float* logits_trace, const uint8_t* in_set, int B, int R
     }
     const dim3 grid(T, B);
     prof_begin(KC_MISC, st);
-    k_rank_count<<<grid, RL_THREADS, 0, st>>>(in_set, trace_stride, R, T, set_count);
+    k_rank_count<<<grid, RL_THREADS, 0, st>>>(in_set, trace_stride, R, T, set_count, widest);
     ++g_launches; prof_end(st);
     prof_begin(KC_MISC, st);
-    k_rank_loss<<<grid, RL_THREADS, smem, st>>>(logits_trace, in_set, trace_stride, B, R, T, margin, ratio, set_count, part, u_cap);
+    k_rank_loss<<<grid, RL_THREADS, smem, st>>>(logits_trace, in_set, trace_stride, R, T, margin, ratio, set_count, widest, part, u_cap);
     ++g_launches; prof_end(st);
     prof_begin(KC_MISC, st);
     k_rank_final<<<1, RL_THREADS, 0, st>>>(part, B, T, out);

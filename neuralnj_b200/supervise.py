@@ -280,19 +280,93 @@ def make_batch(files: Sequence[Tuple[str, str]], rng=_random) -> dict:
     }
 
 
-def evaluate(files: Sequence[Tuple[str, str]], agent, env, cfgs=None, epoch: int = 0, ratio_factor: float = 0.5, rng=_random) -> dict:
-    """The quantities `eval_on_dataset` logs for a validation set (`train.py:356-430`), for files of one shape: the loss along a label
-    trajectory, the share of steps where the argmax action is admissible, and the normalised RF distance of the argmax tree to the
-    label tree."""
+def evaluate(files: Sequence[Tuple[str, str]], agent, env, cfgs=None, epoch: int = 0, ratio_factor: float = 0.5, rng=_random,
+             with_likelihood: bool = False) -> dict:
+    """The quantities `eval_on_dataset` logs for a validation set (`train.py:356-430`), for files of one shape: the loss along a sampled
+    label trajectory, the share of its steps whose top-scoring pair is admissible, the normalised RF distance of the argmax tree to the
+    label tree and - with `with_likelihood` - the branch-optimised log-likelihoods of the label topology (`scores_ref`, `train.py:381`) and
+    of the argmax tree (`scores`, `:387`) from the GPU likelihood (needs the real sequences in the files)."""
     from .rollout import reinforce_rollout
     batch = make_batch(files, rng)
-    sup = supervise_rollout(batch, agent, env, eval=True)
+    sup = supervise_rollout(batch, agent, env, eval=True, branch_optimize=with_likelihood)
     loss = balanced_elu_loss(sup, epoch=epoch, ratio_factor=ratio_factor)
     hits = []
     for t, lg in enumerate(sup[0]):
         top = lg.argmax(dim=1).cpu().tolist()
         hits.append([top[b] in sup[1][t][b] for b in range(len(top))])
-    reinforce_rollout(batch, agent, env, cfgs, eval=True, argmax=True)
+    _, _, scores, _ = reinforce_rollout(batch, agent, env, cfgs, eval=True, argmax=True, branch_optimize=with_likelihood)
     rf = [normalized_rf(batch["label_newick"][b], env.states[b].subtrees[0].utree_op_str) for b in range(len(files))]
-    return {"loss": loss["loss"], "precision": loss["precision"], "argmax_in_action_set": float(np.mean(hits)),
-            "normalized_rf": rf, "normalized_rf_mean": float(np.mean(rf))}
+    out = {"loss": loss["loss"], "precision": loss["precision"], "argmax_in_action_set": float(np.mean(hits)),
+           "normalized_rf": rf, "normalized_rf_mean": float(np.mean(rf))}
+    if with_likelihood:
+        ref, got = sup.scores.double().cpu(), scores.double().cpu()
+        out.update({"llh_label_tree": ref.tolist(), "llh_argmax_tree": got.tolist(), "llh_diff_mean": float((ref - got).mean())})
+    return out
+
+
+def evaluate_dir(data_dir: str, agent, cfgs, device, batch: int = 32, limit: Optional[int] = None, epoch: int = 0,
+                 ratio_factor: float = 0.5, with_likelihood: bool = False, seed: int = 0) -> dict:
+    """`eval_on_dataset` over a directory tree of `<name>.phy` + `<name>.tre` pairs (the layout of the reference's
+    data_gen/data/test/len*/taxa*): files are grouped by directory (one shape per directory, like `PhySampler`, `train.py:297-299`)
+    and evaluated `batch` at a time; means are over files."""
+    import os
+    from .environment import PhyInferEnv
+    rng = _random.Random(seed)
+    groups = {}
+    for root, _, names in sorted(os.walk(data_dir)):
+        for n in sorted(names):
+            if n.endswith(".phy") and os.path.exists(os.path.join(root, n[:-4] + ".tre")):
+                groups.setdefault(root, []).append((os.path.join(root, n), os.path.join(root, n[:-4] + ".tre")))
+    per_dir, rows = {}, []
+    for root, files in groups.items():
+        files = files[:limit] if limit else files
+        acc = []
+        for k in range(0, len(files), batch):
+            chunk = files[k:k + batch]
+            env = PhyInferEnv(cfgs, device)
+            res = evaluate(chunk, agent, env, cfgs=cfgs, epoch=epoch, ratio_factor=ratio_factor, rng=rng, with_likelihood=with_likelihood)
+            acc.append((len(chunk), res))
+        tot = sum(n for n, _ in acc)
+        row = {"files": tot, "loss": sum(n * r["loss"] for n, r in acc) / tot, "precision": sum(n * r["precision"] for n, r in acc) / tot,
+               "argmax_in_action_set": sum(n * r["argmax_in_action_set"] for n, r in acc) / tot,
+               "normalized_rf_mean": sum(n * r["normalized_rf_mean"] for n, r in acc) / tot}
+        if with_likelihood:
+            row["llh_diff_mean"] = sum(n * r["llh_diff_mean"] for n, r in acc) / tot
+        per_dir[os.path.relpath(root, data_dir)] = row
+        rows.append(row)
+    if not rows:
+        raise NnjError(f"{data_dir}: no <name>.phy / <name>.tre pairs found")
+    n = sum(r["files"] for r in rows)
+    return {"files": n, "loss": sum(r["files"] * r["loss"] for r in rows) / n,
+            "normalized_rf_mean": sum(r["files"] * r["normalized_rf_mean"] for r in rows) / n, "by_directory": per_dir}
+
+
+def main(argv=None):
+    """Validation of a checkpoint on labelled alignments: `python -m neuralnj_b200.supervise --config_path cfg.yaml --data_dir DIR`."""
+    import argparse
+    import json
+    from .config import empty_config
+    from .rollout import _load_policy
+    ap = argparse.ArgumentParser(description="NeuralNJ validation metrics (train.py eval_on_dataset) on the B200 path")
+    ap.add_argument("--config_path", type=str, default="")
+    ap.add_argument("--data_dir", type=str, required=True)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--limit", type=int, default=None, help="files per directory")
+    ap.add_argument("--epoch", type=int, default=0, help="position in the K-ratio schedule of the loss (train.py:495)")
+    ap.add_argument("--likelihood", action="store_true", help="also score label and argmax trees with the GPU likelihood")
+    ap.add_argument("--precision", type=str, default=None, choices=["fp32", "bf16x3"])
+    args = ap.parse_args(argv)
+    cfgs = empty_config()
+    if args.config_path:
+        cfgs.merge_from_file(args.config_path)
+    device = torch.device("cuda:0")
+    agent = _load_policy(cfgs, device, args.precision)
+    ratio_factor = getattr(cfgs, "ratio_factor", 0.5)
+    out = evaluate_dir(args.data_dir, agent, cfgs, device, batch=args.batch, limit=args.limit, epoch=args.epoch,
+                       ratio_factor=ratio_factor, with_likelihood=args.likelihood)
+    print(json.dumps(out, indent=1))
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,8 @@
 """Generate tests/golden/ by executing the UNMODIFIED reference (build container only).
 
     python oracle/make_golden.py            # writes tests/golden/*.npz + tests/golden/msa/*.phy
+    python oracle/make_golden.py supervise  # teacher-forced rollouts + pre-training loss (tests/golden/supervise/, see main_supervise)
+    python oracle/make_golden.py all50      # all 128 files of data_gen/data/test/len1024/taxa50 in one record (tests/golden/all50/)
     python oracle/make_golden.py wide       # round 2: 16 files of data_gen/data/test/len1024/taxa50 + 4 of len1024/taxa100
                                             #          as "lite" records under tests/golden/wide/ (see main_wide)
 
@@ -382,9 +384,78 @@ def main_supervise():
         assert dl < 1e-5
 
 
+def main_all50():
+    """The whole of data_gen/data/test/len1024/taxa50 (128 alignments - the set SURVEY.md 8(d) names for configs[1]) through the
+    unmodified reference: merge list, Newick, selected_log_ps and per-step max |logit| / top-2 gap of every file, in ONE record
+    (tests/golden/all50/len1024_taxa50.npz) together with the inputs as bit-packed one-hot tokens (25.6 KB per alignment)."""
+    torch.set_num_threads(8)
+    import utils as ref_utils
+    import finetune_rl_search as ref_main
+    from environment import PhyInferEnv
+    from model import PhyloATTN
+    from phydata import load_pi_instance
+
+    torch.autograd.set_detect_anomaly(False)
+    cfgs = ref_utils.empty_config()
+    cfgs.merge_from_file(os.path.join(REF, "config/finetune_reinforce_search_example.yaml"))
+    ref_main.cfgs = cfgs
+    ref_main.device = torch.device("cpu")
+    torch.manual_seed(0)
+    model = PhyloATTN(cfgs).eval()
+    sd = O.init_state_dict(0)
+    for k, v in model.state_dict().items():
+        assert torch.equal(sd[k], v), k
+    d = "data_gen/data/test/len1024/taxa50"
+    files = sorted(f for f in os.listdir(os.path.join(REF, d)) if f.endswith(".phy"))
+    rec = {k: [] for k in ("bits", "keys", "merges", "newick", "slp", "lmax", "gap", "src")}
+    for k, fn in enumerate(files):
+        batch = load_pi_instance(os.path.join(REF, d, fn))
+        env = PhyInferEnv(cfgs, torch.device("cpu"))
+        got = {"logits": [], "merges": []}
+        orig_dec, orig_step = model.decode_zxr, env.step
+
+        def dec(*a, **kw):
+            o = orig_dec(*a, **kw)
+            got["logits"].append(o["logits"].detach().clone())
+            return o
+
+        def step(actions, *a, **kw):
+            n = env.states[0].num_trees
+            got["merges"].append([list(map(int, env.tree_pairs_dict[n][int(x)])) for x in actions])
+            return orig_step(actions, *a, **kw)
+
+        model.decode_zxr, env.step = dec, step
+        try:
+            t = time.time()
+            sel, _, _, _ = ref_main.reinforce_rollout(batch, model, env, cfgs, eval=True, argmax=True, branch_optimize=False)
+            dt = time.time() - t
+        finally:
+            del model.decode_zxr
+        data = batch["data"].numpy().astype(np.uint8)
+        assert data.max() <= 1 and (batch["seq_weights"] != 0).all()
+        rec["bits"].append(np.packbits(data.reshape(-1)))
+        rec["keys"].append(batch["seq_keys"][0])
+        rec["merges"].append(np.array(got["merges"], dtype=np.int8)[:, 0])
+        rec["newick"].append(env.states[0].subtrees[0].utree_op_str)
+        rec["slp"].append(sel.numpy().astype(np.float32)[0])
+        rec["lmax"].append([float(lg.abs().max()) for lg in got["logits"]])
+        rec["gap"].append([float(lg.topk(2, dim=1).values.diff(dim=1).abs().max()) if lg.shape[1] > 1 else np.inf for lg in got["logits"]])
+        rec["src"].append(fn)
+        rel = min(g / m for g, m in zip(rec["gap"][-1], rec["lmax"][-1]) if np.isfinite(g))
+        print(f"[{k:3d}] {fn}: reference rollout {dt:.1f}s, min relative top-2 gap {rel:.2e}", flush=True)
+    out_dir = os.path.join(GOLD, "all50")
+    os.makedirs(out_dir, exist_ok=True)
+    np.savez_compressed(os.path.join(out_dir, "len1024_taxa50.npz"), shape=np.array([50, 1024, 4]), data_bits=np.stack(rec["bits"]),
+                        seq_keys=np.array(rec["keys"]), merges=np.stack(rec["merges"]), newick=np.array(rec["newick"]),
+                        selected_log_ps=np.stack(rec["slp"]), step_max_abs_logit=np.array(rec["lmax"], dtype=np.float32),
+                        step_top2_gap=np.array(rec["gap"], dtype=np.float32), source=np.array(rec["src"]))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "wide":
         main_wide()
+    elif len(sys.argv) > 1 and sys.argv[1] == "all50":
+        main_all50()
     elif len(sys.argv) > 1 and sys.argv[1] == "supervise":
         main_supervise()
     else:

@@ -209,3 +209,32 @@ def test_evaluate_on_label_files(gpu_models, tmp_path):
     assert abs(res["loss"] - g["loss"][0]) <= 1e-3 * abs(g["loss"][0])
     assert 0.0 <= res["argmax_in_action_set"] <= 1.0 and len(res["normalized_rf"]) == 2
     assert all(0.0 <= x <= 1.0 for x in res["normalized_rf"])
+    # with the likelihood scorer: the label topology (the tree that generated the data) is not beaten by much, if at all, by an untrained policy's tree
+    random.seed(int(g["random_seed"][0]))
+    res2 = S.evaluate(files, gpu_models["bf16x3"], env, cfgs=inference_config(), with_likelihood=True)
+    assert res2["loss"] == res["loss"] and len(res2["llh_label_tree"]) == 2
+    assert all(np.isfinite(res2["llh_label_tree"])) and all(np.isfinite(res2["llh_argmax_tree"]))
+    assert all(a > b for a, b in zip(res2["llh_label_tree"], res2["llh_argmax_tree"]))
+
+
+def test_evaluate_dir_and_cli(gpu_models, tmp_path, capsys):
+    """Directory walk (<name>.phy + <name>.tre pairs, one shape per directory) and the command line around it."""
+    import json
+    import shutil
+    from neuralnj_b200 import inference_config
+    from neuralnj_b200 import supervise as S
+    g = load("sup_20x256_b2")
+    d = tmp_path / "len256" / "taxa20"
+    d.mkdir(parents=True)
+    for b, stem in enumerate(("t20x256_10", "t20x256_103")):
+        shutil.copyfile(os.path.join(GOLD, "msa", stem + ".phy"), d / f"{stem}.phy")
+        (d / f"{stem}.tre").write_text(str(g["label_newick"][b]) + "\n")
+    shutil.copyfile(os.path.join(GOLD, "msa", "t20x256_104.phy"), d / "unlabelled.phy")          # no .tre next to it: skipped
+    res = S.evaluate_dir(str(tmp_path), gpu_models["bf16x3"], inference_config(), torch.device("cuda:0"), batch=1, ratio_factor=0.5)
+    assert res["files"] == 2 and list(res["by_directory"]) == [os.path.join("len256", "taxa20")]
+    assert 0.0 < res["loss"] < 10.0 and 0.0 <= res["normalized_rf_mean"] <= 1.0
+    out = S.main(["--data_dir", str(tmp_path), "--limit", "1", "--precision", "fp32"])
+    assert out["files"] == 1
+    assert json.loads(capsys.readouterr().out)["files"] == 1
+    with pytest.raises(S.NnjError):
+        S.evaluate_dir(str(tmp_path / "len256" / "taxa20" / "nothing"), gpu_models["fp32"], inference_config(), torch.device("cuda:0"))
