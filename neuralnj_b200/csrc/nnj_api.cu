@@ -230,8 +230,30 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
     m->embed = EmbedW{B0 + e_w1, B0 + e_b1, B0 + e_w2t, B0 + e_b2};
     m->nj = NjW{B0 + h_t, B0 + h_b, B0 + g_t, B0 + g_b, B0 + q_w, B0 + q_b, B0 + k_t, B0 + k_b, B0 + s_t, B0 + s_b, B0 + s2_w, s2_b};
     {   // bf16 hi/lo planes of the two [64][64] weights used as K-major B operands by the tensor-core pair-score kernel
-        std::vector<uint16_t> planes(4 * 4096);
+        std::vector<uint16_t> planes(4 * 4096 + 4 * 8192);
         const float* src[2] = {tensors[ti + 6] /*g_linear_last*/, tensors[ti + 12] /*s_out.0*/};
+        {   // mma.sync B fragments (NjFrag) of the merge / node-derive weights: B[k][n] = W[n][k] for the torch Linear weights, Wq as it is
+            const float* wsrc[4] = {tensors[ti + 4] /*h_linear_last*/, tensors[ti + 10] /*g_attn_k*/, tensors[ti + 8] /*g_attn_q*/, tensors[ti + 6] /*g_linear_last*/};
+            const bool transposed[4] = {true, true, false, true};
+            for (int w = 0; w < 4; ++w) {
+                uint16_t* out = planes.data() + 4 * 4096 + (size_t)w * 8192;
+                auto Bm = [&](int k, int n) { return transposed[w] ? wsrc[w][n * 64 + k] : wsrc[w][k * 64 + n]; };
+                for (int ks = 0; ks < 4; ++ks)
+                    for (int nt = 0; nt < 8; ++nt)
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int g = lane >> 2, t = lane & 3, n = nt * 8 + g;
+                            const int kk[4] = {ks * 16 + 2 * t, ks * 16 + 2 * t + 1, ks * 16 + 2 * t + 8, ks * 16 + 2 * t + 9};
+                            uint16_t* e = out + ((size_t)(ks * 8 + nt) * 32 + lane) * 8;
+                            for (int i = 0; i < 4; ++i) {
+                                const float v = Bm(kk[i], n);
+                                const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                                const __nv_bfloat16 l = NNJ_LO_BF16(__float2bfloat16_rn(v - __bfloat162float(h)));
+                                e[i] = __bfloat16_as_ushort(h);
+                                e[4 + i] = __bfloat16_as_ushort(l);
+                            }
+                        }
+            }
+        }
         for (int w = 0; w < 2; ++w)
             for (int i = 0; i < 4096; ++i) {
                 __nv_bfloat16 h = __float2bfloat16_rn(src[w][i]);
@@ -244,6 +266,8 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
         if (e != cudaSuccess) { cudaFree(m->blob); if (m->blob_bf) cudaFree(m->blob_bf); delete m; return set_cuda_error(e, __FILE__, __LINE__); }
         const uint16_t* pb = reinterpret_cast<const uint16_t*>(m->blob_bf);
         m->nj_bf = NjBf{pb, pb + 4096, pb + 8192, pb + 12288};
+        const uint4* pf = reinterpret_cast<const uint4*>(pb + 4 * 4096);
+        m->nj_frag = NjFrag{pf, pf + 1024, pf + 2048, pf + 3072};
     }
     {   // shared-memory images of the encoder weights for the tcgen05 kernels (EncTcW)
         constexpr size_t QKV = 2 * 192 * 64, OW = 2 * 64 * 64, W1 = 2 * 256 * 64, W2 = 2 * 64 * 256;   // bf16 elements

@@ -48,6 +48,9 @@ struct NjW {                                                        // model.py:
 };
 
 struct NjBf { const void *wgh, *wgl, *wsh, *wsl; };
+// The four [64 k][64 n] weights of the merge / node-derive products as mma.sync B fragments (bf16 hi / lo):
+// entry [(k16 * 8 + n8) * 32 + lane] = { hi(b0 b1), hi(b2 b3), lo(b0 b1), lo(b2 b3) } of m16n8k16, 16 KB per weight.
+struct NjFrag { const uint4 *h, *k, *q, *g; };                       // h_linear_last^T, g_attn_k^T, g_attn_q, g_linear_last^T
 // Encoder weights for the tcgen05 kernels: ready-to-copy shared-memory images (bf16 hi plane, then lo plane; every [N][64]
 // block K-major SWIZZLE_128B), one set per layer, plus the stacked q|k|v biases.
 struct EncTcW {
@@ -65,6 +68,7 @@ struct Model {
     std::vector<LayerW> layers;
     NjW nj;
     NjBf nj_bf;
+    NjFrag nj_frag;
     void* blob_bf;               // device allocation behind nj_bf
     std::vector<EncTcW> enc_tc;  // per layer
     void* blob_enc;              // device allocation behind enc_tc

@@ -27,12 +27,176 @@ struct Pool {
     int S, nCT;
 };
 
+// ------------------------------------------------------------------ [128 x 64] x [64 x 64] on the legacy tensor path
+// The five 64 x 64 products of the merge step (gate, Y, K, K', G) and the four of the node-derive step are the part of those kernels
+// that does not shrink with the number of live nodes.  In the tensor-core precision mode they run on mma.sync.m16n8k16 bf16 register
+// fragments - A split into hi / lo on the fly from the fp32 tile in shared memory, B from the fragment-packed weights (NjFrag),
+// hi*hi + hi*lo + lo*hi with fp32 accumulation like every other contraction of that mode.  Warp w owns tile rows 16w .. 16w+15.
+__device__ __forceinline__ void nj_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void load_wfrag(float* __restrict__ Ws, const uint4* __restrict__ Wf) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int idx = it * NTHREADS + threadIdx.x;
+        reinterpret_cast<uint4*>(Ws)[idx] = __ldg(Wf + idx);
+    }
+}
+// c[nt][0..1] += row g, columns nt*8 + 2t, +1;  c[nt][2..3]: row g + 8   (g = lane / 4, t = lane % 4)
+__device__ __forceinline__ void warp_mma64(float (&c)[8][4], const float* __restrict__ As, const float* __restrict__ Ws) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const float* ap = As + (warp * 16 + g) * LDA + 2 * t;
+    const uint4* wf = reinterpret_cast<const uint4*>(Ws) + lane;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const float2 v0 = *reinterpret_cast<const float2*>(ap + ks * 16), v1 = *reinterpret_cast<const float2*>(ap + 8 * LDA + ks * 16);
+        const float2 v2 = *reinterpret_cast<const float2*>(ap + ks * 16 + 8), v3 = *reinterpret_cast<const float2*>(ap + 8 * LDA + ks * 16 + 8);
+        uint32_t ah[4], al[4];
+        split2(v0.x, v0.y, ah[0], al[0]); split2(v1.x, v1.y, ah[1], al[1]);
+        split2(v2.x, v2.y, ah[2], al[2]); split2(v3.x, v3.y, ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const uint4 wv = wf[(ks * 8 + nt) * 32];
+            nj_mma(c[nt], al, wv.x, wv.y);       // lo * hi
+            nj_mma(c[nt], ah, wv.z, wv.w);       // hi * lo
+            nj_mma(c[nt], ah, wv.x, wv.y);       // hi * hi
+        }
+    }
+}
+__device__ __forceinline__ void frag_set_bias(float (&c)[8][4], const float* __restrict__ bias) {
+    const int t = threadIdx.x & 3;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const float2 b = bias ? __ldg(reinterpret_cast<const float2*>(bias + nt * 8 + 2 * t)) : make_float2(0.f, 0.f);
+        c[nt][0] = b.x; c[nt][1] = b.y; c[nt][2] = b.x; c[nt][3] = b.y;
+    }
+}
+// Regroup a fragment into runs of four columns (16-byte stores, the pair packing of the bf16 planes): the two lanes of a column pair swap
+// one n-tile of each tile pair p = (2p, 2p+1).  Even t ends up with columns 2t .. 2t+3 of tile 2p, odd t with columns 2t-2 .. 2t+1 of tile
+// 2p+1; q[p][h] is the run of row g + 8h and starts at column frag_col4(p).
+__device__ __forceinline__ void frag_to_quads(const float (&c)[8][4], float4 (&q)[4][2]) {
+    const bool odd = threadIdx.x & 1;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float a0 = c[2 * p][2 * h], a1 = c[2 * p][2 * h + 1], b0 = c[2 * p + 1][2 * h], b1 = c[2 * p + 1][2 * h + 1];
+            const float r0 = __shfl_xor_sync(0xffffffffu, odd ? a0 : b0, 1), r1 = __shfl_xor_sync(0xffffffffu, odd ? a1 : b1, 1);
+            q[p][h] = odd ? make_float4(r0, r1, b0, b1) : make_float4(a0, a1, r0, r1);
+        }
+    }
+}
+__device__ __forceinline__ int frag_col4(int p) { const int t = threadIdx.x & 3; return (2 * p + (t & 1)) * 8 + (t >> 1) * 4; }
+
 // ------------------------------------------------------------------ per-node derived tensors
 // xs: [128][LDA] tile of node rows (x).  Produces Y, K' (global) and the kappa partial of the tile.
-__device__ __forceinline__ void derive_tile(float* xs, float* tmp, float* Ws, const NjW& w, float* __restrict__ Yout,
+template <bool TC>
+__device__ __forceinline__ void derive_tile(float* xs, float* tmp, float* Ws, const NjW& w, const NjFrag& wf, float* __restrict__ Yout,
                                             float* __restrict__ Kout, float* __restrict__ kap_out, int row0, int C,
                                             float* red, uint2* __restrict__ Kh = nullptr, uint2* __restrict__ Kl = nullptr,
                                             uint2* __restrict__ Nh = nullptr, uint2* __restrict__ Nl = nullptr, int S = 0, int slot = 0) {
+    if constexpr (TC) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+        const int rr[2] = {warp * 16 + g, warp * 16 + g + 8};      // tile rows of the two fragment halves
+        float c[8][4];
+        float4 q[4][2];
+        // Y = x W_h^T
+        load_wfrag(Ws, wf.h);
+        __syncthreads();
+        frag_set_bias(c, nullptr);
+        warp_mma64(c, xs, Ws);
+        frag_to_quads(c, q);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (row0 + rr[h] < C) st4(Yout + (size_t)(row0 + rr[h]) * D + frag_col4(p), q[p][h]);
+        __syncthreads();
+        // K = x W_k^T + b_k, kappa partial = sum over the tile's rows of b_q . K
+        load_wfrag(Ws, wf.k);
+        __syncthreads();
+        frag_set_bias(c, w.bk);
+        warp_mma64(c, xs, Ws);
+        {
+            float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float2 bq = __ldg(reinterpret_cast<const float2*>(w.bq + nt * 8 + 2 * t));
+                p0 = fmaf(c[nt][0], bq.x, p0); p0 = fmaf(c[nt][1], bq.y, p0);
+                p1 = fmaf(c[nt][2], bq.x, p1); p1 = fmaf(c[nt][3], bq.y, p1);
+            }
+            p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+            if (t == 0) {
+                red[rr[0]] = (row0 + rr[0] < C) ? p0 : 0.f;
+                red[rr[1]] = (row0 + rr[1] < C) ? p1 : 0.f;
+            }
+        }
+        frag_to_quads(c, q);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) st4(tmp + rr[h] * LDA + frag_col4(p), q[p][h]);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float s = (red[threadIdx.x] + red[threadIdx.x + 32]) + (red[threadIdx.x + 64] + red[threadIdx.x + 96]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (threadIdx.x == 0) *kap_out = s;
+        }
+        // K' = K W_q
+        load_wfrag(Ws, wf.q);
+        __syncthreads();
+        frag_set_bias(c, nullptr);
+        warp_mma64(c, tmp, Ws);
+        frag_to_quads(c, q);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int cc = row0 + rr[h];
+                if (cc < C) {
+                    const int c4 = frag_col4(p);
+                    st4(Kout + (size_t)cc * D + c4, q[p][h]);
+                    if (Kh) {
+                        uint2 oh, ol;
+                        split2(q[p][h].x, q[p][h].y, oh.x, ol.x);
+                        split2(q[p][h].z, q[p][h].w, oh.y, ol.y);
+                        Kh[(size_t)cc * 16 + c4 / 4] = oh;
+                        Kl[(size_t)cc * 16 + c4 / 4] = ol;
+                    }
+                }
+            }
+        if (Nh) {
+            // site-major node planes [C][S][128] = [X | G], G = x W_g^T (no bias)
+            __syncthreads();
+            load_wfrag(Ws, wf.g);
+            __syncthreads();
+            frag_set_bias(c, nullptr);
+            warp_mma64(c, xs, Ws);
+            frag_to_quads(c, q);
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int cc = row0 + rr[h];
+                    if (cc < C) {
+                        const int c4 = frag_col4(p);
+                        const float4 xv = ld4(xs + rr[h] * LDA + c4);
+                        const size_t o = ((size_t)cc * S + slot) * 32 + c4 / 4;
+                        uint2 oh, ol;
+                        split2(xv.x, xv.y, oh.x, ol.x);
+                        split2(xv.z, xv.w, oh.y, ol.y);
+                        Nh[o] = oh; Nl[o] = ol;
+                        split2(q[p][h].x, q[p][h].y, oh.x, ol.x);
+                        split2(q[p][h].z, q[p][h].w, oh.y, ol.y);
+                        Nh[o + 16] = oh; Nl[o + 16] = ol;
+                    }
+                }
+        }
+        return;
+    }
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     float acc[8][4];
     // Y = x W_h^T   (bias b_h is added when the pair gate is formed)
@@ -115,9 +279,10 @@ __device__ __forceinline__ void derive_tile(float* xs, float* tmp, float* Ws, co
 }
 
 // grid (nCT, n_nodes, B): derive Y/K'/kappa for physical slots node_list[b][k] (or slot k when null)
+template <bool TC>
 __global__ void __launch_bounds__(NTHREADS) k_node_derive(const float* __restrict__ X, float* __restrict__ Y, float* __restrict__ K,
                                                           float* __restrict__ kap, size_t tree_stride, int S, int C, int nCT,
-                                                          const int32_t* __restrict__ node_list, int list_stride, NjW w,
+                                                          const int32_t* __restrict__ node_list, int list_stride, NjW w, NjFrag wf,
                                                           uint2* __restrict__ Kh, uint2* __restrict__ Kl, uint2* __restrict__ Nh,
                                                           uint2* __restrict__ Nl) {
     extern __shared__ __align__(16) float smem[];
@@ -138,7 +303,7 @@ __global__ void __launch_bounds__(NTHREADS) k_node_derive(const float* __restric
         st4(xs + row * LDA + c4 * 4, v);
     }
     __syncthreads();
-    derive_tile(xs, tmp, Ws, w, Y + base, K + base, kap + ((size_t)b * S + slot) * nCT + ct, row0, C, red,
+    derive_tile<TC>(xs, tmp, Ws, w, wf, Y + base, K + base, kap + ((size_t)b * S + slot) * nCT + ct, row0, C, red,
                 Kh ? Kh + base / 4 : nullptr, Kl ? Kl + base / 4 : nullptr, Nh ? Nh + (size_t)b * C * S * 32 : nullptr,
                 Nl ? Nl + (size_t)b * C * S * 32 : nullptr, S, slot);
 }
@@ -540,11 +705,11 @@ __global__ void k_score_reduce(const float* __restrict__ score_part, int nSG, in
 // ------------------------------------------------------------------ merged-node embedding (+ derived tensors)
 // grid (nCT, B).  Rows = 128 sites of the merge pair.  out_x: where x' goes ([B] stride out_stride);
 // when `derive` the Y/K'/kappa of the new node are produced as well (physical slot new_slot[b]).
-template <bool GLOB>
+template <bool GLOB, bool TC>
 __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict__ Xw, float* __restrict__ Yw, float* __restrict__ Kw,
                                                     float* __restrict__ kapw, const int32_t* __restrict__ slot_of, int slot_stride,
                                                     int Rp, int C, const int32_t* __restrict__ merge_ij, int ij_stride,
-                                                    const float* __restrict__ alpha, int RP, NjW w, float* __restrict__ out_x,
+                                                    const float* __restrict__ alpha, int RP, NjW w, NjFrag wf, float* __restrict__ out_x,
                                                     size_t out_stride, const int32_t* __restrict__ new_slot, int derive,
                                                     uint2* __restrict__ nodes_h, uint2* __restrict__ nodes_l, uint2* __restrict__ kp_h,
                                                     uint2* __restrict__ kp_l, const int32_t* __restrict__ move_dst) {
@@ -562,7 +727,7 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
     const int li = merge_ij[(size_t)b * ij_stride], lj = merge_ij[(size_t)b * ij_stride + 1];
     const int pi = so[li], pj = so[lj];
     if (GLOB) {
-        load_w64(Ws, w.wgt);
+        if constexpr (TC) load_wfrag(Ws, wf.g); else load_w64(Ws, w.wgt);
         for (int r = tid; r < Rp; r += NTHREADS) { s_slot[r] = so[r]; al[r] = alpha[(size_t)b * PAIR_CHUNK * RP + r]; }
     }
     {
@@ -635,6 +800,31 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
         }
         acc_store_smem(acc, xg, ty, tx);
         __syncthreads();
+        if constexpr (TC) {
+            // gate on register fragments: every element of the tile is owned by exactly one thread in both layouts
+            const int lane = tid & 31, warp = tid >> 5;
+            const int rr[2] = {warp * 16 + (lane >> 2), warp * 16 + (lane >> 2) + 8};
+            float c[8][4];
+            float4 q[4][2];
+            frag_set_bias(c, w.bg);
+            warp_mma64(c, xg, Ws);
+            frag_to_quads(c, q);
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float* xp = xs + rr[h] * LDA + frag_col4(p);
+                    const float4 gl = ld4(xg + rr[h] * LDA + frag_col4(p));
+                    float4 xv = ld4(xp);
+                    float wv;
+                    wv = sigmoidf_(q[p][h].x); xv.x = fmaf(wv, gl.x, (1.0f - wv) * xv.x);
+                    wv = sigmoidf_(q[p][h].y); xv.y = fmaf(wv, gl.y, (1.0f - wv) * xv.y);
+                    wv = sigmoidf_(q[p][h].z); xv.z = fmaf(wv, gl.z, (1.0f - wv) * xv.z);
+                    wv = sigmoidf_(q[p][h].w); xv.w = fmaf(wv, gl.w, (1.0f - wv) * xv.w);
+                    st4(xp, xv);
+                }
+            __syncthreads();
+        } else {
         float g[8][4];
         acc_set_bias(g, w.bg, tx);
         tile_mma64(g, xg, Ws, ty, tx);
@@ -650,6 +840,7 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
             st4(xp, xv);
         }
         __syncthreads();
+        }
     }
     if (derive) {
         const int ns = new_slot[b];
@@ -662,7 +853,7 @@ __global__ void __launch_bounds__(NTHREADS) k_merge(Pool pool, float* __restrict
                 st4(Xw + nb + (size_t)c * D + tx * 4, v);
             }
         }
-        derive_tile(xs, xg, Ws, w, Yw + nb, Kw + nb, kapw + ((size_t)b * pool.S + ns) * pool.nCT + ct, row0, C, red,
+        derive_tile<TC>(xs, xg, Ws, w, wf, Yw + nb, Kw + nb, kapw + ((size_t)b * pool.S + ns) * pool.nCT + ct, row0, C, red,
                     kp_h ? kp_h + nb / 4 : nullptr, kp_l ? kp_l + nb / 4 : nullptr, nodes_h ? nodes_h + (size_t)b * C * pool.S * 32 : nullptr,
                     nodes_l ? nodes_l + (size_t)b * C * pool.S * 32 : nullptr, pool.S, ns);
         // ---- compaction: this tile's rows of the last live node (slot Rp-1) -> the freed slot move_dst[b] (k_select).  Everything this
@@ -937,6 +1128,12 @@ static NjBuffers nj_layout(char* base, int B, int S, int R, int C, bool X_in_ws,
 static inline char* ws_align(void* ws) { return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) / 256 * 256); }
 
 static size_t smem_score(int Rp) { return (2 * 4096 + 2 * TILE_ROWS * LDA + 128 + 64 + ((Rp + 3) & ~3) + (size_t)Rp * 32) * sizeof(float); }
+// NNJ_MERGE_TC=0: keep the 64 x 64 products of the merge / node-derive kernels on the CUDA cores in the tensor-core modes too (A/B runs)
+static bool merge_tc_enabled() {
+    static const bool on = [] { const char* v = getenv("NNJ_MERGE_TC"); return !(v && v[0] == '0'); }();
+    return on;
+}
+
 static size_t smem_merge(int Rp) { return (2 * TILE_ROWS * LDA + 4096 + 128 + 2 * ((Rp + 3) & ~3) + 8) * sizeof(float); }
 static const size_t smem_derive = (2 * TILE_ROWS * LDA + 4096 + 128) * sizeof(float);
 
@@ -947,9 +1144,12 @@ static int set_attrs() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     if ((e = cudaFuncSetAttribute(k_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-    if ((e = cudaFuncSetAttribute(k_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-    if ((e = cudaFuncSetAttribute(k_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
-    if ((e = cudaFuncSetAttribute(k_node_derive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_derive)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    if ((e = cudaFuncSetAttribute(k_merge<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    if ((e = cudaFuncSetAttribute(k_merge<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    if ((e = cudaFuncSetAttribute(k_merge<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    if ((e = cudaFuncSetAttribute(k_merge<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    if ((e = cudaFuncSetAttribute(k_node_derive<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_derive)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    if ((e = cudaFuncSetAttribute(k_node_derive<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_derive)) != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     once.done();
     return 0;
 }
@@ -1037,6 +1237,18 @@ static int score_pairs(const Model* m, const Pool& pool, const NjBuffers& nb, co
 static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, float* Xw, const int32_t* slot, int Rp, int C,
                       const int32_t* ij, int ij_stride, int B, float* out_x, size_t out_stride, bool derive, cudaStream_t st) {
     const float inv_scale = 1.0f / sqrtf((float)D * (float)C);
+    const bool mtc = nb.tc && merge_tc_enabled();      // the 64 x 64 products on mma.sync (tensor-core precision modes)
+    auto launch_merge = [&](bool glob) {
+        uint2* nh = (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr; uint2* nl = (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr;
+        uint2* kh = (derive && nb.tc) ? (uint2*)nb.kp_h : nullptr;    uint2* kl = (derive && nb.tc) ? (uint2*)nb.kp_l : nullptr;
+        const int32_t* mv = derive ? nb.free_slot : nullptr;
+        const dim3 grid(nb.nCT, B);
+        const size_t sm = smem_merge(Rp);
+#define NNJ_MERGE_ARGS pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha, nb.RP, m->nj, m->nj_frag, out_x, out_stride, nb.new_slot, derive ? 1 : 0, nh, nl, kh, kl, mv
+        if (glob) { if (mtc) k_merge<true, true><<<grid, NTHREADS, sm, st>>>(NNJ_MERGE_ARGS); else k_merge<true, false><<<grid, NTHREADS, sm, st>>>(NNJ_MERGE_ARGS); }
+        else      { if (mtc) k_merge<false, true><<<grid, NTHREADS, sm, st>>>(NNJ_MERGE_ARGS); else k_merge<false, false><<<grid, NTHREADS, sm, st>>>(NNJ_MERGE_ARGS); }
+#undef NNJ_MERGE_ARGS
+    };
     if (Rp > 2) {
         prof_begin(KC_MERGE, st);     // the merge pair's own attention logits: counted with the merge
         k_alpha1<<<dim3(nb.nSB, B), NTHREADS, 0, st>>>(pool, slot, nb.S, Rp, C, ij, ij_stride, m->nj.bh, nb.alpha_part, nb.nAP, nb.RP);
@@ -1047,17 +1259,11 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
                                                          nb.nAP, nb.RP, inv_scale, nb.alpha, 0, nb.nSB);
         LAUNCH_CHECK();
         prof_begin(KC_MERGE, st);
-        k_merge<true><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
-                                                                         nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0,
-                                                                         (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr, (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr,
-                                                                         (derive && nb.tc) ? (uint2*)nb.kp_h : nullptr, (derive && nb.tc) ? (uint2*)nb.kp_l : nullptr, derive ? nb.free_slot : nullptr);
+        launch_merge(true);
         LAUNCH_CHECK();
     } else {
         prof_begin(KC_MERGE, st);
-        k_merge<false><<<dim3(nb.nCT, B), NTHREADS, smem_merge(Rp), st>>>(pool, Xw, nb.Y, nb.K, nb.kap, slot, nb.S, Rp, C, ij, ij_stride, nb.alpha,
-                                                                          nb.RP, m->nj, out_x, out_stride, nb.new_slot, derive ? 1 : 0,
-                                                                         (derive && nb.tc) ? (uint2*)nb.nodes_h : nullptr, (derive && nb.tc) ? (uint2*)nb.nodes_l : nullptr,
-                                                                         (derive && nb.tc) ? (uint2*)nb.kp_h : nullptr, (derive && nb.tc) ? (uint2*)nb.kp_l : nullptr, derive ? nb.free_slot : nullptr);
+        launch_merge(false);
         LAUNCH_CHECK();
     }
     return 0;
@@ -1065,9 +1271,13 @@ static int merge_pair(const Model* m, const Pool& pool, const NjBuffers& nb, flo
 
 static int derive_all(const Model* m, const float* X, const NjBuffers& nb, int B, int S, int nodes, int C, cudaStream_t st) {
     prof_begin(KC_DERIVE, st);
-    k_node_derive<<<dim3(nb.nCT, nodes, B), NTHREADS, smem_derive, st>>>(X, nb.Y, nb.K, nb.kap, (size_t)S * C * D, S, C, nb.nCT, nullptr, 0, m->nj,
-                                                                         nb.tc ? (uint2*)nb.kp_h : nullptr, nb.tc ? (uint2*)nb.kp_l : nullptr,
-        nb.tc ? (uint2*)nb.nodes_h : nullptr, nb.tc ? (uint2*)nb.nodes_l : nullptr);
+    if (nb.tc && merge_tc_enabled())
+        k_node_derive<true><<<dim3(nb.nCT, nodes, B), NTHREADS, smem_derive, st>>>(X, nb.Y, nb.K, nb.kap, (size_t)S * C * D, S, C, nb.nCT, nullptr, 0, m->nj, m->nj_frag,
+                                                                                   (uint2*)nb.kp_h, (uint2*)nb.kp_l, (uint2*)nb.nodes_h, (uint2*)nb.nodes_l);
+    else
+        k_node_derive<false><<<dim3(nb.nCT, nodes, B), NTHREADS, smem_derive, st>>>(X, nb.Y, nb.K, nb.kap, (size_t)S * C * D, S, C, nb.nCT, nullptr, 0, m->nj, m->nj_frag,
+                                                                                    nb.tc ? (uint2*)nb.kp_h : nullptr, nb.tc ? (uint2*)nb.kp_l : nullptr,
+                                                                                    nb.tc ? (uint2*)nb.nodes_h : nullptr, nb.tc ? (uint2*)nb.nodes_l : nullptr);
     LAUNCH_CHECK();
     return 0;
 }
@@ -1220,9 +1430,13 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
             cudaError_t e1 = cudaMemsetAsync(nb.nodes_h, 0, npb, st), e2 = cudaMemsetAsync(nb.nodes_l, 0, npb, st);
             if (e1 != cudaSuccess || e2 != cudaSuccess) return set_cuda_error(e1 != cudaSuccess ? e1 : e2, __FILE__, __LINE__);
         }
-        k_node_derive<<<dim3(nb.nCT, R, nbt), NTHREADS, smem_derive, st>>>(nb.X, nb.Y, nb.K, nb.kap, tree_stride, S, C, nb.nCT, nullptr, 0, m->nj,
-                                                                           nb.tc ? (uint2*)nb.kp_h : nullptr, nb.tc ? (uint2*)nb.kp_l : nullptr,
-        nb.tc ? (uint2*)nb.nodes_h : nullptr, nb.tc ? (uint2*)nb.nodes_l : nullptr);
+        if (nb.tc && merge_tc_enabled())
+            k_node_derive<true><<<dim3(nb.nCT, R, nbt), NTHREADS, smem_derive, st>>>(nb.X, nb.Y, nb.K, nb.kap, tree_stride, S, C, nb.nCT, nullptr, 0, m->nj, m->nj_frag,
+                                                                                     (uint2*)nb.kp_h, (uint2*)nb.kp_l, (uint2*)nb.nodes_h, (uint2*)nb.nodes_l);
+        else
+            k_node_derive<false><<<dim3(nb.nCT, R, nbt), NTHREADS, smem_derive, st>>>(nb.X, nb.Y, nb.K, nb.kap, tree_stride, S, C, nb.nCT, nullptr, 0, m->nj, m->nj_frag,
+                                                                                      nb.tc ? (uint2*)nb.kp_h : nullptr, nb.tc ? (uint2*)nb.kp_l : nullptr,
+                                                                                      nb.tc ? (uint2*)nb.nodes_h : nullptr, nb.tc ? (uint2*)nb.nodes_l : nullptr);
         LAUNCH_CHECK();
         Pool pool = make_pool(nb.X, nb, S, C);
         int32_t* mg = merges + (size_t)b0 * (R - 1) * 2;

@@ -384,11 +384,12 @@ def main_supervise():
         assert dl < 1e-5
 
 
-def main_all50():
+def main_all50(taxa=50, threads=8):
     """The whole of data_gen/data/test/len1024/taxa50 (128 alignments - the set SURVEY.md 8(d) names for configs[1]) through the
     unmodified reference: merge list, Newick, selected_log_ps and per-step max |logit| / top-2 gap of every file, in ONE record
-    (tests/golden/all50/len1024_taxa50.npz) together with the inputs as bit-packed one-hot tokens (25.6 KB per alignment)."""
-    torch.set_num_threads(8)
+    (tests/golden/all50/len1024_taxa50.npz) together with the inputs as bit-packed one-hot tokens (25.6 KB per alignment).
+    `all100` does the same for len1024/taxa100 (tests/golden/all100/len1024_taxa100.npz)."""
+    torch.set_num_threads(threads)
     import utils as ref_utils
     import finetune_rl_search as ref_main
     from environment import PhyInferEnv
@@ -405,7 +406,7 @@ def main_all50():
     sd = O.init_state_dict(0)
     for k, v in model.state_dict().items():
         assert torch.equal(sd[k], v), k
-    d = "data_gen/data/test/len1024/taxa50"
+    d = f"data_gen/data/test/len1024/taxa{taxa}"
     files = sorted(f for f in os.listdir(os.path.join(REF, d)) if f.endswith(".phy"))
     rec = {k: [] for k in ("bits", "keys", "merges", "newick", "slp", "lmax", "gap", "src")}
     for k, fn in enumerate(files):
@@ -443,9 +444,9 @@ def main_all50():
         rec["src"].append(fn)
         rel = min(g / m for g, m in zip(rec["gap"][-1], rec["lmax"][-1]) if np.isfinite(g))
         print(f"[{k:3d}] {fn}: reference rollout {dt:.1f}s, min relative top-2 gap {rel:.2e}", flush=True)
-    out_dir = os.path.join(GOLD, "all50")
+    out_dir = os.path.join(GOLD, f"all{taxa}")
     os.makedirs(out_dir, exist_ok=True)
-    np.savez_compressed(os.path.join(out_dir, "len1024_taxa50.npz"), shape=np.array([50, 1024, 4]), data_bits=np.stack(rec["bits"]),
+    np.savez_compressed(os.path.join(out_dir, f"len1024_taxa{taxa}.npz"), shape=np.array([taxa, 1024, 4]), data_bits=np.stack(rec["bits"]),
                         seq_keys=np.array(rec["keys"]), merges=np.stack(rec["merges"]), newick=np.array(rec["newick"]),
                         selected_log_ps=np.stack(rec["slp"]), step_max_abs_logit=np.array(rec["lmax"], dtype=np.float32),
                         step_top2_gap=np.array(rec["gap"], dtype=np.float32), source=np.array(rec["src"]))
@@ -456,6 +457,8 @@ if __name__ == "__main__":
         main_wide()
     elif len(sys.argv) > 1 and sys.argv[1] == "all50":
         main_all50()
+    elif len(sys.argv) > 1 and sys.argv[1] == "all100":
+        main_all50(taxa=100, threads=int(os.environ.get("NNJ_GOLDEN_THREADS", "8")))
     elif len(sys.argv) > 1 and sys.argv[1] == "supervise":
         main_supervise()
     else:
