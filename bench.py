@@ -271,7 +271,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3"])
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip latency_b1 / gpu_eager_baseline / the weak-scaling second measurement")
     ap.add_argument("--cpu-trees", type=int, default=2)
@@ -479,7 +479,8 @@ def main():
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 tcgen05, fp32 accumulate) + f32"}[args.precision],
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 tcgen05, fp32 accumulate) + f32",
+                      "bf16": "bf16 encoder (one-product tcgen05, fp32 accumulate) + bf16x3 NJ loop + f32"}[args.precision],
             "data": "synthetic",
             "config": {"workload": f"configs[{1 if args.workload == 'config2' else 3}]: synthetic MSAs, {R_TAXA} taxa x {L_SITES} sites, Argmax, sharded by alignment: {shard}",
                        "global_batch": main_run["n_global"], "parallelism": f"alignment-sharded x{world}, no collectives",

@@ -47,7 +47,11 @@ typedef struct nnj_config {
 
 typedef enum nnj_precision {
     NNJ_PREC_FP32 = 0,        /* fp32 CUDA-core arithmetic everywhere                       */
-    NNJ_PREC_BF16X3 = 1       /* dense contractions on tcgen05: split-bf16 (hi*hi+hi*lo+lo*hi), fp32 accumulate */
+    NNJ_PREC_BF16X3 = 1,      /* dense contractions on tcgen05: split-bf16 (hi*hi+hi*lo+lo*hi), fp32 accumulate */
+    NNJ_PREC_BF16 = 2         /* "bf16 encoder": the encoder's contractions (row q|k|v, Q K^T, P V, out projections, column q|k|v, FFN) take
+                                 plain bf16 operands - one tcgen05 product, fp32 accumulate, the lo planes neither written nor read; residual
+                                 stream, LayerNorm, softmax statistics stay fp32 and the NJ loop keeps the split form.  Scores stay within
+                                 1e-2 relative of the fp32 reference; Argmax topologies are NOT guaranteed to match it. */
 } nnj_precision;
 
 typedef enum nnj_select_mode {

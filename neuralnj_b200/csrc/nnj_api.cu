@@ -140,7 +140,7 @@ int nnj_model_create(nnj_model** out, const nnj_config* cfg, const float* const*
     if (cfg->embed_dim != 64 || cfg->num_heads != 8 || cfg->vocab_size != 4 || cfg->patch_size != 1 || cfg->num_layers < 1)
         return set_error(NNJ_ERR_INVALID,
                          "model_create: unsupported config (need embed_dim 64, num_heads 8, vocab_size 4, patch_size 1, num_layers >= 1)");
-    if (cfg->precision != NNJ_PREC_FP32 && cfg->precision != NNJ_PREC_BF16X3)
+    if (cfg->precision != NNJ_PREC_FP32 && cfg->precision != NNJ_PREC_BF16X3 && cfg->precision != NNJ_PREC_BF16)
         return set_error(NNJ_ERR_INVALID, "model_create: unknown precision mode");
     const int Lyr = cfg->num_layers;
     if (n_tensors != Lyr * 26 + 16) return set_error(NNJ_ERR_INVALID, "model_create: expected 26 tensors per layer + 16");

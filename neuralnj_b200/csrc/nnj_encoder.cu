@@ -547,6 +547,7 @@ __global__ void __launch_bounds__(NTHREADS) k_softmax_rows_split(const float* __
 template <int NCH>
 __global__ void __launch_bounds__(NTHREADS) k_softmax_rows_split_reg(const float* __restrict__ S, __nv_bfloat16* __restrict__ Ph,
                                                                      __nv_bfloat16* __restrict__ Pl, int C, const uint8_t* __restrict__ mask) {
+    // Pl == nullptr (NNJ_PREC_BF16): P leaves as one bf16 plane
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + warp;
     if (row >= C) return;
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(NTHREADS) k_softmax_rows_split_reg(const float
             split2(v[c][4] * inv, v[c][5] * inv, hh.z, ll.z);
             split2(v[c][6] * inv, v[c][7] * inv, hh.w, ll.w);
             *reinterpret_cast<uint4*>(Ph + base + j) = hh;
-            *reinterpret_cast<uint4*>(Pl + base + j) = ll;
+            if (Pl) *reinterpret_cast<uint4*>(Pl + base + j) = ll;
         }
     }
 }
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(NTHREADS) k_softmax_rows_split_reg(const float
 // ------------------------------------------------------------------ host-side driver
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static bool use_tc(const Model* m, int C) { return m->cfg.precision == NNJ_PREC_BF16X3 && (C % 8) == 0; }
+static bool use_tc(const Model* m, int C) { return m->cfg.precision != NNJ_PREC_FP32 && (C % 8) == 0; }
 
 // Which per-token stages run on tcgen05 over the site-major residual stream (nnj_encoder_tc.cu): bit 0 LN1 + row q|k|v,
 // bit 1 the fused column block (at most 128 taxa), bit 2 the feed-forward block.  NNJ_ENC_TC overrides the default (all) for bisecting.
@@ -711,18 +712,20 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
                     k_ln_qkv_rowtc<<<dim3(tiles, nb), NTHREADS, smem_qkv, st>>>(xb, xstr, R, C, lw.row, row_scale, mb, qh, ql, kh, kl, vh, vl, xsm);
                     LAUNCH_CHECK();
                 }
-                if (int e = launch_tc_gemm(KC_ROW_QK, qh, ql, kh, kl, S, nb * H, C, C, KD, KD, (size_t)C * KD, KD, (size_t)C * KD, C, (size_t)C * C, st)) return e;
+                const int products = m->cfg.precision == NNJ_PREC_BF16 ? 1 : 3;
+                __nv_bfloat16* Plo = products == 1 ? nullptr : P + pp;      // one-product mode: the register softmax writes the hi plane only
+                if (int e = launch_tc_gemm(KC_ROW_QK, qh, ql, kh, kl, S, nb * H, C, C, KD, KD, (size_t)C * KD, KD, (size_t)C * KD, C, (size_t)C * C, st, products)) return e;
                 prof_begin(KC_ROW_SOFTMAX, st);
-                if (C <= 512) k_softmax_rows_split_reg<2><<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, P + pp, C, mb);
-                else if (C <= 1024) k_softmax_rows_split_reg<4><<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, P + pp, C, mb);
+                if (C <= 512) k_softmax_rows_split_reg<2><<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, Plo, C, mb);
+                else if (C <= 1024) k_softmax_rows_split_reg<4><<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, Plo, C, mb);
                 else k_softmax_rows_split<<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, P + pp, C, mb);
                 LAUNCH_CHECK();
                 if (mk & 1) {
                     if (int e = launch_tc_gemm_bmn(KC_ROW_PV, P, P + pp, vh, vl, q /*ctx fp32 [B,H,C,R*8]*/, nb * H, C, KD, C, C, (size_t)C * C, KD,
-                                                   (size_t)C * KD, KD, (size_t)C * KD, st)) return e;
+                                                   (size_t)C * KD, KD, (size_t)C * KD, st, products)) return e;
                 } else {
                     if (int e = launch_tc_gemm(KC_ROW_PV, P, P + pp, vh, vl, q /*ctx fp32 [B,H,C,R*8]*/, nb * H, C, KD, C, C, (size_t)C * C, C,
-                                               (size_t)KD * C, KD, (size_t)C * KD, st)) return e;
+                                               (size_t)KD * C, KD, (size_t)C * KD, st, products)) return e;
                 }
             } else {
                 prof_begin(KC_LN_QKV, st);

@@ -71,6 +71,7 @@ struct RowQkvArgs {
     const float *ln_g, *ln_b, *qkvb;
     float q_scale; const uint8_t* mask;
     __nv_bfloat16 *qh, *ql, *kh, *kl, *vh, *vl; // [B,H,C,R*8]
+    int one;                                    // NNJ_PREC_BF16: hi * hi products only, the lo planes are neither used nor written
 };
 
 constexpr int K1_W = 49152;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(ET_THREADS, 2) k_enc_rowqkv_tc(const RowQkvArg
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                umma_split_k64(tmem_base, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_s), smem_u32(w_s) + K1_W / 2, idesc, 0u);
+                umma_split_k64(tmem_base, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_s), smem_u32(w_s) + K1_W / 2, idesc, 0u, a.one);
                 umma_commit(bar);
             }
             __syncwarp();
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(ET_THREADS, 2) k_enc_rowqkv_tc(const RowQkvArg
                     split2(o[6], o[7], hi4.w, lo4.w);
                     const size_t off = (((size_t)b * H + hf * 4 + hh) * a.C + c) * KD + (size_t)r * DH;
                     *reinterpret_cast<uint4*>(ph + off) = hi4;
-                    *reinterpret_cast<uint4*>(pl + off) = lo4;
+                    if (!a.one) *reinterpret_cast<uint4*>(pl + off) = lo4;
                 }
             }
         }
@@ -170,6 +171,7 @@ struct FfnTcArgs {
     int T, B, tiles_per_tree;
     const uint4 *w1, *w2;                       // EncTcW images (64 KB each)
     const float *ln_g, *ln_b, *b1, *b2;
+    int one;                                    // NNJ_PREC_BF16: hi * hi products only
 };
 
 constexpr int K3_THREADS = 512;             // 16 warps: TMEM lane quarter q = warp & 3 (row = 32 q + lane), column quarter cq = warp >> 2 (16 of every 64 columns)
@@ -256,14 +258,20 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t wh = umma_desc_lo(smem_u32(w1_s)), wl = umma_desc_lo(smem_u32(w1_s) + 32768);
-                umma_ts<false>(t_d1, t_a0 + 32, wh, id_d1);      // small terms first
-                umma_ts<true>(t_d1, t_a0, wl, id_d1);
-                umma_ts<true>(t_d1, t_a0, wh, id_d1);
+                if (a.one) {
+                    umma_ts<false>(t_d1, t_a0, wh, id_d1);
 #pragma unroll
-                for (int kk = 1; kk < 4; ++kk) {
-                    umma_ts<true>(t_d1, t_a0 + 32 + kk * 8, wh + kk * 2, id_d1);
-                    umma_ts<true>(t_d1, t_a0 + kk * 8, wl + kk * 2, id_d1);
-                    umma_ts<true>(t_d1, t_a0 + kk * 8, wh + kk * 2, id_d1);
+                    for (int kk = 1; kk < 4; ++kk) umma_ts<true>(t_d1, t_a0 + kk * 8, wh + kk * 2, id_d1);
+                } else {
+                    umma_ts<false>(t_d1, t_a0 + 32, wh, id_d1);      // small terms first
+                    umma_ts<true>(t_d1, t_a0, wl, id_d1);
+                    umma_ts<true>(t_d1, t_a0, wh, id_d1);
+#pragma unroll
+                    for (int kk = 1; kk < 4; ++kk) {
+                        umma_ts<true>(t_d1, t_a0 + 32 + kk * 8, wh + kk * 2, id_d1);
+                        umma_ts<true>(t_d1, t_a0 + kk * 8, wl + kk * 2, id_d1);
+                        umma_ts<true>(t_d1, t_a0 + kk * 8, wh + kk * 2, id_d1);
+                    }
                 }
                 umma_commit(bars + 0);
             }
@@ -299,14 +307,20 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_enc_ffn_tc(const FfnTcArgs a)
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t wh = umma_desc_lo(smem_u32(w2_s) + ch * 8192), wl = umma_desc_lo(smem_u32(w2_s) + 32768 + ch * 8192);
-                    if (ch == 0) umma_ts<false>(t_d2, ta + 32, wh, id_d2); else umma_ts<true>(t_d2, ta + 32, wh, id_d2);   // small terms first
-                    umma_ts<true>(t_d2, ta, wl, id_d2);
-                    umma_ts<true>(t_d2, ta, wh, id_d2);
+                    if (a.one) {
+                        if (ch == 0) umma_ts<false>(t_d2, ta, wh, id_d2); else umma_ts<true>(t_d2, ta, wh, id_d2);
 #pragma unroll
-                    for (int kk = 1; kk < 4; ++kk) {
-                        umma_ts<true>(t_d2, ta + 32 + kk * 8, wh + kk * 2, id_d2);
-                        umma_ts<true>(t_d2, ta + kk * 8, wl + kk * 2, id_d2);
-                        umma_ts<true>(t_d2, ta + kk * 8, wh + kk * 2, id_d2);
+                        for (int kk = 1; kk < 4; ++kk) umma_ts<true>(t_d2, ta + kk * 8, wh + kk * 2, id_d2);
+                    } else {
+                        if (ch == 0) umma_ts<false>(t_d2, ta + 32, wh, id_d2); else umma_ts<true>(t_d2, ta + 32, wh, id_d2);   // small terms first
+                        umma_ts<true>(t_d2, ta, wl, id_d2);
+                        umma_ts<true>(t_d2, ta, wh, id_d2);
+#pragma unroll
+                        for (int kk = 1; kk < 4; ++kk) {
+                            umma_ts<true>(t_d2, ta + 32 + kk * 8, wh + kk * 2, id_d2);
+                            umma_ts<true>(t_d2, ta + kk * 8, wl + kk * 2, id_d2);
+                            umma_ts<true>(t_d2, ta + kk * 8, wh + kk * 2, id_d2);
+                        }
                     }
                     if (ch == 0) umma_commit(bars + 1);
                     else if (ch == 1) umma_commit(bars + 2);
@@ -350,6 +364,7 @@ struct ColBlkArgs {
     const uint4* w_img;                          // EncTcW::row_o | col_qkv | col_o, contiguous (80 KB)
     const float *rob, *ln_g, *ln_b, *qkvb, *cob;
     float q_scale_log2e; const uint8_t* mask;
+    int one;                                     // NNJ_PREC_BF16: hi * hi products only in the three projections
 };
 
 constexpr int K2_THREADS = 512;
@@ -658,7 +673,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                umma_split_k64(t_o, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_ro), smem_u32(w_ro) + 8192, id64, 0u);
+                umma_split_k64(t_o, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_ro), smem_u32(w_ro) + 8192, id64, 0u, a.one);
                 umma_commit(bar);
             }
             __syncwarp();
@@ -684,7 +699,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                umma_split_k64(t_qkv, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_qkv), smem_u32(w_qkv) + 24576, id192, 0u);
+                umma_split_k64(t_qkv, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_qkv), smem_u32(w_qkv) + 24576, id192, 0u, a.one);
                 umma_commit(bar);
             }
             __syncwarp();
@@ -744,7 +759,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k_enc_colblock_tc(const ColBlkA
         if (warp == 0) {
             tc_fence_after();
             if (elect_one()) {
-                umma_split_k64(t_o, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_co), smem_u32(w_co) + 8192, id64, 0u);
+                umma_split_k64(t_o, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_co), smem_u32(w_co) + 8192, id64, 0u, a.one);
                 umma_commit(bar);
             }
             __syncwarp();
@@ -828,6 +843,7 @@ int launch_enc_rowqkv_tc(const Model* m, int layer, const float* xs, size_t xs_t
     a.w_img = tw.row_qkv; a.ln_g = lw.row.ln_g; a.ln_b = lw.row.ln_b; a.qkvb = tw.row_qkvb; a.q_scale = q_scale; a.mask = mask;
     a.qh = (__nv_bfloat16*)qh; a.ql = (__nv_bfloat16*)ql; a.kh = (__nv_bfloat16*)kh; a.kl = (__nv_bfloat16*)kl;
     a.vh = (__nv_bfloat16*)vh; a.vl = (__nv_bfloat16*)vl;
+    a.one = m->cfg.precision == NNJ_PREC_BF16;
     const int work = B * a.tiles_per_tree;
     const int grid = work < 2 * sm_count() ? work : 2 * sm_count();
     prof_begin(KC_LN_QKV, st);
@@ -848,6 +864,7 @@ int launch_enc_colblock_tc(const Model* m, int layer, float* xs, size_t xs_tree_
     a.x = xs; a.x_tree_stride = xs_tree_stride; a.R = R; a.C = C; a.B = B; a.groups_per_tree = (C + s_tile - 1) / s_tile;
     a.ctx = ctx; a.w_img = tw.row_o; a.rob = lw.row.ob; a.ln_g = lw.col.ln_g; a.ln_b = lw.col.ln_b; a.qkvb = tw.col_qkvb; a.cob = lw.col.ob;
     a.q_scale_log2e = (1.0f / sqrtf((float)DH)) * 1.4426950408889634f; a.mask = mask;
+    a.one = m->cfg.precision == NNJ_PREC_BF16;
     const int work = B * a.groups_per_tree;
     const int grid = work < sm_count() ? work : sm_count();
     prof_begin(KC_COL_ATTN, st);
@@ -873,6 +890,7 @@ int launch_enc_ffn_tc(const Model* m, int layer, float* xs, size_t xs_tree_strid
     FfnTcArgs a;
     a.x = xs; a.x_tree_stride = xs_tree_stride; a.T = R * C; a.B = B; a.tiles_per_tree = (R * C + 127) / 128;
     a.w1 = tw.w1; a.w2 = tw.w2; a.ln_g = lw.ffn.ln_g; a.ln_b = lw.ffn.ln_b; a.b1 = lw.ffn.b1; a.b2 = lw.ffn.b2;
+    a.one = m->cfg.precision == NNJ_PREC_BF16;
     const int work = B * a.tiles_per_tree;
     const int grid = work < sm_count() ? work : sm_count();
     prof_begin(KC_FFN, st);

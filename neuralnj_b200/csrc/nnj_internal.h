@@ -132,8 +132,9 @@ int run_rollout(Model* m, const int8_t* data, const float* state0, const uint8_t
                 cudaStream_t st);
 
 // tcgen05 split-bf16 GEMM (nnj_tc.cu)
+// products: 3 = hi*hi + hi*lo + lo*hi (NNJ_PREC_BF16X3), 1 = hi*hi only (NNJ_PREC_BF16: plain bf16 operands, the lo planes are not read)
 int launch_tc_gemm(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
-                   size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st);
+                   size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st, int products = 3);
 int launch_alpha_tc(const Model* m, const float* X, const float* Y, size_t tree_stride, const int32_t* slot_of, int slot_stride, const int32_t* pair_i,
                     const int32_t* pair_j, int pair_stride, int n0, int nc, int S, int n_live, int C, int B, const void* kp_h, const void* kp_l, float* xf,
                     int pc, float* alpha_part, int alpha_pairs, int nSG, int RP, int* n_part, cudaStream_t st);
@@ -154,9 +155,9 @@ int launch_score_big(const Model* m, const float* xf, int pc, const void* nodes_
                      const uint8_t* mask, float* score_part, int nSG, int* n_part, cudaStream_t st);
 int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, int bn, int nsplit, int chunks_per_split, size_t split_stride,
-                      cudaStream_t st);
+                      cudaStream_t st, int products = 3);
 int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
-                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st);
+                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st, int products = 3);
 // tcgen05 encoder kernels over the site-major residual stream (nnj_encoder_tc.cu)
 int launch_enc_rowqkv_tc(const Model* m, int layer, const float* xs, size_t xs_tree_stride, int B, int R, int C, float q_scale, const uint8_t* mask,
                          void* qh, void* ql, void* kh, void* kl, void* vh, void* vl, cudaStream_t st);

@@ -35,7 +35,10 @@ struct TcGemmArgs {
 //
 // Persistent: grid = min(tiles, SMs); every role walks the same static tile list (groups of N tiles dealt out round robin, see below).  The TMA ring and its barriers run on across tiles, and the accumulator
 // is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i drains while the tensor core works on tile i+1.
-template <int BN, bool BMN>
+//
+// ONE (precision NNJ_PREC_BF16, plain bf16 operands): only A_hi * B_hi is formed.  The lo planes are never fetched; their slots of
+// a physical stage hold a second logical stage instead (ring depth 2 * NSTG at half the bytes per stage), one UMMA per k-step.
+template <int BN, bool BMN, bool ONE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
           const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcGemmArgs g) {
@@ -44,9 +47,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     constexpr int NSTG = BN == 256 ? 2 : TC_STAGES;    // 128 x 256 tiles: 96 KB per stage (a 128 x 256 x 16 UMMA runs at 75 % of the tensor peak, 128 x 128 at 60 %)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = smem_align1024(smem_raw);
+    constexpr int NL = ONE ? 2 * NSTG : NSTG;          // logical ring depth
+    constexpr int LSTAGE = ONE ? STAGE / 2 : STAGE;    // bytes a logical stage receives
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + NSTG * STAGE);
-    uint64_t* empty = full + NSTG;
-    uint64_t* acc_full = empty + NSTG;      // [2]
+    uint64_t* empty = full + NL;
+    uint64_t* acc_full = empty + NL;        // [2]
     uint64_t* acc_free = acc_full + 2;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
     float* epi = reinterpret_cast<float*>(tiles + NSTG * STAGE + 256);     // [4 warps][32][TC_EPI_LD]
@@ -66,7 +71,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     const int n_groups = n_tiles / gsz;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NL; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1); mbar_init(acc_full + 1, 1);
         mbar_init(acc_free, 4); mbar_init(acc_free + 1, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -87,22 +92,24 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
             const int kc0 = split * g.chunks_per_split;
             const int nchunks = max(0, min(total_chunks - kc0, g.chunks_per_split));
             for (int kk = 0; kk < nchunks; ++kk, ++gc) {
-                const int s = gc % NSTG, kc = kc0 + kk;
-                if (gc >= NSTG) mbar_wait(&empty[s], ((gc / NSTG) - 1) & 1);
-                uint8_t* st = tiles + s * STAGE;
+                const int s = gc % NL, kc = kc0 + kk;
+                if (gc >= NL) mbar_wait(&empty[s], ((gc / NL) - 1) & 1);
+                // ONE: logical stage s lives in physical stage s / 2, in the hi (even s) or lo (odd s) plane slots
+                uint8_t* st = ONE ? tiles + (s >> 1) * STAGE + (s & 1) * TC_PLANE_BYTES : tiles + s * STAGE;
+                uint8_t* stb = ONE ? tiles + (s >> 1) * STAGE + 2 * TC_PLANE_BYTES + (s & 1) * B_PLANE : st + 2 * TC_PLANE_BYTES;
                 if (elect_one()) {
-                    mbar_expect_tx(&full[s], STAGE);
+                    mbar_expect_tx(&full[s], LSTAGE);
                     tma_load_3d(st, &mapAh, &full[s], kc * TC_BK, m0, z);
-                    tma_load_3d(st + TC_PLANE_BYTES, &mapAl, &full[s], kc * TC_BK, m0, z);
+                    if (!ONE) tma_load_3d(st + TC_PLANE_BYTES, &mapAl, &full[s], kc * TC_BK, m0, z);
                     if (BMN) {
 #pragma unroll
                         for (int nb = 0; nb < BN / 64; ++nb) {
-                            tma_load_3d(st + 2 * TC_PLANE_BYTES + nb * 8192, &mapBh, &full[s], n0 + nb * 64, kc * TC_BK, z);
-                            tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE + nb * 8192, &mapBl, &full[s], n0 + nb * 64, kc * TC_BK, z);
+                            tma_load_3d(stb + nb * 8192, &mapBh, &full[s], n0 + nb * 64, kc * TC_BK, z);
+                            if (!ONE) tma_load_3d(stb + B_PLANE + nb * 8192, &mapBl, &full[s], n0 + nb * 64, kc * TC_BK, z);
                         }
                     } else {
-                        tma_load_3d(st + 2 * TC_PLANE_BYTES, &mapBh, &full[s], kc * TC_BK, n0, z);
-                        tma_load_3d(st + 2 * TC_PLANE_BYTES + B_PLANE, &mapBl, &full[s], kc * TC_BK, n0, z);
+                        tma_load_3d(stb, &mapBh, &full[s], kc * TC_BK, n0, z);
+                        if (!ONE) tma_load_3d(stb + B_PLANE, &mapBl, &full[s], kc * TC_BK, n0, z);
                     }
                 }
                 __syncwarp();
@@ -121,11 +128,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
             const uint32_t t_acc = tmem_base + ab * BN;
             if (ti >= 2) { mbar_wait(acc_free + ab, ((ti >> 1) - 1) & 1); tc_fence_after(); }   // the epilogue has drained this accumulator
             for (int kk = 0; kk < nchunks; ++kk, ++gc) {
-                const int s = gc % NSTG, kc = kc0 + kk;
-                mbar_wait(&full[s], (gc / NSTG) & 1);
+                const int s = gc % NL, kc = kc0 + kk;
+                mbar_wait(&full[s], (gc / NL) & 1);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(tiles + s * STAGE), a_lo = a_hi + TC_PLANE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = b_hi + B_PLANE;
+                const uint32_t a_hi = ONE ? smem_u32(tiles + (s >> 1) * STAGE + (s & 1) * TC_PLANE_BYTES) : smem_u32(tiles + s * STAGE);
+                const uint32_t a_lo = a_hi + TC_PLANE_BYTES;
+                const uint32_t b_hi = ONE ? smem_u32(tiles + (s >> 1) * STAGE + 2 * TC_PLANE_BYTES + (s & 1) * B_PLANE) : a_hi + 2 * TC_PLANE_BYTES;
+                const uint32_t b_lo = b_hi + B_PLANE;
                 const int kvalid = min(TC_BK, g.K - kc * TC_BK);
                 const int ksteps = (kvalid + 15) / 16;
                 if (elect_one()) {
@@ -133,15 +142,22 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
                     const uint32_t dah = umma_desc_lo(a_hi), dal = umma_desc_lo(a_lo);
                     const uint32_t dbh = BMN ? umma_desc_lo(b_hi, 8192) : umma_desc_lo(b_hi), dbl = BMN ? umma_desc_lo(b_lo, 8192) : umma_desc_lo(b_lo);
                     constexpr uint32_t BSTEP = BMN ? 128u : 2u;
-                    if (kk == 0) umma_ss<false>(t_acc, dal, dbh, idesc); else umma_ss<true>(t_acc, dal, dbh, idesc);   // small terms first
-                    umma_ss<true>(t_acc, dah, dbl, idesc);
-                    umma_ss<true>(t_acc, dah, dbh, idesc);
+                    if (ONE) {
+                        if (kk == 0) umma_ss<false>(t_acc, dah, dbh, idesc); else umma_ss<true>(t_acc, dah, dbh, idesc);
 #pragma unroll
-                    for (int k = 1; k < 4; ++k) {
-                        if (k < ksteps) {
-                            umma_ss<true>(t_acc, dal + k * 2, dbh + k * BSTEP, idesc);
-                            umma_ss<true>(t_acc, dah + k * 2, dbl + k * BSTEP, idesc);
-                            umma_ss<true>(t_acc, dah + k * 2, dbh + k * BSTEP, idesc);
+                        for (int k = 1; k < 4; ++k)
+                            if (k < ksteps) umma_ss<true>(t_acc, dah + k * 2, dbh + k * BSTEP, idesc);
+                    } else {
+                        if (kk == 0) umma_ss<false>(t_acc, dal, dbh, idesc); else umma_ss<true>(t_acc, dal, dbh, idesc);   // small terms first
+                        umma_ss<true>(t_acc, dah, dbl, idesc);
+                        umma_ss<true>(t_acc, dah, dbh, idesc);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k) {
+                            if (k < ksteps) {
+                                umma_ss<true>(t_acc, dal + k * 2, dbh + k * BSTEP, idesc);
+                                umma_ss<true>(t_acc, dah + k * 2, dbl + k * BSTEP, idesc);
+                                umma_ss<true>(t_acc, dah + k * 2, dbh + k * BSTEP, idesc);
+                            }
                         }
                     }
                     umma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
@@ -497,13 +513,16 @@ static int tc_sm_count() { return sm_count(); }    // of the current device (cac
 
 // C[z] = (Ah+Al)[z] * (Bh+Bl)[z] with B MN-major: B planes [Z][K][N] (N contiguous, pitch ldb).  128 x 128 tiles.
 int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
-                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st) {
+                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st, int products) {
     static DevOnce once;      // per device, not per process
     constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
     constexpr int SMEM256 = 2 * (6 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
+    const bool one = products == 1;
     if (once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM256);
+        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<256, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM256);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<256, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM256);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
         once.done();
     }
@@ -517,8 +536,8 @@ int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, 
     const int n_tiles = ((N + bn - 1) / bn) * ((M + TC_BM - 1) / TC_BM) * Z;
     const dim3 grid(n_tiles < tc_sm_count() ? n_tiles : tc_sm_count());
     prof_begin(cls, st);
-    if (bn == 256) k_tc_gemm<256, true><<<grid, TC_THREADS, SMEM256, st>>>(mAh, mAl, mBh, mBl, g);
-    else k_tc_gemm<128, true><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g);
+    if (bn == 256) { if (one) k_tc_gemm<256, true, true><<<grid, TC_THREADS, SMEM256, st>>>(mAh, mAl, mBh, mBl, g); else k_tc_gemm<256, true, false><<<grid, TC_THREADS, SMEM256, st>>>(mAh, mAl, mBh, mBl, g); }
+    else { if (one) k_tc_gemm<128, true, true><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g); else k_tc_gemm<128, true, false><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g); }
     ++g_launches;
     prof_end(st);
     cudaError_t e = cudaGetLastError();
@@ -531,15 +550,18 @@ int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, 
 // its partial tile at C + s*split_stride.
 int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, int bn, int nsplit, int chunks_per_split, size_t split_stride,
-                      cudaStream_t st) {
+                      cudaStream_t st, int products) {
     static DevOnce once;      // per device, not per process
     constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
     constexpr int SMEM64 = TC_STAGES * (3 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
     constexpr int SMEM256 = 2 * (6 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
+    const bool one = products == 1;
     if (once.need()) {
-        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM256);
+        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<256, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM256);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM128);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_gemm<256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM256);
         if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
         once.done();
     }
@@ -552,9 +574,10 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
     const int n_tiles = ((N + bn - 1) / bn) * nsplit * ((M + TC_BM - 1) / TC_BM) * Z;
     const dim3 grid(n_tiles < tc_sm_count() ? n_tiles : tc_sm_count());
     prof_begin(cls, st);
-    if (bn == 256) k_tc_gemm<256, false><<<grid, TC_THREADS, SMEM256, st>>>(mAh, mAl, mBh, mBl, g);
-    else if (bn == 128) k_tc_gemm<128, false><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g);
-    else k_tc_gemm<64, false><<<grid, TC_THREADS, SMEM64, st>>>(mAh, mAl, mBh, mBl, g);
+    if (one && bn == 64) return set_error(NNJ_ERR_INVALID, "tc_gemm: the one-product form has no 64-column tile");
+    if (bn == 256) { if (one) k_tc_gemm<256, false, true><<<grid, TC_THREADS, SMEM256, st>>>(mAh, mAl, mBh, mBl, g); else k_tc_gemm<256, false, false><<<grid, TC_THREADS, SMEM256, st>>>(mAh, mAl, mBh, mBl, g); }
+    else if (bn == 128) { if (one) k_tc_gemm<128, false, true><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g); else k_tc_gemm<128, false, false><<<grid, TC_THREADS, SMEM128, st>>>(mAh, mAl, mBh, mBl, g); }
+    else k_tc_gemm<64, false, false><<<grid, TC_THREADS, SMEM64, st>>>(mAh, mAl, mBh, mBl, g);
     ++g_launches;
     prof_end(st);
     cudaError_t e = cudaGetLastError();
@@ -563,9 +586,9 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
 }
 
 int launch_tc_gemm(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
-                   size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st) {
+                   size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st, int products) {
     const int bn = (N >= 256 && N % 256 == 0) ? 256 : 128;     // 128 x 256 tiles when they divide N (row-attention logits)
-    return launch_tc_gemm_ex(cls, Ah, Al, Bh, Bl, Cm, Z, M, N, K, lda, sA, ldb, sB, ldc, sC, bn, 1, (K + TC_BK - 1) / TC_BK, 0, st);
+    return launch_tc_gemm_ex(cls, Ah, Al, Bh, Bl, Cm, Z, M, N, K, lda, sA, ldb, sB, ldc, sC, bn, 1, (K + TC_BK - 1) / TC_BK, 0, st, products);
 }
 
 // Stand-alone building block (also the unit-test entry): fp32 A [Z][M][K], B [Z][N][K] -> C [Z][M][N].

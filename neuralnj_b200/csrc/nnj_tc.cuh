@@ -263,8 +263,14 @@ __device__ __forceinline__ void a_store8(uint8_t* hi, uint8_t* lo, int row, int 
 // (A planes 16 KB, W planes N*128 B).  Call from ONE elected lane.  first_acc = 0 starts a fresh accumulator.
 // Descriptor low words advance by 2 (32 B >> 4) per 16-element k-step (cheap-issue forms above).
 __device__ __forceinline__ void umma_split_k64(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, uint32_t idesc,
-                                               uint32_t first_acc) {
+                                               uint32_t first_acc, int one = 0) {
     const uint32_t dah = umma_desc_lo(a_hi), dal = umma_desc_lo(a_lo), dwh = umma_desc_lo(w_hi), dwl = umma_desc_lo(w_lo);
+    if (one) {      // NNJ_PREC_BF16: plain bf16 operands, hi * hi only
+        if (first_acc) umma_ss<true>(tmem_d, dah, dwh, idesc); else umma_ss<false>(tmem_d, dah, dwh, idesc);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) umma_ss<true>(tmem_d, dah + 2 * k, dwh + 2 * k, idesc);
+        return;
+    }
     if (first_acc) umma_ss<true>(tmem_d, dal, dwh, idesc); else umma_ss<false>(tmem_d, dal, dwh, idesc);   // small terms first
     umma_ss<true>(tmem_d, dah, dwl, idesc);
     umma_ss<true>(tmem_d, dah, dwh, idesc);

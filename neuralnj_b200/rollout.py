@@ -260,7 +260,7 @@ def main(argv=None):
     ap.add_argument("--stop_step", type=int, default=100)
     ap.add_argument("--evolution_model", type=str, default="GTR+I+G")
     ap.add_argument("--branch_optimize", action="store_true")
-    ap.add_argument("--precision", type=str, default=None, choices=["fp32", "bf16x3"],
+    ap.add_argument("--precision", type=str, default=None, choices=["fp32", "bf16x3", "bf16"],
                     help="arithmetic of the CUDA path (not a reference flag); default bf16x3: tcgen05 split-bf16, topologies identical to fp32")
     args = ap.parse_args(argv)
     PRECISION = args.precision

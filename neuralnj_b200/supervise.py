@@ -354,7 +354,7 @@ def main(argv=None):
     ap.add_argument("--limit", type=int, default=None, help="files per directory")
     ap.add_argument("--epoch", type=int, default=0, help="position in the K-ratio schedule of the loss (train.py:495)")
     ap.add_argument("--likelihood", action="store_true", help="also score label and argmax trees with the GPU likelihood")
-    ap.add_argument("--precision", type=str, default=None, choices=["fp32", "bf16x3"])
+    ap.add_argument("--precision", type=str, default=None, choices=["fp32", "bf16x3", "bf16"])
     args = ap.parse_args(argv)
     cfgs = empty_config()
     if args.config_path:

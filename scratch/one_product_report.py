@@ -17,8 +17,9 @@ from neuralnj_b200.environment import format_rtree_topology
 CASES = ["ex50x1024_73", "ex50x1024_71", "t20x256_10", "t20x256_103", "t20x256_104", "t20x256_117", "t20x256_120", "t50x256_a", "t100x256_a", "t20x512_a", "t50x512_a"]
 cfgs = inference_config()
 torch.manual_seed(0)
-model = PhyloATTN(cfgs, precision="bf16x3").cuda().eval()
-out = {"library": os.environ.get("NNJ_LIB_PATH", "neuralnj_b200/libnnj.so"), "cases": {}}
+PREC = os.environ.get("NNJ_REPORT_PRECISION", "bf16x3")     # "bf16": the shipped one-product encoder mode (NNJ_PREC_BF16)
+model = PhyloATTN(cfgs, precision=PREC).cuda().eval()
+out = {"library": os.environ.get("NNJ_LIB_PATH", "neuralnj_b200/libnnj.so"), "precision": PREC, "cases": {}}
 tot_steps = tot_match = 0
 for name in CASES:
     g = Golden(name)
