@@ -461,6 +461,30 @@ def main():
                 extras["supervised_eval"] = supervised_eval_rate(model, data, mask, merges, R_TAXA)
             except Exception as exc:   # noqa: BLE001
                 extras["supervised_eval"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if rank == 0 and world == 1 and not args.no_extras and args.workload == "config2" and args.precision == "bf16x3":
+        # The north star's "bf16 encoder" (precision="bf16": one tcgen05 product per encoder contraction, NJ loop unchanged) on the same
+        # batch: what the encoder kernels reach without the 3-product split.  NOT the headline - the mode does not keep the reference's
+        # Argmax topologies with these weights; reported so that the split's cost is a measured number.
+        try:
+            m1p = PhyloATTN(inference_config(), precision="bf16").to(dev).eval()
+            m1p.load_state_dict(model.state_dict())
+            for _ in range(2):
+                m1p.rollout_fused(data, mask)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(2):
+                m1p_merges, _, _ = m1p.rollout_fused(data, mask)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 2
+            same = int((m1p_merges == merges).all(dim=2).all(dim=1).sum())
+            extras["bf16_encoder_mode"] = {"value": round(B_local / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms, 2), "steps": 2,
+                                           "merge_lists_identical_to_bf16x3": f"{same}/{B_local}",
+                                           "note": "precision='bf16' (NNJ_PREC_BF16): scores within 1e-2 relative of the reference, topologies not guaranteed"}
+            del m1p
+        except Exception as exc:   # noqa: BLE001
+            extras["bf16_encoder_mode"] = {"error": f"{type(exc).__name__}: {exc}"}
     weak = None
     if world > 1 and args.scaling == "strong" and not args.no_extras:
         w = timed("weak", max(1, min(args.steps, 3)), 1, False)
