@@ -345,7 +345,7 @@ def main(argv=None):
     """Validation of a checkpoint on labelled alignments: `python -m neuralnj_b200.supervise --config_path cfg.yaml --data_dir DIR`."""
     import argparse
     import json
-    from .config import empty_config
+    from .config import empty_config, inference_config
     from .rollout import _load_policy
     ap = argparse.ArgumentParser(description="NeuralNJ validation metrics (train.py eval_on_dataset) on the B200 path")
     ap.add_argument("--config_path", type=str, default="")
@@ -356,9 +356,11 @@ def main(argv=None):
     ap.add_argument("--likelihood", action="store_true", help="also score label and argmax trees with the GPU likelihood")
     ap.add_argument("--precision", type=str, default=None, choices=["fp32", "bf16x3", "bf16"])
     args = ap.parse_args(argv)
-    cfgs = empty_config()
     if args.config_path:
+        cfgs = empty_config()
         cfgs.merge_from_file(args.config_path)
+    else:       # no YAML given: the shipped inference model (config/finetune_reinforce_search_example.yaml:24-30)
+        cfgs = inference_config()
     device = torch.device("cuda:0")
     agent = _load_policy(cfgs, device, args.precision)
     ratio_factor = getattr(cfgs, "ratio_factor", 0.5)
