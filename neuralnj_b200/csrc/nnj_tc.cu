@@ -226,6 +226,176 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2), 256 x 256 tiles, 3-product split
+// k_tc_gemm<256, .> moves 96 KB per k-chunk and SM (A 32 KB + B 64 KB, hi + lo) and sits at ~86 % of the chip's L2 -> SM throughput with
+// the tensor pipe 55 % busy.  Here two CTAs of a cluster (one TPC) share a 256-row tile: each loads its own 128 rows of A and only HALF of
+// the B tile (64 KB per chunk and SM), the rank-0 CTA issues 256 x 256 x 16 UMMAs that read both halves, and each CTA drains its own 128
+// accumulator rows.  64 KB stages -> a 3-deep ring.  Barriers (same offsets in both CTAs):
+//   full[s]     leader only: its producer expects the bytes of BOTH CTAs' loads (each TMA names the leader's barrier)
+//   empty[s]    both: the leader's tcgen05.commit multicasts the arrival when the stage's MMAs have retired
+//   acc_full[b] both: multicast commit after the last k-chunk of a tile
+//   acc_free[b] leader only, 8 arrivals: the four epilogue warps of both CTAs (the peer's arrive remotely)
+// Requires an even number of 128-row blocks; N tiles of 256 (a ragged last tile runs an UMMA of N = 16 ceil(n_left / 16), half per CTA).
+constexpr int G2_STAGE = 4 * TC_PLANE_BYTES;      // A_hi, A_lo, B_hi (half), B_lo (half): 64 KB
+constexpr int G2_NSTG = 3;
+constexpr int G2_SMEM = G2_NSTG * G2_STAGE + 1024 + 256 + TC_EPI_BYTES;
+template <bool BMN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_tc_gemm2(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+           const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcGemmArgs g) {
+    constexpr int BN = 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = smem_align1024(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + G2_NSTG * G2_STAGE);
+    uint64_t* empty = full + G2_NSTG;
+    uint64_t* acc_full = empty + G2_NSTG;      // [2]
+    uint64_t* acc_free = acc_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+    float* epi = reinterpret_cast<float*>(tiles + G2_NSTG * G2_STAGE + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const int total_chunks = (g.K + TC_BK - 1) / TC_BK;
+    const int nt = (g.N + BN - 1) / BN, mt2 = (g.M + 2 * TC_BM - 1) / (2 * TC_BM);
+    const int n_tiles = g.Z * mt2 * nt;
+    const int gsz = (BMN && g.Z * mt2 >= ncl) ? nt : 1;      // see k_tc_gemm: the N tiles of a row block back to back on one SM pair
+    const int n_groups = n_tiles / gsz;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G2_NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1); mbar_init(acc_full + 1, 1);
+        mbar_init(acc_free, 8); mbar_init(acc_free + 1, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer's barriers exist before anything arrives on them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int gc = 0;
+        for (int grp = cid; grp < n_groups; grp += ncl) for (int t = grp * gsz; t < (grp + 1) * gsz; ++t) {
+            const int xi = t % nt, r0 = t / nt, z = r0 / mt2;
+            const int n0 = xi * BN, m0 = (r0 - z * mt2) * 2 * TC_BM + (int)rank * TC_BM;
+            const int n_left = g.N - n0;
+            const int n_umma = n_left >= BN ? BN : ((n_left + 15) & ~15);
+            const int nb0 = n0 + (int)rank * (n_umma >> 1);           // this CTA's half of the B tile
+            for (int kc = 0; kc < total_chunks; ++kc, ++gc) {
+                const int s = gc % G2_NSTG;
+                if (gc >= G2_NSTG) mbar_wait(&empty[s], ((gc / G2_NSTG) - 1) & 1);
+                uint8_t* st = tiles + s * G2_STAGE;
+                if (elect_one()) {
+                    const uint32_t fb = mapa_u32(smem_u32(&full[s]), 0);
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * G2_STAGE);
+                    tma_load_3d_2sm(st, &mapAh, fb, kc * TC_BK, m0, z);
+                    tma_load_3d_2sm(st + TC_PLANE_BYTES, &mapAl, fb, kc * TC_BK, m0, z);
+                    if (BMN) {
+#pragma unroll
+                        for (int nb = 0; nb < 2; ++nb) {
+                            tma_load_3d_2sm(st + 2 * TC_PLANE_BYTES + nb * 8192, &mapBh, fb, nb0 + nb * 64, kc * TC_BK, z);
+                            tma_load_3d_2sm(st + 3 * TC_PLANE_BYTES + nb * 8192, &mapBl, fb, nb0 + nb * 64, kc * TC_BK, z);
+                        }
+                    } else {
+                        tma_load_3d_2sm(st + 2 * TC_PLANE_BYTES, &mapBh, fb, kc * TC_BK, nb0, z);
+                        tma_load_3d_2sm(st + 3 * TC_PLANE_BYTES, &mapBl, fb, kc * TC_BK, nb0, z);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            int gc = 0, ti = 0;
+            for (int grp = cid; grp < n_groups; grp += ncl) for (int t = grp * gsz; t < (grp + 1) * gsz; ++t, ++ti) {
+                const int n_left = g.N - (t % nt) * BN;
+                const uint32_t idesc = umma_idesc_bf16(2 * TC_BM, n_left >= BN ? BN : ((n_left + 15) & ~15)) | (BMN ? (1u << 16) : 0u);
+                const int ab = ti & 1;
+                const uint32_t t_acc = tmem_base + ab * BN;
+                if (ti >= 2) { mbar_wait(acc_free + ab, ((ti >> 1) - 1) & 1); tc_fence_after(); }
+                for (int kc = 0; kc < total_chunks; ++kc, ++gc) {
+                    const int s = gc % G2_NSTG;
+                    mbar_wait(&full[s], (gc / G2_NSTG) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(tiles + s * G2_STAGE), a_lo = a_hi + TC_PLANE_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = b_hi + TC_PLANE_BYTES;
+                    const int kvalid = min(TC_BK, g.K - kc * TC_BK);
+                    const int ksteps = (kvalid + 15) / 16;
+                    if (elect_one()) {
+                        const uint32_t dah = umma_desc_lo(a_hi), dal = umma_desc_lo(a_lo);
+                        const uint32_t dbh = BMN ? umma_desc_lo(b_hi, 8192) : umma_desc_lo(b_hi), dbl = BMN ? umma_desc_lo(b_lo, 8192) : umma_desc_lo(b_lo);
+                        constexpr uint32_t BSTEP = BMN ? 128u : 2u;
+                        if (kc == 0) umma_ss2<false>(t_acc, dal, dbh, idesc); else umma_ss2<true>(t_acc, dal, dbh, idesc);   // small terms first
+                        umma_ss2<true>(t_acc, dah, dbl, idesc);
+                        umma_ss2<true>(t_acc, dah, dbh, idesc);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k) {
+                            if (k < ksteps) {
+                                umma_ss2<true>(t_acc, dal + k * 2, dbh + k * BSTEP, idesc);
+                                umma_ss2<true>(t_acc, dah + k * 2, dbl + k * BSTEP, idesc);
+                                umma_ss2<true>(t_acc, dah + k * 2, dbh + k * BSTEP, idesc);
+                            }
+                        }
+                        umma_commit2_mc(&empty[s], 3);                              // frees the stage in both CTAs
+                        if (kc == total_chunks - 1) umma_commit2_mc(acc_full + ab, 3);   // accumulator complete, both CTAs
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t free0 = mapa_u32(smem_u32(acc_free), 0);
+        int ti = 0;
+        for (int grp = cid; grp < n_groups; grp += ncl) for (int t = grp * gsz; t < (grp + 1) * gsz; ++t, ++ti) {
+            const int xi = t % nt, r0 = t / nt, z = r0 / mt2;
+            const int n0 = xi * BN, m0 = (r0 - z * mt2) * 2 * TC_BM + (int)rank * TC_BM;
+            const int ab = ti & 1;
+            mbar_wait(acc_full + ab, (ti >> 1) & 1);
+            tc_fence_after();
+            const int m = m0 + q * 32 + lane;
+            float* crow = g.C + (size_t)z * g.sC + (size_t)m * g.ldc;
+            float* stg = epi + q * (32 * TC_EPI_LD);
+            const bool vec_ok = (g.ldc & 3) == 0 && (g.sC & 3) == 0;
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; ++cb) {
+                const int n = n0 + cb * 32;
+                if (n >= g.N) break;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + cb * 32, v);
+                if (n + 31 < g.N && vec_ok) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st4(stg + lane * TC_EPI_LD + j * 4, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                    __syncwarp();
+                    const int rr = lane >> 3, c4 = (lane & 7) * 4;
+                    float* cbase = g.C + (size_t)z * g.sC + (size_t)(m0 + q * 32) * g.ldc + n + c4;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + rr;
+                        if (m0 + q * 32 + row < g.M) st4(cbase + (size_t)row * g.ldc, ld4(stg + row * TC_EPI_LD + c4));
+                    }
+                    __syncwarp();
+                } else if (m < g.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n + j < g.N) crow[n + j] = __uint_as_float(v[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(free0 + ab * 8);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // nobody leaves (or frees tensor memory) while the pair still works on shared state
+    if (warp == 1) { tc_fence_after(); tmem_dealloc2(tmem_base, 2 * BN); }
+}
+
 // fp32 -> (hi, lo) bf16 planes: hi = bf16(x), lo = bf16(x - hi)
 __global__ void k_split_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -511,6 +681,52 @@ static int make_tmap_mn_major(CUtensorMap* map, const void* base, int N, int K, 
 
 static int tc_sm_count() { return sm_count(); }    // of the current device (cached per device, nnj_api.cu)
 
+// ---- CTA-pair GEMM (k_tc_gemm2).  NNJ_GEMM_2SM: bit 0 = the K-major instantiation (Q K^T), bit 1 = the MN-major one (P V); default both.
+static int gemm2_mask() {
+    static const int mk = [] { const char* v = getenv("NNJ_GEMM_2SM"); return v ? (atoi(v) & 3) : 3; }();
+    return mk;
+}
+template <bool BMN>
+static int gemm2_clusters() {      // CTA pairs that can be resident at once on the current device (cached per device)
+    static std::atomic<int> cache[64];
+    const int dev = current_device() & 63;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * tc_sm_count()); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = G2_SMEM;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, k_tc_gemm2<BMN>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = tc_sm_count() / 2; }
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+// maps: A box 64 x 128 rows; B K-major box 64 x 128 rows (half an N tile) or MN-major 64 x 64
+template <bool BMN>
+static int launch_tc_gemm2(int cls, const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl, const TcGemmArgs& g,
+                           cudaStream_t st) {
+    static DevOnce once;
+    if (once.need()) {
+        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm2<BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+        if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+        once.done();
+    }
+    const int n_pairs = ((g.N + 255) / 256) * ((g.M + 2 * TC_BM - 1) / (2 * TC_BM)) * g.Z;
+    const int ncl = gemm2_clusters<BMN>();
+    const dim3 grid(2 * (n_pairs < ncl ? n_pairs : ncl));
+    prof_begin(cls, st);
+    k_tc_gemm2<BMN><<<grid, TC_THREADS, G2_SMEM, st>>>(mAh, mAl, mBh, mBl, g);
+    ++g_launches;
+    prof_end(st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    return 0;
+}
+static bool gemm2_ok(int bit, int M, int N, int bn, int nsplit, int products) {
+    return (gemm2_mask() >> bit & 1) && bn == 256 && nsplit == 1 && products == 3 && M % (2 * TC_BM) == 0 && N >= 256;
+}
+
 // C[z] = (Ah+Al)[z] * (Bh+Bl)[z] with B MN-major: B planes [Z][K][N] (N contiguous, pitch ldb).  128 x 128 tiles.
 int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
                        size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st, int products) {
@@ -533,6 +749,7 @@ int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, 
     if (int e = make_tmap_mn_major(&mBl, Bl, N, K, Z, ldb, sB)) return e;
     TcGemmArgs g{Cm, M, N, K, ldc, sC, Z, 1, (K + TC_BK - 1) / TC_BK, 0};
     const int bn = N > 128 ? 256 : 128;         // 128 x 256 tiles: a UMMA with N = 256 runs at 75 % of the tensor peak, N = 128 at 60 %
+    if (gemm2_ok(1, M, N, bn, 1, products)) return launch_tc_gemm2<true>(cls, mAh, mAl, mBh, mBl, g, st);
     const int n_tiles = ((N + bn - 1) / bn) * ((M + TC_BM - 1) / TC_BM) * Z;
     const dim3 grid(n_tiles < tc_sm_count() ? n_tiles : tc_sm_count());
     prof_begin(cls, st);
@@ -571,6 +788,12 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
     if (int e = make_tmap_k_major(&mBh, Bh, K, N, Z, ldb, sB, bn)) return e;
     if (int e = make_tmap_k_major(&mBl, Bl, K, N, Z, ldb, sB, bn)) return e;
     TcGemmArgs g{Cm, M, N, K, ldc, sC, Z, nsplit, chunks_per_split, split_stride};
+    if (gemm2_ok(0, M, N, bn, nsplit, products) && N % 256 == 0) {
+        CUtensorMap mBh2, mBl2;      // half an N tile per CTA of the pair
+        if (int e = make_tmap_k_major(&mBh2, Bh, K, N, Z, ldb, sB, 128)) return e;
+        if (int e = make_tmap_k_major(&mBl2, Bl, K, N, Z, ldb, sB, 128)) return e;
+        return launch_tc_gemm2<false>(cls, mAh, mAl, mBh2, mBl2, g, st);
+    }
     const int n_tiles = ((N + bn - 1) / bn) * nsplit * ((M + TC_BM - 1) / TC_BM) * Z;
     const dim3 grid(n_tiles < tc_sm_count() ? n_tiles : tc_sm_count());
     prof_begin(cls, st);

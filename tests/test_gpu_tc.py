@@ -26,7 +26,8 @@ def _gemm(A, B):
     return out
 
 
-@pytest.mark.parametrize("Z,M,N,K", [(1, 128, 128, 64), (2, 256, 128, 128), (3, 1024, 1024, 400), (1, 200, 72, 1000), (2, 384, 400, 1024)])
+@pytest.mark.parametrize("Z,M,N,K", [(1, 128, 128, 64), (2, 256, 128, 128), (3, 1024, 1024, 400), (1, 200, 72, 1000), (2, 384, 400, 1024),
+                                     (1, 256, 256, 64), (5, 512, 768, 200), (150, 256, 256, 128)])   # the last three: CTA-pair kernel (k_tc_gemm2), 1 / 30 / 150 tile pairs
 def test_split_bf16_gemm_matches_fp64(Z, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(Z * 1000 + M + N + K)
     A = torch.randn(Z, M, K, device="cuda", generator=g)
