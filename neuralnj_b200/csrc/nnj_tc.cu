@@ -396,6 +396,163 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CU
     if (warp == 1) { tc_fence_after(); tmem_dealloc2(tmem_base, 2 * BN); }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant for ctx = P V with 256 < N <= 512: ONE pass over A
+// With two N tiles per row block, P (the A operand, streamed from DRAM: 2 x 4.3 GB per 128 trees and layer) was fetched twice.  Here a
+// CTA pair owns a 256-row block and ALL N columns: per k-step two UMMAs, N = 256 into accumulator columns [0, 256) and
+// N2 = 16 ceil((N - 256) / 16) into [256, 256 + N2), so P is read once.  The accumulator is not double-buffered (TMEM: 256 + N2 columns);
+// the TMA ring keeps filling during the epilogue.  B (MN-major) per CTA and plane: four 64-column blocks - blocks 0, 1 = this CTA's half
+// of the first UMMA's columns, blocks 2, 3 = its half of the second's.  96 KB stages, 2-deep ring.
+constexpr int G2W_STAGE = 6 * TC_PLANE_BYTES;     // A_hi, A_lo (16 KB each), B_hi, B_lo (32 KB each)
+constexpr int G2W_NSTG = 2;
+constexpr int G2W_SMEM = G2W_NSTG * G2W_STAGE + 1024 + 256 + TC_EPI_BYTES;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_tc_gemm2w(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+            const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcGemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = smem_align1024(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + G2W_NSTG * G2W_STAGE);
+    uint64_t* empty = full + G2W_NSTG;
+    uint64_t* acc_full = empty + G2W_NSTG;     // [1]
+    uint64_t* acc_free = acc_full + 1;         // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 1);
+    float* epi = reinterpret_cast<float*>(tiles + G2W_NSTG * G2W_STAGE + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const int total_chunks = (g.K + TC_BK - 1) / TC_BK;
+    const int mt2 = (g.M + 2 * TC_BM - 1) / (2 * TC_BM);
+    const int n_tiles = g.Z * mt2;
+    const int n2 = (g.N - 256 + 15) & ~15;       // columns of the second UMMA (16 .. 256)
+    const int h2 = n2 >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G2W_NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_free, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int gc = 0;
+        for (int t = cid; t < n_tiles; t += ncl) {
+            const int z = t / mt2;
+            const int m0 = (t - z * mt2) * 2 * TC_BM + (int)rank * TC_BM;
+            const int c1 = (int)rank * 128, c2 = 256 + (int)rank * h2;     // first column of this CTA's half of each UMMA
+            for (int kc = 0; kc < total_chunks; ++kc, ++gc) {
+                const int s = gc % G2W_NSTG;
+                if (gc >= G2W_NSTG) mbar_wait(&empty[s], ((gc / G2W_NSTG) - 1) & 1);
+                uint8_t* st = tiles + s * G2W_STAGE;
+                if (elect_one()) {
+                    const uint32_t fb = mapa_u32(smem_u32(&full[s]), 0);
+                    if (rank == 0) mbar_expect_tx(&full[s], 2 * G2W_STAGE);
+                    tma_load_3d_2sm(st, &mapAh, fb, kc * TC_BK, m0, z);
+                    tma_load_3d_2sm(st + TC_PLANE_BYTES, &mapAl, fb, kc * TC_BK, m0, z);
+                    uint8_t *bh = st + 2 * TC_PLANE_BYTES, *bl = st + 4 * TC_PLANE_BYTES;
+#pragma unroll
+                    for (int nb = 0; nb < 2; ++nb) {
+                        tma_load_3d_2sm(bh + nb * 8192, &mapBh, fb, c1 + nb * 64, kc * TC_BK, z);
+                        tma_load_3d_2sm(bl + nb * 8192, &mapBl, fb, c1 + nb * 64, kc * TC_BK, z);
+                        tma_load_3d_2sm(bh + (2 + nb) * 8192, &mapBh, fb, c2 + nb * 64, kc * TC_BK, z);
+                        tma_load_3d_2sm(bl + (2 + nb) * 8192, &mapBl, fb, c2 + nb * 64, kc * TC_BK, z);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            const uint32_t id1 = umma_idesc_bf16(2 * TC_BM, 256) | (1u << 16), id2 = umma_idesc_bf16(2 * TC_BM, n2) | (1u << 16);
+            int gc = 0, ti = 0;
+            for (int t = cid; t < n_tiles; t += ncl, ++ti) {
+                if (ti >= 1) { mbar_wait(acc_free, (ti - 1) & 1); tc_fence_after(); }
+                for (int kc = 0; kc < total_chunks; ++kc, ++gc) {
+                    const int s = gc % G2W_NSTG;
+                    mbar_wait(&full[s], (gc / G2W_NSTG) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(tiles + s * G2W_STAGE), a_lo = a_hi + TC_PLANE_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = a_hi + 4 * TC_PLANE_BYTES;
+                    const int kvalid = min(TC_BK, g.K - kc * TC_BK);
+                    const int ksteps = (kvalid + 15) / 16;
+                    if (elect_one()) {
+                        const uint32_t dah = umma_desc_lo(a_hi), dal = umma_desc_lo(a_lo);
+                        const uint32_t dbh = umma_desc_lo(b_hi, 8192), dbl = umma_desc_lo(b_lo, 8192);
+                        const uint32_t dbh2 = umma_desc_lo(b_hi + 16384, 8192), dbl2 = umma_desc_lo(b_lo + 16384, 8192);
+                        const uint32_t t1 = tmem_base, t2 = tmem_base + 256;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < ksteps) {
+                                if (kc == 0 && k == 0) { umma_ss2<false>(t1, dal, dbh, id1); umma_ss2<false>(t2, dal, dbh2, id2); }
+                                else { umma_ss2<true>(t1, dal + k * 2, dbh + k * 128, id1); umma_ss2<true>(t2, dal + k * 2, dbh2 + k * 128, id2); }
+                                umma_ss2<true>(t1, dah + k * 2, dbl + k * 128, id1);
+                                umma_ss2<true>(t2, dah + k * 2, dbl2 + k * 128, id2);
+                                umma_ss2<true>(t1, dah + k * 2, dbh + k * 128, id1);
+                                umma_ss2<true>(t2, dah + k * 2, dbh2 + k * 128, id2);
+                            }
+                        }
+                        umma_commit2_mc(&empty[s], 3);
+                        if (kc == total_chunks - 1) umma_commit2_mc(acc_full, 3);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t free0 = mapa_u32(smem_u32(acc_free), 0);
+        int ti = 0;
+        for (int t = cid; t < n_tiles; t += ncl, ++ti) {
+            const int z = t / mt2;
+            const int m0 = (t - z * mt2) * 2 * TC_BM + (int)rank * TC_BM;
+            mbar_wait(acc_full, ti & 1);
+            tc_fence_after();
+            const int m = m0 + q * 32 + lane;
+            float* crow = g.C + (size_t)z * g.sC + (size_t)m * g.ldc;
+            float* stg = epi + q * (32 * TC_EPI_LD);
+            const bool vec_ok = (g.ldc & 3) == 0 && (g.sC & 3) == 0;
+#pragma unroll 1
+            for (int cb = 0; cb < 16; ++cb) {
+                const int n = cb * 32;
+                if (n >= g.N) break;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+                if (n + 31 < g.N && vec_ok) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        st4(stg + lane * TC_EPI_LD + j * 4, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                    __syncwarp();
+                    const int rr = lane >> 3, c4 = (lane & 7) * 4;
+                    float* cbase = g.C + (size_t)z * g.sC + (size_t)(m0 + q * 32) * g.ldc + n + c4;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + rr;
+                        if (m0 + q * 32 + row < g.M) st4(cbase + (size_t)row * g.ldc, ld4(stg + row * TC_EPI_LD + c4));
+                    }
+                    __syncwarp();
+                } else if (m < g.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n + j < g.N) crow[n + j] = __uint_as_float(v[j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(free0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc2(tmem_base, 512); }
+}
+
 // fp32 -> (hi, lo) bf16 planes: hi = bf16(x), lo = bf16(x - hi)
 __global__ void k_split_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -681,9 +838,10 @@ static int make_tmap_mn_major(CUtensorMap* map, const void* base, int N, int K, 
 
 static int tc_sm_count() { return sm_count(); }    // of the current device (cached per device, nnj_api.cu)
 
-// ---- CTA-pair GEMM (k_tc_gemm2).  NNJ_GEMM_2SM: bit 0 = the K-major instantiation (Q K^T), bit 1 = the MN-major one (P V); default both.
+// ---- CTA-pair GEMM (k_tc_gemm2).  NNJ_GEMM_2SM: bit 0 = the K-major instantiation (Q K^T), bit 1 = the MN-major one (P V), bit 2 = the
+// one-pass form of P V for 256 < N <= 512 (k_tc_gemm2w); default all.
 static int gemm2_mask() {
-    static const int mk = [] { const char* v = getenv("NNJ_GEMM_2SM"); return v ? (atoi(v) & 3) : 3; }();
+    static const int mk = [] { const char* v = getenv("NNJ_GEMM_2SM"); return v ? (atoi(v) & 7) : 7; }();
     return mk;
 }
 template <bool BMN>
@@ -723,6 +881,26 @@ static int launch_tc_gemm2(int cls, const CUtensorMap& mAh, const CUtensorMap& m
     if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
     return 0;
 }
+// one pass over A for 256 < N <= 512 (NNJ_GEMM_2SM bit 2 = off switch: value 3 keeps the two-tile form)
+static int launch_tc_gemm2w(int cls, const CUtensorMap& mAh, const CUtensorMap& mAl, const CUtensorMap& mBh, const CUtensorMap& mBl, const TcGemmArgs& g,
+                            cudaStream_t st) {
+    static DevOnce once;
+    if (once.need()) {
+        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm2w, cudaFuncAttributeMaxDynamicSharedMemorySize, G2W_SMEM);
+        if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+        once.done();
+    }
+    const int n_pairs = ((g.M + 2 * TC_BM - 1) / (2 * TC_BM)) * g.Z;
+    const int ncl = gemm2_clusters<true>();
+    const dim3 grid(2 * (n_pairs < ncl ? n_pairs : ncl));
+    prof_begin(cls, st);
+    k_tc_gemm2w<<<grid, TC_THREADS, G2W_SMEM, st>>>(mAh, mAl, mBh, mBl, g);
+    ++g_launches;
+    prof_end(st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    return 0;
+}
 static bool gemm2_ok(int bit, int M, int N, int bn, int nsplit, int products) {
     return (gemm2_mask() >> bit & 1) && bn == 256 && nsplit == 1 && products == 3 && M % (2 * TC_BM) == 0 && N >= 256;
 }
@@ -749,6 +927,7 @@ int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, 
     if (int e = make_tmap_mn_major(&mBl, Bl, N, K, Z, ldb, sB)) return e;
     TcGemmArgs g{Cm, M, N, K, ldc, sC, Z, 1, (K + TC_BK - 1) / TC_BK, 0};
     const int bn = N > 128 ? 256 : 128;         // 128 x 256 tiles: a UMMA with N = 256 runs at 75 % of the tensor peak, N = 128 at 60 %
+    if (gemm2_ok(1, M, N, bn, 1, products) && (gemm2_mask() & 4) && N > 256 && N <= 512) return launch_tc_gemm2w(cls, mAh, mAl, mBh, mBl, g, st);
     if (gemm2_ok(1, M, N, bn, 1, products)) return launch_tc_gemm2<true>(cls, mAh, mAl, mBh, mBl, g, st);
     const int n_tiles = ((N + bn - 1) / bn) * ((M + TC_BM - 1) / TC_BM) * Z;
     const dim3 grid(n_tiles < tc_sm_count() ? n_tiles : tc_sm_count());

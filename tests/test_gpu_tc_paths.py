@@ -174,3 +174,19 @@ def test_lane_quarter_modes_agree_with_the_two_way_split(tmp_path):
                 idx = [i * n - i * (i + 1) // 2 + (j - i - 1) for i, j in (m0[b, t].tolist(), m1[b, t].tolist())]
                 assert abs(float(a0[idx[0]] - a0[idx[1]])) / scale < LOGIT_TOL and abs(float(a1[idx[0]] - a1[idx[1]])) / scale < LOGIT_TOL
             off += P
+
+
+# Row-attention GEMM dispatch (nnj_tc.cu): ctx = P V has N = 8 R columns and M = C rows.  C % 256 == 0 selects the CTA-pair kernels:
+# N <= 256 (R <= 32) k_tc_gemm2<true> with one (ragged) N tile, 256 < N <= 512 the one-pass k_tc_gemm2w (second UMMA of 16 .. 256 columns:
+# R = 33 -> 16, 45 -> 112, 50 -> 144, 64 -> 256), N > 512 k_tc_gemm2<true> with three N tiles; C = 384 (odd number of 128-row blocks) stays on
+# the single-CTA kernel.  S = Q K^T (N = C) runs the K-major pair kernel whenever C % 256 == 0.
+@pytest.mark.parametrize("R,C", [(32, 256), (33, 256), (45, 256), (64, 512), (70, 256), (50, 384)])
+def test_row_gemm_variants_encoder_matches_oracle(R, C, sd0, gpu_models):
+    import nnj_oracle as O
+    data = O.evolved_msa(1, R, C, seed=R + C)
+    mask = torch.zeros(1, C, dtype=torch.bool)
+    mask[0, C - 24:] = True
+    ref = O.encode(sd0, data, mask)
+    got = gpu_models["bf16x3"].encode_zxr(data.cuda(), mask.cuda()).cpu()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err < 5e-5, err
