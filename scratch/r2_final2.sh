@@ -4,7 +4,7 @@
 cd $GRAFT_REPO_ROOT
 o=gpurun_out/r02ev2; mkdir -p $o
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > $o/smi.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > $o/pytest.log 2>&1; echo rc=$? >> $o/pytest.log; tail -3 $o/pytest.log
+timeout 1200 python -m pytest tests -m gpu -x -q > $o/pytest.log 2>&1; echo rc=$? >> $o/pytest.log; tail -3 $o/pytest.log
 timeout 900 python bench.py --steps 5 --warmup 3 > $o/bench.json 2> $o/bench.err; tail -2 $o/bench.err
 timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > $o/bench_reference.json 2> $o/bench_reference.err; tail -2 $o/bench_reference.err
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $o/launches.csv python scratch/prof_rollout.py 128 1 > $o/ncu_launch.log 2>&1
@@ -19,5 +19,7 @@ cap merge_late k_merge 40
 cap derive k_node_derive 0
 cap rowqk_bf16 k_tc_gemm 2 bf16
 cap rowpv_bf16 k_tc_gemm 3 bf16
-# the other 13 captures (score / alpha / column block / ffn / rowqkv / softmax / 3-product row GEMMs) are those of scratch/r2_evidence.sh: kernels unchanged since
+cap rowqk k_tc_gemm2 2
+cap rowpv k_tc_gemm2w 1
+# the other 11 captures (score / alpha / column block / ffn / rowqkv / softmax) are those of scratch/r2_evidence.sh: kernels unchanged since
 ls -la $o | tail -50
