@@ -714,13 +714,22 @@ int run_encoder(Model* m, const int8_t* data, const uint8_t* mask, int B, int R,
                 }
                 const int products = m->cfg.precision == NNJ_PREC_BF16 ? 1 : 3;
                 __nv_bfloat16* Plo = products == 1 ? nullptr : P + pp;      // one-product mode: the register softmax writes the hi plane only
+                const bool fused = (mk & 1) && row_qk_softmax_ok(C, products);   // softmax in the Q K^T epilogue: S never leaves the chip
+                if (fused) {
+                    float* rowsum = S;                                            // [nb * H][C]: the logits buffer is free in this form
+                    if (int e = launch_row_qk_softmax(KC_ROW_QK, qh, ql, kh, kl, P, P + pp, rowsum, mb, H, nb * H, C, KD, st)) return e;
+                    if (int e = launch_tc_gemm_bmn(KC_ROW_PV, P, P + pp, vh, vl, q /*ctx fp32 [B,H,C,R*8]*/, nb * H, C, KD, C, C, (size_t)C * C, KD,
+                                                   (size_t)C * KD, KD, (size_t)C * KD, st, products, rowsum)) return e;
+                } else {
                 if (int e = launch_tc_gemm(KC_ROW_QK, qh, ql, kh, kl, S, nb * H, C, C, KD, KD, (size_t)C * KD, KD, (size_t)C * KD, C, (size_t)C * C, st, products)) return e;
                 prof_begin(KC_ROW_SOFTMAX, st);
                 if (C <= 512) k_softmax_rows_split_reg<2><<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, Plo, C, mb);
                 else if (C <= 1024) k_softmax_rows_split_reg<4><<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, Plo, C, mb);
                 else k_softmax_rows_split<<<dim3((C + 7) / 8, nb * H), NTHREADS, 0, st>>>(S, P, P + pp, C, mb);
                 LAUNCH_CHECK();
-                if (mk & 1) {
+                }
+                if (fused) {
+                } else if (mk & 1) {
                     if (int e = launch_tc_gemm_bmn(KC_ROW_PV, P, P + pp, vh, vl, q /*ctx fp32 [B,H,C,R*8]*/, nb * H, C, KD, C, C, (size_t)C * C, KD,
                                                    (size_t)C * KD, KD, (size_t)C * KD, st, products)) return e;
                 } else {

@@ -157,7 +157,12 @@ int launch_tc_gemm_ex(int cls, const void* Ah, const void* Al, const void* Bh, c
                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, int bn, int nsplit, int chunks_per_split, size_t split_stride,
                       cudaStream_t st, int products = 3);
 int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
-                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st, int products = 3);
+                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st, int products = 3, const float* row_div = nullptr);
+// S = Q K^T of the tied row attention with the softmax in the epilogue: unnormalised exp(s - max) as bf16 hi / lo planes + the row sums, which the
+// P V launch takes as `row_div` (k_tc_gemm2s, CTA pairs; site count a multiple of 256)
+bool row_qk_softmax_ok(int C, int products);
+int launch_row_qk_softmax(int cls, const void* Qh, const void* Ql, const void* Kh, const void* Kl, void* Ph, void* Pl, float* rowsum, const uint8_t* mask,
+                          int heads, int Z, int C, int K, cudaStream_t st);
 // tcgen05 encoder kernels over the site-major residual stream (nnj_encoder_tc.cu)
 int launch_enc_rowqkv_tc(const Model* m, int layer, const float* xs, size_t xs_tree_stride, int B, int R, int C, float q_scale, const uint8_t* mask,
                          void* qh, void* ql, void* kh, void* kl, void* vh, void* vl, cudaStream_t st);

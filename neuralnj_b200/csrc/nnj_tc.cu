@@ -28,6 +28,7 @@ constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_LD * 4;      // one tile per epilog
 struct TcGemmArgs {
     float* C; int M, N, K, ldc; size_t sC; int Z;
     int nsplit, chunks_per_split; size_t split_stride;
+    const float* row_div = nullptr;     // MN-major instantiations: output row m of batch z is divided by row_div[z * M + m] (P V after k_tc_gemm2s)
 };
 
 // BMN: B is given MN-major, [Z][K][N] with N contiguous (e.g. V of the row attention, [key site][taxon*8+d]); its tiles are loaded
@@ -190,6 +191,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUt
                 else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                if (BMN && g.row_div) {
+                    const float rs = m < g.M ? 1.0f / g.row_div[(size_t)z * g.M + m] : 1.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
                 }
                 const int n = n0 + cb * 32;
                 if (n + 31 < g.N && vec_ok) {
@@ -365,6 +371,11 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CU
                 if (n >= g.N) break;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + cb * 32, v);
+                if (BMN && g.row_div) {
+                    const float rs = m < g.M ? 1.0f / g.row_div[(size_t)z * g.M + m] : 1.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
+                }
                 if (n + 31 < g.N && vec_ok) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -393,6 +404,204 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CU
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();          // nobody leaves (or frees tensor memory) while the pair still works on shared state
+    if (warp == 1) { tc_fence_after(); tmem_dealloc2(tmem_base, 2 * BN); }
+}
+
+// ------------------------------------------------------------------ Q K^T with the row softmax in the epilogue (S never reaches HBM)
+// A CTA pair owns a 256-query row block and walks its N / 256 key tiles TWICE:
+//   pass A  one product (hi * hi, lo planes not fetched): every epilogue thread owns one query row (TMEM lane = row) and keeps the running maximum of
+//           its row in a register.  Any shift within a few units of the true maximum yields the exact softmax, so bf16 operands suffice here.
+//   pass B  the 3-product split; epilogue e = 2^((s - m) log2 e) (masked keys: s = -10000, axial_attention.py:81-82), e -> bf16 hi / lo straight to
+//           the P planes (UNNORMALISED), row sums of e accumulated in the same register and written once per row: the P V epilogue divides by them.
+// Accumulators stay double-buffered across all 2 N / 256 tiles, so both epilogues hide behind the next tile's MMAs.  Replaces the S round trip
+// (4 B written + 4 B read per logit) and the separate softmax pass.  exp arguments are clamped at +80 (pass A's maximum is approximate).
+constexpr int G2S_EPI_PITCH = 80;                           // bytes per staged row of 32 bf16 (64 B + 16: conflict-free 16-byte accesses)
+constexpr int G2S_EPI_WARP = 2 * 32 * G2S_EPI_PITCH;        // hi + lo tile of one epilogue warp
+constexpr int G2S_SMEM = G2_NSTG * G2_STAGE + 1024 + 256 + 4 * G2S_EPI_WARP;
+struct TcSoftArgs {
+    __nv_bfloat16 *Ph, *Pl;      // [Z][M][N] unnormalised probabilities (hi / lo planes)
+    float* rowsum;               // [Z][M]
+    const uint8_t* mask;         // [Z / heads][N] or null
+    int heads;
+};
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+            const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcGemmArgs g, const TcSoftArgs sa) {
+    constexpr int BN = 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = smem_align1024(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + G2_NSTG * G2_STAGE);
+    uint64_t* empty = full + G2_NSTG;
+    uint64_t* acc_full = empty + G2_NSTG;      // [2]
+    uint64_t* acc_free = acc_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
+    uint8_t* epi = tiles + G2_NSTG * G2_STAGE + 256;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const int total_chunks = (g.K + TC_BK - 1) / TC_BK;
+    const int nt = g.N / BN, mt2 = g.M / (2 * TC_BM);       // host guarantees N % 256 == 0, M % 256 == 0
+    const int n_items = g.Z * mt2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G2_NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1); mbar_init(acc_full + 1, 1);
+        mbar_init(acc_free, 8); mbar_init(acc_free + 1, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int gc = 0;
+        for (int it = cid; it < n_items; it += ncl) {
+            const int z = it / mt2;
+            const int m0 = (it - z * mt2) * 2 * TC_BM + (int)rank * TC_BM;
+            for (int t = 0; t < 2 * nt; ++t) {
+                const bool three = t >= nt;
+                const int nb0 = (three ? t - nt : t) * BN + (int)rank * (BN / 2);
+                for (int kc = 0; kc < total_chunks; ++kc, ++gc) {
+                    const int s = gc % G2_NSTG;
+                    if (gc >= G2_NSTG) mbar_wait(&empty[s], ((gc / G2_NSTG) - 1) & 1);
+                    uint8_t* st = tiles + s * G2_STAGE;
+                    if (elect_one()) {
+                        const uint32_t fb = mapa_u32(smem_u32(&full[s]), 0);
+                        if (rank == 0) mbar_expect_tx(&full[s], three ? 2 * G2_STAGE : G2_STAGE);
+                        tma_load_3d_2sm(st, &mapAh, fb, kc * TC_BK, m0, z);
+                        tma_load_3d_2sm(st + 2 * TC_PLANE_BYTES, &mapBh, fb, kc * TC_BK, nb0, z);
+                        if (three) {
+                            tma_load_3d_2sm(st + TC_PLANE_BYTES, &mapAl, fb, kc * TC_BK, m0, z);
+                            tma_load_3d_2sm(st + 3 * TC_PLANE_BYTES, &mapBl, fb, kc * TC_BK, nb0, z);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            const uint32_t idesc = umma_idesc_bf16(2 * TC_BM, BN);
+            int gc = 0, ti = 0;
+            for (int it = cid; it < n_items; it += ncl) {
+                for (int t = 0; t < 2 * nt; ++t, ++ti) {
+                    const bool three = t >= nt;
+                    const int ab = ti & 1;
+                    const uint32_t t_acc = tmem_base + ab * BN;
+                    if (ti >= 2) { mbar_wait(acc_free + ab, ((ti >> 1) - 1) & 1); tc_fence_after(); }
+                    for (int kc = 0; kc < total_chunks; ++kc, ++gc) {
+                        const int s = gc % G2_NSTG;
+                        mbar_wait(&full[s], (gc / G2_NSTG) & 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(tiles + s * G2_STAGE), a_lo = a_hi + TC_PLANE_BYTES;
+                        const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = b_hi + TC_PLANE_BYTES;
+                        const int kvalid = min(TC_BK, g.K - kc * TC_BK);
+                        const int ksteps = (kvalid + 15) / 16;
+                        if (elect_one()) {
+                            const uint32_t dah = umma_desc_lo(a_hi), dal = umma_desc_lo(a_lo), dbh = umma_desc_lo(b_hi), dbl = umma_desc_lo(b_lo);
+                            if (three) {
+                                if (kc == 0) umma_ss2<false>(t_acc, dal, dbh, idesc); else umma_ss2<true>(t_acc, dal, dbh, idesc);   // small terms first
+                                umma_ss2<true>(t_acc, dah, dbl, idesc);
+                                umma_ss2<true>(t_acc, dah, dbh, idesc);
+#pragma unroll
+                                for (int k = 1; k < 4; ++k) {
+                                    if (k < ksteps) {
+                                        umma_ss2<true>(t_acc, dal + k * 2, dbh + k * 2, idesc);
+                                        umma_ss2<true>(t_acc, dah + k * 2, dbl + k * 2, idesc);
+                                        umma_ss2<true>(t_acc, dah + k * 2, dbh + k * 2, idesc);
+                                    }
+                                }
+                            } else {
+                                if (kc == 0) umma_ss2<false>(t_acc, dah, dbh, idesc); else umma_ss2<true>(t_acc, dah, dbh, idesc);
+#pragma unroll
+                                for (int k = 1; k < 4; ++k)
+                                    if (k < ksteps) umma_ss2<true>(t_acc, dah + k * 2, dbh + k * 2, idesc);
+                            }
+                            umma_commit2_mc(&empty[s], 3);
+                            if (kc == total_chunks - 1) umma_commit2_mc(acc_full + ab, 3);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t free0 = mapa_u32(smem_u32(acc_free), 0);
+        uint8_t* stg_h = epi + q * G2S_EPI_WARP;
+        uint8_t* stg_l = stg_h + 32 * G2S_EPI_PITCH;
+        constexpr float L2E = 1.4426950408889634f;
+        int ti = 0;
+        for (int it = cid; it < n_items; it += ncl) {
+            const int z = it / mt2;
+            const int m0 = (it - z * mt2) * 2 * TC_BM + (int)rank * TC_BM;
+            const int m = m0 + q * 32 + lane;                         // this thread's query row
+            const uint8_t* mk = sa.mask ? sa.mask + (size_t)(z / sa.heads) * g.N : nullptr;
+            float rmax = -INFINITY, rsum = 0.f, ms = 0.f;
+            for (int t = 0; t < 2 * nt; ++t, ++ti) {
+                const bool three = t >= nt;
+                const int n0 = (three ? t - nt : t) * BN;
+                if (t == nt) ms = -rmax * L2E;
+                const int ab = ti & 1;
+                mbar_wait(acc_full + ab, (ti >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int cb = 0; cb < BN / 32; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + cb * 32, v);
+                    const int n = n0 + cb * 32;
+                    if (mk) {
+                        const uint4 k0 = *reinterpret_cast<const uint4*>(mk + n), k1 = *reinterpret_cast<const uint4*>(mk + n + 16);
+                        const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if ((kw[j >> 2] >> (8 * (j & 3))) & 0xffu) v[j] = __float_as_uint(-10000.0f);
+                    }
+                    if (!three) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) rmax = fmaxf(rmax, __uint_as_float(v[j]));
+                    } else {
+                        uint32_t hh[16], ll[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float e0 = ex2_approx(fminf(fmaf(__uint_as_float(v[j]), L2E, ms), 115.0f));
+                            const float e1 = ex2_approx(fminf(fmaf(__uint_as_float(v[j + 1]), L2E, ms), 115.0f));
+                            rsum += e0 + e1;
+                            split2(e0, e1, hh[j >> 1], ll[j >> 1]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            *reinterpret_cast<uint4*>(stg_h + lane * G2S_EPI_PITCH + c * 16) = make_uint4(hh[4 * c], hh[4 * c + 1], hh[4 * c + 2], hh[4 * c + 3]);
+                            *reinterpret_cast<uint4*>(stg_l + lane * G2S_EPI_PITCH + c * 16) = make_uint4(ll[4 * c], ll[4 * c + 1], ll[4 * c + 2], ll[4 * c + 3]);
+                        }
+                        __syncwarp();
+                        // 8 rows x 64 contiguous bytes per store instruction and plane
+                        const int rr = lane >> 2, c16 = (lane & 3) * 16;
+                        const size_t gbase = ((size_t)z * g.M + (m0 + q * 32)) * g.N + n;
+#pragma unroll
+                        for (int i8 = 0; i8 < 4; ++i8) {
+                            const int row = i8 * 8 + rr;
+                            const size_t go = (gbase + (size_t)row * g.N) * 2 + c16;
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(sa.Ph) + go) = *reinterpret_cast<const uint4*>(stg_h + row * G2S_EPI_PITCH + c16);
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(sa.Pl) + go) = *reinterpret_cast<const uint4*>(stg_l + row * G2S_EPI_PITCH + c16);
+                        }
+                        __syncwarp();
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(free0 + ab * 8);
+            }
+            sa.rowsum[(size_t)z * g.M + m] = rsum;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
     if (warp == 1) { tc_fence_after(); tmem_dealloc2(tmem_base, 2 * BN); }
 }
 
@@ -522,6 +731,11 @@ k_tc_gemm2w(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
                 if (n >= g.N) break;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+                if (g.row_div) {
+                    const float rs = m < g.M ? 1.0f / g.row_div[(size_t)z * g.M + m] : 1.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * rs);
+                }
                 if (n + 31 < g.N && vec_ok) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -905,9 +1119,41 @@ static bool gemm2_ok(int bit, int M, int N, int bn, int nsplit, int products) {
     return (gemm2_mask() >> bit & 1) && bn == 256 && nsplit == 1 && products == 3 && M % (2 * TC_BM) == 0 && N >= 256;
 }
 
+// S = Q K^T with the softmax in the epilogue (k_tc_gemm2s).  NNJ_ROW_FUSED=0 keeps the three-kernel form (GEMM, softmax pass, GEMM).
+bool row_qk_softmax_ok(int C, int products) {
+    static const int on = [] { const char* v = getenv("NNJ_ROW_FUSED"); return v ? atoi(v) : 1; }();
+    return on && products == 3 && (gemm2_mask() & 1) && C >= 256 && C % 256 == 0;
+}
+int launch_row_qk_softmax(int cls, const void* Qh, const void* Ql, const void* Kh, const void* Kl, void* Ph, void* Pl, float* rowsum, const uint8_t* mask,
+                          int heads, int Z, int C, int K, cudaStream_t st) {
+    static DevOnce once;
+    if (once.need()) {
+        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm2s, cudaFuncAttributeMaxDynamicSharedMemorySize, G2S_SMEM);
+        if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+        once.done();
+    }
+    CUtensorMap mAh, mAl, mBh, mBl;
+    if (int e = make_tmap_k_major(&mAh, Qh, K, C, Z, K, (size_t)C * K, TC_BM)) return e;
+    if (int e = make_tmap_k_major(&mAl, Ql, K, C, Z, K, (size_t)C * K, TC_BM)) return e;
+    if (int e = make_tmap_k_major(&mBh, Kh, K, C, Z, K, (size_t)C * K, 128)) return e;
+    if (int e = make_tmap_k_major(&mBl, Kl, K, C, Z, K, (size_t)C * K, 128)) return e;
+    TcGemmArgs g{nullptr, C, C, K, C, (size_t)C * C, Z, 1, (K + TC_BK - 1) / TC_BK, 0};
+    TcSoftArgs sa{(__nv_bfloat16*)Ph, (__nv_bfloat16*)Pl, rowsum, mask, heads};
+    const int n_items = (C / (2 * TC_BM)) * Z;
+    const int ncl = gemm2_clusters<false>();
+    const dim3 grid(2 * (n_items < ncl ? n_items : ncl));
+    prof_begin(cls, st);
+    k_tc_gemm2s<<<grid, TC_THREADS, G2S_SMEM, st>>>(mAh, mAl, mBh, mBl, g, sa);
+    ++g_launches;
+    prof_end(st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, __FILE__, __LINE__);
+    return 0;
+}
+
 // C[z] = (Ah+Al)[z] * (Bh+Bl)[z] with B MN-major: B planes [Z][K][N] (N contiguous, pitch ldb).  128 x 128 tiles.
 int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, const void* Bl, float* Cm, int Z, int M, int N, int K, size_t lda,
-                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st, int products) {
+                       size_t sA, size_t ldb, size_t sB, int ldc, size_t sC, cudaStream_t st, int products, const float* row_div) {
     static DevOnce once;      // per device, not per process
     constexpr int SMEM128 = TC_STAGES * (4 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
     constexpr int SMEM256 = 2 * (6 * TC_PLANE_BYTES) + 1024 + 256 + TC_EPI_BYTES;
@@ -926,6 +1172,7 @@ int launch_tc_gemm_bmn(int cls, const void* Ah, const void* Al, const void* Bh, 
     if (int e = make_tmap_mn_major(&mBh, Bh, N, K, Z, ldb, sB)) return e;
     if (int e = make_tmap_mn_major(&mBl, Bl, N, K, Z, ldb, sB)) return e;
     TcGemmArgs g{Cm, M, N, K, ldc, sC, Z, 1, (K + TC_BK - 1) / TC_BK, 0};
+    g.row_div = row_div;
     const int bn = N > 128 ? 256 : 128;         // 128 x 256 tiles: a UMMA with N = 256 runs at 75 % of the tensor peak, N = 128 at 60 %
     if (gemm2_ok(1, M, N, bn, 1, products) && (gemm2_mask() & 4) && N > 256 && N <= 512) return launch_tc_gemm2w(cls, mAh, mAl, mBh, mBl, g, st);
     if (gemm2_ok(1, M, N, bn, 1, products)) return launch_tc_gemm2<true>(cls, mAh, mAl, mBh, mBl, g, st);
