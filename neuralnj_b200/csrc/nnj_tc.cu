@@ -430,9 +430,12 @@ k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
     constexpr int BN = 256;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = smem_align1024(smem_raw);
+    // the ring is cut into 6 half slots of 32 KB ([A plane 16 KB][B half-tile plane 16 KB]), each with its own barrier pair: a one-product chunk
+    // takes one half slot (hi planes), a 3-product chunk two (hi planes, then lo planes).  Position p in the ring -> slot p % 6, use p / 6.
+    constexpr int NH = 2 * G2_NSTG, HSLOT = G2_STAGE / 2;
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + G2_NSTG * G2_STAGE);
-    uint64_t* empty = full + G2_NSTG;
-    uint64_t* acc_full = empty + G2_NSTG;      // [2]
+    uint64_t* empty = full + NH;
+    uint64_t* acc_full = empty + NH;           // [2]
     uint64_t* acc_free = acc_full + 2;         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 2);
     uint8_t* epi = tiles + G2_NSTG * G2_STAGE + 256;
@@ -445,7 +448,7 @@ k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
     const int n_items = g.Z * mt2;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G2_NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NH; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1); mbar_init(acc_full + 1, 1);
         mbar_init(acc_free, 8); mbar_init(acc_free + 1, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -458,47 +461,47 @@ k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        int gc = 0;
+        int pos = 0;
         for (int it = cid; it < n_items; it += ncl) {
             const int z = it / mt2;
             const int m0 = (it - z * mt2) * 2 * TC_BM + (int)rank * TC_BM;
             for (int t = 0; t < 2 * nt; ++t) {
                 const bool three = t >= nt;
                 const int nb0 = (three ? t - nt : t) * BN + (int)rank * (BN / 2);
-                for (int kc = 0; kc < total_chunks; ++kc, ++gc) {
-                    const int s = gc % G2_NSTG;
-                    if (gc >= G2_NSTG) mbar_wait(&empty[s], ((gc / G2_NSTG) - 1) & 1);
-                    uint8_t* st = tiles + s * G2_STAGE;
-                    if (elect_one()) {
-                        const uint32_t fb = mapa_u32(smem_u32(&full[s]), 0);
-                        if (rank == 0) mbar_expect_tx(&full[s], three ? 2 * G2_STAGE : G2_STAGE);
-                        tma_load_3d_2sm(st, &mapAh, fb, kc * TC_BK, m0, z);
-                        tma_load_3d_2sm(st + 2 * TC_PLANE_BYTES, &mapBh, fb, kc * TC_BK, nb0, z);
-                        if (three) {
-                            tma_load_3d_2sm(st + TC_PLANE_BYTES, &mapAl, fb, kc * TC_BK, m0, z);
-                            tma_load_3d_2sm(st + 3 * TC_PLANE_BYTES, &mapBl, fb, kc * TC_BK, nb0, z);
+                for (int kc = 0; kc < total_chunks; ++kc) {
+                    for (int h = 0; h < (three ? 2 : 1); ++h, ++pos) {
+                        const int s = pos % NH;
+                        if (pos >= NH) mbar_wait(&empty[s], ((pos / NH) - 1) & 1);
+                        uint8_t* st = tiles + s * HSLOT;
+                        if (elect_one()) {
+                            const uint32_t fb = mapa_u32(smem_u32(&full[s]), 0);
+                            if (rank == 0) mbar_expect_tx(&full[s], 2 * HSLOT);
+                            tma_load_3d_2sm(st, h ? &mapAl : &mapAh, fb, kc * TC_BK, m0, z);
+                            tma_load_3d_2sm(st + TC_PLANE_BYTES, h ? &mapBl : &mapBh, fb, kc * TC_BK, nb0, z);
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
         if (rank == 0) {
             const uint32_t idesc = umma_idesc_bf16(2 * TC_BM, BN);
-            int gc = 0, ti = 0;
+            int pos = 0, ti = 0;
             for (int it = cid; it < n_items; it += ncl) {
                 for (int t = 0; t < 2 * nt; ++t, ++ti) {
                     const bool three = t >= nt;
                     const int ab = ti & 1;
                     const uint32_t t_acc = tmem_base + ab * BN;
                     if (ti >= 2) { mbar_wait(acc_free + ab, ((ti >> 1) - 1) & 1); tc_fence_after(); }
-                    for (int kc = 0; kc < total_chunks; ++kc, ++gc) {
-                        const int s = gc % G2_NSTG;
-                        mbar_wait(&full[s], (gc / G2_NSTG) & 1);
+                    for (int kc = 0; kc < total_chunks; ++kc) {
+                        const int s = pos % NH, s2 = (pos + 1) % NH;
+                        mbar_wait(&full[s], (pos / NH) & 1);
+                        if (three) mbar_wait(&full[s2], ((pos + 1) / NH) & 1);
+                        pos += three ? 2 : 1;
                         tc_fence_after();
-                        const uint32_t a_hi = smem_u32(tiles + s * G2_STAGE), a_lo = a_hi + TC_PLANE_BYTES;
-                        const uint32_t b_hi = a_hi + 2 * TC_PLANE_BYTES, b_lo = b_hi + TC_PLANE_BYTES;
+                        const uint32_t a_hi = smem_u32(tiles + s * HSLOT), b_hi = a_hi + TC_PLANE_BYTES;
+                        const uint32_t a_lo = smem_u32(tiles + s2 * HSLOT), b_lo = a_lo + TC_PLANE_BYTES;
                         const int kvalid = min(TC_BK, g.K - kc * TC_BK);
                         const int ksteps = (kvalid + 15) / 16;
                         if (elect_one()) {
@@ -522,6 +525,7 @@ k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
                                     if (k < ksteps) umma_ss2<true>(t_acc, dah + k * 2, dbh + k * 2, idesc);
                             }
                             umma_commit2_mc(&empty[s], 3);
+                            if (three) umma_commit2_mc(&empty[s2], 3);
                             if (kc == total_chunks - 1) umma_commit2_mc(acc_full + ab, 3);
                         }
                         __syncwarp();
@@ -540,7 +544,24 @@ k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
             const int z = it / mt2;
             const int m0 = (it - z * mt2) * 2 * TC_BM + (int)rank * TC_BM;
             const int m = m0 + q * 32 + lane;                         // this thread's query row
-            const uint8_t* mk = sa.mask ? sa.mask + (size_t)(z / sa.heads) * g.N : nullptr;
+            // padding mask of this tree as bits: lane l of the warp holds the 32 keys of column blocks l, l + 32, ... (N <= 4096), fetched once per
+            // row block; a block's word reaches all lanes by shuffle (a global load per column block sat exposed in the epilogue: 15 % of the samples)
+            uint32_t mbits[4] = {0u, 0u, 0u, 0u};
+            if (sa.mask) {
+                const uint8_t* mk = sa.mask + (size_t)(z / sa.heads) * g.N;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int c0 = (w * 32 + lane) * 32;
+                    if (c0 < g.N) {
+                        const uint4 k0 = *reinterpret_cast<const uint4*>(mk + c0), k1 = *reinterpret_cast<const uint4*>(mk + c0 + 16);
+                        const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+                        uint32_t bits = 0u;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) bits |= ((kw[j >> 2] >> (8 * (j & 3))) & 0xffu) ? (1u << j) : 0u;
+                        mbits[w] = bits;
+                    }
+                }
+            }
             float rmax = -INFINITY, rsum = 0.f, ms = 0.f;
             for (int t = 0; t < 2 * nt; ++t, ++ti) {
                 const bool three = t >= nt;
@@ -554,12 +575,15 @@ k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * BN + cb * 32, v);
                     const int n = n0 + cb * 32;
-                    if (mk) {
-                        const uint4 k0 = *reinterpret_cast<const uint4*>(mk + n), k1 = *reinterpret_cast<const uint4*>(mk + n + 16);
-                        const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+                    {
+                        const int blk = n >> 5;
+                        const uint32_t src = blk < 32 ? mbits[0] : (blk < 64 ? mbits[1] : (blk < 96 ? mbits[2] : mbits[3]));
+                        const uint32_t bits = __shfl_sync(0xffffffffu, src, blk & 31);
+                        if (bits) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if ((kw[j >> 2] >> (8 * (j & 3))) & 0xffu) v[j] = __float_as_uint(-10000.0f);
+                            for (int j = 0; j < 32; ++j)
+                                if ((bits >> j) & 1u) v[j] = __float_as_uint(-10000.0f);
+                        }
                     }
                     if (!three) {
 #pragma unroll
@@ -1122,7 +1146,7 @@ static bool gemm2_ok(int bit, int M, int N, int bn, int nsplit, int products) {
 // S = Q K^T with the softmax in the epilogue (k_tc_gemm2s).  NNJ_ROW_FUSED=0 keeps the three-kernel form (GEMM, softmax pass, GEMM).
 bool row_qk_softmax_ok(int C, int products) {
     static const int on = [] { const char* v = getenv("NNJ_ROW_FUSED"); return v ? atoi(v) : 1; }();
-    return on && products == 3 && (gemm2_mask() & 1) && C >= 256 && C % 256 == 0;
+    return on && products == 3 && (gemm2_mask() & 1) && C >= 256 && C % 256 == 0 && C <= 4096;
 }
 int launch_row_qk_softmax(int cls, const void* Qh, const void* Ql, const void* Kh, const void* Kl, void* Ph, void* Pl, float* rowsum, const uint8_t* mask,
                           int heads, int Z, int C, int K, cudaStream_t st) {
