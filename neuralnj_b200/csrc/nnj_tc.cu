@@ -271,7 +271,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CU
     if (threadIdx.x == 0) {
         for (int s = 0; s < G2_NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1); mbar_init(acc_full + 1, 1);
-        mbar_init(acc_free, 8); mbar_init(acc_free + 1, 8);
+        mbar_init(acc_free, rank == 0 ? 5 : 4); mbar_init(acc_free + 1, rank == 0 ? 5 : 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc2(tmem_slot, 2 * BN);
@@ -350,10 +350,18 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CU
                     __syncwarp();
                 }
             }
+        } else {      // relay: the peer's epilogue warps arrive locally (cheap CTA-scope release); one cluster-scope arrive per tile goes to the leader
+            const uint32_t free0 = mapa_u32(smem_u32(acc_free), 0);
+            int ti = 0;
+            for (int grp = cid; grp < n_groups; grp += ncl) for (int t = grp * gsz; t < (grp + 1) * gsz; ++t, ++ti) {
+                const int ab = ti & 1;
+                mbar_wait(acc_free + ab, (ti >> 1) & 1);
+                if (elect_one()) mbar_arrive_cluster(free0 + ab * 8);
+                __syncwarp();
+            }
         }
     } else {
         const int q = warp & 3;
-        const uint32_t free0 = mapa_u32(smem_u32(acc_free), 0);
         int ti = 0;
         for (int grp = cid; grp < n_groups; grp += ncl) for (int t = grp * gsz; t < (grp + 1) * gsz; ++t, ++ti) {
             const int xi = t % nt, r0 = t / nt, z = r0 / mt2;
@@ -398,7 +406,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CU
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(free0 + ab * 8);
+            if (lane == 0) mbar_arrive(acc_free + ab);      // local (CTA-scope release): the peer's relay warp forwards it to the leader
         }
     }
     tc_fence_before();
@@ -450,7 +458,7 @@ k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
     if (threadIdx.x == 0) {
         for (int s = 0; s < NH; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1); mbar_init(acc_full + 1, 1);
-        mbar_init(acc_free, 8); mbar_init(acc_free + 1, 8);
+        mbar_init(acc_free, rank == 0 ? 5 : 4); mbar_init(acc_free + 1, rank == 0 ? 5 : 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc2(tmem_slot, 2 * BN);
@@ -532,10 +540,19 @@ k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
                     }
                 }
             }
+        } else {      // relay (see k_tc_gemm2)
+            const uint32_t free0 = mapa_u32(smem_u32(acc_free), 0);
+            int ti = 0;
+            for (int it = cid; it < n_items; it += ncl)
+                for (int t = 0; t < 2 * nt; ++t, ++ti) {
+                    const int ab = ti & 1;
+                    mbar_wait(acc_free + ab, (ti >> 1) & 1);
+                    if (elect_one()) mbar_arrive_cluster(free0 + ab * 8);
+                    __syncwarp();
+                }
         }
     } else {
         const int q = warp & 3;
-        const uint32_t free0 = mapa_u32(smem_u32(acc_free), 0);
         uint8_t* stg_h = epi + q * G2S_EPI_WARP;
         uint8_t* stg_l = stg_h + 32 * G2S_EPI_PITCH;
         constexpr float L2E = 1.4426950408889634f;
@@ -618,7 +635,7 @@ k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(free0 + ab * 8);
+                if (lane == 0) mbar_arrive(acc_free + ab);      // local (CTA-scope release): the peer's relay warp forwards it to the leader
             }
             sa.rowsum[(size_t)z * g.M + m] = rsum;
         }
@@ -662,7 +679,7 @@ k_tc_gemm2w(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
     if (threadIdx.x == 0) {
         for (int s = 0; s < G2W_NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_free, 8);
+        mbar_init(acc_free, rank == 0 ? 5 : 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc2(tmem_slot, 512);
@@ -735,10 +752,17 @@ k_tc_gemm2w(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
                     __syncwarp();
                 }
             }
+        } else {      // relay (see k_tc_gemm2)
+            const uint32_t free0 = mapa_u32(smem_u32(acc_free), 0);
+            int ti = 0;
+            for (int t = cid; t < n_tiles; t += ncl, ++ti) {
+                mbar_wait(acc_free, ti & 1);
+                if (elect_one()) mbar_arrive_cluster(free0);
+                __syncwarp();
+            }
         }
     } else {
         const int q = warp & 3;
-        const uint32_t free0 = mapa_u32(smem_u32(acc_free), 0);
         int ti = 0;
         for (int t = cid; t < n_tiles; t += ncl, ++ti) {
             const int z = t / mt2;
@@ -782,7 +806,7 @@ k_tc_gemm2w(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(free0);
+            if (lane == 0) mbar_arrive(acc_free);
         }
     }
     tc_fence_before();
