@@ -38,7 +38,7 @@ for name in names:
 head = ("round 2 (" + rnd + "): ncu --set full --import-source on --clock-control none, python scratch/prof_rollout.py 128 1 (one 128-alignment chunk, 50 x 1024, bf16x3); one launch per kernel\n"
         "score_incr = k_score_inc launch #15 (NJ step 16, 33 pairs per tree); score_late = k_score_inc launch #30 (19 pairs: narrow mode); score_small = k_score_small launch #4 (12 pairs);\n"
         "alpha_incr = k_alpha_v3 launch #20 (step 16); alpha_late = k_alpha_v3 launch #36 (4-way site split, ~18 pairs); alpha_small = k_alpha_small launch #4; step0 = first launch, 256 pairs per tree;\n"
-        "rowqk = k_tc_gemm2<0> launch #2, rowpv = k_tc_gemm2w launch #1 (the CTA-pair row GEMMs, layer 1 / 2); merge = k_merge launch #20 (30 live nodes), merge_late = launch #40 (10 live nodes); derive = k_node_derive; *_bf16 = the same GEMM launches with precision=\"bf16\" (one product)\n")
+        "rowqk = k_tc_gemm2s launch #2 (Q K^T + softmax on CTA pairs), rowpv = k_tc_gemm2w launch #1 (one-pass P V on CTA pairs); merge = k_merge launch #20 (30 live nodes), merge_late = launch #40 (10 live nodes); derive = k_node_derive; *_bf16 = the same GEMM launches with precision=\"bf16\" (one product)\n")
 open(f"profiles/{rnd}_ncu_full_summary_b128.txt", "w").write(head + "\n".join(out) + "\n")
 json.dump(tr, open(f"profiles/{rnd}_traffic_b128.json", "w"), indent=1)
 # launch list
@@ -63,6 +63,7 @@ byc = collections.defaultdict(float)
 def klass(k):
     if k in cls: return cls[k]
     if k.startswith("k_tc_gemm2w"): return "row_pv_gemm"
+    if k.startswith("k_tc_gemm2s"): return "row_qk_gemm"
     if k.startswith("k_tc_gemm2<"): return "row_pv_gemm" if k.startswith("k_tc_gemm2<1") else "row_qk_gemm"
     if k.startswith("k_tc_gemm<"):      # <BN, BMN, ONE>: MN-major B = the P V GEMM
         return "row_pv_gemm" if k.split(",")[1].strip().startswith("1") else "row_qk_gemm"

@@ -19,7 +19,7 @@ cap merge_late k_merge 40
 cap derive k_node_derive 0
 cap rowqk_bf16 k_tc_gemm 2 bf16
 cap rowpv_bf16 k_tc_gemm 3 bf16
-cap rowqk k_tc_gemm2 2
+cap rowqk k_tc_gemm2s 2
 cap rowpv k_tc_gemm2w 1
 # the other 11 captures (score / alpha / column block / ffn / rowqkv / softmax) are those of scratch/r2_evidence.sh: kernels unchanged since
 ls -la $o | tail -50
