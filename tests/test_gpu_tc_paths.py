@@ -190,3 +190,42 @@ def test_row_gemm_variants_encoder_matches_oracle(R, C, sd0, gpu_models):
     got = gpu_models["bf16x3"].encode_zxr(data.cuda(), mask.cuda()).cpu()
     err = float((got - ref).abs().max() / ref.abs().max())
     assert err < 5e-5, err
+
+
+_ENC_SCRIPT = r"""
+import sys, torch
+root, out = sys.argv[1], sys.argv[2]
+sys.path.insert(0, root); sys.path.insert(0, root + "/oracle")
+import nnj_oracle as O
+from neuralnj_b200 import PhyloATTN, inference_config
+torch.manual_seed(0)
+model = PhyloATTN(inference_config(), precision="bf16x3").to("cuda:0").eval()
+res = {}
+for R, C in ((50, 512), (20, 256)):
+    data = O.evolved_msa(2, R, C, seed=R + C)
+    mask = torch.zeros(2, C, dtype=torch.bool); mask[1, C - 40:] = True
+    res[(R, C)] = model.encode_zxr(data.cuda(), mask.cuda()).cpu()
+torch.save(res, out)
+"""
+
+
+@pytest.mark.parametrize("env", [{"NNJ_ROW_FUSED": "0"}, {"NNJ_ROW_FUSED": "0", "NNJ_GEMM_2SM": "3"}, {"NNJ_GEMM_2SM": "0"}, {"NNJ_MERGE_TC": "0"}],
+                         ids=["softmax_pass", "two_tile_pv", "single_cta_gemms", "merge_cuda_cores"])
+def test_row_attention_fallback_forms_match_oracle(env, sd0, tmp_path):
+    """The diagnostic switches of the row attention select the forms the fused CTA-pair kernels replaced (three-kernel softmax, two-N-tile
+    P V, single-CTA GEMMs); each must still meet the encoder tolerance against the oracle.  Switches are read once per process."""
+    import os
+    import subprocess
+    import sys
+    import nnj_oracle as O
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = str(tmp_path / "enc.pt")
+    subprocess.run([sys.executable, "-c", _ENC_SCRIPT, root, path], check=True, env={**os.environ, **env}, timeout=300)
+    res = torch.load(path)
+    for (R, C), got in res.items():
+        data = O.evolved_msa(2, R, C, seed=R + C)
+        mask = torch.zeros(2, C, dtype=torch.bool)
+        mask[1, C - 40:] = True
+        ref = O.encode(sd0, data, mask)
+        err = float((got - ref).abs().max() / ref.abs().max())
+        assert err < 5e-5, (env, R, C, err)
