@@ -10,7 +10,12 @@
 //   warp 0   : TMA producer (one elected lane), 4 boxes per stage (A_hi, A_lo, B_hi, B_lo; 64 KB)
 //   warp 1   : TMEM allocator + single-thread MMA issuer (12 x UMMA 128x128x16 per stage), tcgen05.commit
 //   warps 2-5: epilogue, one TMEM lane quarter each: tcgen05.ld -> registers -> global (fp32, or softmax-ready)
-// Every mbarrier wait is bounded (trap after ~2 s) so that a protocol bug surfaces as an error, not a hang.
+// Every mbarrier wait is bounded (trap after ~20 s) so that a protocol bug surfaces as an error, not a hang.
+//
+// CTA-pair kernels (cta_group::2, clusters of two CTAs on one TPC; further down): k_tc_gemm2 (256 x 256 tiles, half the B tile per SM),
+// k_tc_gemm2s (Q K^T with the row softmax in the epilogue - the default of the tied row attention), k_tc_gemm2w (P V in one pass over P).
+// The single-CTA k_tc_gemm serves shapes without an even number of 128-row blocks, split-K launches, the 64 / 128-column tiles and the
+// one-product mode (NNJ_PREC_BF16).
 #include "nnj_internal.h"
 #include "nnj_tc.cuh"
 
