@@ -659,8 +659,12 @@ k_tc_gemm2s(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
 // of the first UMMA's columns, blocks 2, 3 = its half of the second's.  96 KB stages, 2-deep ring.
 constexpr int G2W_STAGE = 6 * TC_PLANE_BYTES;     // A_hi, A_lo (16 KB each), B_hi, B_lo (32 KB each)
 constexpr int G2W_NSTG = 2;
-constexpr int G2W_SMEM = G2W_NSTG * G2W_STAGE + 1024 + 256 + TC_EPI_BYTES;
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+// The accumulator is not double-buffered, so the epilogue is serial with the MMAs: EIGHT epilogue warps (two per TMEM lane quarter, alternating
+// 32-column blocks) drain it; their staging tiles are unpadded [32 rows][128 B] with the 16-byte chunk index XOR-swizzled by the row.
+constexpr int G2W_THREADS = 320;
+constexpr int G2W_EPI_BYTES = 8 * 32 * 128;
+constexpr int G2W_SMEM = G2W_NSTG * G2W_STAGE + 1024 + 256 + G2W_EPI_BYTES;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2W_THREADS, 1)
 k_tc_gemm2w(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
             const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcGemmArgs g) {
     extern __shared__ uint8_t smem_raw[];
@@ -684,7 +688,7 @@ k_tc_gemm2w(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
     if (threadIdx.x == 0) {
         for (int s = 0; s < G2W_NSTG; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_free, rank == 0 ? 5 : 4);
+        mbar_init(acc_free, rank == 0 ? 9 : 8);      // eight local epilogue warps (+ the peer's relay in the leader)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc2(tmem_slot, 512);
@@ -776,10 +780,11 @@ k_tc_gemm2w(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
             tc_fence_after();
             const int m = m0 + q * 32 + lane;
             float* crow = g.C + (size_t)z * g.sC + (size_t)m * g.ldc;
-            float* stg = epi + q * (32 * TC_EPI_LD);
+            const int eh = (warp - 2) >> 2;                          // which of the quarter's two warps: column blocks eh, eh + 2, ...
+            float* stg = epi + (warp - 2) * (32 * 32);
             const bool vec_ok = (g.ldc & 3) == 0 && (g.sC & 3) == 0;
 #pragma unroll 1
-            for (int cb = 0; cb < 16; ++cb) {
+            for (int cb = eh; cb < 16; cb += 2) {
                 const int n = cb * 32;
                 if (n >= g.N) break;
                 uint32_t v[32];
@@ -792,15 +797,15 @@ k_tc_gemm2w(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ C
                 if (n + 31 < g.N && vec_ok) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        st4(stg + lane * TC_EPI_LD + j * 4, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                        st4(stg + lane * 32 + ((j ^ (lane & 7)) << 2), make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
                     __syncwarp();
                     const int rr = lane >> 3, c4 = (lane & 7) * 4;
                     float* cbase = g.C + (size_t)z * g.sC + (size_t)(m0 + q * 32) * g.ldc + n + c4;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int row = it * 4 + rr;
-                        if (m0 + q * 32 + row < g.M) st4(cbase + (size_t)row * g.ldc, ld4(stg + row * TC_EPI_LD + c4));
+                        if (m0 + q * 32 + row < g.M) st4(cbase + (size_t)row * g.ldc, ld4(stg + row * 32 + ((((lane & 7) ^ (row & 7))) << 2)));
                     }
                     __syncwarp();
                 } else if (m < g.M) {
@@ -1161,7 +1166,7 @@ static int launch_tc_gemm2w(int cls, const CUtensorMap& mAh, const CUtensorMap& 
     const int ncl = gemm2_clusters<true>();
     const dim3 grid(2 * (n_pairs < ncl ? n_pairs : ncl));
     prof_begin(cls, st);
-    k_tc_gemm2w<<<grid, TC_THREADS, G2W_SMEM, st>>>(mAh, mAl, mBh, mBl, g);
+    k_tc_gemm2w<<<grid, G2W_THREADS, G2W_SMEM, st>>>(mAh, mAl, mBh, mBl, g);
     ++g_launches;
     prof_end(st);
     cudaError_t e = cudaGetLastError();
