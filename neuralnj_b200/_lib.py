@@ -43,48 +43,96 @@ def _mtime(path: str) -> float:
     return os.path.getmtime(path) if os.path.exists(path) else -1.0
 
 
+def _source_hash(flags_now: str) -> str:
+    """sha256 over the compile flags and the bytes of every source and header: what libnnj.so was built from."""
+    import hashlib
+    h = hashlib.sha256(flags_now.encode())
+    for path in sorted([os.path.join(_HERE, "csrc", s) for s in SOURCES] + [os.path.abspath(x) for x in _headers()]):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _read(path: str) -> str:
+    try:
+        with open(path) as f:
+            return f.read()
+    except OSError:
+        return ""
+
+
+HASH_TAG = LIB_PATH + ".srchash"      # travels with the .so (git-ignored as a built artefact, not gpurun-ignored)
+
+
 def build(force: bool = False, verbose: bool = False, jobs: int = 0) -> str:
     """Compile csrc/*.cu for sm_100a into neuralnj_b200/libnnj.so (in-tree, travels with the repo).
 
-    Every source becomes an object under neuralnj_b200/_build/ (compiled in parallel, rebuilt when the source or any header is
-    newer - or always with force=True / NNJ_FORCE_BUILD=1), then the objects are linked.  nvcc cross-compiles without a GPU."""
+    Up to date means: libnnj.so exists and the hash of flags + sources + headers recorded beside it (libnnj.so.srchash) equals
+    the tree's - file times do not survive a snapshot copy, contents do.  Otherwise every source becomes an object under
+    neuralnj_b200/_build/ (compiled in parallel, rebuilt when the source or any header is newer - or always with force=True /
+    NNJ_FORCE_BUILD=1), then the objects are linked.  The whole rebuild holds an exclusive file lock and the library is moved into
+    place atomically, so the ranks of one torchrun job (bench.py calls build() on every rank) neither compile into each other's
+    objects nor load a half-written library: the first rank builds, the others wait and find it up to date.
+    nvcc cross-compiles without a GPU."""
+    import fcntl
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("NNJ_EXTRA_NVCC_FLAGS", "").split()
-    os.makedirs(OBJ_DIR, exist_ok=True)
-    flags_tag = os.path.join(OBJ_DIR, "flags.txt")
     flags_now = " ".join(NVCC_FLAGS + extra)
-    if _mtime(flags_tag) < 0 or open(flags_tag).read() != flags_now:
-        force = True
-    hdr_t = max(_mtime(h) for h in _headers())
-    todo, objs = [], []
-    for src in SOURCES:
-        sp, op = os.path.join(_HERE, "csrc", src), os.path.join(OBJ_DIR, src[:-3] + ".o")
-        objs.append(op)
-        if force or _mtime(op) < max(_mtime(sp), hdr_t):
-            todo.append((sp, op))
-    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared", "-cudart", "static")]
+    want = _source_hash(flags_now)
 
-    def cc(job):
-        sp, op = job
-        cmd = [nvcc] + compile_flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", op]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        return sp, r
+    def up_to_date() -> bool:
+        return os.path.exists(LIB_PATH) and _read(HASH_TAG) == want
 
-    if todo:
-        with ThreadPoolExecutor(max_workers=jobs or min(len(todo), os.cpu_count() or 4)) as ex:
-            for sp, r in ex.map(cc, todo):
+    if not force and up_to_date():
+        return LIB_PATH
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and up_to_date():      # another process finished the same build while this one waited
+                return LIB_PATH
+            flags_tag = os.path.join(OBJ_DIR, "flags.txt")
+            if _read(flags_tag) != flags_now:
+                force = True
+            hdr_t = max(_mtime(h) for h in _headers())
+            todo, objs = [], []
+            for src in SOURCES:
+                sp, op = os.path.join(_HERE, "csrc", src), os.path.join(OBJ_DIR, src[:-3] + ".o")
+                objs.append(op)
+                if force or _mtime(op) < max(_mtime(sp), hdr_t):
+                    todo.append((sp, op))
+            compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared", "-cudart", "static")]
+
+            def cc(job):
+                sp, op = job
+                cmd = [nvcc] + compile_flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", op]
+                r = subprocess.run(cmd, capture_output=True, text=True)
+                return sp, r
+
+            if todo:
+                with ThreadPoolExecutor(max_workers=jobs or min(len(todo), os.cpu_count() or 4)) as ex:
+                    for sp, r in ex.map(cc, todo):
+                        if r.returncode != 0:
+                            raise NnjError(f"nvcc failed on {sp}:\n" + r.stdout + r.stderr)
+                        if verbose:
+                            sys.stderr.write(r.stderr)
+            if todo or _mtime(LIB_PATH) < max(_mtime(o) for o in objs):
+                tmp = LIB_PATH + f".tmp{os.getpid()}"
+                r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", tmp] + objs,
+                                   capture_output=True, text=True)
                 if r.returncode != 0:
-                    raise NnjError(f"nvcc failed on {sp}:\n" + r.stdout + r.stderr)
-                if verbose:
-                    sys.stderr.write(r.stderr)
-    if todo or _mtime(LIB_PATH) < max(_mtime(o) for o in objs):
-        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB_PATH] + objs,
-                           capture_output=True, text=True)
-        if r.returncode != 0:
-            raise NnjError("nvcc link failed:\n" + r.stdout + r.stderr)
-        with open(flags_tag, "w") as f:
-            f.write(flags_now)
+                    if os.path.exists(tmp):
+                        os.remove(tmp)
+                    raise NnjError("nvcc link failed:\n" + r.stdout + r.stderr)
+                os.replace(tmp, LIB_PATH)
+                with open(flags_tag, "w") as f:
+                    f.write(flags_now)
+            with open(HASH_TAG, "w") as f:
+                f.write(want)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

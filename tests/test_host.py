@@ -32,6 +32,27 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert b"bad arguments" in L.nnj_last_error()
 
 
+def test_build_is_keyed_by_source_contents_not_file_times():
+    """A snapshot copy (the GPU box) does not keep file times: build() must recognise an up-to-date libnnj.so by the hash of
+    flags + sources + headers recorded beside it, and concurrent callers (the ranks of one torchrun job) must not rebuild it."""
+    import subprocess
+    import sys
+    _lib.build()
+    flags = " ".join(_lib.NVCC_FLAGS + os.environ.get("NNJ_EXTRA_NVCC_FLAGS", "").split())
+    assert open(_lib.HASH_TAG).read() == _lib._source_hash(flags)
+    before = os.stat(_lib.LIB_PATH).st_mtime_ns
+    src = os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", "nnj_api.cu")
+    st = os.stat(src)
+    try:
+        os.utime(src)                                    # newer than the library, same bytes
+        code = "from neuralnj_b200 import _lib; _lib.build(); print(_lib.lib().nnj_abi_version())"
+        procs = [subprocess.Popen([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.PIPE, text=True) for _ in range(2)]
+        assert [p.communicate(timeout=600)[0].strip() for p in procs] == ["1", "1"]
+    finally:
+        os.utime(src, ns=(st.st_atime_ns, st.st_mtime_ns))
+    assert os.stat(_lib.LIB_PATH).st_mtime_ns == before
+
+
 def test_sm100a_cubin_is_embedded():
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
