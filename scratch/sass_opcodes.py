@@ -23,7 +23,7 @@ for line in txt.splitlines():
 out = [f"cuobjdump -sass neuralnj_b200/libnnj.so (sm_100a), instruction counts per kernel; built from commit-tree sources by __graft_entry__.build()",
        f"{'kernel':52s} {'instr':>7s} " + " ".join(f"{n:>9s}" for n, _ in pats)]
 tot = collections.Counter()
-for k in sorted(set(order), key=lambda k: -counts[k]["UTC*MMA"] * 1000 - counts[k]["HMMA(mma.sync)"]):
+for k in sorted(set(order), key=lambda k: (-counts[k]["UTC*MMA"] * 1000 - counts[k]["HMMA(mma.sync)"], k)):
     c = counts[k]
     out.append(f"{k[:52]:52s} {c['instructions']:7d} " + " ".join(f"{c[n]:9d}" for n, _ in pats))
     tot.update(c)
