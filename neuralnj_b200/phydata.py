@@ -22,6 +22,17 @@ for _ch, _v in _CODE.items():
     _LUT[ord(_ch)] = _v
 
 
+class _Known(dict):
+    """str.translate table: the seven symbols of `_CODE` map to themselves, anything else to a gap (phydata.py:536-543)."""
+
+    def __missing__(self, key):
+        return "-"
+
+
+_KNOWN = _Known({ord(c): c for c in _CODE})
+_LUT32 = np.ascontiguousarray(_LUT).view(np.uint32).reshape(256)     # one 4-byte gather per symbol instead of four 1-byte ones
+
+
 def load_phy_file_multirow(path: str) -> Tuple[List[str], List[str], int, int]:
     """PHYLIP reader: first block `name sequence`, further interleaved blocks without names (phydata.py:499-548)."""
     with open(path) as f:
@@ -49,7 +60,7 @@ def load_phy_file_multirow(path: str) -> Tuple[List[str], List[str], int, int]:
     for nm in names:
         if len(seqs[nm]) != n_sites:
             raise ValueError(f"{path}: sequence {nm} has {len(seqs[nm])} sites, header says {n_sites}")
-        out.append("".join(ch if ch in _CODE else "-" for ch in seqs[nm]))
+        out.append(seqs[nm].translate(_KNOWN))
     return out, names, n_taxa, n_sites
 
 
@@ -66,7 +77,7 @@ def load_alignment_file(path: str) -> Tuple[List[str], List[str], int, int]:
                 seqs.append("")
             elif names:
                 seqs[-1] += ln.replace(" ", "").upper()
-    seqs = ["".join(ch if ch in _CODE else "-" for ch in s) for s in seqs]
+    seqs = [s.translate(_KNOWN) for s in seqs]
     return seqs, names, len(names), max((len(s) for s in seqs), default=0)
 
 
@@ -81,7 +92,7 @@ def encode_sequences(seqs: List[str]) -> Tuple[np.ndarray, np.ndarray]:
     # the reference zips the rows into columns (truncating to the shortest row) and pads the rest
     raw[:, cols_real:] = ord("*")
     weights[cols_real:] = 0.0
-    return _LUT[raw], weights
+    return _LUT32[raw].view(np.int8).reshape(raw.shape[0], L, 4), weights
 
 
 def load_pi_instance(file_path: str) -> dict:

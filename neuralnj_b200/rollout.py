@@ -153,20 +153,69 @@ def _cfg(c):
     return c
 
 
-def Argmax_inference(test_file_path, write_dir, write_file_name=None, branch_optimize=False, cfgs=None, device=None, precision=None):
+def _stack_instances(instances) -> dict:
+    """Batch dicts of `load_pi_instance` (one alignment each, equal taxa / site counts) -> one batch dict."""
+    out = {}
+    for k in instances[0]:
+        vals = [inst[k] for inst in instances]
+        out[k] = torch.cat(vals, dim=0) if torch.is_tensor(vals[0]) else [x for v in vals for x in v]
+    return out
+
+
+def _rank_share(items):
+    """This rank's contiguous share of `items` when a process group is up (alignments are independent: no collective)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return items
+    from .shard import shard_bounds
+    lo, hi = shard_bounds(len(items), dist.get_rank(), dist.get_world_size())
+    return items[lo:hi]
+
+
+def Argmax_inference(test_file_path, write_dir, write_file_name=None, branch_optimize=False, cfgs=None, device=None, precision=None,
+                     files_per_call=1, policy_network=None):
+    """One `.tre` per `.phy` of a directory (finetune_rl_search.py:478-509).
+
+    `files_per_call=1` is the reference's loop: one alignment per call (expanded to `cfgs.env.batch_size` copies, :444).
+    `files_per_call=N` (not a reference argument) stacks up to N alignments of EQUAL taxa and site counts into one rollout call -
+    what the batched kernels are built for (hundreds of trees/s instead of one 15 ms call per file); alignments of other shapes go
+    into their own calls, nothing is padded, and the rollout of an alignment does not depend on its batch mates, so the trees
+    are the ones the per-file loop writes.  Under an initialised process group every rank takes a contiguous share of the sorted
+    file list and writes its own trees (no collective); the return value lists this rank's files."""
     c = _cfg(cfgs)
     device = device or torch.device("cuda")
     env = PhyInferEnv(c, device)
-    policy = _load_policy(c, device, precision)
+    policy = policy_network if policy_network is not None else _load_policy(c, device, precision)
     os.makedirs(write_dir, exist_ok=True)
+    files = _rank_share(sorted(f for f in os.listdir(test_file_path) if f.endswith(".phy")))
     written = []
-    for file in sorted(f for f in os.listdir(test_file_path) if f.endswith(".phy")):
-        res = Agmax_one_instance(c, os.path.join(test_file_path, file), policy, env, branch_optimize=branch_optimize)
-        dst = os.path.join(write_dir, file[:-4] + ".tre")
-        with open(dst, "w") as f:
-            f.write(res["best_tree_str"])
-        written.append(dst)
-    return written
+    if files_per_call <= 1:
+        for file in files:
+            res = Agmax_one_instance(c, os.path.join(test_file_path, file), policy, env, branch_optimize=branch_optimize)
+            dst = os.path.join(write_dir, file[:-4] + ".tre")
+            with open(dst, "w") as f:
+                f.write(res["best_tree_str"])
+            written.append(dst)
+        return written
+
+    pending = {}                      # (taxa, sites) -> [(file, instance), ...]
+
+    def run(items):
+        batch = _stack_instances([inst for _, inst in items])
+        _, _, _, trees = reinforce_rollout(batch, policy, env, c, eval=True, argmax=True, get_all_tree=True, branch_optimize=branch_optimize)
+        for (file, _), tree in zip(items, trees):
+            with open(os.path.join(write_dir, file[:-4] + ".tre"), "w") as f:
+                f.write(tree)
+
+    for file in files:
+        inst = load_pi_instance(os.path.join(test_file_path, file))
+        shape = tuple(inst["data"].shape[1:3])
+        pending.setdefault(shape, []).append((file, inst))
+        if len(pending[shape]) == files_per_call:
+            run(pending.pop(shape))
+    for shape in sorted(pending):
+        run(pending[shape])
+    return [os.path.join(write_dir, file[:-4] + ".tre") for file in files]
 
 
 def RL_Search(cfgs, MSA_file, policy_network, env, c_best_tree_file=None, raw_tree_file=None, scorer=None, stop_step=None,
@@ -262,6 +311,8 @@ def main(argv=None):
     ap.add_argument("--branch_optimize", action="store_true")
     ap.add_argument("--precision", type=str, default=None, choices=["fp32", "bf16x3", "bf16"],
                     help="arithmetic of the CUDA path (not a reference flag); default bf16x3: tcgen05 split-bf16, topologies identical to fp32")
+    ap.add_argument("--files_per_call", type=int, default=1,
+                    help="Argmax: alignments of equal shape stacked into one rollout call (not a reference flag); 1 = the reference's per-file loop")
     args = ap.parse_args(argv)
     PRECISION = args.precision
     cfgs = empty_config()
@@ -271,7 +322,7 @@ def main(argv=None):
     name = os.path.basename(os.path.normpath(cfgs.instance_path))
     write_dir = f"output/{args.infer_opt}_dim{cfgs.model.embed_dim}_patch{cfgs.model.patch_size}/{name}"
     if args.infer_opt == "Argmax":
-        return Argmax_inference(cfgs.instance_path, write_dir, None, branch_optimize=args.branch_optimize)
+        return Argmax_inference(cfgs.instance_path, write_dir, None, branch_optimize=args.branch_optimize, files_per_call=args.files_per_call)
     if args.infer_opt == "Search":
         return Search_inference(cfgs.instance_path, write_dir, None)
     raise SystemExit(f'--infer_opt {args.infer_opt}: "Finetune" (NeuralNJ-RL) trains the policy and is outside this path')
