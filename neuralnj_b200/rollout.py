@@ -183,7 +183,10 @@ def Argmax_inference(test_file_path, write_dir, write_file_name=None, branch_opt
     are the ones the per-file loop writes.  Under an initialised process group every rank takes a contiguous share of the sorted
     file list and writes its own trees (no collective); the return value lists this rank's files."""
     c = _cfg(cfgs)
-    device = device or torch.device("cuda")
+    if device is None:                # one process per GPU under torchrun: the rank's own device
+        import torch.distributed as dist
+        ranked = dist.is_available() and dist.is_initialized() and "LOCAL_RANK" in os.environ
+        device = torch.device("cuda", int(os.environ["LOCAL_RANK"])) if ranked else torch.device("cuda")
     env = PhyInferEnv(c, device)
     policy = policy_network if policy_network is not None else _load_policy(c, device, precision)
     os.makedirs(write_dir, exist_ok=True)
