@@ -20,6 +20,7 @@ Printed keys beyond the base contract:
                  NJ loop's DRAM bytes per tree against SURVEY 8(d)'s 334 MB streaming figure
   kernels        per-class milliseconds / launches / share of the profiled step
   latency_b1_ms  one alignment, device-resident input -> merge list (median of 7)
+  directory_inference  Argmax_inference over PHYLIP files of the timed batch: per-file loop vs files_per_call=128 (wall clock, host work included)
   tree_llh       the Search-mode scorer: 32 topologies of the batch scored with the GPU likelihood (branch lengths / + model search)
   gpu_eager_baseline  the reference formulation (the oracle restatement) in torch eager on this GPU at B = 1 / 8 / 32
   parity_check   after the timed region: alignments of the bench batch replayed on the CPU oracle
@@ -199,6 +200,52 @@ def llh_scoring_rate(merges, onehot, R):
         torch.cuda.synchronize()
         dt = time.time() - t0
         out[key] = {"s": round(dt, 3), "trees_per_s": round(ch.shape[0] / dt, 1), "best_llh": round(float(ll.max()), 3)}
+    return out
+
+
+def write_phylip_files(onehot, dirpath):
+    """int8 one-hot alignments [n, R, L, 4] (gap = 1111) -> dirpath/msaNNNN.phy, sequential PHYLIP with taxa named taxon1..taxonR."""
+    import numpy as np
+    d = onehot.numpy()
+    n, R, L = d.shape[:3]
+    tok = np.where(d.sum(-1) == 4, 4, d.argmax(-1))
+    letters = np.frombuffer(b"ACGT-", dtype=np.uint8)
+    os.makedirs(dirpath)
+    for b in range(n):
+        rows = [f"taxon{r + 1} " + letters[tok[b, r]].tobytes().decode() for r in range(R)]
+        with open(os.path.join(dirpath, f"msa{b:04d}.phy"), "w") as f:
+            f.write(f"{R} {L}\n" + "\n".join(rows) + "\n")
+
+
+def directory_inference_rate(model, data_host, R, L, dev):
+    """The file-level entry point (`Argmax_inference`, finetune_rl_search.py:478-509) on alignments of the timed batch written as
+    PHYLIP files: wall clock over everything a user of the entry point pays - parsing and encoding the files, H2D, the rollout,
+    the host tree objects, Newick strings and the .tre files.  `files_per_call_128`: equal-shape alignments stacked into one device
+    call; `per_file_loop`: the reference's one-alignment-per-call loop (on 16 of the files)."""
+    import tempfile
+    import torch
+    from neuralnj_b200 import Argmax_inference, inference_config
+    n = min(128, data_host.shape[0])
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        dirs = {}
+        for label, cnt in (("files_per_call_128", n), ("per_file_loop", min(16, n))):
+            dirs[label] = os.path.join(tmp, label)
+            write_phylip_files(data_host[:cnt], dirs[label])
+        cfgs = inference_config()
+        trees = {}
+        for label, fpc in (("per_file_loop", 1), ("files_per_call_128", 128)):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            written = Argmax_inference(dirs[label], os.path.join(tmp, "out_" + label), None, cfgs=cfgs, device=dev, files_per_call=fpc,
+                                       policy_network=model)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out[label] = {"files": len(written), "s": round(dt, 3), "trees_per_s": round(len(written) / dt, 1)}
+            trees[label] = [open(w).read() for w in written]
+        k = len(trees["per_file_loop"])
+        out["same_trees_as_per_file_loop"] = trees["files_per_call_128"][:k] == trees["per_file_loop"]
+    out["note"] = "wall clock incl. PHYLIP parsing, H2D, rollout, host tree objects, Newick and .tre writing; one process, host work not overlapped with the device"
     return out
 
 
@@ -461,6 +508,10 @@ def main():
                 extras["supervised_eval"] = supervised_eval_rate(model, data, mask, merges, R_TAXA)
             except Exception as exc:   # noqa: BLE001
                 extras["supervised_eval"] = {"error": f"{type(exc).__name__}: {exc}"}
+            try:
+                extras["directory_inference"] = directory_inference_rate(model, data_host, R_TAXA, L_SITES, dev)
+            except Exception as exc:   # noqa: BLE001
+                extras["directory_inference"] = {"error": f"{type(exc).__name__}: {exc}"}
     if rank == 0 and world == 1 and not args.no_extras and args.workload == "config2" and args.precision == "bf16x3":
         # The north star's "bf16 encoder" (precision="bf16": one tcgen05 product per encoder contraction, NJ loop unchanged) on the same
         # batch: what the encoder kernels reach without the 3-product split.  NOT the headline - the mode does not keep the reference's

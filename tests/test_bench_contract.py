@@ -56,3 +56,23 @@ def test_reference_arm_prints_one_contract_line():
     _check_common(d)
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_directory_inference_side_measurement_on_the_oracle_stand_in(tmp_path, monkeypatch):
+    """bench.py's `directory_inference` extra: synthetic alignments -> PHYLIP files -> `Argmax_inference` per file and stacked.
+    The files must read back as the one-hot batch they were written from, and the measurement's bookkeeping is exercised with the
+    CPU oracle standing in for the device model (test infrastructure; on the GPU box the bench passes its own model)."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    from neuralnj_b200 import load_pi_instance
+    from test_entry_batched_cpu import OracleAgent
+    data = bench.synthetic_msa(3, 6, 64, 7)
+    bench.write_phylip_files(data, str(tmp_path / "phy"))
+    for b in range(3):
+        inst = load_pi_instance(str(tmp_path / "phy" / f"msa{b:04d}.phy"))
+        assert torch.equal(inst["data"][0], data[b]) and inst["seq_keys"][0] == [f"taxon{r + 1}" for r in range(6)]
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    out = bench.directory_inference_rate(OracleAgent(), data, 6, 64, torch.device("cpu"))
+    assert out["files_per_call_128"]["files"] == 3 and out["per_file_loop"]["files"] == 3
+    assert out["same_trees_as_per_file_loop"] is True and out["files_per_call_128"]["trees_per_s"] > 0
